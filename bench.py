@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""Headline benchmark: top-k queries/sec of the retrieval hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Workload at every N: BASELINE.json configs[1] — batched IR evaluation, 10,000 queries against the
+49,688 x 384 fp32 catalog, top-100 (one "step" = one pass over one 10,000-query batch). With N > 1 every
+rank holds a replica of the catalog and its own query batch (queries are independent units: weak scaling,
+no data-path collective), and the same run also measures the row-sharded catalog + NCCL all-gather +
+device merge path on a larger catalog (key "sharded"), which is the north_star's route for catalogs that
+do not fit one GPU.
+
+Prints ONE JSON line (rank 0). `value` = device-resident throughput; `e2e` = through the public API with
+pinned-host queries in and host results out, copies inside the timed region; `roofline` = the dominant
+kernel against the measured bf16 tensor peak (or HBM peak for the GEMV path); `cpu_baseline` = the oracle
+port of the reference path (sentence-transformers cos_sim + torch.topk) on this box's host cores.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+C2 = dict(Q=10_000, N=49_688, D=384, k=100)
+CATALOG_SEED, QUERY_SEED = 1234, 4321
+METRIC = "top-k queries/sec (IR-eval batch: 10,000 queries x 49,688x384 fp32 catalog, top-100)"
+
+
+def _peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained"), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
+
+    FIELDS = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc, self.thread = index, [], None, None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def _cpu_reference_qps(sample_queries: int, budget_s: float, threads: int | None = None):
+    """The reference's CPU path for this workload (oracle port): cos_sim -> torch.topk(100), all host threads."""
+    import torch
+
+    from oracle import oracle
+
+    if threads:
+        torch.set_num_threads(threads)
+    items = oracle.synth_isotropic(C2["N"], C2["D"], CATALOG_SEED)
+    queries = oracle.synth_isotropic(sample_queries, C2["D"], QUERY_SEED)
+    oracle.cos_topk(queries[:64], items, C2["k"])  # warm the thread pool
+    done, t0 = 0, time.perf_counter()
+    while done < sample_queries:
+        oracle.cos_topk(queries[done : done + 500], items, C2["k"], sorted=False)
+        done += min(500, sample_queries - done)
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return done / dt, done, torch.get_num_threads()
+
+
+def run_reference(args, rank: int):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port; sentence-transformers is
+    not installable here), rank 0 only, each step a bounded sample of the C2 batch."""
+    if rank != 0:
+        return
+    import torch
+
+    from oracle import oracle
+
+    sample = 500
+    items = oracle.synth_isotropic(C2["N"], C2["D"], CATALOG_SEED)
+    queries = oracle.synth_isotropic(sample, C2["D"], QUERY_SEED)
+    for _ in range(args.warmup):
+        oracle.cos_topk(queries, items, C2["k"], sorted=False)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle.cos_topk(queries, items, C2["k"], sorted=False)
+    dt = time.perf_counter() - t0
+    qps = sample * args.steps / dt
+    cores = torch.get_num_threads()
+    sample_desc = f"{sample} of the 10,000 queries per step against the full 49,688x384 fp32 catalog; cos_sim (normalize both + mm) + torch.topk(100, sorted=False), torch CPU"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C2: 10,000 queries x 49,688x384 fp32 catalog, top-100 (bounded sample per step)", "Q": C2["Q"], "N": C2["N"], "D": C2["D"], "k": C2["k"]},
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample_desc, "host_cpus": os.cpu_count()},
+        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"], help="catalog storage dtype (headline: f32, the reference's)")
+    ap.add_argument("--path", default="auto", choices=["auto", "gemv", "gemm"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import instacart_next_order_recommendation_b200 as icr
+    from instacart_next_order_recommendation_b200 import ops
+
+    assert torch.cuda.is_available(), "bench.py needs a B200"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run"
+    path = {"auto": ops.PATH_AUTO, "gemv": ops.PATH_GEMV, "gemm": ops.PATH_GEMM}[args.path]
+    tdtype = torch.float32 if args.dtype == "f32" else torch.bfloat16
+    Q, N, D, k = C2["Q"], C2["N"], C2["D"], C2["k"]
+
+    # ---- synthetic inputs (isotropic unit vectors); catalog replica per rank, distinct queries per rank
+    g = torch.Generator(device=dev).manual_seed(CATALOG_SEED)
+    items = torch.nn.functional.normalize(torch.randn(N, D, device=dev, generator=g), dim=1)
+    g.manual_seed(QUERY_SEED + rank)
+    queries = torch.nn.functional.normalize(torch.randn(Q, D, device=dev, generator=g), dim=1)
+    catalog = icr.DeviceCatalog(items, dtype=tdtype)
+    queries_dev = queries.to(tdtype)
+    queries_host = queries.cpu().pin_memory()
+    out_v_host = torch.empty(Q, k, dtype=torch.float32).pin_memory()
+    out_i_host = torch.empty(Q, k, dtype=torch.int64).pin_memory()
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step_device():
+        return catalog.topk(queries_dev, k, path=path)
+
+    def step_e2e():
+        qd = queries_host.to(dev, non_blocking=True)
+        v, i = catalog.topk(qd, k, path=path)
+        out_v_host.copy_(v, non_blocking=True)
+        out_i_host.copy_(i, non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        stops = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        barrier()
+        for s in range(steps):
+            flush.zero_()  # evict L2 between timed iterations (not timed)
+            starts[s].record()
+            fn()
+            stops[s].record()
+        barrier()
+        ms = [a.elapsed_time(b) for a, b in zip(starts, stops)]
+        total = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(total, op=dist.ReduceOp.MAX)
+        return total.item(), ms
+
+    for _ in range(args.warmup):
+        step_device()
+    launches_per_step = ops.last_launch_count()
+    with ClockSampler(local_rank) as clocks:
+        total_ms, per_step = timed(step_device, args.steps)
+    for _ in range(3):
+        step_e2e()
+    e2e_ms, _ = timed(step_e2e, args.steps)
+
+    # ---- dominant kernel alone (CUDA events recorded by the library around that kernel's launches) -------------
+    kt = ops.kernel_timing(step_device, args.steps, flush=flush)
+    peaks = _peaks()
+    flops = 2.0 * Q * N * D
+    if kt["kernel"] == "gemm_topk":
+        roof = {"bound": "tensor", "achieved": flops / (kt["ms_per_step"] * 1e-3) / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s"}
+        roof["note"] = f"algorithmic 2*Q*N*D flops; fp32 parity costs {kt.get('mma_terms', 1)} fp16 MMA terms per flop; peak = {peaks['source']} bf16 burst"
+    else:
+        # GEMV passes re-read the catalog once per group of <=7 queries: bytes are per launch
+        bytes_per_launch = N * D * (4 if args.dtype == "f32" else 2)
+        roof = {"bound": "hbm", "achieved": bytes_per_launch / (kt["ms_per_launch"] * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s"}
+        roof["note"] = f"catalog bytes per GEMV launch (L2-resident after the first pass); peak = {peaks['source']} HBM copy"
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    roof["traffic"] = None
+    roof["kernel"] = kt["kernel"]
+    roof["kernel_ms_per_step"] = kt["ms_per_step"]
+    roof["kernel_launches_per_step"] = kt["launches_per_step"]
+
+    sharded = None
+    if world > 1 and not args.no_sharded:
+        sharded = bench_sharded(icr, dist, dev, rank, world, args, tdtype)
+
+    value = world * Q * args.steps / (total_ms * 1e-3)
+    e2e = world * Q * args.steps / (e2e_ms * 1e-3)
+    line = {
+        "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": "C2: batched IR eval, 10,000 queries x 49,688x384 catalog, top-100 (BASELINE.json configs[1])",
+                   "Q_per_gpu": Q, "N": N, "D": D, "k": k, "catalog_dtype": args.dtype, "path": args.path,
+                   "multi_gpu": "catalog replica + own query batch per rank (no data-path collective)" if world > 1 else "single GPU",
+                   "l2": "512 MiB buffer zeroed between timed iterations (L2 flush)", "seeds": [CATALOG_SEED, QUERY_SEED]},
+        "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": Q * D * 4, "d2h_bytes_per_step": Q * k * 12,
+                "note": "pinned-host fp32 queries in, (scores f32, ids i64) out to pinned host; catalog resident in HBM as the index is"},
+        "gpu_launches": launches_per_step * args.steps,
+        "roofline": roof,
+        "clocks": clocks.summary(),
+        "ms_per_step_min": min(per_step),
+    }
+    if sharded is not None:
+        line["sharded"] = sharded
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        qps, nq, cores = _cpu_reference_qps(sample_queries=4000, budget_s=15.0)
+        line["cpu_baseline"] = {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "host_cpus": os.cpu_count(),
+                                "sample": f"{nq} of the 10,000 queries against the full catalog: oracle port of cos_sim + torch.topk(100), torch CPU"}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_sharded(icr, dist, dev, rank, world, args, tdtype):
+    """Row-sharded catalog (fixed total size, strong scaling): local fused top-k -> NCCL all-gather -> K4 merge."""
+    import torch
+
+    total_rows, D, Q, k = 8 * 49_688 * 4, 384, 1024, 100
+    lo, hi = icr.shard_bounds(total_rows, world, rank)
+    g = torch.Generator(device=dev).manual_seed(CATALOG_SEED + 100 + rank)
+    rows = torch.nn.functional.normalize(torch.randn(hi - lo, D, device=dev, generator=g), dim=1)
+    cat = icr.ShardedCatalog(rows, row_offset=lo, total_rows=total_rows, dtype=tdtype)
+    g2 = torch.Generator(device=dev).manual_seed(QUERY_SEED)
+    q = torch.nn.functional.normalize(torch.randn(Q, D, device=dev, generator=g2), dim=1).to(tdtype)
+    for _ in range(3):
+        cat.topk(q, k)
+    steps = max(3, args.steps // 2)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dist.barrier()
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(steps):
+        cat.topk(q, k)
+    ev1.record()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return {"workload": f"row-sharded {total_rows}x{D} {args.dtype} catalog over {world} GPUs, {Q}-query batches, top-{k}, NCCL all-gather + device merge",
+            "value": Q * steps / (t.item() * 1e-3), "unit": "queries/s", "scaling": "strong", "ms_per_step": t.item() / steps,
+            "exchange_bytes_per_rank": Q * k * 16}
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,161 @@
+/*
+ * icr_b200.h — C ABI of the B200-native retrieval hot path (cosine scoring + top-k,
+ * dense cos_sim, MultipleNegativesRankingLoss fwd/bwd, shard-candidate merge).
+ *
+ * This header is the drop-in boundary. The reference (chen-bowen/instacart_next_order_
+ * recommendation) has no FFI of its own: the calls replaced are Python calls into
+ * sentence-transformers 5.2.2 + torch. Each entry point cites the reference call site it
+ * stands in for. INTEGRATION.md shows the ctypes binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - Plain C, no C++ types or exceptions cross this line.
+ *   - Every pointer except `stream` is a DEVICE pointer owned by the caller. The library
+ *     never allocates or frees device memory and keeps no pointer after return.
+ *   - `stream` is a cudaStream_t passed as void*; kernels are enqueued on it and the call
+ *     returns without synchronising.
+ *   - Matrices are row-major, contiguous in the embedding dimension, `ld*` = row stride in
+ *     ELEMENTS. Row starts must be 16-byte aligned.
+ *   - Return value: 0 = ok, negative = icr_status; icr_last_error_string() gives the text
+ *     for the calling thread. There is no CPU fallback: a device that is not sm_100 is
+ *     ICR_ERR_DEVICE.
+ */
+#ifndef ICR_B200_H
+#define ICR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ICR_ABI_VERSION 1
+#define ICR_MAX_K 256 /* largest k of one fused top-k call (reference: top_k <= 100, schemas.py:34) */
+
+typedef enum {
+  ICR_OK = 0,
+  ICR_ERR_ARG = -1,       /* bad shape / stride / null pointer           */
+  ICR_ERR_DTYPE = -2,     /* dtype not supported by this entry point     */
+  ICR_ERR_ALIGN = -3,     /* pointer or row stride not 16-byte aligned   */
+  ICR_ERR_K = -4,         /* k < 1 or k > ICR_MAX_K                      */
+  ICR_ERR_WORKSPACE = -5, /* workspace too small (see *_workspace_bytes) */
+  ICR_ERR_CUDA = -6,      /* CUDA runtime / driver error                 */
+  ICR_ERR_DEVICE = -7     /* current device is not sm_100                */
+} icr_status;
+
+typedef enum { ICR_F32 = 0, ICR_BF16 = 1 } icr_dtype;
+
+/* which kernel family serves a cos_topk call */
+typedef enum {
+  ICR_PATH_AUTO = 0,
+  ICR_PATH_GEMV = 1, /* K1: streaming CUDA-core GEMV + fused top-k, small query batches */
+  ICR_PATH_GEMM = 2  /* K2: tcgen05/TMEM GEMM + threshold-filter epilogue                */
+} icr_path;
+
+int icr_abi_version(void);
+const char* icr_last_error_string(void);
+/* 1 if the CURRENT device is compute capability 10.x, 0 otherwise, <0 on CUDA error. */
+int icr_device_supported(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Catalog preparation (once per index load; replaces the per-call re-normalisation that
+ * sentence_transformers.util.cos_sim does on every /recommend,
+ * reference src/inference/serve_recommendations.py:214,250).
+ *   inv_norms[r] = 1 / max(||x_r||_2, 1e-12)            (F.normalize's eps)
+ * ------------------------------------------------------------------------------------- */
+int icr_row_inv_norms(const void* x, int64_t rows, int64_t dim, int64_t ld, int dtype,
+                      float* inv_norms, void* stream);
+
+/* fp32 rows -> L2-normalised, scaled by 2^8 and split into an fp16 (hi | lo) pair per row:
+ * planes[r, 0:dim] = hi, planes[r, dim_pad:dim_pad+dim] = lo, row stride 2*dim_pad fp16
+ * elements, dim_pad = dim rounded up to 64, padding zero-filled. This is the operand
+ * format of the fp32-parity tensor-core path (three fp16 MMAs with fp32 accumulation). */
+int icr_split_f16_planes(const float* x, int64_t rows, int64_t dim, int64_t ld,
+                         uint16_t* planes, void* stream);
+int64_t icr_planes_row_elems(int64_t dim); /* = 2 * round_up(dim, 64) */
+
+/* ---------------------------------------------------------------------------------------
+ * Fused cosine top-k  ==  torch.topk(cos_sim(queries, catalog), k, dim=1, sorted=True)
+ * with ties broken by the lower catalog row.
+ * Stands in for: cos_sim + argsort + walk (serve_recommendations.py:213-225, 250-262);
+ * cos_sim + torch.topk(100) + heap merge inside InformationRetrievalEvaluator (constructed
+ * at src/training/train_sbert.py:197-202); cos_sim + np.argsort per row
+ * (src/baselines/content_based.py:54-63, scripts/compare_untrained_vs_trained.py:74-84).
+ *
+ *   queries      [Q, D] dtype, row stride ldq
+ *   catalog      [N, D] dtype, row stride ldc          (the shard's rows when sharded)
+ *   cat_planes   optional (may be NULL): icr_split_f16_planes(catalog); used by the GEMM
+ *                path for ICR_F32 catalogs; if NULL it is built in the workspace per call
+ *   exclude_mask optional (may be NULL): N bytes, non-zero = row never returned
+ *                (exclude_product_ids semantics, serve_recommendations.py:216-221)
+ *   row_offset   added to every returned id (global numbering of a row shard)
+ *   out_scores   [Q, k] f32 descending; out_ids [Q, k] i64. If fewer than k rows are
+ *                eligible the tail is (-inf, -1).
+ * ------------------------------------------------------------------------------------- */
+size_t icr_cos_topk_workspace_bytes(int64_t Q, int64_t N, int64_t D, int dtype, int k, int path,
+                                    int have_planes);
+int icr_cos_topk(const void* queries, int64_t Q, int64_t ldq,
+                 const void* catalog, int64_t N, int64_t ldc,
+                 int64_t D, int dtype,
+                 const uint16_t* cat_planes, const uint8_t* exclude_mask,
+                 int k, int64_t row_offset, int path,
+                 float* out_scores, int64_t* out_ids,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* number of kernel launches the last icr_cos_topk call on this thread enqueued */
+int icr_last_launch_count(void);
+
+/* Optional timing of the dominant kernel of subsequent calls made by this thread (used by bench.py for
+ * the roofline figure): CUDA events are recorded on the call's stream around each launch of the GEMV /
+ * GEMM scoring kernel. collect() waits for the recorded events and returns their summed duration;
+ * kernel_id 1 = gemv_topk, 2 = gemm_topk; mma_terms = fp16 MMA products issued per algorithmic product. */
+int icr_profile_enable(int on);
+int icr_profile_collect(float* total_ms, int* launches, int* kernel_id, int* mma_terms);
+
+/* ---------------------------------------------------------------------------------------
+ * Dense cosine similarity  ==  sentence_transformers.util.cos_sim(a, b) -> f32 [Qa, Nb]
+ * (hook-compatible path: MNRL similarity_fct, evaluator score_functions).
+ * ------------------------------------------------------------------------------------- */
+size_t icr_cos_sim_dense_workspace_bytes(int64_t Qa, int64_t Nb, int64_t D, int dtype);
+int icr_cos_sim_dense(const void* a, int64_t Qa, int64_t lda,
+                      const void* b, int64_t Nb, int64_t ldb,
+                      int64_t D, int dtype,
+                      float* out, int64_t ldo,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Shard-candidate merge (K4): G lists of k_in (score, id) per query, as gathered by an
+ * allgather of every rank's icr_cos_topk output, -> global top-k_out. Replaces the
+ * per-chunk Python heapq merge of InformationRetrievalEvaluator.
+ *   cand_scores [G, Q, k_in] f32, cand_ids [G, Q, k_in] i64 (id < 0 = empty slot)
+ * ------------------------------------------------------------------------------------- */
+size_t icr_topk_merge_workspace_bytes(int64_t Q, int G, int k_in, int k_out);
+int icr_topk_merge(const float* cand_scores, const int64_t* cand_ids,
+                   int64_t Q, int G, int k_in, int k_out,
+                   float* out_scores, int64_t* out_ids,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * MultipleNegativesRankingLoss (sentence-transformers; constructed at
+ * src/training/train_sbert.py:182-185):
+ *   loss = mean_i CE( scale * cos_sim(A, P)[i, :], i )
+ * fwd saves per-row lse / inverse norms for bwd. Internal math is fp32.
+ *   a, p        [B, D] dtype;  loss: 1 float;  lse, inv_a, inv_p: B floats each
+ *   grad_out    1 float (dL/dloss);  grad_a, grad_p [B, D] dtype (row strides ldga, ldgp)
+ * ------------------------------------------------------------------------------------- */
+size_t icr_mnrl_workspace_bytes(int64_t B, int64_t D);
+int icr_mnrl_fwd(const void* a, int64_t lda, const void* p, int64_t ldp,
+                 int64_t B, int64_t D, int dtype, float scale,
+                 float* loss, float* lse, float* inv_a, float* inv_p,
+                 void* workspace, size_t workspace_bytes, void* stream);
+int icr_mnrl_bwd(const void* a, int64_t lda, const void* p, int64_t ldp,
+                 int64_t B, int64_t D, int dtype, float scale,
+                 const float* lse, const float* inv_a, const float* inv_p,
+                 const float* grad_out,
+                 void* grad_a, int64_t ldga, void* grad_p, int64_t ldgp,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ICR_B200_H */

@@ -1,0 +1,421 @@
+// extern "C" entry points of libicr_b200.so (declared in include/icr_b200.h).
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace icr {
+
+static thread_local char g_err[512] = "";
+static thread_local int g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) at %s", static_cast<int>(e), cudaGetErrorString(e), what);
+  return ICR_ERR_CUDA;
+}
+void count_launch() { ++g_launches; }
+
+// ---- optional timing of the dominant kernel (bench.py's roofline leg) -------------------------
+static thread_local bool g_prof_on = false;
+static thread_local int g_prof_kernel = 0, g_prof_terms = 1;
+static thread_local std::vector<cudaEvent_t> g_prof_events;  // pairs: begin, end
+static thread_local size_t g_prof_used = 0;
+
+void profile_begin(int kernel_id, int mma_terms, cudaStream_t st) {
+  if (!g_prof_on) return;
+  if (g_prof_used + 2 > g_prof_events.size()) {
+    cudaEvent_t a, b;
+    if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+    g_prof_events.push_back(a);
+    g_prof_events.push_back(b);
+  }
+  g_prof_kernel = kernel_id;
+  g_prof_terms = mma_terms;
+  cudaEventRecord(g_prof_events[g_prof_used], st);
+}
+void profile_end(cudaStream_t st) {
+  if (!g_prof_on || g_prof_used + 2 > g_prof_events.size()) return;
+  cudaEventRecord(g_prof_events[g_prof_used + 1], st);
+  g_prof_used += 2;
+}
+
+// kernels' host launchers (defined in the other translation units)
+int launch_row_inv_norms(const void* x, int64_t rows, int64_t dim, int64_t ld, int dtype, float* inv, cudaStream_t st);
+int launch_split_planes(const float* x, int64_t rows, int64_t dim, int64_t ld, uint16_t* planes, cudaStream_t st);
+int gemv_grid(int64_t N);
+int launch_gemv_topk(const void* cat, int64_t N, int64_t ldc, int D, int dtype, const void* q, int64_t ldq, int Q,
+                     const uint8_t* mask, int k, uint64_t* part_keys, int* part_cnt, int grid, cudaStream_t st);
+size_t select_scratch_bytes(int64_t Q, int nseg, int seg_cap, int k);
+int launch_select(const uint64_t* seg_keys, const int* seg_cnt, int64_t Q, int nseg, int seg_stride, int seg_cap,
+                  const uint64_t* carry_in, const int* carry_cnt_in, uint64_t* carry_out, int* carry_cnt_out,
+                  float* tau_out, float* out_scores, int64_t* out_ids, int64_t id_offset, int k, void* scratch,
+                  size_t scratch_bytes, cudaStream_t st);
+int launch_merge_lists(const float* cs, const int64_t* ci, int64_t Q, int G, int k_in, int k_out, float* os, int64_t* oi,
+                       cudaStream_t st);
+int launch_cos_sim_dense(const void* a, int64_t Qa, int64_t lda, const void* b, int64_t Nb, int64_t ldb, int D, int dtype,
+                         const float* inva, const float* invb, float* out, int64_t ldo, cudaStream_t st);
+// GEMM path (gemm_topk.cu)
+size_t gemm_topk_workspace_bytes(int64_t Q, int64_t N, int64_t D, int dtype, int k, int have_planes);
+int launch_gemm_topk(const void* queries, int64_t Q, int64_t ldq, const void* catalog, int64_t N, int64_t ldc, int64_t D,
+                     int dtype, const uint16_t* cat_planes, const uint8_t* mask, int k, int64_t row_offset, float* out_scores,
+                     int64_t* out_ids, void* ws, size_t ws_bytes, cudaStream_t st);
+bool gemm_topk_supported(int64_t Q, int64_t N, int64_t D, int dtype, int k, const uint8_t* mask);
+
+int launch_mnrl_dispatch(const MnrlArgs& g, int dtype, bool bwd, cudaStream_t st);
+
+static int elem_size(int dtype) { return dtype == ICR_F32 ? 4 : 2; }
+static int vec_elems(int dtype) { return dtype == ICR_F32 ? 4 : 8; }
+
+static int check_matrix(const char* name, const void* p, int64_t rows, int64_t dim, int64_t ld, int dtype) {
+  if (dtype != ICR_F32 && dtype != ICR_BF16) {
+    set_error("%s: unsupported dtype %d (0 = f32, 1 = bf16)", name, dtype);
+    return ICR_ERR_DTYPE;
+  }
+  if (rows < 0 || dim <= 0 || ld < dim) {
+    set_error("%s: bad shape rows=%lld dim=%lld ld=%lld", name, (long long)rows, (long long)dim, (long long)ld);
+    return ICR_ERR_ARG;
+  }
+  if (rows > 0 && p == nullptr) {
+    set_error("%s: null pointer", name);
+    return ICR_ERR_ARG;
+  }
+  if (dim % vec_elems(dtype) != 0) {
+    set_error("%s: embedding dim %lld must be a multiple of %d for 16-byte vector access", name, (long long)dim, vec_elems(dtype));
+    return ICR_ERR_ALIGN;
+  }
+  if ((reinterpret_cast<uintptr_t>(p) & 15) != 0 || (ld * elem_size(dtype)) % 16 != 0) {
+    set_error("%s: base pointer and row stride must be 16-byte aligned", name);
+    return ICR_ERR_ALIGN;
+  }
+  return ICR_OK;
+}
+
+static int check_device() {
+  int dev = 0;
+  ICR_CUDA_CHECK(cudaGetDevice(&dev));
+  static thread_local int cached_dev = -1, cached_ok = 0;
+  if (dev != cached_dev) {
+    int major = 0;
+    ICR_CUDA_CHECK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    cached_dev = dev;
+    cached_ok = (major == 10);
+  }
+  if (!cached_ok) {
+    set_error("device %d is not compute capability 10.x (B200); there is no fallback path", dev);
+    return ICR_ERR_DEVICE;
+  }
+  return ICR_OK;
+}
+
+constexpr int kGemvQueryChunk = 252;  // queries per GEMV workspace round (multiple of 7)
+
+static size_t gemv_ws_bytes(int64_t Q, int64_t N, int k) {
+  const int grid = gemv_grid(N);
+  const int64_t qc = Q < kGemvQueryChunk ? Q : kGemvQueryChunk;
+  size_t b = 0;
+  b += align_up(static_cast<size_t>(qc) * grid * k * sizeof(uint64_t), 256);
+  b += align_up(static_cast<size_t>(qc) * grid * sizeof(int), 256);
+  b += align_up(select_scratch_bytes(qc, grid, k, k), 256);
+  return b + 256;
+}
+
+}  // namespace icr
+
+using namespace icr;
+
+extern "C" {
+
+int icr_abi_version(void) { return ICR_ABI_VERSION; }
+const char* icr_last_error_string(void) { return g_err; }
+int icr_last_launch_count(void) { return g_launches; }
+
+int icr_device_supported(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return ICR_ERR_CUDA;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return ICR_ERR_CUDA;
+  return major == 10 ? 1 : 0;
+}
+
+int icr_profile_enable(int on) {
+  g_prof_on = on != 0;
+  g_prof_used = 0;
+  return ICR_OK;
+}
+
+int icr_profile_collect(float* total_ms, int* launches, int* kernel_id, int* mma_terms) {
+  float sum = 0.f;
+  for (size_t i = 0; i + 1 < g_prof_used; i += 2) {
+    ICR_CUDA_CHECK(cudaEventSynchronize(g_prof_events[i + 1]));
+    float ms = 0.f;
+    ICR_CUDA_CHECK(cudaEventElapsedTime(&ms, g_prof_events[i], g_prof_events[i + 1]));
+    sum += ms;
+  }
+  if (total_ms) *total_ms = sum;
+  if (launches) *launches = static_cast<int>(g_prof_used / 2);
+  if (kernel_id) *kernel_id = g_prof_kernel;
+  if (mma_terms) *mma_terms = g_prof_terms;
+  g_prof_used = 0;
+  return ICR_OK;
+}
+
+int icr_row_inv_norms(const void* x, int64_t rows, int64_t dim, int64_t ld, int dtype, float* inv_norms, void* stream) {
+  g_launches = 0;
+  int rc = check_matrix("row_inv_norms.x", x, rows, dim, ld, dtype);
+  if (rc) return rc;
+  if ((rc = check_device())) return rc;
+  if (rows > 0 && !inv_norms) {
+    set_error("row_inv_norms: null output");
+    return ICR_ERR_ARG;
+  }
+  return launch_row_inv_norms(x, rows, dim, ld, dtype, inv_norms, static_cast<cudaStream_t>(stream));
+}
+
+int64_t icr_planes_row_elems(int64_t dim) { return 2 * ((dim + 63) / 64 * 64); }
+
+int icr_split_f16_planes(const float* x, int64_t rows, int64_t dim, int64_t ld, uint16_t* planes, void* stream) {
+  g_launches = 0;
+  int rc = check_matrix("split_f16_planes.x", x, rows, dim, ld, ICR_F32);
+  if (rc) return rc;
+  if ((rc = check_device())) return rc;
+  if (rows > 0 && (!planes || (reinterpret_cast<uintptr_t>(planes) & 127))) {
+    set_error("split_f16_planes: planes must be non-null and 128-byte aligned");
+    return ICR_ERR_ALIGN;
+  }
+  return launch_split_planes(x, rows, dim, ld, planes, static_cast<cudaStream_t>(stream));
+}
+
+static int resolve_path(int path, int64_t Q, int64_t N, int64_t D, int dtype, int k, const uint8_t* mask) {
+  if (path == ICR_PATH_GEMV || path == ICR_PATH_GEMM) return path;
+  // small batches are HBM-bound GEMVs; larger ones are tensor-core work
+  const int gemv_max_q = (dtype == ICR_F32) ? 7 : 3;
+  if (Q > gemv_max_q && gemm_topk_supported(Q, N, D, dtype, k, mask)) return ICR_PATH_GEMM;
+  return ICR_PATH_GEMV;
+}
+
+size_t icr_cos_topk_workspace_bytes(int64_t Q, int64_t N, int64_t D, int dtype, int k, int path, int have_planes) {
+  if (Q <= 0 || N <= 0 || k <= 0) return 256;
+  if (path == ICR_PATH_AUTO) {
+    const size_t a = gemv_ws_bytes(Q, N, k);
+    const size_t b = gemm_topk_supported(Q, N, D, dtype, k, nullptr) ? gemm_topk_workspace_bytes(Q, N, D, dtype, k, have_planes) : 0;
+    return a > b ? a : b;
+  }
+  if (path == ICR_PATH_GEMM) return gemm_topk_workspace_bytes(Q, N, D, dtype, k, have_planes);
+  return gemv_ws_bytes(Q, N, k);
+}
+
+int icr_cos_topk(const void* queries, int64_t Q, int64_t ldq, const void* catalog, int64_t N, int64_t ldc, int64_t D,
+                 int dtype, const uint16_t* cat_planes, const uint8_t* exclude_mask, int k, int64_t row_offset, int path,
+                 float* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes, void* stream) {
+  g_launches = 0;
+  int rc;
+  if ((rc = check_matrix("cos_topk.queries", queries, Q, D, ldq, dtype))) return rc;
+  if ((rc = check_matrix("cos_topk.catalog", catalog, N, D, ldc, dtype))) return rc;
+  if (k < 1 || k > ICR_MAX_K) {
+    set_error("cos_topk: k=%d outside [1, %d]", k, ICR_MAX_K);
+    return ICR_ERR_K;
+  }
+  if (N >= 0xffffffffll) {
+    set_error("cos_topk: a shard holds at most 2^32-2 rows (got %lld)", (long long)N);
+    return ICR_ERR_ARG;
+  }
+  if (Q > 0 && (!out_scores || !out_ids)) {
+    set_error("cos_topk: null output");
+    return ICR_ERR_ARG;
+  }
+  if ((rc = check_device())) return rc;
+  if (Q == 0) return ICR_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int p = resolve_path(path, Q, N, D, dtype, k, exclude_mask);
+  const size_t need = icr_cos_topk_workspace_bytes(Q, N, D, dtype, k, p, cat_planes != nullptr);
+  if (workspace_bytes < need || (need > 256 && !workspace)) {
+    set_error("cos_topk: workspace %zu bytes < required %zu", workspace_bytes, need);
+    return ICR_ERR_WORKSPACE;
+  }
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) {
+    set_error("cos_topk: workspace must be 256-byte aligned");
+    return ICR_ERR_ALIGN;
+  }
+  if (p == ICR_PATH_GEMM) {
+    if (!gemm_topk_supported(Q, N, D, dtype, k, exclude_mask)) {
+      set_error("cos_topk: GEMM path does not support this problem (Q=%lld N=%lld D=%lld k=%d mask=%d)", (long long)Q,
+                (long long)N, (long long)D, k, exclude_mask != nullptr);
+      return ICR_ERR_ARG;
+    }
+    return launch_gemm_topk(queries, Q, ldq, catalog, N, ldc, D, dtype, cat_planes, exclude_mask, k, row_offset, out_scores,
+                            out_ids, workspace, workspace_bytes, st);
+  }
+  if (N == 0) {
+    // nothing eligible: (-inf, -1) everywhere, produced by a select over zero segments
+  }
+  // ---- GEMV path: rounds of <= kGemvQueryChunk queries share the workspace -----------------------
+  if (D > 4096) {
+    set_error("cos_topk: GEMV path supports D <= 4096 (got %lld)", (long long)D);
+    return ICR_ERR_ARG;
+  }
+  const int grid = gemv_grid(N);
+  const int64_t qc = Q < kGemvQueryChunk ? Q : kGemvQueryChunk;
+  char* w = static_cast<char*>(workspace);
+  uint64_t* part_keys = reinterpret_cast<uint64_t*>(w);
+  w += align_up(static_cast<size_t>(qc) * grid * k * sizeof(uint64_t), 256);
+  int* part_cnt = reinterpret_cast<int*>(w);
+  w += align_up(static_cast<size_t>(qc) * grid * sizeof(int), 256);
+  void* scratch = w;
+  const size_t scratch_bytes = align_up(select_scratch_bytes(qc, grid, k, k), 256);
+  const size_t esz = elem_size(dtype);
+  for (int64_t q0 = 0; q0 < Q; q0 += qc) {
+    const int nq = static_cast<int>(Q - q0 < qc ? Q - q0 : qc);
+    const char* qptr = static_cast<const char*>(queries) + q0 * ldq * esz;
+    rc = launch_gemv_topk(catalog, N, ldc, static_cast<int>(D), dtype, qptr, ldq, nq, exclude_mask, k, part_keys, part_cnt, grid, st);
+    if (rc) return rc;
+    rc = launch_select(part_keys, part_cnt, nq, grid, k, k, nullptr, nullptr, nullptr, nullptr, nullptr, out_scores + q0 * k,
+                       out_ids + q0 * k, row_offset, k, scratch, scratch_bytes, st);
+    if (rc) return rc;
+  }
+  return ICR_OK;
+}
+
+size_t icr_cos_sim_dense_workspace_bytes(int64_t Qa, int64_t Nb, int64_t D, int dtype) {
+  (void)D;
+  (void)dtype;
+  return align_up(static_cast<size_t>(Qa > 0 ? Qa : 0) * 4, 256) + align_up(static_cast<size_t>(Nb > 0 ? Nb : 0) * 4, 256) + 256;
+}
+
+int icr_cos_sim_dense(const void* a, int64_t Qa, int64_t lda, const void* b, int64_t Nb, int64_t ldb, int64_t D, int dtype,
+                      float* out, int64_t ldo, void* workspace, size_t workspace_bytes, void* stream) {
+  g_launches = 0;
+  int rc;
+  if ((rc = check_matrix("cos_sim_dense.a", a, Qa, D, lda, dtype))) return rc;
+  if ((rc = check_matrix("cos_sim_dense.b", b, Nb, D, ldb, dtype))) return rc;
+  if (ldo < Nb || (Qa > 0 && Nb > 0 && !out)) {
+    set_error("cos_sim_dense: bad output (ldo=%lld, Nb=%lld)", (long long)ldo, (long long)Nb);
+    return ICR_ERR_ARG;
+  }
+  if ((rc = check_device())) return rc;
+  if (Qa == 0 || Nb == 0) return ICR_OK;
+  const size_t need = icr_cos_sim_dense_workspace_bytes(Qa, Nb, D, dtype);
+  if (workspace_bytes < need || !workspace) {
+    set_error("cos_sim_dense: workspace %zu bytes < required %zu", workspace_bytes, need);
+    return ICR_ERR_WORKSPACE;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* inva = static_cast<float*>(workspace);
+  float* invb = reinterpret_cast<float*>(static_cast<char*>(workspace) + align_up(static_cast<size_t>(Qa) * 4, 256));
+  if ((rc = launch_row_inv_norms(a, Qa, D, lda, dtype, inva, st))) return rc;
+  if ((rc = launch_row_inv_norms(b, Nb, D, ldb, dtype, invb, st))) return rc;
+  return launch_cos_sim_dense(a, Qa, lda, b, Nb, ldb, static_cast<int>(D), dtype, inva, invb, out, ldo, st);
+}
+
+size_t icr_topk_merge_workspace_bytes(int64_t Q, int G, int k_in, int k_out) {
+  (void)Q;
+  (void)G;
+  (void)k_in;
+  (void)k_out;
+  return 256;
+}
+
+int icr_topk_merge(const float* cand_scores, const int64_t* cand_ids, int64_t Q, int G, int k_in, int k_out, float* out_scores,
+                   int64_t* out_ids, void* workspace, size_t workspace_bytes, void* stream) {
+  g_launches = 0;
+  (void)workspace;
+  (void)workspace_bytes;
+  if (Q < 0 || G < 1 || k_in < 1 || k_out < 1 || k_out > ICR_MAX_K) {
+    set_error("topk_merge: bad arguments Q=%lld G=%d k_in=%d k_out=%d", (long long)Q, G, k_in, k_out);
+    return ICR_ERR_ARG;
+  }
+  if (Q > 0 && (!cand_scores || !cand_ids || !out_scores || !out_ids)) {
+    set_error("topk_merge: null pointer");
+    return ICR_ERR_ARG;
+  }
+  int rc;
+  if ((rc = check_device())) return rc;
+  return launch_merge_lists(cand_scores, cand_ids, Q, G, k_in, k_out, out_scores, out_ids, static_cast<cudaStream_t>(stream));
+}
+
+size_t icr_mnrl_workspace_bytes(int64_t B, int64_t D) {
+  (void)D;
+  return align_up(static_cast<size_t>(B > 0 ? B : 0) * sizeof(float), 256) + 256;
+}
+
+static int mnrl_common(const void* a, int64_t lda, const void* p, int64_t ldp, int64_t B, int64_t D, int dtype, void* workspace,
+                       size_t workspace_bytes) {
+  int rc;
+  if ((rc = check_matrix("mnrl.anchors", a, B, D, lda, dtype))) return rc;
+  if ((rc = check_matrix("mnrl.positives", p, B, D, ldp, dtype))) return rc;
+  if (B < 1 || B > (1 << 24)) {
+    set_error("mnrl: batch %lld outside [1, 2^24]", (long long)B);
+    return ICR_ERR_ARG;
+  }
+  if (!workspace || workspace_bytes < icr_mnrl_workspace_bytes(B, D)) {
+    set_error("mnrl: workspace %zu bytes < required %zu", workspace_bytes, icr_mnrl_workspace_bytes(B, D));
+    return ICR_ERR_WORKSPACE;
+  }
+  return check_device();
+}
+
+int icr_mnrl_fwd(const void* a, int64_t lda, const void* p, int64_t ldp, int64_t B, int64_t D, int dtype, float scale,
+                 float* loss, float* lse, float* inv_a, float* inv_p, void* workspace, size_t workspace_bytes, void* stream) {
+  g_launches = 0;
+  int rc = mnrl_common(a, lda, p, ldp, B, D, dtype, workspace, workspace_bytes);
+  if (rc) return rc;
+  if (!loss || !lse || !inv_a || !inv_p) {
+    set_error("mnrl_fwd: null output");
+    return ICR_ERR_ARG;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MnrlArgs g{};
+  g.a = a;
+  g.p = p;
+  g.lda = lda;
+  g.ldp = ldp;
+  g.B = static_cast<int>(B);
+  g.D = static_cast<int>(D);
+  g.scale = scale;
+  g.lse = lse;
+  g.inv_a = inv_a;
+  g.inv_p = inv_p;
+  g.counter = static_cast<unsigned int*>(workspace);
+  g.row_loss = reinterpret_cast<float*>(static_cast<char*>(workspace) + 256);
+  g.loss = loss;
+  ICR_CUDA_CHECK(cudaMemsetAsync(g.counter, 0, sizeof(unsigned int), st));
+  return launch_mnrl_dispatch(g, dtype, false, st);
+}
+
+int icr_mnrl_bwd(const void* a, int64_t lda, const void* p, int64_t ldp, int64_t B, int64_t D, int dtype, float scale,
+                 const float* lse, const float* inv_a, const float* inv_p, const float* grad_out, void* grad_a, int64_t ldga,
+                 void* grad_p, int64_t ldgp, void* workspace, size_t workspace_bytes, void* stream) {
+  g_launches = 0;
+  int rc = mnrl_common(a, lda, p, ldp, B, D, dtype, workspace, workspace_bytes);
+  if (rc) return rc;
+  if (!lse || !inv_a || !inv_p || !grad_out || !grad_a || !grad_p || ldga < D || ldgp < D) {
+    set_error("mnrl_bwd: null pointer or bad gradient stride");
+    return ICR_ERR_ARG;
+  }
+  MnrlArgs g{};
+  g.a = a;
+  g.p = p;
+  g.lda = lda;
+  g.ldp = ldp;
+  g.B = static_cast<int>(B);
+  g.D = static_cast<int>(D);
+  g.scale = scale;
+  g.lse = const_cast<float*>(lse);
+  g.inv_a = const_cast<float*>(inv_a);
+  g.inv_p = const_cast<float*>(inv_p);
+  g.grad_out = grad_out;
+  g.grad_a = grad_a;
+  g.grad_p = grad_p;
+  g.ldga = ldga;
+  g.ldgp = ldgp;
+  return launch_mnrl_dispatch(g, dtype, true, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,85 @@
+// K5: row inverse norms and the fp16 (hi|lo) operand planes of the fp32-parity tensor path.
+#include "common.cuh"
+
+namespace icr {
+
+// one warp per row; 128-bit loads; inv = 1 / max(||x||, eps)   (torch F.normalize semantics)
+template <typename T>
+__global__ void __launch_bounds__(256) row_inv_norms_kernel(const T* __restrict__ x, int64_t rows, int64_t dim, int64_t ld,
+                                                            float* __restrict__ inv) {
+  constexpr int VEC = Elem<T>::VEC;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const int nvec = static_cast<int>(dim / VEC);
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    const T* row = x + r * ld;
+    float ss = 0.f;
+    for (int v = lane; v < nvec; v += 32) {
+      float f[VEC];
+      Elem<T>::unpack(ldg_stream(row + static_cast<int64_t>(v) * VEC), f);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) ss = fmaf(f[i], f[i], ss);
+    }
+    for (int e = nvec * VEC + lane; e < dim; e += 32) {
+      const float f = Elem<T>::to_f32(row[e]);
+      ss = fmaf(f, f, ss);
+    }
+    ss = warp_sum(ss);
+    if (lane == 0) inv[r] = 1.0f / fmaxf(sqrtf(ss), kNormEps);
+  }
+}
+
+// one warp per row: normalise (fp32), scale by 2^8, split into fp16 hi + fp16 lo.
+// hi + lo carries ~22 significant bits of the normalised value; hi*hi + hi*lo + lo*hi on the
+// tensor cores (fp32 accumulate) then reproduces the fp32 dot product to ~1e-6 relative.
+__global__ void __launch_bounds__(256) split_f16_planes_kernel(const float* __restrict__ x, int64_t rows, int64_t dim, int64_t ld,
+                                                               __half* __restrict__ planes, int64_t dim_pad) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    const float* row = x + r * ld;
+    float ss = 0.f;
+    for (int e = lane; e < dim; e += 32) {
+      const float f = row[e];
+      ss = fmaf(f, f, ss);
+    }
+    ss = warp_sum(ss);
+    const float inv = 256.0f / fmaxf(sqrtf(ss), kNormEps);
+    __half* hi = planes + r * (2 * dim_pad);
+    __half* lo = hi + dim_pad;
+    for (int e = lane; e < dim_pad; e += 32) {
+      float v = (e < dim) ? row[e] * inv : 0.f;
+      const __half h = __float2half_rn(v);
+      const __half l = __float2half_rn(v - __half2float(h));
+      hi[e] = h;
+      lo[e] = l;
+    }
+  }
+}
+
+int launch_row_inv_norms(const void* x, int64_t rows, int64_t dim, int64_t ld, int dtype, float* inv, cudaStream_t st) {
+  if (rows == 0) return ICR_OK;
+  const int threads = 256;
+  const int64_t want = (rows + 7) / 8;
+  const int blocks = static_cast<int>(want < 148 * 16 ? want : 148 * 16);
+  if (dtype == ICR_F32)
+    row_inv_norms_kernel<float><<<blocks, threads, 0, st>>>(static_cast<const float*>(x), rows, dim, ld, inv);
+  else
+    row_inv_norms_kernel<__nv_bfloat16><<<blocks, threads, 0, st>>>(static_cast<const __nv_bfloat16*>(x), rows, dim, ld, inv);
+  ICR_LAUNCH_CHECK();
+  return ICR_OK;
+}
+
+int launch_split_planes(const float* x, int64_t rows, int64_t dim, int64_t ld, uint16_t* planes, cudaStream_t st) {
+  if (rows == 0) return ICR_OK;
+  const int64_t dim_pad = (dim + 63) / 64 * 64;
+  const int64_t want = (rows + 7) / 8;
+  const int blocks = static_cast<int>(want < 148 * 16 ? want : 148 * 16);
+  split_f16_planes_kernel<<<blocks, 256, 0, st>>>(x, rows, dim, ld, reinterpret_cast<__half*>(planes), dim_pad);
+  ICR_LAUNCH_CHECK();
+  return ICR_OK;
+}
+
+}  // namespace icr

@@ -1,0 +1,141 @@
+"""Embedding index: the reference's on-disk catalog cache plus its device-resident form.
+
+``EmbeddingIndex`` keeps the reference's format byte for byte
+(src/inference/serve_recommendations.py:66-130; file names from src/constants.py:88-92):
+
+    <corpus dir>/.embedding_index/<sha256(model_dir|corpus_path)[:16]>/
+        manifest.json   {"corpus_path", "model_dir", "corpus_mtime", "n_products"}
+        embeddings.npy  float32 [N, D]
+        product_ids.json
+
+``DeviceCatalog`` is what the kernels read: the same rows resident in HBM (fp32, or bf16
+on request), plus — for fp32 — the fp16 (hi|lo) operand planes of the tensor-core path,
+built once at load instead of re-normalising the catalog on every request as
+``sentence_transformers.util.cos_sim`` does (serve_recommendations.py:214).
+"""
+
+from __future__ import annotations
+
+import hashlib
+import json
+import logging
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from . import ops
+from .similarity import default_device, to_device_matrix
+
+logger = logging.getLogger(__name__)
+
+INDEX_SUBDIR = ".embedding_index"
+MANIFEST_FILENAME = "manifest.json"
+EMBEDDINGS_FILENAME = "embeddings.npy"
+PRODUCT_IDS_FILENAME = "product_ids.json"
+
+
+class EmbeddingIndex:
+    """Disk cache of product embeddings, keyed by corpus path + model dir + corpus mtime."""
+
+    def __init__(self, corpus_path: Path, model_dir: Path | str):
+        self.corpus_path = Path(corpus_path).resolve()
+        self.model_dir = model_dir
+        self._dir = self._index_dir()
+
+    def _index_dir(self) -> Path:
+        key = hashlib.sha256(f"{self.model_dir!s}|{self.corpus_path!s}".encode()).hexdigest()[:16]
+        return self.corpus_path.parent / INDEX_SUBDIR / key
+
+    @property
+    def directory(self) -> Path:
+        return self._dir
+
+    def _corpus_mtime(self):
+        try:
+            return self.corpus_path.stat().st_mtime
+        except OSError:
+            return None
+
+    def load(self, product_ids: list[str]) -> np.ndarray | None:
+        """Embeddings if every validity check of the reference passes, else None."""
+        try:
+            meta = json.loads((self._dir / MANIFEST_FILENAME).read_text())
+        except (OSError, json.JSONDecodeError):
+            return None
+        if meta.get("corpus_path") != str(self.corpus_path) or meta.get("model_dir") != str(self.model_dir):
+            return None
+        mtime = self._corpus_mtime()
+        if mtime is None or meta.get("corpus_mtime") != mtime:
+            return None
+        try:
+            embeddings = np.load(self._dir / EMBEDDINGS_FILENAME)
+            cached_ids = json.loads((self._dir / PRODUCT_IDS_FILENAME).read_text())
+        except (OSError, ValueError):
+            return None
+        if cached_ids != product_ids or len(embeddings) != len(product_ids):
+            return None
+        return embeddings
+
+    def save(self, product_ids: list[str], embeddings: np.ndarray) -> None:
+        self._dir.mkdir(parents=True, exist_ok=True)
+        mtime = self._corpus_mtime()
+        manifest = {
+            "corpus_path": str(self.corpus_path),
+            "model_dir": str(self.model_dir),
+            "corpus_mtime": 0 if mtime is None else mtime,
+            "n_products": len(product_ids),
+        }
+        (self._dir / MANIFEST_FILENAME).write_text(json.dumps(manifest, indent=2))
+        np.save(self._dir / EMBEDDINGS_FILENAME, np.asarray(embeddings).astype(np.float32))
+        (self._dir / PRODUCT_IDS_FILENAME).write_text(json.dumps(product_ids))
+        logger.info("Saved embedding index to %s (%d products)", self._dir, len(product_ids))
+
+
+class DeviceCatalog:
+    """Catalog rows resident in HBM, with whatever the kernels want precomputed.
+
+    dtype float32 keeps the reference's numerics (scores within 1e-5 of the fp32 oracle);
+    dtype bfloat16 halves the bytes a batch-1 request streams (scores within 2e-3).
+    """
+
+    def __init__(self, embeddings, *, device: torch.device | None = None, dtype: torch.dtype = torch.float32,
+                 row_offset: int = 0, build_planes: bool | None = None):
+        if dtype not in (torch.float32, torch.bfloat16):
+            raise TypeError("catalog dtype must be float32 or bfloat16")
+        dev = device if device is not None else (embeddings.device if isinstance(embeddings, torch.Tensor) and embeddings.is_cuda else default_device())
+        self.rows = to_device_matrix(embeddings, device=dev, dtype=dtype)
+        self.rows = ops._rows(self.rows)
+        self.row_offset = int(row_offset)
+        self.planes: torch.Tensor | None = None
+        if build_planes is None:
+            build_planes = dtype == torch.float32
+        if build_planes and dtype == torch.float32 and self.rows.shape[0] > 0:
+            self.planes = ops.split_f16_planes(self.rows)
+
+    @property
+    def device(self) -> torch.device:
+        return self.rows.device
+
+    @property
+    def dtype(self) -> torch.dtype:
+        return self.rows.dtype
+
+    def __len__(self) -> int:
+        return self.rows.shape[0]
+
+    @property
+    def dim(self) -> int:
+        return self.rows.shape[1]
+
+    @property
+    def nbytes(self) -> int:
+        return self.rows.numel() * self.rows.element_size() + (0 if self.planes is None else self.planes.numel() * 2)
+
+    def topk(self, queries, k: int, *, exclude_mask: torch.Tensor | None = None, path: int = ops.PATH_AUTO):
+        """(values [Q,k], global ids [Q,k]) of the k most cosine-similar rows per query."""
+        q = to_device_matrix(queries, device=self.device, dtype=self.dtype)
+        k = min(int(k), len(self))
+        if k < 1:
+            return (torch.empty(q.shape[0], 0, device=self.device), torch.empty(q.shape[0], 0, dtype=torch.int64, device=self.device))
+        return ops.cos_topk(q, self.rows, k, cat_planes=self.planes, exclude_mask=exclude_mask, row_offset=self.row_offset, path=path)

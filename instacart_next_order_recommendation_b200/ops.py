@@ -1,0 +1,248 @@
+"""Tensor-level wrappers over the C ABI: CUDA tensors in, CUDA tensors out.
+
+PyTorch is plumbing here (device memory from the caching allocator, the current stream);
+the arithmetic runs in libicr_b200.so. Non-CUDA tensors raise: there is no fallback.
+"""
+
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import ICR_BF16, ICR_F32, MAX_K, PATH_AUTO, PATH_GEMM, PATH_GEMV  # noqa: F401
+
+_DTYPES = {torch.float32: ICR_F32, torch.bfloat16: ICR_BF16}
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise TypeError(f"libicr_b200 supports float32 and bfloat16 embeddings, got {t.dtype}") from None
+
+
+def _require_cuda(name: str, t: torch.Tensor) -> None:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: the retrieval path runs only as sm_100a kernels (no CPU fallback)")
+
+
+def _rows(t: torch.Tensor) -> torch.Tensor:
+    """2-D, contiguous in the embedding dimension (row stride may exceed dim)."""
+    if t.dim() != 2:
+        raise ValueError(f"expected a [rows, dim] matrix, got shape {tuple(t.shape)}")
+    vec = 16 // t.element_size()
+    if t.shape[1] % vec:
+        # zero columns change neither dot products nor norms; they make rows 16-byte multiples
+        t = torch.nn.functional.pad(t, (0, vec - t.shape[1] % vec))
+    if t.shape[1] > 0 and (t.stride(1) != 1 or (t.shape[0] > 1 and (t.stride(0) < t.shape[1] or t.stride(0) % vec))):
+        t = t.contiguous()
+    if t.data_ptr() % 16:
+        t = t.clone(memory_format=torch.contiguous_format)
+    return t
+
+
+def _ld(t: torch.Tensor) -> int:
+    return t.stride(0) if t.shape[0] > 1 else t.shape[1]
+
+
+def _stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def last_launch_count() -> int:
+    return _lib.load().icr_last_launch_count()
+
+
+def kernel_timing(step_fn, steps: int, flush: torch.Tensor | None = None) -> dict:
+    """Run `step_fn` `steps` times with the library timing its dominant kernel (CUDA events on the launch stream)."""
+    import ctypes
+
+    lib = _lib.load()
+    torch.cuda.synchronize()
+    lib.icr_profile_enable(1)
+    total, n_launch = 0.0, 0
+    kid, terms = ctypes.c_int(0), ctypes.c_int(1)
+    try:
+        for _ in range(steps):
+            if flush is not None:
+                flush.zero_()
+            step_fn()
+            ms, n = ctypes.c_float(0), ctypes.c_int(0)
+            _lib.check(lib.icr_profile_collect(ctypes.byref(ms), ctypes.byref(n), ctypes.byref(kid), ctypes.byref(terms)))
+            total += ms.value
+            n_launch += n.value
+    finally:
+        lib.icr_profile_enable(0)
+    return {
+        "kernel": {1: "gemv_topk", 2: "gemm_topk"}.get(kid.value, "none"),
+        "ms_per_step": total / max(steps, 1),
+        "ms_per_launch": total / max(n_launch, 1),
+        "launches_per_step": n_launch / max(steps, 1),
+        "mma_terms": terms.value,
+    }
+
+
+def row_inv_norms(x: torch.Tensor) -> torch.Tensor:
+    """inv[r] = 1 / max(||x_r||, 1e-12) as f32 [rows]."""
+    _require_cuda("x", x)
+    x = _rows(x)
+    lib = _lib.load()
+    out = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.icr_row_inv_norms(x.data_ptr(), x.shape[0], x.shape[1], _ld(x), _dtype_code(x), out.data_ptr(), _stream(x.device)))
+    return out
+
+
+def split_f16_planes(x: torch.Tensor) -> torch.Tensor:
+    """fp32 [rows, D] -> normalised fp16 (hi | lo) planes [rows, 2*round_up(D,64)] (tensor-path operand)."""
+    _require_cuda("x", x)
+    if x.dtype != torch.float32:
+        raise TypeError("split_f16_planes expects float32 rows")
+    x = _rows(x)
+    lib = _lib.load()
+    planes = torch.empty(x.shape[0], lib.icr_planes_row_elems(x.shape[1]), dtype=torch.float16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.icr_split_f16_planes(x.data_ptr(), x.shape[0], x.shape[1], _ld(x), planes.data_ptr(), _stream(x.device)))
+    return planes
+
+
+def cos_topk(
+    queries: torch.Tensor,
+    catalog: torch.Tensor,
+    k: int,
+    *,
+    cat_planes: torch.Tensor | None = None,
+    exclude_mask: torch.Tensor | None = None,
+    row_offset: int = 0,
+    path: int = PATH_AUTO,
+    out: tuple[torch.Tensor, torch.Tensor] | None = None,
+):
+    """(values f32 [Q,k] descending, ids int64 [Q,k]) == torch.topk(cos_sim(q, c), k, dim=1)."""
+    _require_cuda("queries", queries)
+    _require_cuda("catalog", catalog)
+    if queries.dtype != catalog.dtype:
+        queries = queries.to(catalog.dtype)
+    queries, catalog = _rows(queries), _rows(catalog)
+    if queries.shape[1] != catalog.shape[1]:
+        raise ValueError(f"embedding dims differ: {queries.shape[1]} vs {catalog.shape[1]}")
+    Q, D = queries.shape
+    N = catalog.shape[0]
+    dev = catalog.device
+    lib = _lib.load()
+    dt = _dtype_code(catalog)
+    if exclude_mask is not None:
+        _require_cuda("exclude_mask", exclude_mask)
+        if exclude_mask.dtype not in (torch.uint8, torch.bool) or exclude_mask.numel() != N:
+            raise ValueError("exclude_mask must be uint8/bool with one entry per catalog row")
+        exclude_mask = exclude_mask.contiguous().view(torch.uint8)
+    if cat_planes is not None:
+        if cat_planes.dtype != torch.float16 or cat_planes.shape != (N, lib.icr_planes_row_elems(D)) or not cat_planes.is_contiguous():
+            raise ValueError("cat_planes must be the contiguous output of split_f16_planes(catalog)")
+    if out is None:
+        vals = torch.empty(Q, k, dtype=torch.float32, device=dev)
+        ids = torch.empty(Q, k, dtype=torch.int64, device=dev)
+    else:
+        vals, ids = out
+    with torch.cuda.device(dev):
+        need = lib.icr_cos_topk_workspace_bytes(Q, N, D, dt, k, path, int(cat_planes is not None))
+        ws = _workspace(need, dev)
+        _lib.check(
+            lib.icr_cos_topk(
+                queries.data_ptr(), Q, _ld(queries), catalog.data_ptr(), N, _ld(catalog), D, dt, _ptr(cat_planes), _ptr(exclude_mask),
+                k, row_offset, path, vals.data_ptr(), ids.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev),
+            )
+        )
+    return vals, ids
+
+
+def cos_sim_dense(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """f32 [Qa, Nb] cosine similarity matrix."""
+    _require_cuda("a", a)
+    _require_cuda("b", b)
+    if a.dtype != b.dtype:
+        a = a.to(b.dtype)
+    a, b = _rows(a), _rows(b)
+    if a.shape[1] != b.shape[1]:
+        raise ValueError(f"embedding dims differ: {a.shape[1]} vs {b.shape[1]}")
+    lib = _lib.load()
+    dev = b.device
+    out = torch.empty(a.shape[0], b.shape[0], dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        ws = _workspace(lib.icr_cos_sim_dense_workspace_bytes(a.shape[0], b.shape[0], a.shape[1], _dtype_code(b)), dev)
+        _lib.check(
+            lib.icr_cos_sim_dense(
+                a.data_ptr(), a.shape[0], _ld(a), b.data_ptr(), b.shape[0], _ld(b), a.shape[1], _dtype_code(b), out.data_ptr(),
+                max(out.shape[1], 1), ws.data_ptr(), ws.numel(), _stream(dev),
+            )
+        )
+    return out
+
+
+def topk_merge(cand_scores: torch.Tensor, cand_ids: torch.Tensor, k_out: int):
+    """[G,Q,k_in] shard candidates -> global (values [Q,k_out], ids [Q,k_out])."""
+    _require_cuda("cand_scores", cand_scores)
+    _require_cuda("cand_ids", cand_ids)
+    if cand_scores.dim() != 3 or cand_scores.shape != cand_ids.shape:
+        raise ValueError("cand_scores / cand_ids must both be [G, Q, k_in]")
+    cand_scores = cand_scores.contiguous().float()
+    cand_ids = cand_ids.contiguous().long()
+    G, Q, k_in = cand_scores.shape
+    lib = _lib.load()
+    dev = cand_scores.device
+    vals = torch.empty(Q, k_out, dtype=torch.float32, device=dev)
+    ids = torch.empty(Q, k_out, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        ws = _workspace(lib.icr_topk_merge_workspace_bytes(Q, G, k_in, k_out), dev)
+        _lib.check(
+            lib.icr_topk_merge(cand_scores.data_ptr(), cand_ids.data_ptr(), Q, G, k_in, k_out, vals.data_ptr(), ids.data_ptr(),
+                               ws.data_ptr(), ws.numel(), _stream(dev))
+        )
+    return vals, ids
+
+
+def mnrl_forward(anchors: torch.Tensor, positives: torch.Tensor, scale: float):
+    """Returns (loss f32 scalar tensor, saved=(lse, inv_a, inv_p))."""
+    _require_cuda("anchors", anchors)
+    _require_cuda("positives", positives)
+    if anchors.dtype != positives.dtype or anchors.shape != positives.shape:
+        raise ValueError("anchors and positives must share dtype and shape [B, D]")
+    a, p = _rows(anchors), _rows(positives)
+    B, D = a.shape
+    dev = a.device
+    lib = _lib.load()
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    saved = torch.empty(3, B, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        ws = _workspace(lib.icr_mnrl_workspace_bytes(B, D), dev)
+        _lib.check(
+            lib.icr_mnrl_fwd(a.data_ptr(), _ld(a), p.data_ptr(), _ld(p), B, D, _dtype_code(a), float(scale), loss.data_ptr(),
+                             saved[0].data_ptr(), saved[1].data_ptr(), saved[2].data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev))
+        )
+    return loss, saved
+
+
+def mnrl_backward(anchors: torch.Tensor, positives: torch.Tensor, scale: float, saved: torch.Tensor, grad_out: torch.Tensor):
+    a, p = _rows(anchors), _rows(positives)
+    B, D = a.shape
+    dev = a.device
+    lib = _lib.load()
+    ga = torch.empty_like(a, memory_format=torch.contiguous_format)
+    gp = torch.empty_like(p, memory_format=torch.contiguous_format)
+    go = grad_out.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
+    with torch.cuda.device(dev):
+        ws = _workspace(lib.icr_mnrl_workspace_bytes(B, D), dev)
+        _lib.check(
+            lib.icr_mnrl_bwd(a.data_ptr(), _ld(a), p.data_ptr(), _ld(p), B, D, _dtype_code(a), float(scale), saved[0].data_ptr(),
+                             saved[1].data_ptr(), saved[2].data_ptr(), go.data_ptr(), ga.data_ptr(), D, gp.data_ptr(), D,
+                             ws.data_ptr(), ws.numel(), _stream(dev))
+        )
+    D0 = anchors.shape[1]
+    return (ga[:, :D0], gp[:, :D0]) if D0 != D else (ga, gp)

@@ -1,0 +1,109 @@
+"""Row-sharded catalogs across the GPUs of one box (one process per GPU, NCCL over NVLink).
+
+Catalog rows are independent and top-k is decomposable (global top-k ⊆ union of shard
+top-k), so the path shards with ONE exchange step: every rank scores the replicated query
+batch against its contiguous row block with the fused kernel, the per-rank [Q, k]
+(score, global id) candidates are all-gathered, and K4 (``icr_topk_merge``) selects the global
+top-k on every rank. The reference has no multi-GPU path at all; this is the
+extension BASELINE.json's north_star defines for catalogs larger than one GPU.
+"""
+
+from __future__ import annotations
+
+from typing import Callable
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .index import DeviceCatalog
+
+
+def shard_bounds(n_rows: int, world_size: int, rank: int) -> tuple[int, int]:
+    """Contiguous block [lo, hi) of rank `rank`: blocks of ceil(N/G) rows, the last ones may be short or empty."""
+    per = (n_rows + world_size - 1) // world_size
+    lo = min(n_rows, rank * per)
+    return lo, min(n_rows, lo + per)
+
+
+def pack_candidates(vals: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
+    """[Q,k] f32 + [Q,k] i64 -> one int64 [2,Q,k] buffer (score bits in plane 0) for a single collective."""
+    return torch.stack([vals.contiguous().view(torch.int32).to(torch.int64), ids.to(torch.int64)])
+
+
+def unpack_candidates(buf: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+    """[G,2,Q,k] int64 -> (scores f32 [G,Q,k], ids i64 [G,Q,k])."""
+    scores = buf[:, 0].to(torch.int32).view(torch.float32)
+    return scores.contiguous(), buf[:, 1].contiguous()
+
+
+class ShardedCatalog:
+    """This rank's block of a row-sharded catalog plus the exchange + merge step."""
+
+    def __init__(
+        self,
+        local_rows,
+        *,
+        row_offset: int,
+        total_rows: int,
+        group: dist.ProcessGroup | None = None,
+        dtype: torch.dtype = torch.float32,
+        device: torch.device | None = None,
+        _local_topk: Callable | None = None,
+        _merge: Callable | None = None,
+    ):
+        self.group = group
+        self.world_size = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.total_rows = int(total_rows)
+        self.row_offset = int(row_offset)
+        # test seams: the gloo/CPU tests of the host logic plug the oracle in here; product code never does
+        self._local_topk = _local_topk
+        self._merge = _merge
+        if _local_topk is None:
+            self.local = DeviceCatalog(local_rows, device=device, dtype=dtype, row_offset=row_offset)
+            self.n_local = len(self.local)
+            self.device = self.local.device
+        else:
+            self.local = local_rows
+            self.n_local = len(local_rows)
+            self.device = torch.device("cpu") if device is None else device
+
+    @classmethod
+    def from_full(cls, embeddings, *, group=None, **kw) -> "ShardedCatalog":
+        """Every rank holds (or can address) the full host matrix and keeps only its block."""
+        ws = dist.get_world_size(group) if dist.is_initialized() else 1
+        rk = dist.get_rank(group) if dist.is_initialized() else 0
+        lo, hi = shard_bounds(len(embeddings), ws, rk)
+        return cls(embeddings[lo:hi], row_offset=lo, total_rows=len(embeddings), group=group, **kw)
+
+    def local_topk(self, queries, k: int):
+        """[Q,k] candidates of this shard with GLOBAL ids; short shards pad with (-inf, -1)."""
+        kk = min(k, self.n_local)
+        if self._local_topk is not None:
+            vals, ids = self._local_topk(queries, self.local, kk, self.row_offset)
+        elif kk > 0:
+            vals, ids = self.local.topk(queries, kk)
+        else:
+            Q = queries.shape[0] if hasattr(queries, "shape") and len(queries.shape) == 2 else 1
+            vals = torch.empty(Q, 0, dtype=torch.float32, device=self.device)
+            ids = torch.empty(Q, 0, dtype=torch.int64, device=self.device)
+        if kk < k:
+            Q = vals.shape[0]
+            vals = torch.cat([vals, torch.full((Q, k - kk), float("-inf"), dtype=torch.float32, device=vals.device)], dim=1)
+            ids = torch.cat([ids, torch.full((Q, k - kk), -1, dtype=torch.int64, device=ids.device)], dim=1)
+        return vals, ids
+
+    def topk(self, queries, k: int):
+        """Global (values [Q,k'], ids [Q,k']) on every rank, k' = min(k, total rows)."""
+        k = min(int(k), self.total_rows)
+        vals, ids = self.local_topk(queries, k)
+        if self.world_size == 1:
+            return vals, ids
+        mine = pack_candidates(vals, ids)
+        # output concatenated along dim 0 (the layout every backend's all_gather_into_tensor accepts)
+        gathered = torch.empty((self.world_size * mine.shape[0], *mine.shape[1:]), dtype=mine.dtype, device=mine.device)
+        dist.all_gather_into_tensor(gathered, mine, group=self.group)
+        scores, gids = unpack_candidates(gathered.view(self.world_size, *mine.shape))
+        merge = self._merge if self._merge is not None else ops.topk_merge
+        return merge(scores, gids, k)

@@ -1,0 +1,301 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle, on a B200.
+
+Tolerances are BASELINE.json's: top-k scores within 1e-5 relative for fp32 and 2e-3 for bf16
+(oracle = fp32 math on the bf16-rounded inputs), ids identical except across ties closer than the
+tolerance, MNRL loss and gradients within 1e-4.
+"""
+
+import json
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import instacart_next_order_recommendation_b200 as icr
+from instacart_next_order_recommendation_b200 import ops
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+F32_RTOL = 1e-5
+BF16_RTOL = 2e-3
+MNRL_ATOL = 1e-4
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _device():
+    assert torch.cuda.is_available(), "run with -m gpu on a GPU box"
+    torch.cuda.set_device(0)
+    from instacart_next_order_recommendation_b200 import _lib
+
+    assert _lib.load().icr_device_supported() == 1
+    yield
+    torch.cuda.synchronize()
+
+
+def _check_topk(v, i, rv, ri, rtol):
+    assert v.shape == rv.shape and i.shape == ri.shape
+    v, i = v.cpu(), i.cpu()
+    assert (v[:, :-1] >= v[:, 1:]).all(), "scores must be non-increasing"
+    err, mism = oracle.compare_topk(v, i, rv, ri, rtol=rtol)
+    assert err <= rtol, f"max relative score error {err}"
+    assert mism == 0, f"{mism} id mismatches outside ties"
+    for r in range(i.shape[0]):  # no duplicates
+        assert len(set(i[r].tolist())) == i.shape[1]
+
+
+PATHS = [ops.PATH_GEMV, ops.PATH_GEMM]
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("Q,N,D,k", [(1, 49688, 384, 10), (1, 49688, 384, 100), (3, 5000, 384, 10), (7, 20000, 768, 100),
+                                      (9, 3000, 128, 32), (16, 7777, 384, 100), (1, 300, 64, 256)])
+def test_f32_topk_vs_oracle(path, Q, N, D, k):
+    if path == ops.PATH_GEMM and not _gemm_ok():
+        pytest.skip("GEMM path not built yet")
+    items, _ = oracle.synth_clustered(N, D, seed=1234)
+    queries, _ = oracle.synth_queries_from_items(items, Q, seed=4321)
+    v, i = icr.cos_topk(queries.cuda(), items.cuda(), k, path=path)
+    rv, ri = oracle.cos_topk(queries, items, k)
+    _check_topk(v, i, rv, ri, F32_RTOL)
+
+
+def _gemm_ok():
+    try:
+        q = torch.randn(128, 64, device="cuda")
+        c = torch.randn(1024, 64, device="cuda")
+        ops.cos_topk(q, c, 10, path=ops.PATH_GEMM)
+        torch.cuda.synchronize()
+        return True
+    except ValueError:
+        return False
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_isotropic_and_unnormalised_inputs(path):
+    if path == ops.PATH_GEMM and not _gemm_ok():
+        pytest.skip("GEMM path not built yet")
+    items = oracle.synth_isotropic(30000, 384, seed=1234)
+    queries = oracle.synth_isotropic(5, 384, seed=4321)
+    v, i = icr.cos_topk(queries.cuda(), items.cuda(), 100, path=path)
+    _check_topk(v, i, *oracle.cos_topk(queries, items, 100), F32_RTOL)
+    un_c = oracle.synth_unnormalised(9000, 384, seed=7)
+    un_q = oracle.synth_unnormalised(4, 384, seed=8)
+    v, i = icr.cos_topk(un_q.cuda(), un_c.cuda(), 50, path=path)
+    _check_topk(v, i, *oracle.cos_topk(un_q, un_c, 50), F32_RTOL)
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("Q,N,D,k", [(1, 40000, 768, 100), (3, 10000, 384, 10), (6, 25000, 768, 100)])
+def test_bf16_topk_vs_fp32_math_on_rounded_inputs(path, Q, N, D, k):
+    if path == ops.PATH_GEMM and not _gemm_ok():
+        pytest.skip("GEMM path not built yet")
+    items, _ = oracle.synth_clustered(N, D, seed=1234)
+    queries, _ = oracle.synth_queries_from_items(items, Q, seed=4321)
+    ib, qb = items.bfloat16(), queries.bfloat16()
+    v, i = icr.cos_topk(qb.cuda(), ib.cuda(), k, path=path)
+    rv, ri = oracle.cos_topk(qb.float(), ib.float(), k)
+    _check_topk(v, i, rv, ri, BF16_RTOL)
+    # the kernel accumulates in fp32: it is in fact much closer than the bf16 tolerance
+    err, _ = oracle.compare_topk(v.cpu(), i.cpu(), rv, ri, rtol=BF16_RTOL)
+    assert err < 5e-5
+
+
+def test_known_answers_on_device():
+    d = 384
+    e = torch.eye(d, device="cuda")
+    s = icr.cos_sim(e[3] * 7.5, e[:8])
+    assert s.shape == (1, 8) and s[0, 3].item() == pytest.approx(1.0, abs=1e-6) and s[0, 4].item() == 0.0
+    assert icr.cos_sim(-2 * e[3], e[3]).item() == pytest.approx(-1.0, abs=1e-6)
+    z = icr.cos_sim(torch.zeros(d, device="cuda"), e[:5])
+    assert torch.isfinite(z).all() and (z == 0).all()
+    q = torch.zeros(d)
+    q[:6] = torch.tensor([0.1, -0.9, 0.5, 0.3, 0.0, 0.7])
+    v, i = icr.cos_topk(q.cuda(), e, 3)
+    assert i.tolist() == [[5, 2, 3]]
+    # ties: equal scores come back in ascending row order
+    c = torch.ones(1000, 64, device="cuda")
+    v, i = icr.cos_topk(torch.ones(64, device="cuda"), c, 17)
+    assert i.tolist() == [list(range(17))]
+    # k clamps to the catalog size; numpy / list inputs are uploaded
+    v, i = icr.cos_topk(np.ones(8, dtype=np.float32), [[1.0] * 8, [-1.0] * 8], 10)
+    assert v.shape == (1, 2) and i.tolist() == [[0, 1]]
+
+
+def test_dense_cos_sim_vs_oracle():
+    a = oracle.synth_unnormalised(130, 384, seed=3)
+    b = oracle.synth_unnormalised(777, 384, seed=4)
+    got = icr.cos_sim(a.cuda(), b.cuda()).cpu()
+    ref = oracle.cos_sim(a, b)
+    # all-scores check: absolute, because cosines near 0 have unbounded relative error
+    assert (got - ref).abs().max() <= 1e-5 * max(1.0, ref.abs().max().item())
+    got = icr.cos_sim(a.bfloat16().cuda(), b.bfloat16().cuda()).cpu()
+    ref = oracle.cos_sim(a.bfloat16().float(), b.bfloat16().float())
+    assert (got - ref).abs().max() <= 1e-5
+    # odd embedding dim (padded internally), 1-D operand
+    a = torch.randn(50), torch.randn(9, 50)
+    assert (icr.cos_sim(a[0], a[1]).cpu() - oracle.cos_sim(a[0], a[1])).abs().max() < 1e-6
+
+
+def test_exclusion_mask_and_row_offset():
+    items, _ = oracle.synth_clustered(8000, 384, seed=5)
+    queries, _ = oracle.synth_queries_from_items(items, 2, seed=6)
+    rv, ri = oracle.cos_topk(queries, items, 40)
+    mask = torch.zeros(8000, dtype=torch.uint8)
+    banned = ri[0, :20:2]
+    mask[banned] = 1
+    v, i = ops.cos_topk(queries[:1].cuda(), items.cuda(), 10, exclude_mask=mask.cuda(), row_offset=1_000_000, path=ops.PATH_GEMV)
+    want = [int(x) for x in ri[0].tolist() if x not in set(banned.tolist())][:10]
+    assert (i[0].cpu() - 1_000_000).tolist() == want
+
+
+def test_merge_of_fake_shards_equals_global_topk():
+    items, _ = oracle.synth_clustered(20000, 384, seed=9)
+    queries, _ = oracle.synth_queries_from_items(items, 33, seed=10)
+    k, G = 100, 8
+    rv, ri = oracle.cos_topk(queries, items, k)
+    cs, ci = [], []
+    from instacart_next_order_recommendation_b200.sharded import shard_bounds
+
+    for r in range(G):
+        lo, hi = shard_bounds(20000, G, r)
+        v, i = ops.cos_topk(queries.cuda(), items[lo:hi].cuda(), k, row_offset=lo)
+        cs.append(v)
+        ci.append(i)
+    v, i = ops.topk_merge(torch.stack(cs), torch.stack(ci), k)
+    _check_topk(v, i, rv, ri, F32_RTOL)
+    # empty slots (-inf, -1) from short shards are ignored
+    cs[3][:, 50:] = float("-inf")
+    ci[3][:, 50:] = -1
+    v2, i2 = ops.topk_merge(torch.stack(cs), torch.stack(ci), k)
+    assert (i2 >= 0).all()
+
+
+def test_recommender_dropin_matches_reference_golden(golden_dir, tmp_path):
+    z = np.load(golden_dir / "embeddings_small.npz")
+    gold = json.loads((golden_dir / "recommend_golden.json").read_text())
+    pids = [str(p) for p in z["product_ids"]]
+
+    class Enc:
+        def encode(self, texts, batch_size=64, show_progress_bar=False, normalize_embeddings=True, **kw):
+            tab = {"c": z["items"], "q": z["queries"]}
+            return np.stack([tab[t.split(":")[0]][int(t.split(":")[1])] for t in texts]).astype(np.float32)
+
+    corpus = tmp_path / "eval_corpus.json"
+    corpus.write_text(json.dumps({pid: f"c:{i}" for i, pid in enumerate(pids)}))
+    for dtype, tol in ((torch.float32, 1e-5),):
+        rec = icr.MonitoredRecommender("fake-model", corpus, model=Enc(), catalog_dtype=dtype)
+        assert (corpus.parent / ".embedding_index").exists()
+        for case in gold["cases"]:
+            got = rec.recommend(f"q:{case['q']}", top_k=case["top_k"], exclude_product_ids=set(case["exclude"]))
+            assert [p for p, _ in got] == [p for p, _ in case["result"]], case
+            np.testing.assert_allclose([s for _, s in got], [s for _, s in case["result"]], rtol=tol)
+        m = rec.last_metrics
+        assert m.num_recommendations == len(got) and m.user_id == "anonymous" and m.similarity_compute_time_ms > 0
+        # very long exclusion list -> device-side mask path, same semantics as the reference walk
+        excl = set(pids[::2])
+        got = rec.recommend("q:1", top_k=10, exclude_product_ids=excl)
+        want = oracle.recommend_tail(z["queries"][1], z["items"], pids, 10, excl)
+        assert [p for p, _ in got] == [p for p, _ in want]
+    # second construction hits the on-disk index written by the first
+    rec2 = icr.Recommender("fake-model", corpus, model=Enc())
+    np.testing.assert_array_equal(rec2.product_embeddings, z["items"])
+
+
+def test_ir_evaluator_and_rank_all_against_oracle(golden_dir):
+    z = np.load(golden_dir / "embeddings_small.npz")
+    gold = json.loads((golden_dir / "metrics_golden.json").read_text())
+    pids = [str(p) for p in z["product_ids"]]
+    qids = list(gold["rank_all_top100"].keys())
+    got = icr.rank_all(z["queries"], z["items"], qids, pids, limit=100)
+    assert got == gold["rank_all_top100"]  # the reference's own ContentBasedBaseline.rank_all output
+    rel = {k: set(v) for k, v in gold["relevant"].items()}
+    m = icr.compute_ir_metrics(got, rel)
+    for key, val in gold["metrics"].items():
+        assert m[key] == pytest.approx(val, abs=1e-12)
+
+    class Enc:
+        def encode(self, texts, **kw):
+            tab = {"c": z["items"], "q": z["queries"]}
+            return np.stack([tab[t.split(":")[0]][int(t.split(":")[1])] for t in texts]).astype(np.float32)
+
+    queries = {qid: f"q:{i}" for i, qid in enumerate(qids)}
+    corpus = {pid: f"c:{i}" for i, pid in enumerate(pids)}
+    ev = icr.InformationRetrievalEvaluator(queries, corpus, rel, name="order-recommendation")
+    out = ev(Enc())
+    assert ev.primary_metric in out and 0.0 <= out[ev.primary_metric] <= 1.0
+    # same numbers from the oracle's chunked-topk + heap restatement of the upstream evaluator core
+    keep = [i for i, q in enumerate(qids) if rel.get(q)]
+    lists = oracle.ir_eval_topk(z["queries"][keep], z["items"], max_k=100)
+    ids = np.array([[ci for _, ci in l] for l in lists])
+    want = ev.compute_metrics_from_ids(ids)
+    for k, val in want.items():
+        assert out[f"order-recommendation_cosine_{k}"] == pytest.approx(val, abs=1e-12)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,D,scale", [(256, 384, 20.0), (64, 384, 30.0), (37, 768, 20.0), (8, 64, 20.0), (1024, 384, 20.0)])
+def test_mnrl_forward_backward_vs_autograd(dtype, B, D, scale):
+    g = torch.Generator().manual_seed(2024)
+    items, _ = oracle.synth_clustered(B, D, seed=2024, n_centres=12)
+    a = torch.nn.functional.normalize(items + 0.3 * torch.randn(B, D, generator=g), dim=1)
+    p = items * (1.0 + 0.5 * torch.rand(B, 1, generator=g))  # un-normalised positives exercise the Jacobian
+    a, p = a.to(dtype), p.to(dtype)
+    ad = a.cuda().requires_grad_(True)
+    pd = p.cuda().requires_grad_(True)
+    loss = icr.mnrl_loss(ad, pd, scale)
+    (loss * 1.7).backward()
+    rl, rga, rgp = oracle.mnrl_loss_and_grads(a.float(), p.float(), scale)
+    assert loss.dtype == torch.float32
+    assert abs(loss.item() - rl.item()) <= MNRL_ATOL
+    tol = MNRL_ATOL if dtype == torch.float32 else MNRL_ATOL + 2 ** -8 * rga.abs().max().item() * 1.7  # bf16 output rounding
+    assert (ad.grad.float().cpu() - 1.7 * rga).abs().max() <= tol
+    assert (pd.grad.float().cpu() - 1.7 * rgp).abs().max() <= tol
+
+
+def test_mnrl_known_answers_and_module_interface():
+    B, d, scale = 16, 64, 20.0
+    q, _ = torch.linalg.qr(torch.randn(d, d, generator=torch.Generator().manual_seed(0)))
+    a = q[:B].contiguous().cuda()
+    assert icr.mnrl_loss(a, a.clone(), scale).item() == pytest.approx(math.log(1 + (B - 1) * math.exp(-scale)), abs=1e-6)
+    same = torch.ones(B, d, device="cuda")
+    assert icr.mnrl_loss(same, same, scale).item() == pytest.approx(math.log(B), abs=1e-5)
+
+    class Tower(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.lin = torch.nn.Linear(32, 64)
+
+        def forward(self, feats):
+            return {"sentence_embedding": self.lin(feats["x"])}
+
+    tower = Tower().cuda()
+    loss_mod = icr.MultipleNegativesRankingLoss(tower, scale=30.0)
+    xa, xp = torch.randn(24, 32, device="cuda"), torch.randn(24, 32, device="cuda")
+    loss = loss_mod([{"x": xa}, {"x": xp}], labels=None)
+    loss.backward()
+    ref = oracle.mnrl_loss(tower.lin(xa).detach().cpu(), tower.lin(xp).detach().cpu(), 30.0)
+    assert abs(loss.item() - ref.item()) < 1e-4 and tower.lin.weight.grad is not None
+
+
+def test_full_size_properties_c2_shape():
+    """BASELINE config 2 at full size through size-independent properties (the oracle is too slow for all of it):
+    a row-permuted catalog returns the permuted ids with identical scores, every returned score is reproduced by
+    a direct dot product, and a sample of queries matches the oracle exactly."""
+    N, D, Q, k = 49688, 384, 10000, 100
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    items = torch.nn.functional.normalize(torch.randn(N, D, device="cuda", generator=g), dim=1)
+    queries = torch.nn.functional.normalize(torch.randn(Q, D, device="cuda", generator=g), dim=1)
+    v, i = icr.cos_topk(queries, items, k)
+    assert (v[:, :-1] >= v[:, 1:]).all() and (i >= 0).all() and (i < N).all()
+    direct = (queries[:, None, :] * items[i[:, :5]]).sum(-1)
+    assert (direct - v[:, :5]).abs().max() < 2e-6
+    perm = torch.randperm(N, device="cuda", generator=g)
+    v2, i2 = icr.cos_topk(queries[:512], items[perm], k)
+    assert torch.allclose(v2, v[:512], rtol=1e-6, atol=1e-7)
+    same = perm[i2] == i[:512]
+    assert same.float().mean() > 0.999  # differences only across exact-score ties
+    sample = torch.arange(0, Q, 97, device="cuda")
+    rv, ri = oracle.cos_topk(queries[sample].cpu(), items.cpu(), k)
+    _check_topk(v[sample], i[sample], rv, ri, F32_RTOL)
