@@ -86,6 +86,8 @@ int64_t icr_planes_row_elems(int64_t dim); /* = 2 * round_up(dim, 64) */
  *   catalog      [N, D] dtype, row stride ldc          (the shard's rows when sharded)
  *   cat_planes   optional (may be NULL): icr_split_f16_planes(catalog); used by the GEMM
  *                path for ICR_F32 catalogs; if NULL it is built in the workspace per call
+ *   cat_inv_norms optional (may be NULL): icr_row_inv_norms(catalog); used by the GEMM path
+ *                for ICR_BF16 catalogs; if NULL it is computed in the workspace per call
  *   exclude_mask optional (may be NULL): N bytes, non-zero = row never returned
  *                (exclude_product_ids semantics, serve_recommendations.py:216-221)
  *   row_offset   added to every returned id (global numbering of a row shard)
@@ -97,7 +99,8 @@ size_t icr_cos_topk_workspace_bytes(int64_t Q, int64_t N, int64_t D, int dtype, 
 int icr_cos_topk(const void* queries, int64_t Q, int64_t ldq,
                  const void* catalog, int64_t N, int64_t ldc,
                  int64_t D, int dtype,
-                 const uint16_t* cat_planes, const uint8_t* exclude_mask,
+                 const uint16_t* cat_planes, const float* cat_inv_norms,
+                 const uint8_t* exclude_mask,
                  int k, int64_t row_offset, int path,
                  float* out_scores, int64_t* out_ids,
                  void* workspace, size_t workspace_bytes, void* stream);

@@ -66,8 +66,8 @@ int launch_cos_sim_dense(const void* a, int64_t Qa, int64_t lda, const void* b, 
 // GEMM path (gemm_topk.cu)
 size_t gemm_topk_workspace_bytes(int64_t Q, int64_t N, int64_t D, int dtype, int k, int have_planes);
 int launch_gemm_topk(const void* queries, int64_t Q, int64_t ldq, const void* catalog, int64_t N, int64_t ldc, int64_t D,
-                     int dtype, const uint16_t* cat_planes, const uint8_t* mask, int k, int64_t row_offset, float* out_scores,
-                     int64_t* out_ids, void* ws, size_t ws_bytes, cudaStream_t st);
+                     int dtype, const uint16_t* cat_planes, const float* cat_inv_norms, const uint8_t* mask, int k, int64_t row_offset,
+                     float* out_scores, int64_t* out_ids, void* ws, size_t ws_bytes, cudaStream_t st);
 bool gemm_topk_supported(int64_t Q, int64_t N, int64_t D, int dtype, int k, const uint8_t* mask);
 
 int launch_mnrl_dispatch(const MnrlArgs& g, int dtype, bool bwd, cudaStream_t st);
@@ -213,8 +213,9 @@ size_t icr_cos_topk_workspace_bytes(int64_t Q, int64_t N, int64_t D, int dtype, 
 }
 
 int icr_cos_topk(const void* queries, int64_t Q, int64_t ldq, const void* catalog, int64_t N, int64_t ldc, int64_t D,
-                 int dtype, const uint16_t* cat_planes, const uint8_t* exclude_mask, int k, int64_t row_offset, int path,
-                 float* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes, void* stream) {
+                 int dtype, const uint16_t* cat_planes, const float* cat_inv_norms, const uint8_t* exclude_mask, int k,
+                 int64_t row_offset, int path, float* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes,
+                 void* stream) {
   g_launches = 0;
   int rc;
   if ((rc = check_matrix("cos_topk.queries", queries, Q, D, ldq, dtype))) return rc;
@@ -250,8 +251,8 @@ int icr_cos_topk(const void* queries, int64_t Q, int64_t ldq, const void* catalo
                 (long long)N, (long long)D, k, exclude_mask != nullptr);
       return ICR_ERR_ARG;
     }
-    return launch_gemm_topk(queries, Q, ldq, catalog, N, ldc, D, dtype, cat_planes, exclude_mask, k, row_offset, out_scores,
-                            out_ids, workspace, workspace_bytes, st);
+    return launch_gemm_topk(queries, Q, ldq, catalog, N, ldc, D, dtype, cat_planes, cat_inv_norms, exclude_mask, k, row_offset,
+                            out_scores, out_ids, workspace, workspace_bytes, st);
   }
   if (N == 0) {
     // nothing eligible: (-inf, -1) everywhere, produced by a select over zero segments

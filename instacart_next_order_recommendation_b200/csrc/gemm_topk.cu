@@ -1,11 +1,609 @@
-// K2 placeholder (replaced by the tcgen05 implementation).
+// K2: cosine scoring as a tcgen05 / TMEM tensor-core GEMM whose epilogue never writes scores:
+// it filters them against a per-query threshold and appends the few survivors as candidate keys.
+//
+//   S[128 queries, 256 catalog rows] = A[128, K] * B[256, K]^T        (K-major operands, fp32 accumulate)
+//
+//  * Operands arrive by TMA (cp.async.bulk.tensor.2d, 128-byte swizzle) into a 4-stage shared-memory
+//    ring guarded by mbarriers; one elected thread issues tcgen05.mma (M=128, N=256, K=16) into one of two
+//    256-column TMEM accumulators, so the epilogue of tile i overlaps the MMAs of tile i+1.
+//  * Queries sit on the M axis: after tcgen05.ld every epilogue thread owns ONE query (its TMEM lane) and
+//    sees 32 catalog scores per load. A score survives if it beats the thread's threshold tau — the k-th
+//    best score of the catalog rows already ranked in earlier phases (exact lower bound of the final k-th
+//    score), so survivors are ~k*ln(growth) per phase instead of N.
+//  * The catalog is walked in phases of geometrically growing row ranges; between phases the select kernel
+//    (select.cu) folds the survivors into the running top-k and publishes the new tau. If a thread's
+//    candidate segment fills up anyway (adversarially ordered catalogs), its warp sorts the segment in
+//    shared memory, keeps the k best and raises that thread's tau: exact for any input.
+//  * fp32 catalogs keep fp32 parity on fp16 tensor cores: rows are L2-normalised, scaled by 2^8 and split
+//    into fp16 hi + lo planes (prep.cu); hi*hi + hi*lo + lo*hi accumulated in fp32 reproduces the fp32 dot
+//    product to ~1e-6 relative (measured: profiles/r01_split_precision.txt). bf16 catalogs take one MMA term
+//    on the raw rows and multiply by the two inverse norms in the epilogue.
+//
+// Replaces cos_sim [Q,N] -> torch.topk(100) -> Python heap of sentence-transformers'
+// InformationRetrievalEvaluator (built at reference src/training/train_sbert.py:197-202) and the
+// cos_sim -> np.argsort loops of src/baselines/content_based.py:54-63.
+#include <cuda.h>
+
 #include "common.cuh"
+
 namespace icr {
-bool gemm_topk_supported(int64_t, int64_t, int64_t, int, int, const uint8_t*) { return false; }
-size_t gemm_topk_workspace_bytes(int64_t, int64_t, int64_t, int, int, int) { return 256; }
-int launch_gemm_topk(const void*, int64_t, int64_t, const void*, int64_t, int64_t, int64_t, int, const uint16_t*, const uint8_t*,
-                     int, int64_t, float*, int64_t*, void*, size_t, cudaStream_t) {
-  set_error("GEMM path not built");
-  return ICR_ERR_ARG;
+
+constexpr int BM = 128;   // queries per tile (TMEM lanes)
+constexpr int BN = 256;   // catalog rows per tile (TMEM columns of one accumulator)
+constexpr int BK = 64;    // K elements per pipeline stage = one 128-byte swizzle atom of 16-bit elements
+constexpr int kStages = 4;
+constexpr int kStageABytes = BM * BK * 2;
+constexpr int kStageBBytes = BN * BK * 2;
+constexpr int kStageBytes = kStageABytes + kStageBBytes;
+constexpr int kSegCap = 512;         // candidate keys per (query, chunk) segment
+constexpr int kGemmThreads = 256;    // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warp 3 idle, warps 4-7 epilogue
+constexpr int kTmemCols = 512;       // two 256-column fp32 accumulators
+constexpr uint32_t kSpinLimit = 1u << 24;
+
+struct GemmArgs {
+  int Q, N;
+  int k;
+  int terms;        // 1 (bf16 rows) or 3 (fp16 hi/lo planes)
+  int kb_per_term;  // 64-element K blocks per term
+  int plane_stride; // element offset of the lo plane inside a row (terms == 3)
+  int tile_begin, tile_end;  // catalog tiles [begin, end) of this phase
+  int chunks, tiles_per_chunk;
+  int qblocks;
+  float acc_scale;           // 2^-16 for the plane path, 1 for bf16
+  const float* tau;          // [Q]
+  const float* qinv;         // [Q]  (bf16 path) or null
+  const float* cinv;         // [N]  (bf16 path) or null
+  const uint8_t* mask;       // [N] or null
+  uint64_t* cand;            // [Q][chunks][kSegCap]
+  int* cand_cnt;             // [Q][chunks]
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (spin > kSpinLimit) __trap();  // a protocol bug must abort the launch, not hang the GPU
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand tile in shared memory, rows of 128 bytes, 128-byte swizzle, 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);  // start address, 16-byte units
+  d |= static_cast<uint64_t>(1) << 16;                   // leading byte offset (ignored for swizzled K-major)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;           // stride byte offset between 8-row groups
+  d |= static_cast<uint64_t>(1) << 46;                   // descriptor version (Blackwell)
+  d |= static_cast<uint64_t>(2) << 61;                   // SWIZZLE_128B
+  return d;
+}
+
+// warp-synchronous bitonic sort (descending) of n = power-of-two keys in shared memory
+__device__ __forceinline__ void warp_bitonic_sort_desc(uint64_t* keys, int n, int lane) {
+  __syncwarp();
+  for (int size = 2; size <= n; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = lane; t < (n >> 1); t += 32) {
+        const int lo = ((t / stride) * (stride << 1)) + (t % stride);
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const uint64_t a = keys[lo], b = keys[hi];
+        if ((a < b) == desc) {
+          keys[lo] = b;
+          keys[hi] = a;
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+struct SegState {
+  uint64_t* seg;  // this thread's candidate segment (global)
+  int cnt;
+  float tau;
+};
+
+// Any lane whose segment could overflow during the next 32 scores gets it compacted by the whole warp.
+__device__ __forceinline__ void compact_full_segments(SegState& s, uint64_t* scratch, int k, int lane) {
+  unsigned need = __ballot_sync(kFull, s.cnt > kSegCap - 32);
+  while (need) {
+    const int L = __ffs(need) - 1;
+    need &= need - 1;
+    uint64_t* seg = reinterpret_cast<uint64_t*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(s.seg), L));
+    const int n = __shfl_sync(kFull, s.cnt, L);
+    __syncwarp();
+    for (int i = lane; i < kSegCap; i += 32) scratch[i] = (i < n) ? __ldcg(seg + i) : 0ull;
+    warp_bitonic_sort_desc(scratch, kSegCap, lane);
+    const int kept = n < k ? n : k;
+    for (int i = lane; i < kept; i += 32) seg[i] = scratch[i];
+    const float t_new = (n >= k) ? key_score(scratch[k - 1]) : -INFINITY;
+    if (lane == L) {
+      s.cnt = kept;
+      s.tau = fmaxf(s.tau, t_new);
+    }
+    __syncwarp();
+  }
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmArgs g) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // 128-byte-swizzled tiles need 1024-byte alignment; the allocation carries 1 KB of slack for this
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  // layout: [stages][A 16K | B 32K] | scratch 4 x kSegCap keys | barriers | tmem ptr
+  unsigned char* stage_base = smem;
+  uint64_t* scratch_all = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* bars = scratch_all + 4 * kSegCap;
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kStages;
+  uint64_t* tfull_bar = bars + 2 * kStages;
+  uint64_t* tempty_bar = bars + 2 * kStages + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KI = g.terms * g.kb_per_term;
+  const int items = g.qblocks * g.chunks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&tfull_bar[a]), 1);
+      mbar_init(smem_u32(&tempty_bar[a]), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_b) : "memory");
+  }
+  if (warp == 2) tmem_alloc(smem_u32(tmem_ptr), kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0 && lane == 0) {
+    // ================= TMA producer =================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int w = blockIdx.x; w < items; w += gridDim.x) {
+      const int chunk = w / g.qblocks, qb = w - chunk * g.qblocks;
+      const int t0 = g.tile_begin + chunk * g.tiles_per_chunk;
+      const int t1 = min(g.tile_end, t0 + g.tiles_per_chunk);
+      for (int tile = t0; tile < t1; ++tile) {
+        for (int ki = 0; ki < KI; ++ki) {
+          const int term = ki / g.kb_per_term, kb = ki - term * g.kb_per_term;
+          // plane path: (A,B) planes of term 0,1,2 = (hi,hi), (hi,lo), (lo,hi)
+          const int ka = kb * BK + ((term == 2) ? g.plane_stride : 0);
+          const int kbx = kb * BK + ((term == 1) ? g.plane_stride : 0);
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          mbar_expect_tx(fb, kStageBytes);
+          const uint32_t sa = smem_u32(stage_base + stage * kStageBytes);
+          tma_load_2d(sa, &tma_a, ka, qb * BM, fb);
+          tma_load_2d(sa + kStageABytes, &tma_b, kbx, tile * BN, fb);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ================= MMA issuer =================
+    // instruction descriptor: D=f32, A/B = f16 or bf16, K-major both, N=256, M=128
+    const uint32_t fmt = BF16 ? 1u : 0u;
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(BN >> 3) << 17) | (static_cast<uint32_t>(BM >> 4) << 24);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < items; w += gridDim.x) {
+      const int chunk = w / g.qblocks;
+      const int t0 = g.tile_begin + chunk * g.tiles_per_chunk;
+      const int t1 = min(g.tile_end, t0 + g.tiles_per_chunk);
+      for (int tile = t0; tile < t1; ++tile) {
+        mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int ki = 0; ki < KI; ++ki) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(stage_base + stage * kStageBytes);
+          const uint64_t adesc = smem_desc_sw128(sa);
+          const uint64_t bdesc = smem_desc_sw128(sa + kStageABytes);
+#pragma unroll
+          for (int k4 = 0; k4 < BK / 16; ++k4) {
+            // advancing 16 elements (32 bytes) along K inside the swizzle atom = +2 in the 16-byte address field
+            umma_f16(d_tmem, adesc + static_cast<uint64_t>(k4 * 2), bdesc + static_cast<uint64_t>(k4 * 2), idesc, (ki | k4) != 0 ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&empty_bar[stage]));  // frees the stage when these MMAs have read it
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(smem_u32(&tfull_bar[acc]));  // accumulator complete -> epilogue
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue: threshold filter, one query per thread =================
+    const int ew = warp - 4;  // TMEM lane quarter this warp may read
+    uint64_t* scratch = scratch_all + ew * kSegCap;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < items; w += gridDim.x) {
+      const int chunk = w / g.qblocks, qb = w - chunk * g.qblocks;
+      const int t0 = g.tile_begin + chunk * g.tiles_per_chunk;
+      const int t1 = min(g.tile_end, t0 + g.tiles_per_chunk);
+      const int q = qb * BM + ew * 32 + lane;
+      const bool live = q < g.Q;
+      SegState s;
+      s.seg = g.cand + (static_cast<int64_t>(live ? q : 0) * g.chunks + chunk) * kSegCap;
+      s.cnt = 0;
+      s.tau = live ? g.tau[q] : INFINITY;
+      float qscale = g.acc_scale;
+      if (BF16) qscale *= live ? g.qinv[q] : 0.f;
+      for (int tile = t0; tile < t1; ++tile) {
+        mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * BN);
+        const int row0 = tile * BN;
+#pragma unroll 1
+        for (int cb = 0; cb < BN / 32; ++cb) {
+          compact_full_segments(s, scratch, g.k, lane);
+          uint32_t r[32];
+          tmem_ld32(taddr + cb * 32, r);
+          tmem_ld_wait();
+          const int rbase = row0 + cb * 32;
+          if (rbase + 32 <= g.N) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float sc = __uint_as_float(r[j]) * qscale;
+              if (BF16) sc *= __ldg(g.cinv + rbase + j);
+              if (sc > s.tau) {
+                const int row = rbase + j;
+                if (!(g.mask && g.mask[row])) {
+                  s.seg[s.cnt] = make_key(sc, static_cast<uint32_t>(row));
+                  ++s.cnt;
+                }
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int row = rbase + j;
+              if (row < g.N) {
+                float sc = __uint_as_float(r[j]) * qscale;
+                if (BF16) sc *= __ldg(g.cinv + row);
+                if (sc > s.tau && !(g.mask && g.mask[row])) {
+                  s.seg[s.cnt] = make_key(sc, static_cast<uint32_t>(row));
+                  ++s.cnt;
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+      if (live) g.cand_cnt[static_cast<int64_t>(q) * g.chunks + chunk] = s.cnt;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------
+int launch_row_inv_norms(const void* x, int64_t rows, int64_t dim, int64_t ld, int dtype, float* inv, cudaStream_t st);
+int launch_split_planes(const float* x, int64_t rows, int64_t dim, int64_t ld, uint16_t* planes, cudaStream_t st);
+size_t select_scratch_bytes(int64_t Q, int nseg, int seg_cap, int k);
+int launch_select(const uint64_t* seg_keys, const int* seg_cnt, int64_t Q, int nseg, int seg_stride, int seg_cap,
+                  const uint64_t* carry_in, const int* carry_cnt_in, uint64_t* carry_out, int* carry_cnt_out,
+                  float* tau_out, float* out_scores, int64_t* out_ids, int64_t id_offset, int k, void* scratch,
+                  size_t scratch_bytes, cudaStream_t st);
+
+constexpr size_t kGemmSmemBytes = static_cast<size_t>(kStages) * kStageBytes + 4 * kSegCap * sizeof(uint64_t) + (2 * kStages + 4) * sizeof(uint64_t) + 16 + 1024;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D map over a row-major [rows, cols] matrix of 16-bit elements, box = [box_rows, 64 cols], 128B swizzle
+static int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld_elems, int box_rows, bool bf16) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable");
+    return ICR_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld_elems) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims,
+                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld)", static_cast<int>(r), (long long)rows,
+              (long long)cols, (long long)ld_elems);
+    return ICR_ERR_CUDA;
+  }
+  return ICR_OK;
+}
+
+struct Phase {
+  int tile_begin, tile_end, chunks, tiles_per_chunk;
+};
+
+// Phases of geometrically growing tile ranges. tau after a phase is the exact k-th score of all rows seen,
+// so a phase that multiplies the rows seen by g admits ~k*ln(g) (at most ~k*(g-1)) survivors per query.
+static int plan_phases(int64_t N, int qblocks, int k, Phase* out, int max_phases) {
+  const int T = static_cast<int>((N + BN - 1) / BN);
+  const int growth = 8;
+  int first = (2 * k + BN - 1) / BN;
+  if (first < 2) first = 2;
+  int n = 0, begin = 0, end = first < T ? first : T;
+  while (begin < T && n < max_phases) {
+    if (n == max_phases - 1) end = T;
+    const int tiles = end - begin;
+    // enough work items to fill the machine twice, few enough survivors per segment to stay far from kSegCap
+    int chunks = (2 * 148 + qblocks - 1) / qblocks;
+    const int by_load = n == 0 ? (tiles * BN + kSegCap / 2 - 1) / (kSegCap / 2) : ((growth - 1) * k + 127) / 128;
+    if (chunks < by_load) chunks = by_load;
+    if (chunks > tiles) chunks = tiles;
+    if (chunks < 1) chunks = 1;
+    out[n].tile_begin = begin;
+    out[n].tile_end = end;
+    out[n].tiles_per_chunk = (tiles + chunks - 1) / chunks;
+    out[n].chunks = (tiles + out[n].tiles_per_chunk - 1) / out[n].tiles_per_chunk;
+    ++n;
+    begin = end;
+    const int64_t next = static_cast<int64_t>(end) * growth;
+    end = next < T ? static_cast<int>(next) : T;
+  }
+  return n;
+}
+
+constexpr int kMaxPhases = 16;
+
+struct GemmWs {
+  size_t q_planes, c_planes, qinv, cinv, tau, carry[2], carry_cnt[2], cand, cand_cnt, scratch, total;
+  int max_chunks;
+};
+
+static GemmWs gemm_ws_layout(int64_t Q, int64_t N, int64_t D, int dtype, int k, int have_planes, int have_cinv) {
+  GemmWs w{};
+  const int qblocks = static_cast<int>((Q + BM - 1) / BM);
+  Phase ph[kMaxPhases];
+  const int np = plan_phases(N, qblocks, k, ph, kMaxPhases);
+  int maxc = 1;
+  for (int i = 0; i < np; ++i) maxc = ph[i].chunks > maxc ? ph[i].chunks : maxc;
+  w.max_chunks = maxc;
+  const int64_t dp2 = 2 * ((D + 63) / 64 * 64);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    const size_t o = off;
+    off += align_up(bytes, 1024);
+    return o;
+  };
+  w.q_planes = take(dtype == ICR_F32 ? static_cast<size_t>(Q) * dp2 * 2 : 0);
+  w.c_planes = take((dtype == ICR_F32 && !have_planes) ? static_cast<size_t>(N) * dp2 * 2 : 0);
+  w.qinv = take(dtype == ICR_BF16 ? static_cast<size_t>(Q) * 4 : 0);
+  w.cinv = take((dtype == ICR_BF16 && !have_cinv) ? static_cast<size_t>(N) * 4 : 0);
+  w.tau = take(static_cast<size_t>(Q) * 4);
+  for (int i = 0; i < 2; ++i) {
+    w.carry[i] = take(static_cast<size_t>(Q) * k * 8);
+    w.carry_cnt[i] = take(static_cast<size_t>(Q) * 4);
+  }
+  w.cand = take(static_cast<size_t>(Q) * maxc * kSegCap * 8);
+  w.cand_cnt = take(static_cast<size_t>(Q) * maxc * 4);
+  w.scratch = take(select_scratch_bytes(Q, maxc, kSegCap, k));
+  w.total = off + 1024;
+  return w;
+}
+
+bool gemm_topk_supported(int64_t Q, int64_t N, int64_t D, int dtype, int k, const uint8_t* mask) {
+  (void)mask;
+  if (Q < 1 || N < 1 || k > ICR_MAX_K) return false;
+  if (dtype == ICR_BF16 && D % 8 != 0) return false;
+  if (N > (static_cast<int64_t>(1) << 31) - BN || Q > (static_cast<int64_t>(1) << 30)) return false;
+  return true;
+}
+
+size_t gemm_topk_workspace_bytes(int64_t Q, int64_t N, int64_t D, int dtype, int k, int have_planes) {
+  // sized without cached bf16 inverse norms so that one figure covers both cases
+  return gemm_ws_layout(Q, N, D, dtype, k, have_planes, 0).total;
+}
+
+__global__ void fill_f32_kernel(float* p, int64_t n, float v) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+int launch_gemm_topk(const void* queries, int64_t Q, int64_t ldq, const void* catalog, int64_t N, int64_t ldc, int64_t D,
+                     int dtype, const uint16_t* cat_planes, const float* cat_inv_norms, const uint8_t* mask, int k, int64_t row_offset,
+                     float* out_scores, int64_t* out_ids, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const GemmWs L = gemm_ws_layout(Q, N, D, dtype, k, cat_planes != nullptr, cat_inv_norms != nullptr);
+  if (ws_bytes < L.total) {
+    set_error("gemm_topk: workspace %zu < %zu", ws_bytes, L.total);
+    return ICR_ERR_WORKSPACE;
+  }
+  // 1 KB alignment of every region (TMA global addresses need 16 B; keep it simple)
+  char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~static_cast<uintptr_t>(1023));
+  const int qblocks = static_cast<int>((Q + BM - 1) / BM);
+  const int64_t dp = (D + 63) / 64 * 64;
+  int rc;
+  GemmArgs g{};
+  g.Q = static_cast<int>(Q);
+  g.N = static_cast<int>(N);
+  g.k = k;
+  g.qblocks = qblocks;
+  g.mask = mask;
+  g.tau = reinterpret_cast<float*>(base + L.tau);
+  g.cand = reinterpret_cast<uint64_t*>(base + L.cand);
+  g.cand_cnt = reinterpret_cast<int*>(base + L.cand_cnt);
+  CUtensorMap map_a, map_b;
+  if (dtype == ICR_F32) {
+    uint16_t* qp = reinterpret_cast<uint16_t*>(base + L.q_planes);
+    if ((rc = launch_split_planes(static_cast<const float*>(queries), Q, D, ldq, qp, st))) return rc;
+    const uint16_t* cp = cat_planes;
+    if (!cp) {
+      uint16_t* built = reinterpret_cast<uint16_t*>(base + L.c_planes);
+      if ((rc = launch_split_planes(static_cast<const float*>(catalog), N, D, ldc, built, st))) return rc;
+      cp = built;
+    }
+    if ((rc = make_map(&map_a, qp, Q, 2 * dp, 2 * dp, BM, false))) return rc;
+    if ((rc = make_map(&map_b, cp, N, 2 * dp, 2 * dp, BN, false))) return rc;
+    g.terms = 3;
+    g.kb_per_term = static_cast<int>(dp / BK);
+    g.plane_stride = static_cast<int>(dp);
+    g.acc_scale = 1.0f / 65536.0f;
+  } else {
+    float* qinv = reinterpret_cast<float*>(base + L.qinv);
+    if ((rc = launch_row_inv_norms(queries, Q, D, ldq, dtype, qinv, st))) return rc;
+    const float* cinv = cat_inv_norms;
+    if (!cinv) {
+      float* built = reinterpret_cast<float*>(base + L.cinv);
+      if ((rc = launch_row_inv_norms(catalog, N, D, ldc, dtype, built, st))) return rc;
+      cinv = built;
+    }
+    if ((rc = make_map(&map_a, queries, Q, D, ldq, BM, true))) return rc;
+    if ((rc = make_map(&map_b, catalog, N, D, ldc, BN, true))) return rc;
+    g.terms = 1;
+    g.kb_per_term = static_cast<int>((D + BK - 1) / BK);
+    g.plane_stride = 0;
+    g.acc_scale = 1.0f;
+    g.qinv = qinv;
+    g.cinv = cinv;
+  }
+  static thread_local bool attr_set[2] = {false, false};
+  const int which = dtype == ICR_BF16 ? 1 : 0;
+  if (!attr_set[which]) {
+    if (which)
+      ICR_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmemBytes)));
+    else
+      ICR_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmemBytes)));
+    attr_set[which] = true;
+  }
+  // tau starts at -inf: phase 0 admits every row
+  fill_f32_kernel<<<static_cast<unsigned>((Q + 255) / 256), 256, 0, st>>>(const_cast<float*>(g.tau), Q, -INFINITY);
+  ICR_LAUNCH_CHECK();
+
+  Phase ph[kMaxPhases];
+  const int np = plan_phases(N, qblocks, k, ph, kMaxPhases);
+  const size_t scratch_bytes = select_scratch_bytes(Q, L.max_chunks, kSegCap, k);
+  for (int p = 0; p < np; ++p) {
+    g.tile_begin = ph[p].tile_begin;
+    g.tile_end = ph[p].tile_end;
+    g.chunks = ph[p].chunks;
+    g.tiles_per_chunk = ph[p].tiles_per_chunk;
+    const int items = qblocks * g.chunks;
+    const int grid = items < 148 ? items : 148;
+    profile_begin(kKernelGemm, g.terms, st);
+    if (which)
+      gemm_topk_kernel<true><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(map_a, map_b, g);
+    else
+      gemm_topk_kernel<false><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(map_a, map_b, g);
+    profile_end(st);
+    ICR_LAUNCH_CHECK();
+    const bool last = (p == np - 1);
+    const int cur = p & 1, prev = cur ^ 1;
+    rc = launch_select(g.cand, g.cand_cnt, Q, g.chunks, kSegCap, kSegCap,
+                       p > 0 ? reinterpret_cast<uint64_t*>(base + L.carry[prev]) : nullptr,
+                       p > 0 ? reinterpret_cast<int*>(base + L.carry_cnt[prev]) : nullptr,
+                       last ? nullptr : reinterpret_cast<uint64_t*>(base + L.carry[cur]),
+                       last ? nullptr : reinterpret_cast<int*>(base + L.carry_cnt[cur]),
+                       last ? nullptr : const_cast<float*>(g.tau), last ? out_scores : nullptr, last ? out_ids : nullptr, row_offset, k,
+                       base + L.scratch, scratch_bytes, st);
+    if (rc) return rc;
+  }
+  return ICR_OK;
+}
+
 }  // namespace icr

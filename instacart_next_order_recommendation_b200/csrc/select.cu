@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(kSelectThreads) select_topk_kernel(SelectArgs 
     for (int i = threadIdx.x; i < c; i += blockDim.x) keys[i] = a.carry_in[q * k + i];
     n = c;
   }
-  if (static_cast<int64_t>(nsg) * cap + n <= kSortCap) {
+  if (nsg > 16 && static_cast<int64_t>(nsg) * cap + n <= kSortCap) {
     // flat gather: every slot of every segment in parallel, empty slots become key 0
     const int total = nsg * cap;
     for (int t = threadIdx.x; t < total; t += blockDim.x) {
@@ -78,7 +78,8 @@ __global__ void __launch_bounds__(kSelectThreads) select_topk_kernel(SelectArgs 
     }
     n += total;
   } else {
-    // streaming: append segment after segment, compacting to the k best when the buffer fills
+    // packed: append the valid keys of segment after segment (few, long segments: the GEMM epilogue's),
+    // compacting to the k best whenever the buffer fills
     for (int s = 0; s < nsg; ++s) {
       const int c = cnts ? min(cnts[s], cap) : cap;
       int pos = 0;

@@ -112,6 +112,9 @@ class DeviceCatalog:
             build_planes = dtype == torch.float32
         if build_planes and dtype == torch.float32 and self.rows.shape[0] > 0:
             self.planes = ops.split_f16_planes(self.rows)
+        self.inv_norms: torch.Tensor | None = None
+        if dtype == torch.bfloat16 and self.rows.shape[0] > 0:
+            self.inv_norms = ops.row_inv_norms(self.rows)
 
     @property
     def device(self) -> torch.device:
@@ -138,4 +141,4 @@ class DeviceCatalog:
         k = min(int(k), len(self))
         if k < 1:
             return (torch.empty(q.shape[0], 0, device=self.device), torch.empty(q.shape[0], 0, dtype=torch.int64, device=self.device))
-        return ops.cos_topk(q, self.rows, k, cat_planes=self.planes, exclude_mask=exclude_mask, row_offset=self.row_offset, path=path)
+        return ops.cos_topk(q, self.rows, k, cat_planes=self.planes, cat_inv_norms=self.inv_norms, exclude_mask=exclude_mask, row_offset=self.row_offset, path=path)

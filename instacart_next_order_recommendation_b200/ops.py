@@ -120,6 +120,7 @@ def cos_topk(
     k: int,
     *,
     cat_planes: torch.Tensor | None = None,
+    cat_inv_norms: torch.Tensor | None = None,
     exclude_mask: torch.Tensor | None = None,
     row_offset: int = 0,
     path: int = PATH_AUTO,
@@ -146,6 +147,9 @@ def cos_topk(
     if cat_planes is not None:
         if cat_planes.dtype != torch.float16 or cat_planes.shape != (N, lib.icr_planes_row_elems(D)) or not cat_planes.is_contiguous():
             raise ValueError("cat_planes must be the contiguous output of split_f16_planes(catalog)")
+    if cat_inv_norms is not None:
+        if cat_inv_norms.dtype != torch.float32 or cat_inv_norms.shape != (N,) or not cat_inv_norms.is_contiguous():
+            raise ValueError("cat_inv_norms must be the output of row_inv_norms(catalog)")
     if out is None:
         vals = torch.empty(Q, k, dtype=torch.float32, device=dev)
         ids = torch.empty(Q, k, dtype=torch.int64, device=dev)
@@ -156,8 +160,8 @@ def cos_topk(
         ws = _workspace(need, dev)
         _lib.check(
             lib.icr_cos_topk(
-                queries.data_ptr(), Q, _ld(queries), catalog.data_ptr(), N, _ld(catalog), D, dt, _ptr(cat_planes), _ptr(exclude_mask),
-                k, row_offset, path, vals.data_ptr(), ids.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev),
+                queries.data_ptr(), Q, _ld(queries), catalog.data_ptr(), N, _ld(catalog), D, dt, _ptr(cat_planes), _ptr(cat_inv_norms),
+                _ptr(exclude_mask), k, row_offset, path, vals.data_ptr(), ids.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev),
             )
         )
     return vals, ids

@@ -285,19 +285,21 @@ def synth_unnormalised(n: int, d: int, seed: int) -> torch.Tensor:
 # --------------------------------------------------------------------------------------
 
 
-def compare_topk(values, indices, ref_values, ref_indices, rtol: float, atol: float = 0.0):
+def compare_topk(values, indices, ref_values, ref_indices, rtol: float, atol: float = 0.0, floor: float = 0.05):
     """Returns (max_rel_err_of_scores, n_id_mismatch_outside_ties).
 
-    Scores are compared rank by rank. Ids are compared only at ranks whose gap to both
-    neighbouring reference scores exceeds the tolerance; elsewhere a swap is a legal tie.
+    Scores are compared rank by rank, relative to max(|score|, floor): a cosine near 0 has unbounded
+    relative error even when its absolute error is 1e-8, so the relative tolerance is
+    floored at |score| = `floor`. Ids are compared only at ranks whose gap to both neighbouring
+    reference scores exceeds the tolerance; elsewhere a swap is a legal tie.
     """
     v = np.asarray(values, dtype=np.float64)
     r = np.asarray(ref_values, dtype=np.float64)
     i = np.asarray(indices)
     ri = np.asarray(ref_indices)
-    denom = np.maximum(np.abs(r), 1e-30)
+    denom = np.maximum(np.abs(r), floor)
     rel = np.abs(v - r) / denom
-    tol = rtol * np.abs(r) + atol
+    tol = rtol * denom + atol
     gap_prev = np.full_like(r, np.inf)
     gap_next = np.full_like(r, np.inf)
     gap_prev[:, 1:] = np.abs(r[:, 1:] - r[:, :-1])

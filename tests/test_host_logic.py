@@ -36,13 +36,13 @@ def test_library_exports_every_declared_symbol(lib):
 
 def test_argument_errors_are_reported_without_a_gpu(lib):
     # shape / dtype / alignment validation happens before any CUDA call
-    rc = lib.icr_cos_topk(None, 1, 384, None, 10, 384, 384, 0, None, None, 10, 0, 0, None, None, None, 0, None)
+    rc = lib.icr_cos_topk(None, 1, 384, None, 10, 384, 384, 0, None, None, None, 10, 0, 0, None, None, None, 0, None)
     assert rc == -1 and b"null pointer" in lib.icr_last_error_string()
-    rc = lib.icr_cos_topk(16, 1, 384, 16, 10, 384, 384, 7, None, None, 10, 0, 0, None, None, None, 0, None)
+    rc = lib.icr_cos_topk(16, 1, 384, 16, 10, 384, 384, 7, None, None, None, 10, 0, 0, None, None, None, 0, None)
     assert rc == -2
-    rc = lib.icr_cos_topk(16, 1, 384, 16, 10, 384, 384, 0, None, None, 1000, 0, 0, None, None, None, 0, None)
+    rc = lib.icr_cos_topk(16, 1, 384, 16, 10, 384, 384, 0, None, None, None, 1000, 0, 0, None, None, None, 0, None)
     assert rc == -4
-    rc = lib.icr_cos_topk(8, 1, 384, 16, 10, 384, 384, 0, None, None, 10, 0, 0, None, None, None, 0, None)
+    rc = lib.icr_cos_topk(8, 1, 384, 16, 10, 384, 384, 0, None, None, None, 10, 0, 0, None, None, None, 0, None)
     assert rc == -3
     with pytest.raises(ValueError, match="ICR_ERR_K"):
         _lib.check(-4)
