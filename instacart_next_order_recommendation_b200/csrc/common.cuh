@@ -153,7 +153,8 @@ __device__ __forceinline__ void block_bitonic_sort_desc(uint64_t* keys, int n) {
   for (int size = 2; size <= n; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
       for (int t = threadIdx.x; t < (n >> 1); t += blockDim.x) {
-        const int lo = ((t / stride) * (stride << 1)) + (t % stride);
+        // stride is a power of two: index arithmetic by mask/shift (an integer divide here costs more than the sort)
+        const int lo = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
         const int hi = lo + stride;
         const bool desc = ((lo & size) == 0);
         const uint64_t a = keys[lo], b = keys[hi];

@@ -1,23 +1,30 @@
 // K2: cosine scoring as a tcgen05 / TMEM tensor-core GEMM whose epilogue never writes scores:
 // it filters them against a per-query threshold and appends the few survivors as candidate keys.
 //
-//   S[128 queries, 256 catalog rows] = A[128, K] * B[256, K]^T        (K-major operands, fp32 accumulate)
+//   S[256 queries, 256 catalog rows] = A[256, K] * B[256, K]^T      per CTA PAIR (cta_group::2, fp32 accumulate)
 //
-//  * Operands arrive by TMA (cp.async.bulk.tensor.2d, 128-byte swizzle) into a 4-stage shared-memory
-//    ring guarded by mbarriers; one elected thread issues tcgen05.mma (M=128, N=256, K=16) into one of two
-//    256-column TMEM accumulators, so the epilogue of tile i overlaps the MMAs of tile i+1.
+//  * Two CTAs of a cluster (one TPC) work as a pair: each owns 128 queries (its half of M) and loads only
+//    HALF of every catalog tile (128 of the 256 rows); one elected thread of the leader CTA issues
+//    tcgen05.mma.cta_group::2 (M=256, N=256, K=16) which reads both CTAs' shared memory and writes a
+//    128-lane x 256-column fp32 accumulator into EACH CTA's TMEM. Halving the B traffic per SM is what
+//    takes this loop off the L2-bandwidth limit (profiles/r01_notes.md).
+//  * Operands arrive by TMA (cp.async.bulk.tensor.2d.cta_group::2, 128-byte swizzle) into a shared-memory
+//    ring guarded by mbarriers (transaction bytes of both CTAs land on the leader's "full" barrier;
+//    tcgen05.commit multicasts "empty" to both). Two TMEM accumulators let the epilogue of tile i overlap
+//    the MMAs of tile i+1.
 //  * Queries sit on the M axis: after tcgen05.ld every epilogue thread owns ONE query (its TMEM lane) and
 //    sees 32 catalog scores per load. A score survives if it beats the thread's threshold tau — the k-th
-//    best score of the catalog rows already ranked in earlier phases (exact lower bound of the final k-th
-//    score), so survivors are ~k*ln(growth) per phase instead of N.
+//    best score of the catalog rows already ranked in earlier phases (an exact lower bound of the final
+//    k-th score). The append is predicated, not branched: ~8 instructions per score.
 //  * The catalog is walked in phases of geometrically growing row ranges; between phases the select kernel
 //    (select.cu) folds the survivors into the running top-k and publishes the new tau. If a thread's
 //    candidate segment fills up anyway (adversarially ordered catalogs), its warp sorts the segment in
 //    shared memory, keeps the k best and raises that thread's tau: exact for any input.
 //  * fp32 catalogs keep fp32 parity on fp16 tensor cores: rows are L2-normalised, scaled by 2^8 and split
 //    into fp16 hi + lo planes (prep.cu); hi*hi + hi*lo + lo*hi accumulated in fp32 reproduces the fp32 dot
-//    product to ~1e-6 relative (measured: profiles/r01_split_precision.txt). bf16 catalogs take one MMA term
-//    on the raw rows and multiply by the two inverse norms in the epilogue.
+//    product to ~1e-6 relative (profiles/r01_split_precision.txt). Each pipeline stage holds the four
+//    plane tiles of one 64-wide K block, so no plane is fetched twice. bf16 catalogs take one MMA term on
+//    the raw rows and multiply by the two inverse norms in the epilogue.
 //
 // Replaces cos_sim [Q,N] -> torch.topk(100) -> Python heap of sentence-transformers'
 // InformationRetrievalEvaluator (built at reference src/training/train_sbert.py:197-202) and the
@@ -28,27 +35,26 @@
 
 namespace icr {
 
-constexpr int BM = 128;   // queries per tile (TMEM lanes)
-constexpr int BN = 256;   // catalog rows per tile (TMEM columns of one accumulator)
-constexpr int BK = 64;    // K elements per pipeline stage = one 128-byte swizzle atom of 16-bit elements
-constexpr int kStages = 4;
-constexpr int kStageABytes = BM * BK * 2;
-constexpr int kStageBBytes = BN * BK * 2;
-constexpr int kStageBytes = kStageABytes + kStageBBytes;
+constexpr int BM = 128;          // queries per CTA (TMEM lanes); 256 per pair
+constexpr int BN = 256;          // catalog rows per tile (TMEM columns of one accumulator)
+constexpr int BNH = BN / 2;      // catalog rows of a tile loaded by each CTA of the pair
+constexpr int BK = 64;           // K elements per pipeline stage = one 128-byte swizzle atom of 16-bit elements
+constexpr int kTileBytes = 128 * BK * 2;  // every operand tile in shared memory is 128 rows x 128 bytes
+constexpr int kRingBytes = 192 * 1024;
 constexpr int kSegCap = 512;         // candidate keys per (query, chunk) segment
 constexpr int kGemmThreads = 256;    // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warp 3 idle, warps 4-7 epilogue
 constexpr int kTmemCols = 512;       // two 256-column fp32 accumulators
 constexpr uint32_t kSpinLimit = 1u << 24;
+constexpr int kMaxStages = 6;
 
 struct GemmArgs {
   int Q, N;
   int k;
-  int terms;        // 1 (bf16 rows) or 3 (fp16 hi/lo planes)
-  int kb_per_term;  // 64-element K blocks per term
-  int plane_stride; // element offset of the lo plane inside a row (terms == 3)
+  int kb_per_term;  // 64-element K blocks of the embedding dimension
+  int plane_stride; // element offset of the lo plane inside a row (plane path)
   int tile_begin, tile_end;  // catalog tiles [begin, end) of this phase
-  int chunks, tiles_per_chunk;
-  int qblocks;
+  int chunks;                // balanced tile ranges, see chunk_first_tile
+  int qblocks;               // blocks of 256 queries
   float acc_scale;           // 2^-16 for the plane path, 1 for bf16
   const float* tau;          // [Q]
   const float* qinv;         // [Q]  (bf16 path) or null
@@ -60,15 +66,30 @@ struct GemmArgs {
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+      "}\n" ::"r"(bar), "r"(cta)
+      : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
@@ -85,32 +106,37 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (spin > kSpinLimit) __trap();  // a protocol bug must abort the launch, not hang the GPU
   }
 }
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+// TMA tile load of a CTA pair: data lands in THIS CTA's shared memory, the transaction bytes are
+// credited to the barrier at the same offset in the pair's leader (peer bit of the address cleared)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
       : "memory");
 }
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+// arrives (once all MMAs issued so far have completed) on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(static_cast<uint16_t>(3))
+               : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -123,7 +149,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// wait for the outstanding tcgen05.ld of this thread; the registers are tied to the wait so that no use of
+// them can be scheduled above it
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                 "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]),
+                 "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]),
+                 "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
 
 // K-major operand tile in shared memory, rows of 128 bytes, 128-byte swizzle, 8-row groups 1024 bytes apart
 __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
@@ -142,7 +178,7 @@ __device__ __forceinline__ void warp_bitonic_sort_desc(uint64_t* keys, int n, in
   for (int size = 2; size <= n; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
       for (int t = lane; t < (n >> 1); t += 32) {
-        const int lo = ((t / stride) * (stride << 1)) + (t % stride);
+        const int lo = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
         const int hi = lo + stride;
         const bool desc = ((lo & size) == 0);
         const uint64_t a = keys[lo], b = keys[hi];
@@ -156,10 +192,15 @@ __device__ __forceinline__ void warp_bitonic_sort_desc(uint64_t* keys, int n, in
   }
 }
 
+// chunk c of a phase covers tiles [first(c), first(c+1)): sizes differ by at most one tile
+__device__ __forceinline__ int chunk_first_tile(const GemmArgs& g, int c) {
+  return g.tile_begin + static_cast<int>(static_cast<int64_t>(c) * (g.tile_end - g.tile_begin) / g.chunks);
+}
+
 struct SegState {
-  uint64_t* seg;  // this thread's candidate segment (global)
+  uint64_t* seg;    // this thread's candidate segment (global)
   int cnt;
-  float tau;
+  uint32_t tau_ob;  // order_bits of the threshold: a score survives iff order_bits(score) > tau_ob
 };
 
 // Any lane whose segment could overflow during the next 32 scores gets it compacted by the whole warp.
@@ -175,74 +216,133 @@ __device__ __forceinline__ void compact_full_segments(SegState& s, uint64_t* scr
     warp_bitonic_sort_desc(scratch, kSegCap, lane);
     const int kept = n < k ? n : k;
     for (int i = lane; i < kept; i += 32) seg[i] = scratch[i];
-    const float t_new = (n >= k) ? key_score(scratch[k - 1]) : -INFINITY;
+    const uint32_t t_new = (n >= k) ? static_cast<uint32_t>(scratch[k - 1] >> 32) : 0u;
     if (lane == L) {
       s.cnt = kept;
-      s.tau = fmaxf(s.tau, t_new);
+      s.tau_ob = max(s.tau_ob, t_new);
     }
     __syncwarp();
   }
 }
 
+__device__ __forceinline__ uint32_t order_bits_canonical(float s) {  // s must not be -0.0
+  const uint32_t b = __float_as_uint(s);
+  return b ^ (static_cast<uint32_t>(static_cast<int32_t>(b) >> 31) | 0x80000000u);
+}
+
+// predicated append of key (ob, ~row): no branch, so a warp whose lanes disagree pays nothing extra
+__device__ __forceinline__ void append_if(SegState& s, uint32_t ob, uint32_t nrow) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.gt.u32 p, %1, %2;\n"
+      "@p st.global.v2.u32 [%0], {%3, %1};\n"
+      "}\n" ::"l"(s.seg + s.cnt), "r"(ob), "r"(s.tau_ob), "r"(nrow)
+      : "memory");
+  s.cnt += (ob > s.tau_ob) ? 1 : 0;
+}
+
+// filter 32 accumulator columns (catalog rows rbase .. rbase+31) of this thread's query
 template <bool BF16>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__device__ __forceinline__ void filter32(const uint32_t (&r)[32], SegState& s, float qscale, const float* cinv32, int rbase, bool fast,
+                                         int N, const uint8_t* mask) {
+  if (fast) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float sc;
+      if (BF16) sc = fmaf(__uint_as_float(r[j]) * qscale, cinv32[j], 0.0f);
+      else sc = fmaf(__uint_as_float(r[j]), qscale, 0.0f);  // + 0.0 turns -0.0 into +0.0
+      append_if(s, order_bits_canonical(sc), ~static_cast<uint32_t>(rbase + j));
+    }
+  } else {
+    // last (partial) tile of the catalog, or an exclusion mask: rows are checked one by one
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int row = rbase + j;
+      if (row < N && !(mask && mask[row])) {
+        float sc;
+        if (BF16) sc = fmaf(__uint_as_float(r[j]) * qscale, cinv32[j], 0.0f);
+        else sc = fmaf(__uint_as_float(r[j]), qscale, 0.0f);
+        append_if(s, order_bits_canonical(sc), ~static_cast<uint32_t>(row));
+      }
+    }
+  }
+}
+
+// TERMS = 3: fp16 hi/lo planes (fp32 parity); TERMS = 1: raw bf16 rows
+template <int TERMS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmArgs g) {
+  constexpr bool BF16 = (TERMS == 1);
+  constexpr int kStageTiles = (TERMS == 3) ? 4 : 2;  // A_hi A_lo B_hi B_lo | A B
+  constexpr int kStageBytes = kStageTiles * kTileBytes;
+  constexpr int kStages = kRingBytes / kStageBytes;  // 3 | 6
+  static_assert(kStages <= kMaxStages, "barrier array too small");
+
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  // 128-byte-swizzled tiles need 1024-byte alignment; the allocation carries 1 KB of slack for this
+  // 128-byte-swizzled tiles need 1024-byte alignment; the allocation carries 1 KB of slack for this.
+  // Both CTAs of the pair compute the same offset (same kernel, same static layout).
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  // layout: [stages][A 16K | B 32K] | scratch 4 x kSegCap keys | barriers | tmem ptr
   unsigned char* stage_base = smem;
-  uint64_t* scratch_all = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
-  uint64_t* bars = scratch_all + 4 * kSegCap;
+  uint64_t* scratch_all = reinterpret_cast<uint64_t*>(smem + kRingBytes);          // 4 warps x kSegCap keys
+  float* cinv_all = reinterpret_cast<float*>(scratch_all + 4 * kSegCap);            // 4 warps x BN floats
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cinv_all + 4 * BN);
   uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + kStages;
-  uint64_t* tfull_bar = bars + 2 * kStages;
-  uint64_t* tempty_bar = bars + 2 * kStages + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint64_t* empty_bar = bars + kMaxStages;
+  uint64_t* tfull_bar = bars + 2 * kMaxStages;
+  uint64_t* tempty_bar = bars + 2 * kMaxStages + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int KI = g.terms * g.kb_per_term;
+  const uint32_t rank = cluster_ctarank();  // 0 = leader of the pair
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int KB = g.kb_per_term;
   const int items = g.qblocks * g.chunks;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), 1);
-      mbar_init(smem_u32(&empty_bar[s]), 1);
+      mbar_init(smem_u32(&full_bar[s]), 1);   // leader's arrive.expect_tx; data of both CTAs arrives as tx bytes
+      mbar_init(smem_u32(&empty_bar[s]), 1);  // one multicast tcgen05.commit
     }
     for (int a = 0; a < 2; ++a) {
-      mbar_init(smem_u32(&tfull_bar[a]), 1);
-      mbar_init(smem_u32(&tempty_bar[a]), 4);
+      mbar_init(smem_u32(&tfull_bar[a]), 1);   // one multicast tcgen05.commit
+      mbar_init(smem_u32(&tempty_bar[a]), 8);  // 4 epilogue warps of each CTA (used in the leader only)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_b) : "memory");
   }
-  if (warp == 2) tmem_alloc(smem_u32(tmem_ptr), kTmemCols);
+  if (warp == 2) tmem_alloc_pair(smem_u32(tmem_ptr), kTmemCols);
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();  // peer barriers are initialised and its TMEM allocated before anything crosses CTAs
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0 && lane == 0) {
-    // ================= TMA producer =================
+    // ================= TMA producer (both CTAs; each loads its own queries and its half of B) =================
     int stage = 0;
     uint32_t phase = 0;
-    for (int w = blockIdx.x; w < items; w += gridDim.x) {
+    for (int w = pair; w < items; w += npairs) {
       const int chunk = w / g.qblocks, qb = w - chunk * g.qblocks;
-      const int t0 = g.tile_begin + chunk * g.tiles_per_chunk;
-      const int t1 = min(g.tile_end, t0 + g.tiles_per_chunk);
+      const int t0 = chunk_first_tile(g, chunk), t1 = chunk_first_tile(g, chunk + 1);
+      const int qrow = qb * (2 * BM) + static_cast<int>(rank) * BM;
       for (int tile = t0; tile < t1; ++tile) {
-        for (int ki = 0; ki < KI; ++ki) {
-          const int term = ki / g.kb_per_term, kb = ki - term * g.kb_per_term;
-          // plane path: (A,B) planes of term 0,1,2 = (hi,hi), (hi,lo), (lo,hi)
-          const int ka = kb * BK + ((term == 2) ? g.plane_stride : 0);
-          const int kbx = kb * BK + ((term == 1) ? g.plane_stride : 0);
+        const int crow = tile * BN + static_cast<int>(rank) * BNH;
+        for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
           const uint32_t fb = smem_u32(&full_bar[stage]);
-          mbar_expect_tx(fb, kStageBytes);
+          if (rank == 0) mbar_expect_tx(fb, 2 * kStageBytes);
           const uint32_t sa = smem_u32(stage_base + stage * kStageBytes);
-          tma_load_2d(sa, &tma_a, ka, qb * BM, fb);
-          tma_load_2d(sa + kStageABytes, &tma_b, kbx, tile * BN, fb);
+          if (TERMS == 3) {
+            tma_load_2d_pair(sa, &tma_a, kb * BK, qrow, fb);
+            tma_load_2d_pair(sa + kTileBytes, &tma_a, g.plane_stride + kb * BK, qrow, fb);
+            tma_load_2d_pair(sa + 2 * kTileBytes, &tma_b, kb * BK, crow, fb);
+            tma_load_2d_pair(sa + 3 * kTileBytes, &tma_b, g.plane_stride + kb * BK, crow, fb);
+          } else {
+            tma_load_2d_pair(sa, &tma_a, kb * BK, qrow, fb);
+            tma_load_2d_pair(sa + kTileBytes, &tma_b, kb * BK, crow, fb);
+          }
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -250,41 +350,52 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ================= MMA issuer =================
-    // instruction descriptor: D=f32, A/B = f16 or bf16, K-major both, N=256, M=128
+  } else if (warp == 1 && lane == 0 && rank == 0) {
+    // ================= MMA issuer (leader CTA only) =================
+    // instruction descriptor: D=f32, A/B = f16 or bf16, K-major both, N=256, M=256 (two CTAs x 128)
     const uint32_t fmt = BF16 ? 1u : 0u;
-    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(BN >> 3) << 17) | (static_cast<uint32_t>(BM >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(BN >> 3) << 17) | (static_cast<uint32_t>((2 * BM) >> 4) << 24);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int w = blockIdx.x; w < items; w += gridDim.x) {
+    for (int w = pair; w < items; w += npairs) {
       const int chunk = w / g.qblocks;
-      const int t0 = g.tile_begin + chunk * g.tiles_per_chunk;
-      const int t1 = min(g.tile_end, t0 + g.tiles_per_chunk);
+      const int t0 = chunk_first_tile(g, chunk), t1 = chunk_first_tile(g, chunk + 1);
       for (int tile = t0; tile < t1; ++tile) {
         mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
-        for (int ki = 0; ki < KI; ++ki) {
+        for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(smem_u32(&full_bar[stage]), phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(stage_base + stage * kStageBytes);
-          const uint64_t adesc = smem_desc_sw128(sa);
-          const uint64_t bdesc = smem_desc_sw128(sa + kStageABytes);
+          if (TERMS == 3) {
+            const uint64_t a_hi = smem_desc_sw128(sa), a_lo = smem_desc_sw128(sa + kTileBytes);
+            const uint64_t b_hi = smem_desc_sw128(sa + 2 * kTileBytes), b_lo = smem_desc_sw128(sa + 3 * kTileBytes);
 #pragma unroll
-          for (int k4 = 0; k4 < BK / 16; ++k4) {
-            // advancing 16 elements (32 bytes) along K inside the swizzle atom = +2 in the 16-byte address field
-            umma_f16(d_tmem, adesc + static_cast<uint64_t>(k4 * 2), bdesc + static_cast<uint64_t>(k4 * 2), idesc, (ki | k4) != 0 ? 1u : 0u);
+            for (int k4 = 0; k4 < BK / 16; ++k4) {
+              // advancing 16 elements (32 bytes) along K inside the swizzle atom = +2 in the 16-byte address field
+              const uint64_t o = static_cast<uint64_t>(k4 * 2);
+              umma_f16_pair(d_tmem, a_hi + o, b_hi + o, idesc, (kb | k4) != 0 ? 1u : 0u);
+              umma_f16_pair(d_tmem, a_hi + o, b_lo + o, idesc, 1u);
+              umma_f16_pair(d_tmem, a_lo + o, b_hi + o, idesc, 1u);
+            }
+          } else {
+            const uint64_t adesc = smem_desc_sw128(sa), bdesc = smem_desc_sw128(sa + kTileBytes);
+#pragma unroll
+            for (int k4 = 0; k4 < BK / 16; ++k4) {
+              const uint64_t o = static_cast<uint64_t>(k4 * 2);
+              umma_f16_pair(d_tmem, adesc + o, bdesc + o, idesc, (kb | k4) != 0 ? 1u : 0u);
+            }
           }
-          umma_commit(smem_u32(&empty_bar[stage]));  // frees the stage when these MMAs have read it
+          umma_commit_pair(smem_u32(&empty_bar[stage]));  // frees the stage in both CTAs when these MMAs have read it
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(smem_u32(&tfull_bar[acc]));  // accumulator complete -> epilogue
+        umma_commit_pair(smem_u32(&tfull_bar[acc]));  // accumulator complete -> both epilogues
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -295,63 +406,49 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     // ================= epilogue: threshold filter, one query per thread =================
     const int ew = warp - 4;  // TMEM lane quarter this warp may read
     uint64_t* scratch = scratch_all + ew * kSegCap;
+    float* cinv_s = cinv_all + ew * BN;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int w = blockIdx.x; w < items; w += gridDim.x) {
+    for (int w = pair; w < items; w += npairs) {
       const int chunk = w / g.qblocks, qb = w - chunk * g.qblocks;
-      const int t0 = g.tile_begin + chunk * g.tiles_per_chunk;
-      const int t1 = min(g.tile_end, t0 + g.tiles_per_chunk);
-      const int q = qb * BM + ew * 32 + lane;
+      const int t0 = chunk_first_tile(g, chunk), t1 = chunk_first_tile(g, chunk + 1);
+      const int q = qb * (2 * BM) + static_cast<int>(rank) * BM + ew * 32 + lane;
       const bool live = q < g.Q;
       SegState s;
       s.seg = g.cand + (static_cast<int64_t>(live ? q : 0) * g.chunks + chunk) * kSegCap;
       s.cnt = 0;
-      s.tau = live ? g.tau[q] : INFINITY;
+      s.tau_ob = live ? order_bits(g.tau[q]) : 0xFFFFFFFFu;
       float qscale = g.acc_scale;
       if (BF16) qscale *= live ? g.qinv[q] : 0.f;
       for (int tile = t0; tile < t1; ++tile) {
+        const int row0 = tile * BN;
+        if (BF16) {
+          // stage the tile's 256 catalog inverse norms once per warp (read back as shared-memory broadcasts)
+          __syncwarp();
+          for (int i = lane; i < BN; i += 32) cinv_s[i] = (row0 + i < g.N) ? __ldg(g.cinv + row0 + i) : 0.f;
+          __syncwarp();
+        }
         mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * BN);
-        const int row0 = tile * BN;
+        const bool fast = (row0 + BN <= g.N) && (g.mask == nullptr);
+        uint32_t ra[32], rb[32];
+        tmem_ld32(taddr, ra);
 #pragma unroll 1
-        for (int cb = 0; cb < BN / 32; ++cb) {
+        for (int cb = 0; cb < BN / 32; cb += 2) {
+          // the next 32 columns are in flight while the current 32 are filtered
+          tmem_ld_wait(ra);
+          tmem_ld32(taddr + (cb + 1) * 32, rb);
           compact_full_segments(s, scratch, g.k, lane);
-          uint32_t r[32];
-          tmem_ld32(taddr + cb * 32, r);
-          tmem_ld_wait();
-          const int rbase = row0 + cb * 32;
-          if (rbase + 32 <= g.N) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float sc = __uint_as_float(r[j]) * qscale;
-              if (BF16) sc *= __ldg(g.cinv + rbase + j);
-              if (sc > s.tau) {
-                const int row = rbase + j;
-                if (!(g.mask && g.mask[row])) {
-                  s.seg[s.cnt] = make_key(sc, static_cast<uint32_t>(row));
-                  ++s.cnt;
-                }
-              }
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int row = rbase + j;
-              if (row < g.N) {
-                float sc = __uint_as_float(r[j]) * qscale;
-                if (BF16) sc *= __ldg(g.cinv + row);
-                if (sc > s.tau && !(g.mask && g.mask[row])) {
-                  s.seg[s.cnt] = make_key(sc, static_cast<uint32_t>(row));
-                  ++s.cnt;
-                }
-              }
-            }
-          }
+          filter32<BF16>(ra, s, qscale, cinv_s + cb * 32, row0 + cb * 32, fast, g.N, g.mask);
+          tmem_ld_wait(rb);
+          if (cb + 2 < BN / 32) tmem_ld32(taddr + (cb + 2) * 32, ra);
+          compact_full_segments(s, scratch, g.k, lane);
+          filter32<BF16>(rb, s, qscale, cinv_s + (cb + 1) * 32, row0 + (cb + 1) * 32, fast, g.N, g.mask);
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+        if (lane == 0) mbar_arrive_cluster(smem_u32(&tempty_bar[acc]), 0);  // accumulator drained: tell the leader's MMA thread
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -363,9 +460,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();  // no CTA may exit (or free TMEM) while its peer can still reach it
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    tmem_dealloc_pair(tmem_base, kTmemCols);
   }
 }
 
@@ -378,7 +476,10 @@ int launch_select(const uint64_t* seg_keys, const int* seg_cnt, int64_t Q, int n
                   float* tau_out, float* out_scores, int64_t* out_ids, int64_t id_offset, int k, void* scratch,
                   size_t scratch_bytes, cudaStream_t st);
 
-constexpr size_t kGemmSmemBytes = static_cast<size_t>(kStages) * kStageBytes + 4 * kSegCap * sizeof(uint64_t) + (2 * kStages + 4) * sizeof(uint64_t) + 16 + 1024;
+constexpr size_t kGemmSmemBytes = static_cast<size_t>(kRingBytes) + 4 * kSegCap * sizeof(uint64_t) + 4 * BN * sizeof(float) +
+                                  (2 * kMaxStages + 4) * sizeof(uint64_t) + 16 + 1024;
+static_assert(kGemmSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
+constexpr int kNumSMs = 148;
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -395,8 +496,8 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D map over a row-major [rows, cols] matrix of 16-bit elements, box = [box_rows, 64 cols], 128B swizzle
-static int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld_elems, int box_rows, bool bf16) {
+// 2-D map over a row-major [rows, cols] matrix of 16-bit elements, box = [128 rows, 64 cols], 128B swizzle
+static int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld_elems, bool bf16) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point unavailable");
@@ -404,7 +505,7 @@ static int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols
   }
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld_elems) * 2};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), 128u};
   cuuint32_t estr[2] = {1, 1};
   const CUresult r = enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims,
                          strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -418,7 +519,7 @@ static int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols
 }
 
 struct Phase {
-  int tile_begin, tile_end, chunks, tiles_per_chunk;
+  int tile_begin, tile_end, chunks;
 };
 
 // Phases of geometrically growing tile ranges. tau after a phase is the exact k-th score of all rows seen,
@@ -426,6 +527,7 @@ struct Phase {
 static int plan_phases(int64_t N, int qblocks, int k, Phase* out, int max_phases) {
   const int T = static_cast<int>((N + BN - 1) / BN);
   const int growth = 8;
+  const int npairs = kNumSMs / 2;
   int first = (2 * k + BN - 1) / BN;
   if (first < 2) first = 2;
   int n = 0, begin = 0, end = first < T ? first : T;
@@ -433,15 +535,26 @@ static int plan_phases(int64_t N, int qblocks, int k, Phase* out, int max_phases
     if (n == max_phases - 1) end = T;
     const int tiles = end - begin;
     // enough work items to fill the machine twice, few enough survivors per segment to stay far from kSegCap
-    int chunks = (2 * 148 + qblocks - 1) / qblocks;
+    int chunks = (2 * npairs + qblocks - 1) / qblocks;
     const int by_load = n == 0 ? (tiles * BN + kSegCap / 2 - 1) / (kSegCap / 2) : ((growth - 1) * k + 127) / 128;
     if (chunks < by_load) chunks = by_load;
     if (chunks > tiles) chunks = tiles;
     if (chunks < 1) chunks = 1;
+    // work items go round-robin to the pairs; pick the chunk count (near the floor computed above) whose
+    // busiest pair has the least tiles: rounds * ceil(tiles / chunks)
+    int best = chunks;
+    int64_t best_load = -1;
+    for (int c = chunks; c <= tiles && c < chunks + 24; ++c) {
+      const int64_t rounds = (static_cast<int64_t>(qblocks) * c + npairs - 1) / npairs;
+      const int64_t load = rounds * ((tiles + c - 1) / c);
+      if (best_load < 0 || load < best_load) {
+        best_load = load;
+        best = c;
+      }
+    }
     out[n].tile_begin = begin;
     out[n].tile_end = end;
-    out[n].tiles_per_chunk = (tiles + chunks - 1) / chunks;
-    out[n].chunks = (tiles + out[n].tiles_per_chunk - 1) / out[n].tiles_per_chunk;
+    out[n].chunks = best;
     ++n;
     begin = end;
     const int64_t next = static_cast<int64_t>(end) * growth;
@@ -459,7 +572,7 @@ struct GemmWs {
 
 static GemmWs gemm_ws_layout(int64_t Q, int64_t N, int64_t D, int dtype, int k, int have_planes, int have_cinv) {
   GemmWs w{};
-  const int qblocks = static_cast<int>((Q + BM - 1) / BM);
+  const int qblocks = static_cast<int>((Q + 2 * BM - 1) / (2 * BM));
   Phase ph[kMaxPhases];
   const int np = plan_phases(N, qblocks, k, ph, kMaxPhases);
   int maxc = 1;
@@ -514,9 +627,8 @@ int launch_gemm_topk(const void* queries, int64_t Q, int64_t ldq, const void* ca
     set_error("gemm_topk: workspace %zu < %zu", ws_bytes, L.total);
     return ICR_ERR_WORKSPACE;
   }
-  // 1 KB alignment of every region (TMA global addresses need 16 B; keep it simple)
   char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~static_cast<uintptr_t>(1023));
-  const int qblocks = static_cast<int>((Q + BM - 1) / BM);
+  const int qblocks = static_cast<int>((Q + 2 * BM - 1) / (2 * BM));
   const int64_t dp = (D + 63) / 64 * 64;
   int rc;
   GemmArgs g{};
@@ -529,6 +641,7 @@ int launch_gemm_topk(const void* queries, int64_t Q, int64_t ldq, const void* ca
   g.cand = reinterpret_cast<uint64_t*>(base + L.cand);
   g.cand_cnt = reinterpret_cast<int*>(base + L.cand_cnt);
   CUtensorMap map_a, map_b;
+  int terms;
   if (dtype == ICR_F32) {
     uint16_t* qp = reinterpret_cast<uint16_t*>(base + L.q_planes);
     if ((rc = launch_split_planes(static_cast<const float*>(queries), Q, D, ldq, qp, st))) return rc;
@@ -538,9 +651,9 @@ int launch_gemm_topk(const void* queries, int64_t Q, int64_t ldq, const void* ca
       if ((rc = launch_split_planes(static_cast<const float*>(catalog), N, D, ldc, built, st))) return rc;
       cp = built;
     }
-    if ((rc = make_map(&map_a, qp, Q, 2 * dp, 2 * dp, BM, false))) return rc;
-    if ((rc = make_map(&map_b, cp, N, 2 * dp, 2 * dp, BN, false))) return rc;
-    g.terms = 3;
+    if ((rc = make_map(&map_a, qp, Q, 2 * dp, 2 * dp, false))) return rc;
+    if ((rc = make_map(&map_b, cp, N, 2 * dp, 2 * dp, false))) return rc;
+    terms = 3;
     g.kb_per_term = static_cast<int>(dp / BK);
     g.plane_stride = static_cast<int>(dp);
     g.acc_scale = 1.0f / 65536.0f;
@@ -553,9 +666,9 @@ int launch_gemm_topk(const void* queries, int64_t Q, int64_t ldq, const void* ca
       if ((rc = launch_row_inv_norms(catalog, N, D, ldc, dtype, built, st))) return rc;
       cinv = built;
     }
-    if ((rc = make_map(&map_a, queries, Q, D, ldq, BM, true))) return rc;
-    if ((rc = make_map(&map_b, catalog, N, D, ldc, BN, true))) return rc;
-    g.terms = 1;
+    if ((rc = make_map(&map_a, queries, Q, D, ldq, true))) return rc;
+    if ((rc = make_map(&map_b, catalog, N, D, ldc, true))) return rc;
+    terms = 1;
     g.kb_per_term = static_cast<int>((D + BK - 1) / BK);
     g.plane_stride = 0;
     g.acc_scale = 1.0f;
@@ -563,12 +676,12 @@ int launch_gemm_topk(const void* queries, int64_t Q, int64_t ldq, const void* ca
     g.cinv = cinv;
   }
   static thread_local bool attr_set[2] = {false, false};
-  const int which = dtype == ICR_BF16 ? 1 : 0;
+  const int which = terms == 1 ? 1 : 0;
   if (!attr_set[which]) {
     if (which)
-      ICR_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmemBytes)));
+      ICR_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmemBytes)));
     else
-      ICR_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmemBytes)));
+      ICR_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmemBytes)));
     attr_set[which] = true;
   }
   // tau starts at -inf: phase 0 admits every row
@@ -582,14 +695,14 @@ int launch_gemm_topk(const void* queries, int64_t Q, int64_t ldq, const void* ca
     g.tile_begin = ph[p].tile_begin;
     g.tile_end = ph[p].tile_end;
     g.chunks = ph[p].chunks;
-    g.tiles_per_chunk = ph[p].tiles_per_chunk;
     const int items = qblocks * g.chunks;
-    const int grid = items < 148 ? items : 148;
-    profile_begin(kKernelGemm, g.terms, st);
+    const int pairs = items < kNumSMs / 2 ? items : kNumSMs / 2;
+    const int grid = 2 * pairs;  // whole CTA pairs (cluster dims 2x1x1)
+    profile_begin(kKernelGemm, terms, st);
     if (which)
-      gemm_topk_kernel<true><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(map_a, map_b, g);
+      gemm_topk_kernel<1><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(map_a, map_b, g);
     else
-      gemm_topk_kernel<false><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(map_a, map_b, g);
+      gemm_topk_kernel<3><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(map_a, map_b, g);
     profile_end(st);
     ICR_LAUNCH_CHECK();
     const bool last = (p == np - 1);
