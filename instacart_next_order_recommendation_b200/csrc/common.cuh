@@ -168,6 +168,26 @@ __device__ __forceinline__ void block_bitonic_sort_desc(uint64_t* keys, int n) {
   }
 }
 
+// warp-synchronous bitonic sort (descending) of n = power-of-two keys in shared memory
+__device__ __forceinline__ void warp_bitonic_sort_desc(uint64_t* keys, int n, int lane) {
+  __syncwarp();
+  for (int size = 2; size <= n; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = lane; t < (n >> 1); t += 32) {
+        const int lo = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const uint64_t a = keys[lo], b = keys[hi];
+        if ((a < b) == desc) {
+          keys[lo] = b;
+          keys[hi] = a;
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
 __host__ __device__ __forceinline__ int next_pow2(int x) {
   int p = 1;
   while (p < x) p <<= 1;

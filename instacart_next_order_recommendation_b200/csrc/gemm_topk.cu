@@ -172,26 +172,6 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
   return d;
 }
 
-// warp-synchronous bitonic sort (descending) of n = power-of-two keys in shared memory
-__device__ __forceinline__ void warp_bitonic_sort_desc(uint64_t* keys, int n, int lane) {
-  __syncwarp();
-  for (int size = 2; size <= n; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int t = lane; t < (n >> 1); t += 32) {
-        const int lo = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
-        const int hi = lo + stride;
-        const bool desc = ((lo & size) == 0);
-        const uint64_t a = keys[lo], b = keys[hi];
-        if ((a < b) == desc) {
-          keys[lo] = b;
-          keys[hi] = a;
-        }
-      }
-      __syncwarp();
-    }
-  }
-}
-
 // chunk c of a phase covers tiles [first(c), first(c+1)): sizes differ by at most one tile
 __device__ __forceinline__ int chunk_first_tile(const GemmArgs& g, int c) {
   return g.tile_begin + static_cast<int>(static_cast<int64_t>(c) * (g.tile_end - g.tile_begin) / g.chunks);
@@ -471,6 +451,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 int launch_row_inv_norms(const void* x, int64_t rows, int64_t dim, int64_t ld, int dtype, float* inv, cudaStream_t st);
 int launch_split_planes(const float* x, int64_t rows, int64_t dim, int64_t ld, uint16_t* planes, cudaStream_t st);
 size_t select_scratch_bytes(int64_t Q, int nseg, int seg_cap, int k);
+int launch_select_hist(const uint64_t* seg_keys, const int* seg_cnt, int64_t Q, int nseg, int seg_stride, int seg_cap,
+                       const uint64_t* carry_in, const int* carry_cnt_in, uint64_t* carry_out, int* carry_cnt_out, float* tau_out,
+                       float* out_scores, int64_t* out_ids, int64_t id_offset, int k, cudaStream_t st);
 int launch_select(const uint64_t* seg_keys, const int* seg_cnt, int64_t Q, int nseg, int seg_stride, int seg_cap,
                   const uint64_t* carry_in, const int* carry_cnt_in, uint64_t* carry_out, int* carry_cnt_out,
                   float* tau_out, float* out_scores, int64_t* out_ids, int64_t id_offset, int k, void* scratch,
@@ -690,7 +673,6 @@ int launch_gemm_topk(const void* queries, int64_t Q, int64_t ldq, const void* ca
 
   Phase ph[kMaxPhases];
   const int np = plan_phases(N, qblocks, k, ph, kMaxPhases);
-  const size_t scratch_bytes = select_scratch_bytes(Q, L.max_chunks, kSegCap, k);
   for (int p = 0; p < np; ++p) {
     g.tile_begin = ph[p].tile_begin;
     g.tile_end = ph[p].tile_end;
@@ -707,13 +689,13 @@ int launch_gemm_topk(const void* queries, int64_t Q, int64_t ldq, const void* ca
     ICR_LAUNCH_CHECK();
     const bool last = (p == np - 1);
     const int cur = p & 1, prev = cur ^ 1;
-    rc = launch_select(g.cand, g.cand_cnt, Q, g.chunks, kSegCap, kSegCap,
+    rc = launch_select_hist(g.cand, g.cand_cnt, Q, g.chunks, kSegCap, kSegCap,
                        p > 0 ? reinterpret_cast<uint64_t*>(base + L.carry[prev]) : nullptr,
                        p > 0 ? reinterpret_cast<int*>(base + L.carry_cnt[prev]) : nullptr,
                        last ? nullptr : reinterpret_cast<uint64_t*>(base + L.carry[cur]),
                        last ? nullptr : reinterpret_cast<int*>(base + L.carry_cnt[cur]),
-                       last ? nullptr : const_cast<float*>(g.tau), last ? out_scores : nullptr, last ? out_ids : nullptr, row_offset, k,
-                       base + L.scratch, scratch_bytes, st);
+                            last ? nullptr : const_cast<float*>(g.tau), last ? out_scores : nullptr, last ? out_ids : nullptr, row_offset,
+                            k, st);
     if (rc) return rc;
   }
   return ICR_OK;

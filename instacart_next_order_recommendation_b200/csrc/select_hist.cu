@@ -1,0 +1,273 @@
+// Warp-per-query exact top-k selection by histogram partitioning (no full sort).
+//
+// The GEMM epilogue leaves, per query and phase, a few hundred candidate keys spread over a handful of
+// segments, plus the k keys carried from earlier phases. Only the k largest matter, so instead of sorting
+// everything (select.cu) one warp per query
+//   1. gathers the keys into shared memory (all loads independent, coalesced 8-byte lanes),
+//   2. bins them linearly over [min key, max key] into 256 bins (shared-memory histogram),
+//   3. scans the histogram from the top to find the bin holding the k-th largest key,
+//   4. moves keys above that bin straight to the output, compacts the keys of that bin in place, and
+//      either sorts those few (<= 64) or repeats 2-4 on them with 256x finer bins.
+// Keys are distinct 64-bit values (score bits, ~row), so ties in score are resolved exactly by row and the
+// refinement always terminates. The final phase sorts the k selected keys; earlier phases only need the set
+// and its minimum (the new threshold tau).
+#include "common.cuh"
+
+namespace icr {
+
+constexpr int kHsWarps = 8;       // queries per CTA
+constexpr int kHsCap = 1024;      // keys buffered per query at once
+constexpr int kHsSel = 256;       // >= ICR_MAX_K
+constexpr int kHsBins = 256;
+
+struct HistSelectArgs {
+  const uint64_t* seg_keys;  // [Q][nseg][seg_stride]
+  const int* seg_cnt;        // [Q][nseg]
+  int nseg;
+  int seg_stride;
+  int seg_cap;
+  const uint64_t* carry_in;  // [Q][k] or null
+  const int* carry_cnt_in;   // [Q]
+  uint64_t* carry_out;       // [Q][k] or null (unsorted set)
+  int* carry_cnt_out;        // [Q]
+  float* tau_out;            // [Q] or null
+  float* out_scores;         // [Q][k] or null (sorted descending)
+  int64_t* out_ids;          // [Q][k]
+  int64_t id_offset;
+  int k;
+  int64_t Q;
+};
+
+struct HsSmem {
+  uint64_t buf[kHsWarps][kHsCap];
+  uint64_t sel[kHsWarps][kHsSel];
+  unsigned int hist[kHsWarps][kHsBins];
+  int pref[kHsWarps][33];
+};
+
+__device__ __forceinline__ uint64_t warp_min_u64(uint64_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const uint64_t w = __shfl_xor_sync(kFull, v, o);
+    v = w < v ? w : v;
+  }
+  return v;
+}
+__device__ __forceinline__ uint64_t warp_max_u64(uint64_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const uint64_t w = __shfl_xor_sync(kFull, v, o);
+    v = w > v ? w : v;
+  }
+  return v;
+}
+
+// Moves the k largest of buf[0..n) to sel[0..k) (unordered). n > k on entry. Destroys buf.
+__device__ __forceinline__ void warp_select_topk(uint64_t* buf, int n, int k, uint64_t* sel, unsigned int* hist, int lane) {
+  int need = k, nsel = 0, len = n;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  for (;;) {
+    // ---- key range of the current list ----
+    uint64_t mn = ~0ull, mx = 0ull;
+    for (int i = lane; i < len; i += 32) {
+      const uint64_t key = buf[i];
+      mn = key < mn ? key : mn;
+      mx = key > mx ? key : mx;
+    }
+    mn = warp_min_u64(mn);
+    mx = warp_max_u64(mx);
+    const uint64_t range = mx - mn;
+    const int bits = 64 - __clzll(static_cast<long long>(range | 1ull));
+    const int shift = bits > 8 ? bits - 8 : 0;  // (key - mn) >> shift  in [0, 255]
+    // ---- histogram, indexed from the top: t = 255 - bin ----
+    for (int i = lane; i < kHsBins; i += 32) hist[i] = 0u;
+    __syncwarp();
+    for (int i = lane; i < len; i += 32) atomicAdd(&hist[255 - static_cast<int>((buf[i] - mn) >> shift)], 1u);
+    __syncwarp();
+    // lane L owns t in [8L, 8L+8): cumulative counts from the top bin downwards
+    unsigned int local[8];
+    unsigned int lsum = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      local[j] = hist[lane * 8 + j];
+      lsum += local[j];
+    }
+    unsigned int incl = lsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int v = __shfl_up_sync(kFull, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const unsigned int excl = incl - lsum;
+    // the boundary bin is the first t where the cumulative count reaches `need`
+    int t_star = -1;
+    unsigned int above = 0;
+    if (excl < static_cast<unsigned int>(need) && static_cast<unsigned int>(need) <= incl) {
+      unsigned int c = excl;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (t_star < 0 && c + local[j] >= static_cast<unsigned int>(need)) {
+          t_star = lane * 8 + j;
+          above = c;
+        }
+        c += local[j];
+      }
+    }
+    const unsigned owner = __ballot_sync(kFull, t_star >= 0);
+    const int src = __ffs(owner) - 1;
+    t_star = __shfl_sync(kFull, t_star, src);
+    above = __shfl_sync(kFull, above, src);
+    const int b_star = 255 - t_star;
+    // ---- classify: above the boundary bin -> selected; in it -> compacted in place; below -> dropped ----
+    int nb = 0;
+    for (int base = 0; base < len; base += 32) {
+      const int i = base + lane;
+      const bool valid = i < len;
+      const uint64_t key = valid ? buf[i] : 0ull;
+      const int bin = valid ? static_cast<int>((key - mn) >> shift) : -1;
+      const bool in = bin > b_star, bnd = bin == b_star;
+      const unsigned m_in = __ballot_sync(kFull, in), m_b = __ballot_sync(kFull, bnd);
+      if (in) sel[nsel + __popc(m_in & lt_mask)] = key;
+      // all 32 reads of this round are done (ballot is a warp barrier); writes land at positions <= base
+      if (bnd) buf[nb + __popc(m_b & lt_mask)] = key;
+      nsel += __popc(m_in);
+      nb += __popc(m_b);
+    }
+    __syncwarp();
+    need -= static_cast<int>(above);  // 1 <= need <= nb
+    if (need == nb) {
+      for (int i = lane; i < nb; i += 32) sel[nsel + i] = buf[i];
+      __syncwarp();
+      return;
+    }
+    if (nb <= 64) {
+      for (int i = nb + lane; i < 64; i += 32) buf[i] = 0ull;
+      warp_bitonic_sort_desc(buf, 64, lane);
+      for (int i = lane; i < need; i += 32) sel[nsel + i] = buf[i];
+      __syncwarp();
+      return;
+    }
+    len = nb;  // refine inside the boundary bin (its key range is 256x narrower)
+  }
+}
+
+__global__ void __launch_bounds__(kHsWarps * 32) select_hist_kernel(HistSelectArgs a) {
+  extern __shared__ __align__(16) unsigned char hs_raw[];
+  HsSmem& sm = *reinterpret_cast<HsSmem*>(hs_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * kHsWarps + warp;
+  if (q >= a.Q) return;  // whole warps leave; nothing below synchronises across warps
+  uint64_t* buf = sm.buf[warp];
+  uint64_t* sel = sm.sel[warp];
+  unsigned int* hist = sm.hist[warp];
+  int* pref = sm.pref[warp];
+  const int k = a.k;
+  const int cap = min(a.seg_cap, a.seg_stride);
+
+  int n = 0;
+  if (a.carry_in) {
+    n = min(a.carry_cnt_in[q], k);
+    for (int i = lane; i < n; i += 32) buf[i] = a.carry_in[q * k + i];
+  }
+  const uint64_t* qbase = a.seg_keys + q * a.nseg * static_cast<int64_t>(a.seg_stride);
+  for (int g0 = 0; g0 < a.nseg; g0 += 32) {
+    const int s_mine = g0 + lane;
+    const int my_cnt = (s_mine < a.nseg) ? min(a.seg_cnt[q * a.nseg + s_mine], cap) : 0;
+    int incl = my_cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(kFull, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(kFull, incl, 31);
+    __syncwarp();
+    pref[lane] = incl - my_cnt;
+    if (lane == 31) pref[32] = total;
+    __syncwarp();
+    int done = 0;
+    while (done < total) {
+      if (kHsCap - n < 32) {  // buffer full: keep the k best and go on
+        warp_select_topk(buf, n, k, sel, hist, lane);
+        for (int i = lane; i < k; i += 32) buf[i] = sel[i];
+        n = k;
+        __syncwarp();
+      }
+      const int take = min(kHsCap - n, total - done);
+      for (int i = lane; i < take; i += 32) {
+        const int idx = done + i;
+        // segment holding flat index idx: largest s with pref[s] <= idx (binary search over 32 entries)
+        int s = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1)
+          if (pref[s + step] <= idx) s += step;
+        buf[n + i] = qbase[static_cast<int64_t>(g0 + s) * a.seg_stride + (idx - pref[s])];
+      }
+      n += take;
+      done += take;
+      __syncwarp();
+    }
+  }
+  __syncwarp();
+  int kept = n;
+  if (n > k) {
+    warp_select_topk(buf, n, k, sel, hist, lane);
+    kept = k;
+  } else {
+    for (int i = lane; i < n; i += 32) sel[i] = buf[i];
+    __syncwarp();
+  }
+
+  if (a.carry_out) {
+    for (int i = lane; i < kept; i += 32) a.carry_out[q * k + i] = sel[i];
+    if (lane == 0) a.carry_cnt_out[q] = kept;
+  }
+  if (a.tau_out) {
+    uint64_t mn = ~0ull;
+    for (int i = lane; i < kept; i += 32) mn = sel[i] < mn ? sel[i] : mn;
+    mn = warp_min_u64(mn);
+    if (lane == 0) a.tau_out[q] = (kept >= k) ? key_score(mn) : -INFINITY;
+  }
+  if (a.out_scores) {
+    const int P = next_pow2(kept < 2 ? 2 : kept);
+    for (int i = kept + lane; i < P; i += 32) sel[i] = 0ull;
+    warp_bitonic_sort_desc(sel, P, lane);
+    for (int i = lane; i < k; i += 32) {
+      const bool ok = i < kept;
+      a.out_scores[q * k + i] = ok ? key_score(sel[i]) : -INFINITY;
+      a.out_ids[q * k + i] = ok ? static_cast<int64_t>(key_row(sel[i])) + a.id_offset : -1;
+    }
+  }
+}
+
+int launch_select_hist(const uint64_t* seg_keys, const int* seg_cnt, int64_t Q, int nseg, int seg_stride, int seg_cap,
+                       const uint64_t* carry_in, const int* carry_cnt_in, uint64_t* carry_out, int* carry_cnt_out, float* tau_out,
+                       float* out_scores, int64_t* out_ids, int64_t id_offset, int k, cudaStream_t st) {
+  if (Q == 0) return ICR_OK;
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    ICR_CUDA_CHECK(cudaFuncSetAttribute(select_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(HsSmem))));
+    attr_set = true;
+  }
+  HistSelectArgs a{};
+  a.seg_keys = seg_keys;
+  a.seg_cnt = seg_cnt;
+  a.nseg = nseg;
+  a.seg_stride = seg_stride;
+  a.seg_cap = seg_cap;
+  a.carry_in = carry_in;
+  a.carry_cnt_in = carry_cnt_in;
+  a.carry_out = carry_out;
+  a.carry_cnt_out = carry_cnt_out;
+  a.tau_out = tau_out;
+  a.out_scores = out_scores;
+  a.out_ids = out_ids;
+  a.id_offset = id_offset;
+  a.k = k;
+  a.Q = Q;
+  const unsigned grid = static_cast<unsigned>((Q + kHsWarps - 1) / kHsWarps);
+  select_hist_kernel<<<grid, kHsWarps * 32, sizeof(HsSmem), st>>>(a);
+  ICR_LAUNCH_CHECK();
+  return ICR_OK;
+}
+
+}  // namespace icr
