@@ -193,14 +193,29 @@ __global__ void __launch_bounds__(kHsWarps * 32) select_hist_kernel(HistSelectAr
         __syncwarp();
       }
       const int take = min(kHsCap - n, total - done);
-      for (int i = lane; i < take; i += 32) {
-        const int idx = done + i;
-        // segment holding flat index idx: largest s with pref[s] <= idx (binary search over 32 entries)
-        int s = 0;
+      // 8 independent global loads per lane in flight before the first shared-memory store: the gather is
+      // latency-bound (cold candidates), so memory-level parallelism is what sets its speed
+      for (int i0 = 0; i0 < take; i0 += 32 * 8) {
+        uint64_t v[8];
 #pragma unroll
-        for (int step = 16; step > 0; step >>= 1)
-          if (pref[s + step] <= idx) s += step;
-        buf[n + i] = qbase[static_cast<int64_t>(g0 + s) * a.seg_stride + (idx - pref[s])];
+        for (int u = 0; u < 8; ++u) {
+          const int i = i0 + u * 32 + lane;
+          v[u] = 0ull;
+          if (i < take) {
+            const int idx = done + i;
+            // segment holding flat index idx: largest s with pref[s] <= idx (binary search over 32 entries)
+            int s = 0;
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1)
+              if (pref[s + step] <= idx) s += step;
+            v[u] = __ldcs(qbase + static_cast<int64_t>(g0 + s) * a.seg_stride + (idx - pref[s]));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = i0 + u * 32 + lane;
+          if (i < take) buf[n + i] = v[u];
+        }
       }
       n += take;
       done += take;
