@@ -45,40 +45,45 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
+    """SM clock and throttle reasons sampled every ~5 ms (NVML) while the timed regions run."""
 
-    FIELDS = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown"}
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc, self.thread = index, [], None, None
+        self.index, self.sm, self.max_mhz, self.reasons, self.stop, self.thread = index, [], None, set(), False, None
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+
+            def run():
+                while not self.stop:
+                    try:
+                        self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        bits = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        self.reasons.update(n for b, n in self.REASONS.items() if bits & b)
+                    except Exception:
+                        pass
+                    time.sleep(0.005)
+
+            self.thread = threading.Thread(target=run, daemon=True)
             self.thread.start()
-        except OSError:
-            self.proc = None
+        except Exception:
+            self.thread = None
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
     def __exit__(self, *a):
-        if self.proc:
-            time.sleep(0.15)
-            self.proc.terminate()
+        self.stop = True
+        if self.thread:
             self.thread.join(timeout=2)
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_min_mhz": min(self.sm) if self.sm else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
 def _cpu_reference_qps(sample_queries: int, budget_s: float, threads: int | None = None):
@@ -185,10 +190,8 @@ def main():
         return catalog.topk(queries_dev, k, path=path)
 
     def step_e2e():
-        qd = queries_host.to(dev, non_blocking=True)
-        v, i = catalog.topk(qd, k, path=path)
-        out_v_host.copy_(v, non_blocking=True)
-        out_i_host.copy_(i, non_blocking=True)
+        # public host-to-host API: pinned queries -> H2D -> fused top-k -> D2H of (scores, ids), chunks pipelined on 2 streams
+        catalog.topk_host(queries_host, k, out=(out_v_host, out_i_host), path=path)
 
     def barrier():
         if world > 1:
@@ -214,14 +217,13 @@ def main():
     for _ in range(args.warmup):
         step_device()
     launches_per_step = ops.last_launch_count()
-    with ClockSampler(local_rank) as clocks:
+    with ClockSampler(local_rank) as clocks:  # spans every timed region below
         total_ms, per_step = timed(step_device, args.steps)
-    for _ in range(3):
-        step_e2e()
-    e2e_ms, _ = timed(step_e2e, args.steps)
-
-    # ---- dominant kernel alone (CUDA events recorded by the library around that kernel's launches) -------------
-    kt = ops.kernel_timing(step_device, args.steps, flush=flush)
+        for _ in range(3):
+            step_e2e()
+        e2e_ms, _ = timed(step_e2e, args.steps)
+        # ---- dominant kernel alone (CUDA events recorded by the library around that kernel's launches) ---------
+        kt = ops.kernel_timing(step_device, args.steps, flush=flush)
     peaks = _peaks()
     flops = 2.0 * Q * N * D
     if kt["kernel"] == "gemm_topk":
@@ -253,7 +255,8 @@ def main():
                    "multi_gpu": "catalog replica + own query batch per rank (no data-path collective)" if world > 1 else "single GPU",
                    "l2": "512 MiB buffer zeroed between timed iterations (L2 flush)", "seeds": [CATALOG_SEED, QUERY_SEED]},
         "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": Q * D * 4, "d2h_bytes_per_step": Q * k * 12,
-                "note": "pinned-host fp32 queries in, (scores f32, ids i64) out to pinned host; catalog resident in HBM as the index is"},
+                "note": "DeviceCatalog.topk_host: pinned-host fp32 queries in, (scores f32, ids i64) out to pinned host, 4 chunks pipelined "
+                        "over 2 streams; catalog resident in HBM as the reference keeps its index in memory"},
         "gpu_launches": launches_per_step * args.steps,
         "roofline": roof,
         "clocks": clocks.summary(),

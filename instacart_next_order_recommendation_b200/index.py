@@ -135,6 +135,52 @@ class DeviceCatalog:
     def nbytes(self) -> int:
         return self.rows.numel() * self.rows.element_size() + (0 if self.planes is None else self.planes.numel() * 2)
 
+    def topk_host(self, queries: torch.Tensor, k: int, *, out: tuple[torch.Tensor, torch.Tensor] | None = None,
+                  n_chunks: int = 4, path: int = ops.PATH_AUTO):
+        """Host-to-host top-k: CPU query matrix in, CPU (values [Q,k] f32, ids [Q,k] i64) out.
+
+        The batch is cut into `n_chunks` pieces that go round-robin over two side streams, each doing
+        H2D copy -> fused top-k -> D2H copy, so the copies of one piece overlap the kernels of another
+        (the B200 has separate copy engines for each direction). Pass pinned tensors (and pinned `out`)
+        for truly asynchronous copies. Returns after enqueueing; the current stream waits on the side
+        streams, so `torch.cuda.current_stream().synchronize()` makes the outputs valid.
+        """
+        if queries.is_cuda:
+            raise ValueError("topk_host takes host tensors; use topk() for device-resident queries")
+        if queries.dim() == 1:
+            queries = queries.unsqueeze(0)
+        Q = queries.shape[0]
+        k = min(int(k), len(self))
+        if out is None:
+            out = (torch.empty(Q, k, dtype=torch.float32).pin_memory(), torch.empty(Q, k, dtype=torch.int64).pin_memory())
+        vals_h, ids_h = out
+        if Q == 0 or k < 1:
+            return vals_h, ids_h
+        if not hasattr(self, "_side_streams"):
+            self._side_streams = [torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)]
+        cur = torch.cuda.current_stream(self.device)
+        n_chunks = max(1, min(n_chunks, (Q + 255) // 256))
+        per = -(-Q // n_chunks)
+        start = torch.cuda.Event()
+        start.record(cur)
+        for c in range(n_chunks):
+            lo, hi = c * per, min(Q, (c + 1) * per)
+            if lo >= hi:
+                break
+            st = self._side_streams[c % 2]
+            st.wait_event(start)
+            with torch.cuda.stream(st):
+                qd = queries[lo:hi].to(self.device, non_blocking=True)
+                if qd.dtype != self.dtype:
+                    qd = qd.to(self.dtype)
+                v, i = ops.cos_topk(qd, self.rows, k, cat_planes=self.planes, cat_inv_norms=self.inv_norms,
+                                    row_offset=self.row_offset, path=path)
+                vals_h[lo:hi].copy_(v, non_blocking=True)
+                ids_h[lo:hi].copy_(i, non_blocking=True)
+        for st in self._side_streams:
+            cur.wait_stream(st)
+        return vals_h, ids_h
+
     def topk(self, queries, k: int, *, exclude_mask: torch.Tensor | None = None, path: int = ops.PATH_AUTO):
         """(values [Q,k], global ids [Q,k]) of the k most cosine-similar rows per query."""
         q = to_device_matrix(queries, device=self.device, dtype=self.dtype)

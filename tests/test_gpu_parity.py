@@ -279,6 +279,52 @@ def test_mnrl_known_answers_and_module_interface():
     assert abs(loss.item() - ref.item()) < 1e-4 and tower.lin.weight.grad is not None
 
 
+def test_topk_host_pipeline_equals_device_path():
+    items, _ = oracle.synth_clustered(30000, 384, seed=21)
+    queries, _ = oracle.synth_queries_from_items(items, 3001, seed=22)
+    cat = icr.DeviceCatalog(items)
+    v, i = cat.topk(queries.cuda(), 100)
+    vh, ih = cat.topk_host(queries.pin_memory(), 100)
+    torch.cuda.current_stream().synchronize()
+    assert torch.equal(vh, v.cpu()) and torch.equal(ih, i.cpu())
+    rv, ri = oracle.cos_topk(queries[:200], items, 100)
+    _check_topk(vh[:200], ih[:200], rv, ri, F32_RTOL)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_gemm_path_ties_duplicates_and_adversarial_order(dtype):
+    """Exactness of the threshold filter + histogram select under ties and a catalog sorted by similarity."""
+    if not _gemm_ok():
+        pytest.skip("GEMM path not built yet")
+    g = torch.Generator().manual_seed(3)
+    base = torch.nn.functional.normalize(torch.randn(64, 128, generator=g), dim=1)
+    # 9,000 rows drawn from only 64 distinct vectors: every score has ~140 exact duplicates
+    rows = base[torch.randint(0, 64, (9000,), generator=g)].to(dtype)
+    q = torch.nn.functional.normalize(torch.randn(300, 128, generator=g), dim=1).to(dtype)
+    v, i = ops.cos_topk(q.cuda(), rows.cuda(), 100, path=ops.PATH_GEMM)
+    rv, ri = oracle.cos_topk(q.float(), rows.float(), 100)
+    tol = F32_RTOL if dtype == torch.float32 else BF16_RTOL
+    err, _ = oracle.compare_topk(v.cpu(), i.cpu(), rv, ri, rtol=tol)
+    assert err <= tol
+    i = i.cpu()
+    for r in range(0, 300, 17):
+        assert len(set(i[r].tolist())) == 100
+        # within a run of equal scores the lower rows must win (deterministic tie-break)
+        vr = v[r].cpu()
+        for a, b in zip(range(99), range(1, 100)):
+            if vr[a] == vr[b]:
+                assert i[r, a] < i[r, b]
+    # catalog sorted so that every later row beats all earlier ones for query 0: the running threshold never helps,
+    # segments overflow and the in-kernel compaction has to keep the result exact
+    c = oracle.synth_isotropic(40000, 128, seed=5)
+    q0 = oracle.synth_isotropic(130, 128, seed=6)
+    order = torch.argsort(oracle.cos_sim(q0[:1], c)[0])
+    c_sorted = c[order].to(dtype)
+    v, i = ops.cos_topk(q0.to(dtype).cuda(), c_sorted.cuda(), 100, path=ops.PATH_GEMM)
+    rv, ri = oracle.cos_topk(q0.to(dtype).float(), c_sorted.float(), 100)
+    _check_topk(v, i, rv, ri, tol)
+
+
 def test_full_size_properties_c2_shape():
     """BASELINE config 2 at full size through size-independent properties (the oracle is too slow for all of it):
     a row-permuted catalog returns the permuted ids with identical scores, every returned score is reproduced by
