@@ -71,11 +71,11 @@ def record(name, **kw):
     print(json.dumps(kw), flush=True)
 
 
-def topk_case(name, N, D, Q, k, dtype, path=ops.PATH_AUTO, iters=20, eager=False, cold=True):
+def topk_case(name, N, D, Q, k, dtype, path=ops.PATH_AUTO, iters=20, eager=False, cold=True, graph=False):
     cat_rows = unit_rows(N, D, dtype, 1234)
     cat = icr.DeviceCatalog(cat_rows, dtype=dtype)
     q = unit_rows(Q, D, dtype, 4321)
-    fn = lambda: cat.topk(q, k, path=path)  # noqa: E731
+    fn = (lambda: cat.topk_small(q, k, path=path, copy=False)) if graph else (lambda: cat.topk(q, k, path=path))  # noqa: E731
     med, best = time_gpu(fn, iters=iters, cold=cold)
     kt = ops.kernel_timing(fn, max(3, iters // 4), flush=FLUSH if cold else None)
     esz = 4 if dtype == torch.float32 else 2
@@ -143,6 +143,8 @@ def main():
             for k in (10, 100):
                 topk_case(f"C1 batch-1 top-{k}", 49_688, 384, 1, k, dt, iters=50, eager=(k == 10), cold=True)
             topk_case("C1 batch-1 top-10 (L2-warm)", 49_688, 384, 1, 10, dt, iters=50, cold=False)
+            topk_case("C1 batch-1 top-10, CUDA graph", 49_688, 384, 1, 10, dt, iters=50, cold=True, graph=True)
+            topk_case("C1 batch-1 top-10, CUDA graph (L2-warm)", 49_688, 384, 1, 10, dt, iters=50, cold=False, graph=True)
         for Q in (2, 4, 7):
             topk_case(f"C1-size batch-{Q} top-10", 49_688, 384, Q, 10, f32, iters=30)
     if on("c2"):
@@ -169,10 +171,13 @@ def main():
     if tk:
         lines += ["| config | N | D | Q | k | dtype | L2 | kernel | call ms (median) | queries/s | kernel ms | HBM GB/s (kernel) | TFLOP/s (kernel) | bound | roofline frac (kernel / whole call) | torch eager ms |",
                   "|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|"]
+        def f(x, spec):
+            return "-" if x is None else format(x, spec)
+
         for r in tk:
             lines.append(f"| {r['config']} | {r['N']} | {r['D']} | {r['Q']} | {r['k']} | {r['dtype']} | {r['l2']} | {r['kernel']} | {r['ms']:.4f} | {r['qps']:.4g} | "
-                         f"{r['kernel_ms']:.4f} | {r['hbm_gbs_kernel']:.0f} | {r['tflops_kernel']:.1f} | {r['bound']} | {r['roofline_frac_kernel']:.3f} / {r['roofline_frac_call']:.3f} | "
-                         f"{r.get('torch_eager_ms') if r.get('torch_eager_ms') is None else round(r['torch_eager_ms'], 3)} |")
+                         f"{r['kernel_ms']:.4f} | {f(r['hbm_gbs_kernel'], '.0f')} | {f(r['tflops_kernel'], '.1f')} | {r['bound']} | "
+                         f"{f(r['roofline_frac_kernel'], '.3f')} / {r['roofline_frac_call']:.3f} | {f(r.get('torch_eager_ms'), '.3f')} |")
     mn = [r for r in ROWS if "ours_us" in r]
     if mn:
         lines += ["", "| config | dtype | scale | ours µs (median / min) | torch eager µs (median / min) | speed-up |", "|---|---|---|---|---|---|"]

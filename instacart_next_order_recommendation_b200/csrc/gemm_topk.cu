@@ -41,11 +41,23 @@ constexpr int BNH = BN / 2;      // catalog rows of a tile loaded by each CTA of
 constexpr int BK = 64;           // K elements per pipeline stage = one 128-byte swizzle atom of 16-bit elements
 constexpr int kTileBytes = 128 * BK * 2;  // every operand tile in shared memory is 128 rows x 128 bytes
 constexpr int kRingBytes = 192 * 1024;
-constexpr int kSegCap = 512;         // candidate keys per (query, chunk) segment
-constexpr int kGemmThreads = 256;    // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warp 3 idle, warps 4-7 epilogue
-constexpr int kTmemCols = 512;       // two 256-column fp32 accumulators
+constexpr int kSegCapMax = 512;      // candidate keys per (query, chunk, column half) segment: 256 for k <= 128, else 512
+// warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warp 3 idle, warps 4.. epilogue. With 8 epilogue warps (two per
+// scheduler) warps 4-7 filter accumulator columns 0-127 and warps 8-11 columns 128-255 of the same 128 queries.
+// Measured (profiles/r01_notes.md): once scores are screened 8 at a time (filter32) four warps are enough and
+// leave the MMA-issuing and TMA threads more issue slots: C5 shard 1039 vs 929 TFLOP/s, C4 Q=1024 1373 vs 1232;
+// eight warps only win where survivors are dense (C2 bf16: 694 vs 610). Default 4.
+#ifndef ICR_EPI_WARPS
+#define ICR_EPI_WARPS 4
+#endif
+constexpr int kEpiWarps = ICR_EPI_WARPS;  // 4 or 8
+constexpr int kEpiHalves = kEpiWarps / 4;    // column groups of a tile, one per set of four epilogue warps
+constexpr int kEpiCols = BN / kEpiHalves;   // accumulator columns each epilogue warp filters per tile
+constexpr int kGemmThreads = 128 + kEpiWarps * 32;
+constexpr int kTmemCols = 512;      // two 256-column fp32 accumulators
 constexpr uint32_t kSpinLimit = 1u << 24;
 constexpr int kMaxStages = 6;
+constexpr int kAStatMaxKB = 6;       // A-stationary variant: up to 6 K blocks (D <= 384) of queries stay resident
 
 struct GemmArgs {
   int Q, N;
@@ -60,8 +72,10 @@ struct GemmArgs {
   const float* qinv;         // [Q]  (bf16 path) or null
   const float* cinv;         // [N]  (bf16 path) or null
   const uint8_t* mask;       // [N] or null
-  uint64_t* cand;            // [Q][chunks][kSegCap]
-  int* cand_cnt;             // [Q][chunks]
+  uint64_t* cand;            // [Q][chunks * 2][seg_cap]   (segment = query x chunk x column half)
+  int* cand_cnt;             // [Q][chunks * 2]
+  int seg_cap;
+  uint64_t* compact_scratch; // [gridDim.x][kEpiWarps][kSegCapMax] global scratch of the (rare) in-kernel compaction
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -87,7 +101,9 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) 
       "{\n"
       ".reg .b32 ra;\n"
       "mapa.shared::cluster.u32 ra, %0, %1;\n"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+      // default (.release at CTA scope): a cluster-scope release here costs a MEMBAR + L1 invalidate per tile and
+      // nothing needs it — the TMEM reads are ordered by tcgen05.wait::ld + tcgen05.fence::before_thread_sync
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n"
       "}\n" ::"r"(bar), "r"(cta)
       : "memory");
 }
@@ -184,16 +200,18 @@ struct SegState {
 };
 
 // Any lane whose segment could overflow during the next 32 scores gets it compacted by the whole warp.
-__device__ __forceinline__ void compact_full_segments(SegState& s, uint64_t* scratch, int k, int lane) {
-  unsigned need = __ballot_sync(kFull, s.cnt > kSegCap - 32);
+// `scratch` is global memory (L2-resident): this path only runs when the running threshold fails to prune, e.g. a
+// catalog sorted by similarity to the query, so it trades speed for 16-32 KB of shared memory.
+__device__ __forceinline__ void compact_full_segments(SegState& s, uint64_t* scratch, int cap, int k, int lane) {
+  unsigned need = __ballot_sync(kFull, s.cnt > cap - 32);
   while (need) {
     const int L = __ffs(need) - 1;
     need &= need - 1;
     uint64_t* seg = reinterpret_cast<uint64_t*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(s.seg), L));
     const int n = __shfl_sync(kFull, s.cnt, L);
     __syncwarp();
-    for (int i = lane; i < kSegCap; i += 32) scratch[i] = (i < n) ? __ldcg(seg + i) : 0ull;
-    warp_bitonic_sort_desc(scratch, kSegCap, lane);
+    for (int i = lane; i < cap; i += 32) scratch[i] = (i < n) ? __ldcg(seg + i) : 0ull;
+    warp_bitonic_sort_desc(scratch, cap, lane);
     const int kept = n < k ? n : k;
     for (int i = lane; i < kept; i += 32) seg[i] = scratch[i];
     const uint32_t t_new = (n >= k) ? static_cast<uint32_t>(scratch[k - 1] >> 32) : 0u;
@@ -212,27 +230,46 @@ __device__ __forceinline__ uint32_t order_bits_canonical(float s) {  // s must n
 
 // predicated append of key (ob, ~row): no branch, so a warp whose lanes disagree pays nothing extra
 __device__ __forceinline__ void append_if(SegState& s, uint32_t ob, uint32_t nrow) {
+  uint32_t inc;
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "setp.gt.u32 p, %1, %2;\n"
-      "@p st.global.v2.u32 [%0], {%3, %1};\n"
-      "}\n" ::"l"(s.seg + s.cnt), "r"(ob), "r"(s.tau_ob), "r"(nrow)
+      "setp.gt.u32 p, %2, %3;\n"
+      "@p st.global.v2.u32 [%1], {%4, %2};\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(inc)
+      : "l"(s.seg + s.cnt), "r"(ob), "r"(s.tau_ob), "r"(nrow)
       : "memory");
-  s.cnt += (ob > s.tau_ob) ? 1 : 0;
+  s.cnt += static_cast<int>(inc);
 }
 
-// filter 32 accumulator columns (catalog rows rbase .. rbase+31) of this thread's query
+// Filter 32 accumulator columns (catalog rows rbase .. rbase+31) of this thread's query.
+// Keys carry the score in "raw" units — the accumulator itself (plane path) or accumulator * catalog inverse
+// norm (bf16 path); the per-query positive factor (2^-16, or the query's inverse norm) does not change the
+// order within a query and is applied once, to the k final scores, by the select kernel.
 template <bool BF16>
-__device__ __forceinline__ void filter32(const uint32_t (&r)[32], SegState& s, float qscale, const float* cinv32, int rbase, bool fast,
-                                         int N, const uint8_t* mask) {
+__device__ __forceinline__ void filter32(const uint32_t (&r)[32], SegState& s, const float* cinv32, int rbase, bool fast, int N,
+                                         const uint8_t* mask) {
   if (fast) {
+    // Survivors are rare once the threshold has converged (k / rows-seen per score), so scores are screened 8 at a
+    // time: one max tree + one warp vote (~1-2 instructions per score); only a group in which SOME lane has a
+    // survivor runs the predicated appends (~10 per score). The vote keeps the branch warp-uniform.
+    const float tau_f = unorder_bits(s.tau_ob);  // NaN for dead lanes: every comparison below is false
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      float sc;
-      if (BF16) sc = fmaf(__uint_as_float(r[j]) * qscale, cinv32[j], 0.0f);
-      else sc = fmaf(__uint_as_float(r[j]), qscale, 0.0f);  // + 0.0 turns -0.0 into +0.0
-      append_if(s, order_bits_canonical(sc), ~static_cast<uint32_t>(rbase + j));
+    for (int g8 = 0; g8 < 4; ++g8) {
+      float sc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = g8 * 8 + j;
+        sc[j] = BF16 ? __uint_as_float(r[c]) * cinv32[c] : __uint_as_float(r[c]);
+      }
+      const float m = fmaxf(fmaxf(fmaxf(sc[0], sc[1]), fmaxf(sc[2], sc[3])), fmaxf(fmaxf(sc[4], sc[5]), fmaxf(sc[6], sc[7])));
+      if (__any_sync(kFull, m > tau_f)) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)  // + 0.0 turns -0.0 into +0.0 so that equal scores have equal keys
+          append_if(s, order_bits_canonical(sc[j] + 0.0f), ~static_cast<uint32_t>(rbase + g8 * 8 + j));
+      }
     }
   } else {
     // last (partial) tile of the catalog, or an exclusion mask: rows are checked one by one
@@ -241,37 +278,44 @@ __device__ __forceinline__ void filter32(const uint32_t (&r)[32], SegState& s, f
       const int row = rbase + j;
       if (row < N && !(mask && mask[row])) {
         float sc;
-        if (BF16) sc = fmaf(__uint_as_float(r[j]) * qscale, cinv32[j], 0.0f);
-        else sc = fmaf(__uint_as_float(r[j]), qscale, 0.0f);
+        if (BF16) sc = fmaf(__uint_as_float(r[j]), cinv32[j], 0.0f);
+        else sc = __uint_as_float(r[j]) + 0.0f;
         append_if(s, order_bits_canonical(sc), ~static_cast<uint32_t>(row));
       }
     }
   }
 }
 
-// TERMS = 3: fp16 hi/lo planes (fp32 parity); TERMS = 1: raw bf16 rows
-template <int TERMS>
+// TERMS = 3: fp16 hi/lo planes (fp32 parity); TERMS = 1: raw bf16 rows.
+// ASTAT (bf16, D <= 384): the work item's 128 query rows stay resident in shared memory for all of its catalog
+// tiles ("A-stationary"), so the ring streams catalog tiles only: 31 instead of 62 B/cycle/SM of L2 traffic,
+// which is the difference between L2-bound and tensor-bound for one-term MMAs (profiles/r01_notes.md).
+template <int TERMS, bool ASTAT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmArgs g) {
+  static_assert(!ASTAT || TERMS == 1, "A-stationary is the bf16 variant");
   constexpr bool BF16 = (TERMS == 1);
-  constexpr int kStageTiles = (TERMS == 3) ? 4 : 2;  // A_hi A_lo B_hi B_lo | A B
+  constexpr int kStageTiles = ASTAT ? 1 : ((TERMS == 3) ? 4 : 2);  // B | A_hi A_lo B_hi B_lo | A B
   constexpr int kStageBytes = kStageTiles * kTileBytes;
-  constexpr int kStages = kRingBytes / kStageBytes;  // 3 | 6
+  constexpr int kAResidentBytes = ASTAT ? kAStatMaxKB * kTileBytes : 0;
+  constexpr int kStages = (kRingBytes - kAResidentBytes) / kStageBytes;  // 6 | 3 | 6
   static_assert(kStages <= kMaxStages, "barrier array too small");
 
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // 128-byte-swizzled tiles need 1024-byte alignment; the allocation carries 1 KB of slack for this.
   // Both CTAs of the pair compute the same offset (same kernel, same static layout).
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  unsigned char* stage_base = smem;
-  uint64_t* scratch_all = reinterpret_cast<uint64_t*>(smem + kRingBytes);          // 4 warps x kSegCap keys
-  float* cinv_all = reinterpret_cast<float*>(scratch_all + 4 * kSegCap);            // 4 warps x BN floats
-  uint64_t* bars = reinterpret_cast<uint64_t*>(cinv_all + 4 * BN);
+  unsigned char* a_resident = smem;                    // ASTAT: kb-th K block of the queries at kb * kTileBytes
+  unsigned char* stage_base = smem + kAResidentBytes;
+  float* cinv_all = reinterpret_cast<float*>(smem + kRingBytes);                    // 8 warps x 128 floats
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cinv_all + kEpiWarps * kEpiCols);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kMaxStages;
   uint64_t* tfull_bar = bars + 2 * kMaxStages;
   uint64_t* tempty_bar = bars + 2 * kMaxStages + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+  uint64_t* afull_bar = bars + 2 * kMaxStages + 4;   // ASTAT: resident queries loaded
+  uint64_t* aempty_bar = bars + 2 * kMaxStages + 5;  // ASTAT: every MMA of the work item has read them
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 6);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();  // 0 = leader of the pair
@@ -286,8 +330,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&tfull_bar[a]), 1);   // one multicast tcgen05.commit
-      mbar_init(smem_u32(&tempty_bar[a]), 8);  // 4 epilogue warps of each CTA (used in the leader only)
+      mbar_init(smem_u32(&tempty_bar[a]), 2 * kEpiWarps);  // the epilogue warps of both CTAs (used in the leader only)
     }
+    mbar_init(smem_u32(afull_bar), 1);
+    mbar_init(smem_u32(aempty_bar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_b) : "memory");
@@ -302,11 +348,19 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   if (warp == 0 && lane == 0) {
     // ================= TMA producer (both CTAs; each loads its own queries and its half of B) =================
     int stage = 0;
-    uint32_t phase = 0;
+    uint32_t phase = 0, a_phase = 0;
     for (int w = pair; w < items; w += npairs) {
       const int chunk = w / g.qblocks, qb = w - chunk * g.qblocks;
       const int t0 = chunk_first_tile(g, chunk), t1 = chunk_first_tile(g, chunk + 1);
       const int qrow = qb * (2 * BM) + static_cast<int>(rank) * BM;
+      if (ASTAT) {
+        // the previous work item's MMAs must have finished reading the resident queries
+        mbar_wait(smem_u32(aempty_bar), a_phase ^ 1);
+        const uint32_t ab = smem_u32(afull_bar);
+        if (rank == 0) mbar_expect_tx(ab, 2 * KB * kTileBytes);
+        for (int kb = 0; kb < KB; ++kb) tma_load_2d_pair(smem_u32(a_resident + kb * kTileBytes), &tma_a, kb * BK, qrow, ab);
+        a_phase ^= 1;
+      }
       for (int tile = t0; tile < t1; ++tile) {
         const int crow = tile * BN + static_cast<int>(rank) * BNH;
         for (int kb = 0; kb < KB; ++kb) {
@@ -314,7 +368,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           const uint32_t fb = smem_u32(&full_bar[stage]);
           if (rank == 0) mbar_expect_tx(fb, 2 * kStageBytes);
           const uint32_t sa = smem_u32(stage_base + stage * kStageBytes);
-          if (TERMS == 3) {
+          if (ASTAT) {
+            tma_load_2d_pair(sa, &tma_b, kb * BK, crow, fb);
+          } else if (TERMS == 3) {
             tma_load_2d_pair(sa, &tma_a, kb * BK, qrow, fb);
             tma_load_2d_pair(sa + kTileBytes, &tma_a, g.plane_stride + kb * BK, qrow, fb);
             tma_load_2d_pair(sa + 2 * kTileBytes, &tma_b, kb * BK, crow, fb);
@@ -338,10 +394,15 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
-    uint32_t acc_phase = 0;
+    uint32_t acc_phase = 0, a_phase = 0;
     for (int w = pair; w < items; w += npairs) {
       const int chunk = w / g.qblocks;
       const int t0 = chunk_first_tile(g, chunk), t1 = chunk_first_tile(g, chunk + 1);
+      if (ASTAT) {
+        mbar_wait(smem_u32(afull_bar), a_phase);
+        tc_fence_after();
+        a_phase ^= 1;
+      }
       for (int tile = t0; tile < t1; ++tile) {
         mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
         tc_fence_after();
@@ -350,7 +411,14 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           mbar_wait(smem_u32(&full_bar[stage]), phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(stage_base + stage * kStageBytes);
-          if (TERMS == 3) {
+          if (ASTAT) {
+            const uint64_t adesc = smem_desc_sw128(smem_u32(a_resident + kb * kTileBytes)), bdesc = smem_desc_sw128(sa);
+#pragma unroll
+            for (int k4 = 0; k4 < BK / 16; ++k4) {
+              const uint64_t o = static_cast<uint64_t>(k4 * 2);
+              umma_f16_pair(d_tmem, adesc + o, bdesc + o, idesc, (kb | k4) != 0 ? 1u : 0u);
+            }
+          } else if (TERMS == 3) {
             const uint64_t a_hi = smem_desc_sw128(sa), a_lo = smem_desc_sw128(sa + kTileBytes);
             const uint64_t b_hi = smem_desc_sw128(sa + 2 * kTileBytes), b_lo = smem_desc_sw128(sa + 3 * kTileBytes);
 #pragma unroll
@@ -381,12 +449,15 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           acc_phase ^= 1;
         }
       }
+      if (ASTAT) umma_commit_pair(smem_u32(aempty_bar));  // resident queries may be overwritten in both CTAs
     }
   } else if (warp >= 4) {
     // ================= epilogue: threshold filter, one query per thread =================
-    const int ew = warp - 4;  // TMEM lane quarter this warp may read
-    uint64_t* scratch = scratch_all + ew * kSegCap;
-    float* cinv_s = cinv_all + ew * BN;
+    const int ew = (warp - 4) & 3;   // TMEM lane quarter this warp may read (hardware rule: warp id % 4)
+    const int half = (warp - 4) >> 2;  // which 128 accumulator columns of every tile this warp filters
+    uint64_t* scratch = g.compact_scratch + (static_cast<int64_t>(blockIdx.x) * kEpiWarps + (warp - 4)) * kSegCapMax;
+    float* cinv_s = cinv_all + (warp - 4) * kEpiCols;
+    const int cap = g.seg_cap;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = pair; w < items; w += npairs) {
@@ -394,37 +465,36 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const int t0 = chunk_first_tile(g, chunk), t1 = chunk_first_tile(g, chunk + 1);
       const int q = qb * (2 * BM) + static_cast<int>(rank) * BM + ew * 32 + lane;
       const bool live = q < g.Q;
+      const int64_t seg_index = (static_cast<int64_t>(live ? q : 0) * g.chunks + chunk) * kEpiHalves + half;
       SegState s;
-      s.seg = g.cand + (static_cast<int64_t>(live ? q : 0) * g.chunks + chunk) * kSegCap;
+      s.seg = g.cand + seg_index * cap;
       s.cnt = 0;
       s.tau_ob = live ? order_bits(g.tau[q]) : 0xFFFFFFFFu;
-      float qscale = g.acc_scale;
-      if (BF16) qscale *= live ? g.qinv[q] : 0.f;
       for (int tile = t0; tile < t1; ++tile) {
-        const int row0 = tile * BN;
+        const int row0 = tile * BN + half * kEpiCols;
         if (BF16) {
-          // stage the tile's 256 catalog inverse norms once per warp (read back as shared-memory broadcasts)
+          // stage this warp's 128 catalog inverse norms once per tile (read back as shared-memory broadcasts)
           __syncwarp();
-          for (int i = lane; i < BN; i += 32) cinv_s[i] = (row0 + i < g.N) ? __ldg(g.cinv + row0 + i) : 0.f;
+          for (int i = lane; i < kEpiCols; i += 32) cinv_s[i] = (row0 + i < g.N) ? __ldg(g.cinv + row0 + i) : 0.f;
           __syncwarp();
         }
         mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * BN);
-        const bool fast = (row0 + BN <= g.N) && (g.mask == nullptr);
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * BN + half * kEpiCols);
+        const bool fast = (row0 + kEpiCols <= g.N) && (g.mask == nullptr);
         uint32_t ra[32], rb[32];
         tmem_ld32(taddr, ra);
 #pragma unroll 1
-        for (int cb = 0; cb < BN / 32; cb += 2) {
+        for (int cb = 0; cb < kEpiCols / 32; cb += 2) {
           // the next 32 columns are in flight while the current 32 are filtered
           tmem_ld_wait(ra);
           tmem_ld32(taddr + (cb + 1) * 32, rb);
-          compact_full_segments(s, scratch, g.k, lane);
-          filter32<BF16>(ra, s, qscale, cinv_s + cb * 32, row0 + cb * 32, fast, g.N, g.mask);
+          compact_full_segments(s, scratch, cap, g.k, lane);
+          filter32<BF16>(ra, s, cinv_s + cb * 32, row0 + cb * 32, fast, g.N, g.mask);
           tmem_ld_wait(rb);
-          if (cb + 2 < BN / 32) tmem_ld32(taddr + (cb + 2) * 32, ra);
-          compact_full_segments(s, scratch, g.k, lane);
-          filter32<BF16>(rb, s, qscale, cinv_s + (cb + 1) * 32, row0 + (cb + 1) * 32, fast, g.N, g.mask);
+          if (cb + 2 < kEpiCols / 32) tmem_ld32(taddr + (cb + 2) * 32, ra);
+          compact_full_segments(s, scratch, cap, g.k, lane);
+          filter32<BF16>(rb, s, cinv_s + (cb + 1) * 32, row0 + (cb + 1) * 32, fast, g.N, g.mask);
         }
         tc_fence_before();
         __syncwarp();
@@ -434,7 +504,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           acc_phase ^= 1;
         }
       }
-      if (live) g.cand_cnt[static_cast<int64_t>(q) * g.chunks + chunk] = s.cnt;
+      if (live) g.cand_cnt[seg_index] = s.cnt;
     }
   }
 
@@ -453,14 +523,16 @@ int launch_split_planes(const float* x, int64_t rows, int64_t dim, int64_t ld, u
 size_t select_scratch_bytes(int64_t Q, int nseg, int seg_cap, int k);
 int launch_select_hist(const uint64_t* seg_keys, const int* seg_cnt, int64_t Q, int nseg, int seg_stride, int seg_cap,
                        const uint64_t* carry_in, const int* carry_cnt_in, uint64_t* carry_out, int* carry_cnt_out, float* tau_out,
-                       float* out_scores, int64_t* out_ids, int64_t id_offset, int k, cudaStream_t st);
+                       float* out_scores, int64_t* out_ids, int64_t id_offset, int k, float out_scale, const float* out_qscale,
+                       cudaStream_t st);
 int launch_select(const uint64_t* seg_keys, const int* seg_cnt, int64_t Q, int nseg, int seg_stride, int seg_cap,
                   const uint64_t* carry_in, const int* carry_cnt_in, uint64_t* carry_out, int* carry_cnt_out,
                   float* tau_out, float* out_scores, int64_t* out_ids, int64_t id_offset, int k, void* scratch,
                   size_t scratch_bytes, cudaStream_t st);
 
-constexpr size_t kGemmSmemBytes = static_cast<size_t>(kRingBytes) + 4 * kSegCap * sizeof(uint64_t) + 4 * BN * sizeof(float) +
-                                  (2 * kMaxStages + 4) * sizeof(uint64_t) + 16 + 1024;
+constexpr size_t kGemmSmemBytes = static_cast<size_t>(kRingBytes) + kEpiWarps * kEpiCols * sizeof(float) +
+                                  (2 * kMaxStages + 6) * sizeof(uint64_t) + 16 + 1024;
+static int seg_cap_for(int k) { return k <= 128 ? 256 : kSegCapMax; }
 static_assert(kGemmSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
 constexpr int kNumSMs = 148;
 
@@ -517,9 +589,12 @@ static int plan_phases(int64_t N, int qblocks, int k, Phase* out, int max_phases
   while (begin < T && n < max_phases) {
     if (n == max_phases - 1) end = T;
     const int tiles = end - begin;
-    // enough work items to fill the machine twice, few enough survivors per segment to stay far from kSegCap
+    // enough work items to fill the machine twice, few enough survivors per segment to stay far from its capacity:
+    // phase 0 admits every row (rows per chunk <= cap, i.e. cap/2 per column half); later phases expect
+    // ~(growth-1)*k survivors per query, spread over 2*chunks segments, kept under a quarter of the capacity
+    const int cap = seg_cap_for(k);
     int chunks = (2 * npairs + qblocks - 1) / qblocks;
-    const int by_load = n == 0 ? (tiles * BN + kSegCap / 2 - 1) / (kSegCap / 2) : ((growth - 1) * k + 127) / 128;
+    const int by_load = n == 0 ? (tiles * BN + cap - 1) / cap : ((growth - 1) * k + cap / 2 - 1) / (cap / 2);
     if (chunks < by_load) chunks = by_load;
     if (chunks > tiles) chunks = tiles;
     if (chunks < 1) chunks = 1;
@@ -550,7 +625,7 @@ constexpr int kMaxPhases = 16;
 
 struct GemmWs {
   size_t q_planes, c_planes, qinv, cinv, tau, carry[2], carry_cnt[2], cand, cand_cnt, scratch, total;
-  int max_chunks;
+  int max_chunks, seg_cap;
 };
 
 static GemmWs gemm_ws_layout(int64_t Q, int64_t N, int64_t D, int dtype, int k, int have_planes, int have_cinv) {
@@ -577,9 +652,10 @@ static GemmWs gemm_ws_layout(int64_t Q, int64_t N, int64_t D, int dtype, int k, 
     w.carry[i] = take(static_cast<size_t>(Q) * k * 8);
     w.carry_cnt[i] = take(static_cast<size_t>(Q) * 4);
   }
-  w.cand = take(static_cast<size_t>(Q) * maxc * kSegCap * 8);
-  w.cand_cnt = take(static_cast<size_t>(Q) * maxc * 4);
-  w.scratch = take(select_scratch_bytes(Q, maxc, kSegCap, k));
+  w.seg_cap = seg_cap_for(k);
+  w.cand = take(static_cast<size_t>(Q) * maxc * kEpiHalves * w.seg_cap * 8);
+  w.cand_cnt = take(static_cast<size_t>(Q) * maxc * kEpiHalves * 4);
+  w.scratch = take(static_cast<size_t>(kNumSMs) * kEpiWarps * kSegCapMax * 8);  // in-kernel compaction scratch
   w.total = off + 1024;
   return w;
 }
@@ -623,6 +699,8 @@ int launch_gemm_topk(const void* queries, int64_t Q, int64_t ldq, const void* ca
   g.tau = reinterpret_cast<float*>(base + L.tau);
   g.cand = reinterpret_cast<uint64_t*>(base + L.cand);
   g.cand_cnt = reinterpret_cast<int*>(base + L.cand_cnt);
+  g.seg_cap = L.seg_cap;
+  g.compact_scratch = reinterpret_cast<uint64_t*>(base + L.scratch);
   CUtensorMap map_a, map_b;
   int terms;
   if (dtype == ICR_F32) {
@@ -658,13 +736,14 @@ int launch_gemm_topk(const void* queries, int64_t Q, int64_t ldq, const void* ca
     g.qinv = qinv;
     g.cinv = cinv;
   }
-  static thread_local bool attr_set[2] = {false, false};
-  const int which = terms == 1 ? 1 : 0;
+  // kernel variant: 0 = fp16 planes (3 terms), 1 = bf16 streaming both operands, 2 = bf16 with resident queries
+  static thread_local bool attr_set[3] = {false, false, false};
+  const int which = terms == 3 ? 0 : (g.kb_per_term <= kAStatMaxKB ? 2 : 1);
   if (!attr_set[which]) {
-    if (which)
-      ICR_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmemBytes)));
-    else
-      ICR_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmemBytes)));
+    const int smem = static_cast<int>(kGemmSmemBytes);
+    if (which == 0) ICR_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (which == 1) ICR_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (which == 2) ICR_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set[which] = true;
   }
   // tau starts at -inf: phase 0 admits every row
@@ -681,21 +760,20 @@ int launch_gemm_topk(const void* queries, int64_t Q, int64_t ldq, const void* ca
     const int pairs = items < kNumSMs / 2 ? items : kNumSMs / 2;
     const int grid = 2 * pairs;  // whole CTA pairs (cluster dims 2x1x1)
     profile_begin(kKernelGemm, terms, st);
-    if (which)
-      gemm_topk_kernel<1><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(map_a, map_b, g);
-    else
-      gemm_topk_kernel<3><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(map_a, map_b, g);
+    if (which == 0) gemm_topk_kernel<3, false><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(map_a, map_b, g);
+    if (which == 1) gemm_topk_kernel<1, false><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(map_a, map_b, g);
+    if (which == 2) gemm_topk_kernel<1, true><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(map_a, map_b, g);
     profile_end(st);
     ICR_LAUNCH_CHECK();
     const bool last = (p == np - 1);
     const int cur = p & 1, prev = cur ^ 1;
-    rc = launch_select_hist(g.cand, g.cand_cnt, Q, g.chunks, kSegCap, kSegCap,
+    rc = launch_select_hist(g.cand, g.cand_cnt, Q, g.chunks * kEpiHalves, g.seg_cap, g.seg_cap,
                        p > 0 ? reinterpret_cast<uint64_t*>(base + L.carry[prev]) : nullptr,
                        p > 0 ? reinterpret_cast<int*>(base + L.carry_cnt[prev]) : nullptr,
                        last ? nullptr : reinterpret_cast<uint64_t*>(base + L.carry[cur]),
                        last ? nullptr : reinterpret_cast<int*>(base + L.carry_cnt[cur]),
                             last ? nullptr : const_cast<float*>(g.tau), last ? out_scores : nullptr, last ? out_ids : nullptr, row_offset,
-                            k, st);
+                            k, g.acc_scale, g.qinv, st);  // raw key scores -> cosines on the way out
     if (rc) return rc;
   }
   return ICR_OK;

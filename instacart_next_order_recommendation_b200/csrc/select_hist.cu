@@ -36,6 +36,8 @@ struct HistSelectArgs {
   int64_t id_offset;
   int k;
   int64_t Q;
+  float out_scale;          // final score = key score * out_scale * (out_qscale ? out_qscale[q] : 1)
+  const float* out_qscale;  // [Q] or null
 };
 
 struct HsSmem {
@@ -246,9 +248,10 @@ __global__ void __launch_bounds__(kHsWarps * 32) select_hist_kernel(HistSelectAr
     const int P = next_pow2(kept < 2 ? 2 : kept);
     for (int i = kept + lane; i < P; i += 32) sel[i] = 0ull;
     warp_bitonic_sort_desc(sel, P, lane);
+    const float scale = a.out_scale * (a.out_qscale ? a.out_qscale[q] : 1.0f);
     for (int i = lane; i < k; i += 32) {
       const bool ok = i < kept;
-      a.out_scores[q * k + i] = ok ? key_score(sel[i]) : -INFINITY;
+      a.out_scores[q * k + i] = ok ? key_score(sel[i]) * scale : -INFINITY;
       a.out_ids[q * k + i] = ok ? static_cast<int64_t>(key_row(sel[i])) + a.id_offset : -1;
     }
   }
@@ -256,7 +259,8 @@ __global__ void __launch_bounds__(kHsWarps * 32) select_hist_kernel(HistSelectAr
 
 int launch_select_hist(const uint64_t* seg_keys, const int* seg_cnt, int64_t Q, int nseg, int seg_stride, int seg_cap,
                        const uint64_t* carry_in, const int* carry_cnt_in, uint64_t* carry_out, int* carry_cnt_out, float* tau_out,
-                       float* out_scores, int64_t* out_ids, int64_t id_offset, int k, cudaStream_t st) {
+                       float* out_scores, int64_t* out_ids, int64_t id_offset, int k, float out_scale, const float* out_qscale,
+                       cudaStream_t st) {
   if (Q == 0) return ICR_OK;
   static thread_local bool attr_set = false;
   if (!attr_set) {
@@ -279,6 +283,8 @@ int launch_select_hist(const uint64_t* seg_keys, const int* seg_cnt, int64_t Q, 
   a.id_offset = id_offset;
   a.k = k;
   a.Q = Q;
+  a.out_scale = out_scale;
+  a.out_qscale = out_qscale;
   const unsigned grid = static_cast<unsigned>((Q + kHsWarps - 1) / kHsWarps);
   select_hist_kernel<<<grid, kHsWarps * 32, sizeof(HsSmem), st>>>(a);
   ICR_LAUNCH_CHECK();

@@ -135,6 +135,51 @@ class DeviceCatalog:
     def nbytes(self) -> int:
         return self.rows.numel() * self.rows.element_size() + (0 if self.planes is None else self.planes.numel() * 2)
 
+    # ---- request-sized calls: one CUDA graph per (Q, k) -------------------------------------------------
+    def _graph_for(self, Q: int, k: int, path: int):
+        """Capture prep + scoring + select of a fixed-shape request once; replays cost one graph launch.
+
+        The serve path is launch-latency-bound (a batch-1 request streams 76 MB in ~12 µs of HBM time), so the
+        Python/ctypes work and the gaps between the 2-3 kernels of a call matter more than the kernels.
+        """
+        if not hasattr(self, "_graphs"):
+            self._graphs = {}
+        key = (Q, k, path)
+        entry = self._graphs.get(key)
+        if entry is None:
+            static_q = torch.zeros(Q, self.rows.shape[1], dtype=self.dtype, device=self.device)
+            kw = dict(cat_planes=self.planes, cat_inv_norms=self.inv_norms, row_offset=self.row_offset, path=path)
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):  # warm-up outside capture: one-time attribute setting, lazy module load
+                ops.cos_topk(static_q, self.rows, k, **kw)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                vals, ids = ops.cos_topk(static_q, self.rows, k, **kw)
+            entry = (graph, static_q, vals, ids)
+            self._graphs[key] = entry
+        return entry
+
+    def topk_small(self, queries, k: int, *, path: int = ops.PATH_AUTO, copy: bool = True):
+        """topk() for request-sized batches (Q <= 8) through a cached CUDA graph.
+
+        `queries` may live on the host (numpy / CPU tensor, as SentenceTransformer.encode returns it) or on the
+        device. With copy=False the returned tensors are the graph's static outputs, overwritten by the next call.
+        """
+        q = queries if isinstance(queries, torch.Tensor) else torch.as_tensor(queries)
+        if q.dim() == 1:
+            q = q.unsqueeze(0)
+        k = min(int(k), len(self))
+        if k < 1 or q.shape[0] == 0:
+            return self.topk(q, max(k, 1))
+        graph, static_q, vals, ids = self._graph_for(q.shape[0], k, path)
+        D = min(q.shape[1], static_q.shape[1])
+        static_q[:, :D].copy_(q[:, :D], non_blocking=True)  # H2D (or D2D) + dtype conversion in one op
+        graph.replay()
+        return (vals.clone(), ids.clone()) if copy else (vals, ids)
+
     def topk_host(self, queries: torch.Tensor, k: int, *, out: tuple[torch.Tensor, torch.Tensor] | None = None,
                   n_chunks: int = 4, path: int = ops.PATH_AUTO):
         """Host-to-host top-k: CPU query matrix in, CPU (values [Q,k] f32, ids [Q,k] i64) out.

@@ -6,6 +6,8 @@ the arithmetic runs in libicr_b200.so. Non-CUDA tensors raise: there is no fallb
 
 from __future__ import annotations
 
+import contextlib
+
 import torch
 
 from . import _lib
@@ -39,6 +41,16 @@ def _rows(t: torch.Tensor) -> torch.Tensor:
     if t.data_ptr() % 16:
         t = t.clone(memory_format=torch.contiguous_format)
     return t
+
+
+_NULL_CTX = contextlib.nullcontext()
+
+
+def _on(device: torch.device):
+    """Device guard that costs nothing in the common case (the tensor's device is already current)."""
+    if device.index is None or device.index == torch.cuda.current_device():
+        return _NULL_CTX
+    return torch.cuda.device(device)
 
 
 def _ld(t: torch.Tensor) -> int:
@@ -96,7 +108,7 @@ def row_inv_norms(x: torch.Tensor) -> torch.Tensor:
     x = _rows(x)
     lib = _lib.load()
     out = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         _lib.check(lib.icr_row_inv_norms(x.data_ptr(), x.shape[0], x.shape[1], _ld(x), _dtype_code(x), out.data_ptr(), _stream(x.device)))
     return out
 
@@ -109,7 +121,7 @@ def split_f16_planes(x: torch.Tensor) -> torch.Tensor:
     x = _rows(x)
     lib = _lib.load()
     planes = torch.empty(x.shape[0], lib.icr_planes_row_elems(x.shape[1]), dtype=torch.float16, device=x.device)
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         _lib.check(lib.icr_split_f16_planes(x.data_ptr(), x.shape[0], x.shape[1], _ld(x), planes.data_ptr(), _stream(x.device)))
     return planes
 
@@ -155,7 +167,7 @@ def cos_topk(
         ids = torch.empty(Q, k, dtype=torch.int64, device=dev)
     else:
         vals, ids = out
-    with torch.cuda.device(dev):
+    with _on(dev):
         need = lib.icr_cos_topk_workspace_bytes(Q, N, D, dt, k, path, int(cat_planes is not None))
         ws = _workspace(need, dev)
         _lib.check(
@@ -179,7 +191,7 @@ def cos_sim_dense(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
     dev = b.device
     out = torch.empty(a.shape[0], b.shape[0], dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with _on(dev):
         ws = _workspace(lib.icr_cos_sim_dense_workspace_bytes(a.shape[0], b.shape[0], a.shape[1], _dtype_code(b)), dev)
         _lib.check(
             lib.icr_cos_sim_dense(
@@ -203,7 +215,7 @@ def topk_merge(cand_scores: torch.Tensor, cand_ids: torch.Tensor, k_out: int):
     dev = cand_scores.device
     vals = torch.empty(Q, k_out, dtype=torch.float32, device=dev)
     ids = torch.empty(Q, k_out, dtype=torch.int64, device=dev)
-    with torch.cuda.device(dev):
+    with _on(dev):
         ws = _workspace(lib.icr_topk_merge_workspace_bytes(Q, G, k_in, k_out), dev)
         _lib.check(
             lib.icr_topk_merge(cand_scores.data_ptr(), cand_ids.data_ptr(), Q, G, k_in, k_out, vals.data_ptr(), ids.data_ptr(),
@@ -224,7 +236,7 @@ def mnrl_forward(anchors: torch.Tensor, positives: torch.Tensor, scale: float):
     lib = _lib.load()
     loss = torch.empty((), dtype=torch.float32, device=dev)
     saved = torch.empty(3, B, dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with _on(dev):
         ws = _workspace(lib.icr_mnrl_workspace_bytes(B, D), dev)
         _lib.check(
             lib.icr_mnrl_fwd(a.data_ptr(), _ld(a), p.data_ptr(), _ld(p), B, D, _dtype_code(a), float(scale), loss.data_ptr(),
@@ -241,7 +253,7 @@ def mnrl_backward(anchors: torch.Tensor, positives: torch.Tensor, scale: float, 
     ga = torch.empty_like(a, memory_format=torch.contiguous_format)
     gp = torch.empty_like(p, memory_format=torch.contiguous_format)
     go = grad_out.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
-    with torch.cuda.device(dev):
+    with _on(dev):
         ws = _workspace(lib.icr_mnrl_workspace_bytes(B, D), dev)
         _lib.check(
             lib.icr_mnrl_bwd(a.data_ptr(), _ld(a), p.data_ptr(), _ld(p), B, D, _dtype_code(a), float(scale), saved[0].data_ptr(),

@@ -122,8 +122,9 @@ class Recommender:
             return []
         if top_k + len(excluded_rows) <= ops.MAX_K:
             # exact: the best (top_k + #excluded) rows contain the best top_k non-excluded ones
-            k_fetch = min(n, top_k + len(excluded_rows))
-            vals, ids = self.catalog.topk(query_emb, k_fetch)
+            k_fetch = top_k + len(excluded_rows)
+            k_fetch = min(n, next(b for b in (16, 32, 64, 128, 256) if b >= k_fetch))  # few distinct shapes -> few CUDA graphs
+            vals, ids = self.catalog.topk_small(query_emb, k_fetch, copy=False)
             mask_rows = set(excluded_rows)
         else:
             # unbounded exclusion lists: mask rows on the device instead of over-fetching

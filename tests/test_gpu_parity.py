@@ -279,6 +279,20 @@ def test_mnrl_known_answers_and_module_interface():
     assert abs(loss.item() - ref.item()) < 1e-4 and tower.lin.weight.grad is not None
 
 
+def test_topk_small_cuda_graph_equals_plain_call():
+    items, _ = oracle.synth_clustered(20000, 384, seed=31)
+    queries, _ = oracle.synth_queries_from_items(items, 6, seed=32)
+    for dtype in (torch.float32, torch.bfloat16):
+        cat = icr.DeviceCatalog(items, dtype=dtype)
+        for qn in (1, 3):
+            for rep in range(3):  # replays of the same captured graph with different queries
+                q = queries[rep : rep + qn]
+                v, i = cat.topk(q.cuda(), 16)
+                vs, is_ = cat.topk_small(q.numpy(), 16)  # host numpy in, like SentenceTransformer.encode
+                assert torch.equal(vs, v) and torch.equal(is_, i)
+        assert len(cat._graphs) == 2
+
+
 def test_topk_host_pipeline_equals_device_path():
     items, _ = oracle.synth_clustered(30000, 384, seed=21)
     queries, _ = oracle.synth_queries_from_items(items, 3001, seed=22)
