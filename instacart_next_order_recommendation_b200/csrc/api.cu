@@ -53,7 +53,8 @@ int launch_row_inv_norms(const void* x, int64_t rows, int64_t dim, int64_t ld, i
 int launch_split_planes(const float* x, int64_t rows, int64_t dim, int64_t ld, uint16_t* planes, cudaStream_t st);
 int gemv_grid(int64_t N);
 int launch_gemv_topk(const void* cat, int64_t N, int64_t ldc, int D, int dtype, const void* q, int64_t ldq, int Q,
-                     const uint8_t* mask, int k, uint64_t* part_keys, int* part_cnt, int grid, cudaStream_t st);
+                     const uint8_t* mask, int k, uint64_t* part_keys, int* part_cnt, int grid, float* out_scores, int64_t* out_ids,
+                     int64_t id_offset, unsigned int* done_counter, cudaStream_t st);
 size_t select_scratch_bytes(int64_t Q, int nseg, int seg_cap, int k);
 int launch_select(const uint64_t* seg_keys, const int* seg_cnt, int64_t Q, int nseg, int seg_stride, int seg_cap,
                   const uint64_t* carry_in, const int* carry_cnt_in, uint64_t* carry_out, int* carry_cnt_out,
@@ -125,7 +126,7 @@ static size_t gemv_ws_bytes(int64_t Q, int64_t N, int k) {
   b += align_up(static_cast<size_t>(qc) * grid * k * sizeof(uint64_t), 256);
   b += align_up(static_cast<size_t>(qc) * grid * sizeof(int), 256);
   b += align_up(select_scratch_bytes(qc, grid, k, k), 256);
-  return b + 256;
+  return b + 512;  // + the merge counter
 }
 
 }  // namespace icr
@@ -269,16 +270,16 @@ int icr_cos_topk(const void* queries, int64_t Q, int64_t ldq, const void* catalo
   w += align_up(static_cast<size_t>(qc) * grid * k * sizeof(uint64_t), 256);
   int* part_cnt = reinterpret_cast<int*>(w);
   w += align_up(static_cast<size_t>(qc) * grid * sizeof(int), 256);
-  void* scratch = w;
-  const size_t scratch_bytes = align_up(select_scratch_bytes(qc, grid, k, k), 256);
+  w += align_up(select_scratch_bytes(qc, grid, k, k), 256);
+  unsigned int* done_counter = reinterpret_cast<unsigned int*>(w);
   const size_t esz = elem_size(dtype);
+  // the last CTA of every GEMV launch merges the per-CTA lists itself (no select launch on the latency path)
+  ICR_CUDA_CHECK(cudaMemsetAsync(done_counter, 0, sizeof(unsigned int), st));
   for (int64_t q0 = 0; q0 < Q; q0 += qc) {
     const int nq = static_cast<int>(Q - q0 < qc ? Q - q0 : qc);
     const char* qptr = static_cast<const char*>(queries) + q0 * ldq * esz;
-    rc = launch_gemv_topk(catalog, N, ldc, static_cast<int>(D), dtype, qptr, ldq, nq, exclude_mask, k, part_keys, part_cnt, grid, st);
-    if (rc) return rc;
-    rc = launch_select(part_keys, part_cnt, nq, grid, k, k, nullptr, nullptr, nullptr, nullptr, nullptr, out_scores + q0 * k,
-                       out_ids + q0 * k, row_offset, k, scratch, scratch_bytes, st);
+    rc = launch_gemv_topk(catalog, N, ldc, static_cast<int>(D), dtype, qptr, ldq, nq, exclude_mask, k, part_keys, part_cnt, grid,
+                          out_scores + q0 * k, out_ids + q0 * k, row_offset, done_counter, st);
     if (rc) return rc;
   }
   return ICR_OK;

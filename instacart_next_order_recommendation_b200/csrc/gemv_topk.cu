@@ -1,22 +1,35 @@
 // K1: streaming cosine GEMV with fused top-k for small query batches (Q <= 7 per pass).
 //
-// HBM-bound by design: every catalog row is read exactly once with 128-bit streaming loads
-// (ld.global.nc.L1::no_allocate), RB rows x up to 3 vectors per lane in flight; the row's squared
-// norm is accumulated from the same registers, so no separate normalisation pass or inverse-norm
-// array is read. Scores never reach HBM: each CTA keeps, per query, a shared-memory candidate list
-// guarded by a running threshold (the CTA's k-th best so far) and emits its k best keys; the select
-// kernel (select.cu) merges the per-CTA lists.
+// HBM-bound by design: every catalog row is read exactly once; the row's squared norm is accumulated from
+// the same data, so no separate normalisation pass or inverse-norm array is read. Scores never reach HBM:
+// each CTA keeps, per query, a shared-memory candidate list guarded by a running threshold (the CTA's k-th
+// best so far) and emits its k best keys; the last CTA to finish merges the per-CTA lists in the same launch
+// (no second kernel on the batch-1 latency path).
+//
+// Two ways of moving the rows:
+//   gemv_ring_kernel  (default, contiguous catalogs): a producer warp streams 8-row slabs with 1-D bulk async
+//       copies (cp.async.bulk, the TMA engine) into a shared-memory ring guarded by mbarriers; eight consumer
+//       warps read slabs with conflict-free 128-bit shared loads. The whole ring (up to 192 KB per SM) is in
+//       flight from the first microsecond, independent of consumer register pressure.
+//   gemv_topk_kernel  (row-strided catalogs): 128-bit ld.global.nc.L1::no_allocate, RB rows x 3 vectors per
+//       lane in flight.
 //
 // Replaces, for one request: torch.tensor(catalog) + F.normalize x2 + torch.mm + argsort
 // (reference src/inference/serve_recommendations.py:213-215 via sentence_transformers.util.cos_sim).
 #include "common.cuh"
+#include "ptx.cuh"
+#include "select_warp.cuh"
 
 namespace icr {
 
-constexpr int kGemvThreads = 256;
+constexpr int kGemvThreads = 256;  // compute threads of either kernel
 constexpr int kGemvWarps = kGemvThreads / 32;
 constexpr int kGemvCand = 1024;  // candidate keys per query held in shared memory
-constexpr int kGemvUnroll = 3;   // 16-byte vectors per lane per row kept in flight
+constexpr int kGemvUnroll = 3;   // 16-byte vectors per lane per row kept in flight (direct-load kernel)
+constexpr int kMergeSel = 256;   // >= ICR_MAX_K: output buffer of the in-kernel merge
+constexpr int kSlabRows = 8;     // rows per ring slot
+constexpr int kMaxSlots = 16;
+constexpr int kRingThreads = kGemvThreads + 32;  // + the producer warp
 
 struct GemvArgs {
   const void* cat;
@@ -32,30 +45,71 @@ struct GemvArgs {
   uint64_t* part_keys;  // [Q][gridDim.x][k]
   int* part_cnt;        // [Q][gridDim.x]
   int q0;               // first query of this pass
+  int ring_slots;       // ring kernel: slots of kSlabRows rows
+  // in-kernel merge by the last CTA (skipped when out_scores is null)
+  float* out_scores;           // [Q][k]
+  int64_t* out_ids;            // [Q][k]
+  int64_t id_offset;
+  unsigned int* done_counter;  // zero before the first launch; the merging CTA resets it
 };
 
-// RB rows per warp batch, QT queries per pass; V = RB * (QT + 1) partial sums per lane
-// (QT dot products + the row's squared norm), V in {16, 32}.
-template <typename T, int RB, int QT>
-__global__ void __launch_bounds__(kGemvThreads) gemv_topk_kernel(GemvArgs a) {
-  constexpr int VEC = Elem<T>::VEC;
-  constexpr int V = RB * (QT + 1);
-  constexpr int SH = (V == 32) ? 0 : (V == 16 ? 1 : (V == 8 ? 2 : 3));  // lane -> value index shift
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  // layout: keys [QT][kGemvCand] | qs [QT][Dv*VEC] f32 | ncand [QT] | tau [QT]
-  uint64_t* cand = reinterpret_cast<uint64_t*>(smem_raw);
-  const int nvec = a.D / VEC;
-  const int dpad = nvec * VEC;
-  float* qs = reinterpret_cast<float*>(cand + QT * kGemvCand);
-  int* ncand = reinterpret_cast<int*>(qs + QT * dpad);
-  float* tau = reinterpret_cast<float*>(ncand + QT);
+// barrier over the 256 compute threads: the whole CTA in the direct kernel, a named barrier in the ring kernel
+template <bool NAMED>
+__device__ __forceinline__ void compute_sync() {
+  if (NAMED) ptx::named_sync(1, kGemvThreads);
+  else __syncthreads();
+}
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const T* cat = static_cast<const T*>(a.cat);
+template <bool NAMED>
+__device__ __forceinline__ void compute_bitonic_sort_desc(uint64_t* keys, int n, int tid) {
+  compute_sync<NAMED>();
+  for (int size = 2; size <= n; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = tid; t < (n >> 1); t += kGemvThreads) {
+        const int lo = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const uint64_t a = keys[lo], b = keys[hi];
+        if ((a < b) == desc) {
+          keys[lo] = b;
+          keys[hi] = a;
+        }
+      }
+      compute_sync<NAMED>();
+    }
+  }
+}
+
+// shared-memory carve-up common to both kernels (after `prefix` bytes used by the ring)
+template <int QT>
+struct GemvSmem {
+  uint64_t* cand;       // [QT][kGemvCand]
+  float* qs;            // [QT][dpad]
+  int* ncand;           // [QT]
+  float* tau;           // [QT]
+  int* list_cnt;        // [512]   merge: per-CTA list lengths
+  uint64_t* sel;        // [kMergeSel] merge fallback
+  unsigned int* hist;   // [kHsBins]   merge fallback
+  int* misc;            // [4]
+  __device__ GemvSmem(unsigned char* base, int dpad) {
+    cand = reinterpret_cast<uint64_t*>(base);
+    sel = cand + QT * kGemvCand;
+    qs = reinterpret_cast<float*>(sel + kMergeSel);
+    ncand = reinterpret_cast<int*>(qs + QT * dpad);
+    tau = reinterpret_cast<float*>(ncand + QT);
+    list_cnt = reinterpret_cast<int*>(tau + QT);
+    hist = reinterpret_cast<unsigned int*>(list_cnt + 512);
+    misc = reinterpret_cast<int*>(hist + kHsBins);
+  }
+  static size_t bytes(int D) {
+    return static_cast<size_t>(QT) * kGemvCand * 8 + kMergeSel * 8 + static_cast<size_t>(QT) * D * 4 + QT * 8 + 512 * 4 + kHsBins * 4 + 16;
+  }
+};
+
+// ---- stage the L2-normalised queries in shared memory (fp32) ----------------------------------------
+template <typename T, int QT>
+__device__ __forceinline__ void stage_queries(const GemvArgs& a, float* qs, int dpad, int nq, int warp, int lane) {
   const T* qg = static_cast<const T*>(a.q);
-  const int nq = min(QT, a.Q - a.q0);
-
-  // ---- stage the L2-normalised queries in shared memory (fp32) ------------------------------
   for (int t = warp; t < QT; t += kGemvWarps) {
     if (t < nq) {
       const T* qrow = qg + static_cast<int64_t>(a.q0 + t) * a.ldq;
@@ -73,9 +127,252 @@ __global__ void __launch_bounds__(kGemvThreads) gemv_topk_kernel(GemvArgs a) {
       for (int e = lane; e < dpad; e += 32) qs[t * dpad + e] = 0.f;
     }
   }
+}
+
+// accumulate one 16-byte vector of RB rows against QT queries (+ the rows' squared norms)
+template <typename T, int RB, int QT>
+__device__ __forceinline__ void fma_vector(const uint4 (&c)[RB], const float* qs, int dpad, int v, float (&acc)[RB * (QT + 1)]) {
+  constexpr int VEC = Elem<T>::VEC;
+  float qv[QT][VEC];
+#pragma unroll
+  for (int t = 0; t < QT; ++t) {
+#pragma unroll
+    for (int h = 0; h < VEC / 4; ++h) {
+      const float4 x = *reinterpret_cast<const float4*>(qs + t * dpad + v * VEC + h * 4);
+      qv[t][h * 4 + 0] = x.x;
+      qv[t][h * 4 + 1] = x.y;
+      qv[t][h * 4 + 2] = x.z;
+      qv[t][h * 4 + 3] = x.w;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < RB; ++r) {
+    float f[VEC];
+    Elem<T>::unpack(c[r], f);
+#pragma unroll
+    for (int t = 0; t < QT; ++t) {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) acc[t * RB + r] = fmaf(f[i], qv[t][i], acc[t * RB + r]);
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[QT * RB + r] = fmaf(f[i], f[i], acc[QT * RB + r]);
+  }
+}
+
+// transposing reduction of the RB*(QT+1) partial sums, then threshold test and candidate append
+template <int RB, int QT>
+__device__ __forceinline__ void reduce_and_append(float (&acc)[RB * (QT + 1)], const GemvArgs& a, GemvSmem<QT>& sm, int nq, int64_t r0,
+                                                  int64_t row_limit, int lane) {
+  constexpr int V = RB * (QT + 1);
+  constexpr int SH = (V == 32) ? 0 : (V == 16 ? 1 : (V == 8 ? 2 : 3));  // lane -> value index shift
+  warp_transpose_reduce<V>(acc, lane);
+  const int idx = lane >> SH;  // value index owned by this lane
+  const int t = idx / RB, r = idx % RB;
+  // squared norm of row r lives in the lane group of index QT*RB + r
+  const float ss = __shfl_sync(kFull, acc[0], (QT * RB + r) << SH);
+  const int64_t row = r0 + r;
+  if (t < nq && (lane & ((1 << SH) - 1)) == 0 && row < row_limit) {
+    const bool excluded = a.mask && a.mask[row];
+    const float score = acc[0] * (1.0f / fmaxf(sqrtf(ss), kNormEps));
+    if (!excluded && score > sm.tau[t]) {
+      const int pos = atomicAdd(&sm.ncand[t], 1);
+      if (pos < kGemvCand) sm.cand[t * kGemvCand + pos] = make_key(score, static_cast<uint32_t>(row));
+    }
+  }
+}
+
+// if a list could overflow during the next block of rows (or at the end), keep its k best and raise tau
+template <int QT, bool NAMED>
+__device__ __forceinline__ void refresh_thresholds(const GemvArgs& a, GemvSmem<QT>& sm, int nq, bool last, int block_rows, int tid) {
+  for (int t = 0; t < nq; ++t) {
+    const int n = min(sm.ncand[t], kGemvCand);
+    if (last || n > kGemvCand - block_rows) {
+      uint64_t* keys = sm.cand + t * kGemvCand;
+      const int P = next_pow2(n < 2 ? 2 : n);
+      for (int i = n + tid; i < P; i += kGemvThreads) keys[i] = 0ull;
+      compute_bitonic_sort_desc<NAMED>(keys, P, tid);
+      if (tid == 0) {
+        const int kept = min(n, a.k);
+        sm.ncand[t] = kept;
+        sm.tau[t] = (kept >= a.k) ? key_score(keys[a.k - 1]) : -INFINITY;
+      }
+      compute_sync<NAMED>();
+    }
+  }
+}
+
+// Merge of the G per-CTA lists of query t by a group of GT threads (gtid = index in the group); LISTS * GT >= G.
+template <int QT, int GT, int LISTS, typename Sync>
+__device__ __forceinline__ void merge_query(const GemvArgs& a, GemvSmem<QT>& sm, int t, int gtid, Sync sync) {
+  const int k = a.k, G = gridDim.x, lane = gtid & 31;
+  uint64_t* buf = sm.cand + t * kGemvCand;  // heads first, then the gathered candidates
+  uint64_t* floor_slot = reinterpret_cast<uint64_t*>(sm.list_cnt) + t;
+  int* counter = sm.list_cnt + 64 + t;
+  const int64_t slot0 = static_cast<int64_t>(a.q0 + t) * G;
+  uint64_t my_head[LISTS];
+  int my_cnt[LISTS];
+#pragma unroll
+  for (int j = 0; j < LISTS; ++j) {  // all loads independent and issued back to back
+    const int c = gtid + j * GT;
+    my_cnt[j] = (c < G) ? __ldcg(a.part_cnt + slot0 + c) : 0;
+    my_head[j] = (c < G) ? __ldcg(a.part_keys + (slot0 + c) * k) : 0ull;  // garbage if the list is empty: masked next
+  }
+#pragma unroll
+  for (int j = 0; j < LISTS; ++j) {
+    const int c = gtid + j * GT;
+    if (my_cnt[j] <= 0) my_head[j] = 0ull;
+    if (c < G) buf[c] = my_head[j];
+  }
+  if (gtid == 0) {
+    *counter = 0;
+    *floor_slot = 0ull;  // stays 0 when fewer than k lists are non-empty
+  }
+  sync();
+#pragma unroll
+  for (int j = 0; j < LISTS; ++j) {
+    if (my_head[j] != 0ull) {
+      int rank = 0;
+      for (int i = 0; i < G; ++i) rank += (buf[i] > my_head[j]) ? 1 : 0;
+      if (rank == k - 1) *floor_slot = my_head[j];
+    }
+  }
+  sync();
+  const uint64_t head_floor = *floor_slot;
+  sync();  // everyone has read the floor and is done with the heads in `buf`
+#pragma unroll
+  for (int j = 0; j < LISTS; ++j) {
+    if (my_head[j] != 0ull && my_head[j] >= head_floor) {  // at most k lists qualify
+      const uint64_t* list = a.part_keys + (slot0 + gtid + j * GT) * k;
+      uint64_t key = my_head[j];
+      for (int i = 0;;) {
+        const int pos = atomicAdd(counter, 1);
+        if (pos < kGemvCand) buf[pos] = key;
+        if (++i >= my_cnt[j]) break;
+        key = __ldcg(list + i);
+        if (key < head_floor) break;
+      }
+    }
+  }
+  sync();
+  int n = *counter;
+  const int64_t qo = static_cast<int64_t>(a.q0 + t) * k;
+  if (n <= kGemvCand) {
+    for (int i = gtid; i < n; i += GT) {
+      const uint64_t key = buf[i];
+      int rank = 0;
+      for (int j = 0; j < n; ++j) rank += (buf[j] > key) ? 1 : 0;
+      if (rank < k) {
+        a.out_scores[qo + rank] = key_score(key);
+        a.out_ids[qo + rank] = static_cast<int64_t>(key_row(key)) + a.id_offset;
+      }
+    }
+    for (int i = n + gtid; i < k; i += GT) {  // fewer than k eligible rows in the whole catalog
+      a.out_scores[qo + i] = -INFINITY;
+      a.out_ids[qo + i] = -1;
+    }
+  } else if (gtid < 32) {
+    // overflow (possible only for k > 32): exact streaming merge by one warp, list by list. With several queries in
+    // flight the fallback buffers are shared, so it is serialised through a spin lock on shared memory.
+    int* lock = sm.misc + 2;
+    if (lane == 0) {
+      while (atomicCAS(lock, 0, 1) != 0) {
+      }
+    }
+    __syncwarp();
+    n = 0;
+    for (int c = 0; c < G; ++c) {
+      const int cnt = __ldcg(a.part_cnt + slot0 + c);
+      if (cnt == 0) continue;
+      if (n + cnt > kGemvCand) {
+        warp_select_topk(buf, n, k, sm.sel, sm.hist, lane);
+        for (int i = lane; i < k; i += 32) buf[i] = sm.sel[i];
+        n = k;
+        __syncwarp();
+      }
+      for (int i = lane; i < cnt; i += 32) buf[n + i] = __ldcg(a.part_keys + (slot0 + c) * k + i);
+      n += cnt;
+      __syncwarp();
+    }
+    int kept = n;
+    if (n > k) {
+      warp_select_topk(buf, n, k, sm.sel, sm.hist, lane);
+      kept = k;
+    } else {
+      for (int i = lane; i < n; i += 32) sm.sel[i] = buf[i];
+    }
+    __syncwarp();
+    const int P = next_pow2(kept < 2 ? 2 : kept);
+    for (int i = kept + lane; i < P; i += 32) sm.sel[i] = 0ull;
+    warp_bitonic_sort_desc(sm.sel, P, lane);
+    for (int i = lane; i < k; i += 32) {
+      const bool ok = i < kept;
+      a.out_scores[qo + i] = ok ? key_score(sm.sel[i]) : -INFINITY;
+      a.out_ids[qo + i] = ok ? static_cast<int64_t>(key_row(sm.sel[i])) + a.id_offset : -1;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence_block();
+      atomicExch(lock, 0);
+    }
+  }
+}
+
+// ---- emit this CTA's lists; the last CTA to finish merges all of them -----------------------------------
+template <int QT, bool NAMED>
+__device__ __forceinline__ void emit_and_merge(const GemvArgs& a, GemvSmem<QT>& sm, int nq, bool has_rows, int tid) {
+  const int lane = tid & 31, warp = tid >> 5;
+  const int k = a.k, G = gridDim.x;
+  for (int t = 0; t < nq; ++t) {
+    const int n = has_rows ? sm.ncand[t] : 0;
+    const int64_t slot = static_cast<int64_t>(a.q0 + t) * G + blockIdx.x;
+    for (int i = tid; i < n; i += kGemvThreads) a.part_keys[slot * k + i] = sm.cand[t * kGemvCand + i];
+    if (tid == 0) a.part_cnt[slot] = n;
+  }
+  if (a.out_scores == nullptr) return;  // the caller merges the per-CTA lists with a separate select launch
+
+  __threadfence();
+  compute_sync<NAMED>();
+  if (tid == 0) {
+    sm.misc[0] = (atomicAdd(a.done_counter, 1u) == static_cast<unsigned int>(G) - 1u) ? 1 : 0;
+    sm.misc[2] = 0;  // lock of the merge's overflow fallback
+  }
+  compute_sync<NAMED>();
+  if (!sm.misc[0]) return;
+  __threadfence();
+
+  // Every per-CTA list is sorted, so the k best list HEADS are k distinct keys >= head_floor (the k-th largest
+  // head) and no key below head_floor can be among the k best overall: typically ~2k of the G*k keys survive.
+  // Ranks are found by counting (n^2 comparisons on shared-memory broadcasts, spread over the group's threads),
+  // which also yields the sorted output positions directly. One query: the whole CTA works on it. Several
+  // queries: one warp each, side by side.
+  if (nq == 1) {
+    merge_query<QT, kGemvThreads, 2>(a, sm, 0, tid, [] { compute_sync<NAMED>(); });
+  } else if (warp < nq) {
+    merge_query<QT, 32, 10>(a, sm, warp, lane, [] { __syncwarp(); });
+  }
+  compute_sync<NAMED>();
+  if (tid == 0) *a.done_counter = 0u;  // ready for the next launch that shares this workspace
+}
+
+// =====================================================================================================
+// direct-load kernel: RB rows per warp batch, QT queries per pass; V = RB * (QT + 1) in {16, 32}
+// =====================================================================================================
+template <typename T, int RB, int QT>
+__global__ void __launch_bounds__(kGemvThreads) gemv_topk_kernel(GemvArgs a) {
+  constexpr int VEC = Elem<T>::VEC;
+  constexpr int V = RB * (QT + 1);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int nvec = a.D / VEC;
+  const int dpad = nvec * VEC;
+  GemvSmem<QT> sm(smem_raw, dpad);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const T* cat = static_cast<const T*>(a.cat);
+  const int nq = min(QT, a.Q - a.q0);
+
+  stage_queries<T, QT>(a, sm.qs, dpad, nq, warp, lane);
   if (tid < QT) {
-    ncand[tid] = 0;
-    tau[tid] = -INFINITY;
+    sm.ncand[tid] = 0;
+    sm.tau[tid] = -INFINITY;
   }
   __syncthreads();
 
@@ -89,107 +386,139 @@ __global__ void __launch_bounds__(kGemvThreads) gemv_topk_kernel(GemvArgs a) {
       float acc[V];
 #pragma unroll
       for (int i = 0; i < V; ++i) acc[i] = 0.f;
-
       for (int vb = 0; vb < nvec; vb += 32 * kGemvUnroll) {
-        uint4 c[RB][kGemvUnroll];
+        uint4 c[kGemvUnroll][RB];
 #pragma unroll
         for (int u = 0; u < kGemvUnroll; ++u) {
           const int v = vb + u * 32 + lane;
 #pragma unroll
           for (int r = 0; r < RB; ++r) {
-            if (v < nvec && r0 + r < blk_end)
-              c[r][u] = ldg_stream(cat + (r0 + r) * a.ldc + static_cast<int64_t>(v) * VEC);
-            else
-              c[r][u] = make_uint4(0, 0, 0, 0);
+            if (v < nvec && r0 + r < blk_end) c[u][r] = ldg_stream(cat + (r0 + r) * a.ldc + static_cast<int64_t>(v) * VEC);
+            else c[u][r] = make_uint4(0, 0, 0, 0);
           }
         }
 #pragma unroll
         for (int u = 0; u < kGemvUnroll; ++u) {
           const int v = vb + u * 32 + lane;
-          if (v < nvec) {
-            float qv[QT][VEC];
-#pragma unroll
-            for (int t = 0; t < QT; ++t) {
-#pragma unroll
-              for (int h = 0; h < VEC / 4; ++h) {
-                const float4 x = *reinterpret_cast<const float4*>(qs + t * dpad + v * VEC + h * 4);
-                qv[t][h * 4 + 0] = x.x;
-                qv[t][h * 4 + 1] = x.y;
-                qv[t][h * 4 + 2] = x.z;
-                qv[t][h * 4 + 3] = x.w;
-              }
-            }
-#pragma unroll
-            for (int r = 0; r < RB; ++r) {
-              float f[VEC];
-              Elem<T>::unpack(c[r][u], f);
-#pragma unroll
-              for (int t = 0; t < QT; ++t) {
-#pragma unroll
-                for (int i = 0; i < VEC; ++i) acc[t * RB + r] = fmaf(f[i], qv[t][i], acc[t * RB + r]);
-              }
-#pragma unroll
-              for (int i = 0; i < VEC; ++i) acc[QT * RB + r] = fmaf(f[i], f[i], acc[QT * RB + r]);
-            }
-          }
+          if (v < nvec) fma_vector<T, RB, QT>(c[u], sm.qs, dpad, v, acc);
         }
       }
-      // scalar tail of D (D not a multiple of VEC): cooperative, rare
-      if (dpad < a.D) {
-        // not reachable: the host requires D % VEC == 0
-      }
-
-      warp_transpose_reduce<V>(acc, lane);
-      const int idx = lane >> SH;          // value index owned by this lane
-      const int t = idx / RB, r = idx % RB;
-      // squared norm of row r lives in the lane group of index QT*RB + r
-      const float ss = __shfl_sync(kFull, acc[0], (QT * RB + r) << SH);
-      const int64_t row = r0 + r;
-      if (t < nq && (lane & ((1 << SH) - 1)) == 0 && row < blk_end) {
-        const bool excluded = a.mask && a.mask[row];
-        const float score = acc[0] * (1.0f / fmaxf(sqrtf(ss), kNormEps));
-        if (!excluded && score > tau[t]) {
-          const int pos = atomicAdd(&ncand[t], 1);
-          if (pos < kGemvCand) cand[t * kGemvCand + pos] = make_key(score, static_cast<uint32_t>(row));
-        }
-      }
+      reduce_and_append<RB, QT>(acc, a, sm, nq, r0, blk_end, lane);
     }
     __syncthreads();
-    // ---- threshold refresh: if a list could overflow during the next block, keep its k best ----
-    const bool last = (blk + kBlockRows >= row_end);
-    for (int t = 0; t < nq; ++t) {
-      const int n = min(ncand[t], kGemvCand);
-      if (last || n > kGemvCand - kBlockRows) {
-        uint64_t* keys = cand + t * kGemvCand;
-        const int P = next_pow2(n < 2 ? 2 : n);
-        for (int i = n + tid; i < P; i += kGemvThreads) keys[i] = 0ull;
-        block_bitonic_sort_desc(keys, P);
-        if (tid == 0) {
-          const int kept = min(n, a.k);
-          ncand[t] = kept;
-          tau[t] = (kept >= a.k) ? key_score(keys[a.k - 1]) : -INFINITY;
-        }
-        __syncthreads();
+    refresh_thresholds<QT, false>(a, sm, nq, blk + kBlockRows >= row_end, kBlockRows, tid);
+  }
+  emit_and_merge<QT, false>(a, sm, nq, row_begin < row_end, tid);
+}
+
+// =====================================================================================================
+// ring kernel: producer warp + bulk async copies into a shared-memory ring, 8 consumer warps
+// =====================================================================================================
+template <typename T, int QT>
+__global__ void __launch_bounds__(kRingThreads, 1) gemv_ring_kernel(GemvArgs a) {
+  constexpr int VEC = Elem<T>::VEC;
+  constexpr int RB = (QT == 7) ? 4 : 8;  // rows reduced together (V = RB * (QT + 1) <= 32)
+  constexpr int V = RB * (QT + 1);
+  extern __shared__ __align__(128) unsigned char ring_smem_raw[];
+  const int nvec = a.D / VEC;
+  const int dpad = nvec * VEC;
+  const int row_bytes = a.D * static_cast<int>(sizeof(T));
+  const int slot_bytes = kSlabRows * row_bytes;
+  const int NS = a.ring_slots;
+  unsigned char* ring = ring_smem_raw;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + static_cast<size_t>(NS) * slot_bytes);
+  uint64_t* empty_bar = full_bar + kMaxSlots;
+  GemvSmem<QT> sm(reinterpret_cast<unsigned char*>(empty_bar + kMaxSlots), dpad);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nq = min(QT, a.Q - a.q0);
+  const int64_t row_begin = static_cast<int64_t>(blockIdx.x) * a.rows_per_cta;
+  const int64_t row_end = min(a.N, row_begin + a.rows_per_cta);
+  const int nb = row_begin < row_end ? static_cast<int>((row_end - row_begin + kSlabRows - 1) / kSlabRows) : 0;
+
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&full_bar[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&empty_bar[s]), 1);
+    }
+    ptx::mbar_fence_init();
+  }
+  __syncthreads();  // the only CTA-wide barrier: the producer warp never joins another one
+
+  if (warp == kGemvWarps) {
+    // ================= producer: the whole ring is in flight before the first FMA =================
+    if (lane == 0) {
+      const char* src = static_cast<const char*>(a.cat) + row_begin * row_bytes;
+      for (int b = 0; b < nb; ++b) {
+        const int slot = b % NS;
+        const uint32_t parity = static_cast<uint32_t>(b / NS) & 1u;
+        ptx::mbar_wait(ptx::smem_u32(&empty_bar[slot]), parity ^ 1u);
+        const int64_t r0 = row_begin + static_cast<int64_t>(b) * kSlabRows;
+        const int rows = static_cast<int>(min(static_cast<int64_t>(kSlabRows), row_end - r0));
+        const uint32_t bytes = static_cast<uint32_t>(rows) * row_bytes;
+        const uint32_t fb = ptx::smem_u32(&full_bar[slot]);
+        ptx::mbar_expect_tx(fb, bytes);
+        ptx::bulk_g2s(ptx::smem_u32(ring + static_cast<size_t>(slot) * slot_bytes), src + static_cast<int64_t>(b) * slot_bytes, bytes, fb);
       }
     }
+    return;
   }
 
-  // ---- emit this CTA's k best keys per query (sorted descending) -------------------------------
-  for (int t = 0; t < nq; ++t) {
-    const int n = (row_begin < row_end) ? ncand[t] : 0;
-    const int64_t slot = static_cast<int64_t>(a.q0 + t) * gridDim.x + blockIdx.x;
-    for (int i = tid; i < n; i += kGemvThreads) a.part_keys[slot * a.k + i] = cand[t * kGemvCand + i];
-    if (tid == 0) a.part_cnt[slot] = n;
+  // ================= consumers =================
+  stage_queries<T, QT>(a, sm.qs, dpad, nq, warp, lane);
+  if (tid < QT) {
+    sm.ncand[tid] = 0;
+    sm.tau[tid] = -INFINITY;
   }
+  compute_sync<true>();
+
+  const int iters = (nb + kGemvWarps - 1) / kGemvWarps;
+  constexpr int kItersPerRefresh = 4;
+  constexpr int kBlockRows = kItersPerRefresh * kGemvWarps * kSlabRows;
+  for (int it = 0; it < iters; ++it) {
+    const int b = it * kGemvWarps + warp;
+    if (b < nb) {
+      const int slot = b % NS;
+      const uint32_t parity = static_cast<uint32_t>(b / NS) & 1u;
+      ptx::mbar_wait(ptx::smem_u32(&full_bar[slot]), parity);
+      const unsigned char* slab = ring + static_cast<size_t>(slot) * slot_bytes;
+      const int64_t r0 = row_begin + static_cast<int64_t>(b) * kSlabRows;
+#pragma unroll
+      for (int g = 0; g < kSlabRows / RB; ++g) {
+        float acc[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[i] = 0.f;
+        for (int v = lane; v < nvec; v += 32) {
+          uint4 c[RB];
+#pragma unroll
+          for (int r = 0; r < RB; ++r) {
+            // rows past the end of the catalog were not copied: stale ring bytes, masked by row_limit below
+            c[r] = *reinterpret_cast<const uint4*>(slab + static_cast<size_t>(g * RB + r) * row_bytes + static_cast<size_t>(v) * 16);
+          }
+          fma_vector<T, RB, QT>(c, sm.qs, dpad, v, acc);
+        }
+        reduce_and_append<RB, QT>(acc, a, sm, nq, r0 + g * RB, row_end, lane);
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&empty_bar[slot]));
+    }
+    if ((it + 1) % kItersPerRefresh == 0 || it + 1 == iters) {
+      compute_sync<true>();
+      refresh_thresholds<QT, true>(a, sm, nq, it + 1 == iters, kBlockRows, tid);
+    }
+  }
+  if (iters == 0) {
+    compute_sync<true>();
+    refresh_thresholds<QT, true>(a, sm, nq, true, kBlockRows, tid);
+  }
+  emit_and_merge<QT, true>(a, sm, nq, row_begin < row_end, tid);
 }
 
-static size_t gemv_smem_bytes(int QT, int D) {
-  return static_cast<size_t>(QT) * kGemvCand * sizeof(uint64_t) + static_cast<size_t>(QT) * D * sizeof(float) + QT * 8 + 16;
-}
+// ---- host side --------------------------------------------------------------------------------------------
+constexpr size_t kSmemBudget = 227 * 1024 - 1024;
 
 template <typename T, int RB, int QT>
-static int launch_one(const GemvArgs& a, int grid, cudaStream_t st) {
-  const size_t smem = gemv_smem_bytes(QT, a.D);
+static int launch_direct(const GemvArgs& a, int grid, cudaStream_t st) {
+  const size_t smem = GemvSmem<QT>::bytes(a.D);
   static thread_local size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     ICR_CUDA_CHECK(cudaFuncSetAttribute(gemv_topk_kernel<T, RB, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -202,8 +531,52 @@ static int launch_one(const GemvArgs& a, int grid, cudaStream_t st) {
   return ICR_OK;
 }
 
+template <typename T, int QT>
+static int ring_slots_for(int D) {
+  const size_t fixed = GemvSmem<QT>::bytes(D) + 2 * kMaxSlots * sizeof(uint64_t) + 128;
+  const size_t slot = static_cast<size_t>(kSlabRows) * D * sizeof(T);
+  if (fixed + kGemvWarps * slot > kSmemBudget) return 0;
+  const size_t n = (kSmemBudget - fixed) / slot;
+  // A multiple of the consumer-warp count, so that every slot is only ever consumed by ONE warp (batch b goes to
+  // warp b % 8 and slot b % NS): a slot shared by two warps would let the later one wait on a phase parity that an
+  // mbarrier reports as already complete before the earlier phase has even been filled.
+  return n >= 2 * kGemvWarps ? 2 * kGemvWarps : kGemvWarps;
+}
+
+template <typename T, int QT>
+static int launch_ring(GemvArgs a, int grid, cudaStream_t st) {
+  a.ring_slots = ring_slots_for<T, QT>(a.D);
+  const size_t smem = static_cast<size_t>(a.ring_slots) * kSlabRows * a.D * sizeof(T) + 2 * kMaxSlots * sizeof(uint64_t) + GemvSmem<QT>::bytes(a.D) + 128;
+  static thread_local size_t configured = 0;
+  if (smem > configured) {
+    ICR_CUDA_CHECK(cudaFuncSetAttribute(gemv_ring_kernel<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    configured = smem;
+  }
+  profile_begin(kKernelGemv, 1, st);
+  gemv_ring_kernel<T, QT><<<grid, kRingThreads, smem, st>>>(a);
+  profile_end(st);
+  ICR_LAUNCH_CHECK();
+  return ICR_OK;
+}
+
+static bool g_force_direct = false;  // tuning / test hook, see icr_debug_set
+
+void gemv_force_direct(bool on) { g_force_direct = on; }
+
+// contiguous rows, 16-byte aligned slabs and a ring of at least 4 slots -> bulk-copy ring kernel
+static bool ring_ok(int64_t ldc, int D, int dtype, int qt) {
+  if (g_force_direct || ldc != D) return false;
+  int slots;
+  if (dtype == ICR_F32) slots = qt == 1 ? ring_slots_for<float, 1>(D) : (qt == 3 ? ring_slots_for<float, 3>(D) : ring_slots_for<float, 7>(D));
+  else slots = qt == 1 ? ring_slots_for<__nv_bfloat16, 1>(D) : (qt == 3 ? ring_slots_for<__nv_bfloat16, 3>(D) : ring_slots_for<__nv_bfloat16, 7>(D));
+  // measured at C1 size: with one slot per warp (no load/compute overlap inside a warp) the ring still wins for
+  // 1-3 queries per pass but loses to the direct kernel for 4-7, whose FMA work per slab is larger
+  return qt == 7 ? slots >= 2 * kGemvWarps : slots >= kGemvWarps;
+}
+
 int gemv_grid(int64_t N) {
-  // 2 CTAs per SM when the catalog is large enough to give each CTA >= 64 rows
+  // one CTA per SM for the ring kernel, two for the direct kernel; at least 64 rows per CTA. The workspace is
+  // sized for the larger of the two.
   int64_t g = (N + 63) / 64;
   if (g > 148 * 2) g = 148 * 2;
   if (g < 1) g = 1;
@@ -212,7 +585,8 @@ int gemv_grid(int64_t N) {
 
 // Runs ceil(Q/7) passes (one for Q <= 7). part_keys/part_cnt sized [Q][grid][k] / [Q][grid].
 int launch_gemv_topk(const void* cat, int64_t N, int64_t ldc, int D, int dtype, const void* q, int64_t ldq, int Q,
-                     const uint8_t* mask, int k, uint64_t* part_keys, int* part_cnt, int grid, cudaStream_t st) {
+                     const uint8_t* mask, int k, uint64_t* part_keys, int* part_cnt, int grid, float* out_scores, int64_t* out_ids,
+                     int64_t id_offset, unsigned int* done_counter, cudaStream_t st) {
   GemvArgs a{};
   a.cat = cat;
   a.N = N;
@@ -223,23 +597,32 @@ int launch_gemv_topk(const void* cat, int64_t N, int64_t ldc, int D, int dtype, 
   a.Q = Q;
   a.mask = mask;
   a.k = k;
-  a.rows_per_cta = (N + grid - 1) / grid;
   a.part_keys = part_keys;
   a.part_cnt = part_cnt;
+  a.out_scores = out_scores;
+  a.out_ids = out_ids;
+  a.id_offset = id_offset;
+  a.done_counter = done_counter;
   for (int q0 = 0; q0 < Q;) {
     a.q0 = q0;
     const int rem = Q - q0;
+    const int qt = rem == 1 ? 1 : (rem <= 3 ? 3 : 7);
+    const bool ring = ring_ok(ldc, D, dtype, qt);
+    // the ring kernel owns a whole SM (its ring is the SM's shared memory): one CTA per SM
+    const int g = ring ? (grid < 148 ? grid : 148) : grid;
+    a.rows_per_cta = (N + g - 1) / g;
     int rc;
     if (dtype == ICR_F32) {
-      if (rem == 1) rc = launch_one<float, 8, 1>(a, grid, st), q0 += 1;
-      else if (rem <= 3) rc = launch_one<float, 8, 3>(a, grid, st), q0 += 3;
-      else rc = launch_one<float, 4, 7>(a, grid, st), q0 += 7;
+      if (qt == 1) rc = ring ? launch_ring<float, 1>(a, g, st) : launch_direct<float, 8, 1>(a, g, st);
+      else if (qt == 3) rc = ring ? launch_ring<float, 3>(a, g, st) : launch_direct<float, 8, 3>(a, g, st);
+      else rc = ring ? launch_ring<float, 7>(a, g, st) : launch_direct<float, 4, 7>(a, g, st);
     } else {
-      if (rem == 1) rc = launch_one<__nv_bfloat16, 8, 1>(a, grid, st), q0 += 1;
-      else if (rem <= 3) rc = launch_one<__nv_bfloat16, 8, 3>(a, grid, st), q0 += 3;
-      else rc = launch_one<__nv_bfloat16, 4, 7>(a, grid, st), q0 += 7;
+      if (qt == 1) rc = ring ? launch_ring<__nv_bfloat16, 1>(a, g, st) : launch_direct<__nv_bfloat16, 8, 1>(a, g, st);
+      else if (qt == 3) rc = ring ? launch_ring<__nv_bfloat16, 3>(a, g, st) : launch_direct<__nv_bfloat16, 8, 3>(a, g, st);
+      else rc = ring ? launch_ring<__nv_bfloat16, 7>(a, g, st) : launch_direct<__nv_bfloat16, 4, 7>(a, g, st);
     }
     if (rc != ICR_OK) return rc;
+    q0 += qt;
   }
   return ICR_OK;
 }

@@ -279,6 +279,31 @@ def test_mnrl_known_answers_and_module_interface():
     assert abs(loss.item() - ref.item()) < 1e-4 and tower.lin.weight.grad is not None
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("Q,k", [(1, 10), (1, 100), (2, 32), (5, 200), (7, 10)])
+def test_gemv_row_strided_catalog_and_in_kernel_merge(dtype, Q, k):
+    """Row-strided catalogs take the direct-load GEMV kernel, contiguous ones the bulk-copy ring kernel; both end
+    with the in-kernel merge (rank counting for <=1024 candidates, streaming fallback beyond)."""
+    N, D = 30011, 384
+    items, _ = oracle.synth_clustered(N, D, seed=41)
+    queries, _ = oracle.synth_queries_from_items(items, Q, seed=42)
+    wide = torch.zeros(N, D + 16, dtype=dtype, device="cuda")
+    wide[:, :D] = items.to(dtype).cuda()
+    strided = wide[:, :D]
+    assert strided.stride(0) == D + 16
+    rv, ri = oracle.cos_topk(queries.to(dtype).float(), items.to(dtype).float(), k)
+    tol = F32_RTOL if dtype == torch.float32 else BF16_RTOL
+    for cat in (strided, strided.contiguous()):
+        v, i = ops.cos_topk(queries.to(dtype).cuda(), cat, k, path=ops.PATH_GEMV)
+        _check_topk(v, i, rv, ri, tol)
+    # many equal scores (k > 32 with heavy ties): exercises the merge's overflow fallback
+    dup = items[torch.arange(N) % 50].to(dtype).cuda()
+    v, i = ops.cos_topk(queries[:1].to(dtype).cuda(), dup, 256, path=ops.PATH_GEMV)
+    rv, ri = oracle.cos_topk(queries[:1].to(dtype).float(), dup.float().cpu(), 256)
+    err, _ = oracle.compare_topk(v.cpu(), i.cpu(), rv, ri, rtol=tol)
+    assert err <= tol and len(set(i[0].tolist())) == 256
+
+
 def test_topk_small_cuda_graph_equals_plain_call():
     items, _ = oracle.synth_clustered(20000, 384, seed=31)
     queries, _ = oracle.synth_queries_from_items(items, 6, seed=32)
