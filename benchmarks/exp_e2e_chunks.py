@@ -1,0 +1,22 @@
+"""Experiment: host-to-host top-k (C2) vs number of pipeline chunks."""
+import sys, torch
+sys.path.insert(0, ".")
+import instacart_next_order_recommendation_b200 as icr
+Q, N, D, k = 10000, 49688, 384, 100
+g = torch.Generator(device="cuda").manual_seed(0)
+items = torch.nn.functional.normalize(torch.randn(N, D, device="cuda", generator=g), dim=1)
+cat = icr.DeviceCatalog(items)
+qh = torch.nn.functional.normalize(torch.randn(Q, D, generator=torch.Generator().manual_seed(1)), dim=1).pin_memory()
+ov = torch.empty(Q, k).pin_memory(); oi = torch.empty(Q, k, dtype=torch.int64).pin_memory()
+flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+for nch in (1, 2, 3, 4, 6, 8):
+    for _ in range(3): cat.topk_host(qh, k, out=(ov, oi), n_chunks=nch)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(10):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); cat.topk_host(qh, k, out=(ov, oi), n_chunks=nch); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    print(f"n_chunks={nch}: median {ts[5]:.3f} ms  min {ts[0]:.3f} ms  -> {Q / ts[5] / 1e3:.2f} M q/s", flush=True)

@@ -70,6 +70,14 @@ int launch_gemm_topk(const void* queries, int64_t Q, int64_t ldq, const void* ca
                      int dtype, const uint16_t* cat_planes, const float* cat_inv_norms, const uint8_t* mask, int k, int64_t row_offset,
                      float* out_scores, int64_t* out_ids, void* ws, size_t ws_bytes, cudaStream_t st);
 bool gemm_topk_supported(int64_t Q, int64_t N, int64_t D, int dtype, int k, const uint8_t* mask);
+size_t gemm_dense_workspace_bytes(int64_t Qa, int64_t Nb, int64_t D, int dtype);
+int launch_gemm_dense(const void* a, int64_t Qa, int64_t lda, const void* b, int64_t Nb, int64_t ldb, int64_t D, int dtype, float* out,
+                      int64_t ldo, void* ws, size_t ws_bytes, cudaStream_t st);
+// the tensor-core dense path pays off once there is a tile's worth of work; below that the CUDA-core kernel wins
+static bool dense_use_gemm(int64_t Qa, int64_t Nb, int64_t D, int dtype) {
+  if (dtype == ICR_BF16 && D % 8 != 0) return false;
+  return Qa >= 64 && Nb >= 1024;
+}
 
 int launch_mnrl_dispatch(const MnrlArgs& g, int dtype, bool bwd, cudaStream_t st);
 
@@ -286,8 +294,7 @@ int icr_cos_topk(const void* queries, int64_t Q, int64_t ldq, const void* catalo
 }
 
 size_t icr_cos_sim_dense_workspace_bytes(int64_t Qa, int64_t Nb, int64_t D, int dtype) {
-  (void)D;
-  (void)dtype;
+  if (Qa > 0 && Nb > 0 && dense_use_gemm(Qa, Nb, D, dtype)) return gemm_dense_workspace_bytes(Qa, Nb, D, dtype) + 1024;
   return align_up(static_cast<size_t>(Qa > 0 ? Qa : 0) * 4, 256) + align_up(static_cast<size_t>(Nb > 0 ? Nb : 0) * 4, 256) + 256;
 }
 
@@ -309,6 +316,7 @@ int icr_cos_sim_dense(const void* a, int64_t Qa, int64_t lda, const void* b, int
     return ICR_ERR_WORKSPACE;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dense_use_gemm(Qa, Nb, D, dtype)) return launch_gemm_dense(a, Qa, lda, b, Nb, ldb, D, dtype, out, ldo, workspace, workspace_bytes, st);
   float* inva = static_cast<float*>(workspace);
   float* invb = reinterpret_cast<float*>(static_cast<char*>(workspace) + align_up(static_cast<size_t>(Qa) * 4, 256));
   if ((rc = launch_row_inv_norms(a, Qa, D, lda, dtype, inva, st))) return rc;

@@ -75,6 +75,8 @@ struct GemmArgs {
   uint64_t* cand;            // [Q][chunks * 2][seg_cap]   (segment = query x chunk x column half)
   int* cand_cnt;             // [Q][chunks * 2]
   int seg_cap;
+  float* dense_out;          // K2' mode: write every score to dense_out[q * dense_ld + row] instead of filtering
+  int64_t dense_ld;
   uint64_t* compact_scratch; // [gridDim.x][kEpiWarps][kSegCapMax] global scratch of the (rare) in-kernel compaction
 };
 
@@ -286,11 +288,28 @@ __device__ __forceinline__ void filter32(const uint32_t (&r)[32], SegState& s, c
   }
 }
 
+// K2' (dense cos_sim): same main loop, the epilogue scales and stores all 32 scores of a batch to this query's row.
+template <bool BF16>
+__device__ __forceinline__ void dense_store32(const uint32_t (&r)[32], float* out_row, float qscale, const float* cinv32, int ncols,
+                                              bool vec_ok) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = BF16 ? __uint_as_float(r[j]) * qscale * cinv32[j] : __uint_as_float(r[j]) * qscale;
+  if (ncols >= 32 && vec_ok) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(out_row + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < ncols) out_row[j] = v[j];
+  }
+}
+
 // TERMS = 3: fp16 hi/lo planes (fp32 parity); TERMS = 1: raw bf16 rows.
 // ASTAT (bf16, D <= 384): the work item's 128 query rows stay resident in shared memory for all of its catalog
 // tiles ("A-stationary"), so the ring streams catalog tiles only: 31 instead of 62 B/cycle/SM of L2 traffic,
 // which is the difference between L2-bound and tensor-bound for one-term MMAs (profiles/r01_notes.md).
-template <int TERMS, bool ASTAT>
+template <int TERMS, bool ASTAT, bool DENSE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmArgs g) {
   static_assert(!ASTAT || TERMS == 1, "A-stationary is the bf16 variant");
@@ -469,7 +488,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       SegState s;
       s.seg = g.cand + seg_index * cap;
       s.cnt = 0;
-      s.tau_ob = live ? order_bits(g.tau[q]) : 0xFFFFFFFFu;
+      constexpr bool dense = DENSE;  // compile-time: the top-k instantiation keeps its register budget
+      s.tau_ob = (live && !dense) ? order_bits(g.tau[q]) : 0xFFFFFFFFu;
+      float* out_q = dense ? g.dense_out + static_cast<int64_t>(live ? q : 0) * g.dense_ld : nullptr;
+      const float qscale = dense ? g.acc_scale * ((BF16 && live) ? g.qinv[q] : 1.0f) : 0.f;
+      const bool vec_ok = dense && (g.dense_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.dense_out) & 15) == 0);
       for (int tile = t0; tile < t1; ++tile) {
         const int row0 = tile * BN + half * kEpiCols;
         if (BF16) {
@@ -489,12 +512,20 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           // the next 32 columns are in flight while the current 32 are filtered
           tmem_ld_wait(ra);
           tmem_ld32(taddr + (cb + 1) * 32, rb);
-          compact_full_segments(s, scratch, cap, g.k, lane);
-          filter32<BF16>(ra, s, cinv_s + cb * 32, row0 + cb * 32, fast, g.N, g.mask);
+          if (dense) {
+            if (live) dense_store32<BF16>(ra, out_q + row0 + cb * 32, qscale, cinv_s + cb * 32, g.N - (row0 + cb * 32), vec_ok);
+          } else {
+            compact_full_segments(s, scratch, cap, g.k, lane);
+            filter32<BF16>(ra, s, cinv_s + cb * 32, row0 + cb * 32, fast, g.N, g.mask);
+          }
           tmem_ld_wait(rb);
           if (cb + 2 < kEpiCols / 32) tmem_ld32(taddr + (cb + 2) * 32, ra);
-          compact_full_segments(s, scratch, cap, g.k, lane);
-          filter32<BF16>(rb, s, cinv_s + (cb + 1) * 32, row0 + (cb + 1) * 32, fast, g.N, g.mask);
+          if (dense) {
+            if (live) dense_store32<BF16>(rb, out_q + row0 + (cb + 1) * 32, qscale, cinv_s + (cb + 1) * 32, g.N - (row0 + (cb + 1) * 32), vec_ok);
+          } else {
+            compact_full_segments(s, scratch, cap, g.k, lane);
+            filter32<BF16>(rb, s, cinv_s + (cb + 1) * 32, row0 + (cb + 1) * 32, fast, g.N, g.mask);
+          }
         }
         tc_fence_before();
         __syncwarp();
@@ -504,7 +535,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           acc_phase ^= 1;
         }
       }
-      if (live) g.cand_cnt[seg_index] = s.cnt;
+      if (live && !dense) g.cand_cnt[seg_index] = s.cnt;
     }
   }
 
@@ -741,9 +772,9 @@ int launch_gemm_topk(const void* queries, int64_t Q, int64_t ldq, const void* ca
   const int which = terms == 3 ? 0 : (g.kb_per_term <= kAStatMaxKB ? 2 : 1);
   if (!attr_set[which]) {
     const int smem = static_cast<int>(kGemmSmemBytes);
-    if (which == 0) ICR_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    if (which == 1) ICR_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    if (which == 2) ICR_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (which == 0) ICR_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_kernel<3, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (which == 1) ICR_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_kernel<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (which == 2) ICR_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_kernel<1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set[which] = true;
   }
   // tau starts at -inf: phase 0 admits every row
@@ -760,9 +791,9 @@ int launch_gemm_topk(const void* queries, int64_t Q, int64_t ldq, const void* ca
     const int pairs = items < kNumSMs / 2 ? items : kNumSMs / 2;
     const int grid = 2 * pairs;  // whole CTA pairs (cluster dims 2x1x1)
     profile_begin(kKernelGemm, terms, st);
-    if (which == 0) gemm_topk_kernel<3, false><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(map_a, map_b, g);
-    if (which == 1) gemm_topk_kernel<1, false><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(map_a, map_b, g);
-    if (which == 2) gemm_topk_kernel<1, true><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(map_a, map_b, g);
+    if (which == 0) gemm_topk_kernel<3, false, false><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(map_a, map_b, g);
+    if (which == 1) gemm_topk_kernel<1, false, false><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(map_a, map_b, g);
+    if (which == 2) gemm_topk_kernel<1, true, false><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(map_a, map_b, g);
     profile_end(st);
     ICR_LAUNCH_CHECK();
     const bool last = (p == np - 1);
@@ -776,6 +807,87 @@ int launch_gemm_topk(const void* queries, int64_t Q, int64_t ldq, const void* ca
                             k, g.acc_scale, g.qinv, st);  // raw key scores -> cosines on the way out
     if (rc) return rc;
   }
+  return ICR_OK;
+}
+
+// ---- K2': dense cosine similarity out[q][n] on the same tensor-core main loop -----------------------------
+size_t gemm_dense_workspace_bytes(int64_t Qa, int64_t Nb, int64_t D, int dtype) {
+  const int64_t dp2 = 2 * ((D + 63) / 64 * 64);
+  size_t b = 4096;
+  if (dtype == ICR_F32) b += align_up(static_cast<size_t>(Qa) * dp2 * 2, 1024) + align_up(static_cast<size_t>(Nb) * dp2 * 2, 1024);
+  else b += align_up(static_cast<size_t>(Qa) * 4, 1024) + align_up(static_cast<size_t>(Nb) * 4, 1024);
+  return b;
+}
+
+int launch_gemm_dense(const void* a, int64_t Qa, int64_t lda, const void* b, int64_t Nb, int64_t ldb, int64_t D, int dtype, float* out,
+                      int64_t ldo, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (ws_bytes < gemm_dense_workspace_bytes(Qa, Nb, D, dtype)) {
+    set_error("gemm_dense: workspace too small");
+    return ICR_ERR_WORKSPACE;
+  }
+  char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~static_cast<uintptr_t>(1023));
+  const int64_t dp = (D + 63) / 64 * 64;
+  const int qblocks = static_cast<int>((Qa + 2 * BM - 1) / (2 * BM));
+  const int tiles = static_cast<int>((Nb + BN - 1) / BN);
+  int rc;
+  GemmArgs g{};
+  g.Q = static_cast<int>(Qa);
+  g.N = static_cast<int>(Nb);
+  g.k = 1;
+  g.qblocks = qblocks;
+  g.seg_cap = 256;
+  g.dense_out = out;
+  g.dense_ld = ldo;
+  g.tile_begin = 0;
+  g.tile_end = tiles;
+  CUtensorMap map_a, map_b;
+  int which;
+  if (dtype == ICR_F32) {
+    uint16_t* ap = reinterpret_cast<uint16_t*>(base);
+    uint16_t* bp = reinterpret_cast<uint16_t*>(base + align_up(static_cast<size_t>(Qa) * 2 * dp * 2, 1024));
+    if ((rc = launch_split_planes(static_cast<const float*>(a), Qa, D, lda, ap, st))) return rc;
+    if ((rc = launch_split_planes(static_cast<const float*>(b), Nb, D, ldb, bp, st))) return rc;
+    if ((rc = make_map(&map_a, ap, Qa, 2 * dp, 2 * dp, false))) return rc;
+    if ((rc = make_map(&map_b, bp, Nb, 2 * dp, 2 * dp, false))) return rc;
+    g.kb_per_term = static_cast<int>(dp / BK);
+    g.plane_stride = static_cast<int>(dp);
+    g.acc_scale = 1.0f / 65536.0f;
+    which = 0;
+  } else {
+    float* qinv = reinterpret_cast<float*>(base);
+    float* cinv = reinterpret_cast<float*>(base + align_up(static_cast<size_t>(Qa) * 4, 1024));
+    if ((rc = launch_row_inv_norms(a, Qa, D, lda, dtype, qinv, st))) return rc;
+    if ((rc = launch_row_inv_norms(b, Nb, D, ldb, dtype, cinv, st))) return rc;
+    if ((rc = make_map(&map_a, a, Qa, D, lda, true))) return rc;
+    if ((rc = make_map(&map_b, b, Nb, D, ldb, true))) return rc;
+    g.kb_per_term = static_cast<int>((D + BK - 1) / BK);
+    g.acc_scale = 1.0f;
+    g.qinv = qinv;
+    g.cinv = cinv;
+    which = g.kb_per_term <= kAStatMaxKB ? 2 : 1;
+  }
+  // work items: (query block, chunk of tiles); enough chunks to fill the pairs a few times over
+  const int npairs = kNumSMs / 2;
+  int chunks = (3 * npairs + qblocks - 1) / qblocks;
+  if (chunks > tiles) chunks = tiles;
+  if (chunks < 1) chunks = 1;
+  g.chunks = chunks;
+  static thread_local bool attr_set[3] = {false, false, false};
+  if (!attr_set[which]) {
+    const int smem = static_cast<int>(kGemmSmemBytes);
+    if (which == 0) ICR_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_kernel<3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (which == 1) ICR_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_kernel<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (which == 2) ICR_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_kernel<1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set[which] = true;
+  }
+  const int items = qblocks * chunks;
+  const int grid = 2 * (items < npairs ? items : npairs);
+  profile_begin(kKernelGemm, which == 0 ? 3 : 1, st);
+  if (which == 0) gemm_topk_kernel<3, false, true><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(map_a, map_b, g);
+  if (which == 1) gemm_topk_kernel<1, false, true><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(map_a, map_b, g);
+  if (which == 2) gemm_topk_kernel<1, true, true><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(map_a, map_b, g);
+  profile_end(st);
+  ICR_LAUNCH_CHECK();
   return ICR_OK;
 }
 

@@ -181,7 +181,7 @@ class DeviceCatalog:
         return (vals.clone(), ids.clone()) if copy else (vals, ids)
 
     def topk_host(self, queries: torch.Tensor, k: int, *, out: tuple[torch.Tensor, torch.Tensor] | None = None,
-                  n_chunks: int = 4, path: int = ops.PATH_AUTO):
+                  n_chunks: int = 2, path: int = ops.PATH_AUTO):
         """Host-to-host top-k: CPU query matrix in, CPU (values [Q,k] f32, ids [Q,k] i64) out.
 
         The batch is cut into `n_chunks` pieces that go round-robin over two side streams, each doing

@@ -138,6 +138,20 @@ def test_dense_cos_sim_vs_oracle():
     assert (icr.cos_sim(a[0], a[1]).cpu() - oracle.cos_sim(a[0], a[1])).abs().max() < 1e-6
 
 
+@pytest.mark.parametrize("Qa,Nb,D", [(300, 5000, 384), (257, 5001, 384), (1000, 3000, 768), (64, 1024, 100)])
+def test_dense_cos_sim_tensor_core_path(Qa, Nb, D):
+    """Large enough for the tcgen05 dense epilogue (K2'): fp32 keeps 1e-5 through the fp16 hi/lo planes."""
+    a = oracle.synth_unnormalised(Qa, D, seed=13)
+    b = oracle.synth_unnormalised(Nb, D, seed=14)
+    got = icr.cos_sim(a.cuda(), b.cuda()).cpu()
+    ref = oracle.cos_sim(a, b)
+    assert got.shape == ref.shape
+    assert (got - ref).abs().max() <= 1e-5
+    got = icr.cos_sim(a.bfloat16().cuda(), b.bfloat16().cuda()).cpu()
+    ref = oracle.cos_sim(a.bfloat16().float(), b.bfloat16().float())
+    assert (got - ref).abs().max() <= 1e-5
+
+
 def test_exclusion_mask_and_row_offset():
     items, _ = oracle.synth_clustered(8000, 384, seed=5)
     queries, _ = oracle.synth_queries_from_items(items, 2, seed=6)
