@@ -152,6 +152,61 @@ def test_dense_cos_sim_tensor_core_path(Qa, Nb, D):
     assert (got - ref).abs().max() <= 1e-5
 
 
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_edge_shapes(path, dtype):
+    """Tiny / ragged problems through the C ABI: k > N pads with (-inf, -1), single rows, zero vectors, odd D,
+    query counts that straddle the internal chunking, empty query batches."""
+    tol = F32_RTOL if dtype == torch.float32 else BF16_RTOL
+    g = torch.Generator().manual_seed(77)
+    # k larger than the catalog: the ABI pads, the drop-in clamps
+    c = torch.randn(5, 64, generator=g).to(dtype)
+    q = torch.randn(3, 64, generator=g).to(dtype)
+    v, i = ops.cos_topk(q.cuda(), c.cuda(), 9, path=path)
+    rv, ri = oracle.cos_topk(q.float(), c.float(), 5)
+    assert (i[:, 5:] == -1).all() and torch.isinf(v[:, 5:]).all() and (v[:, 5:] < 0).all()
+    _check_topk(v[:, :5], i[:, :5], rv, ri, tol)
+    v, i = icr.cos_topk(q.cuda(), c.cuda(), 9, path=path)
+    assert v.shape == (3, 5)
+    # one row, one query
+    v, i = ops.cos_topk(q[:1].cuda(), c[:1].cuda(), 1, path=path)
+    assert i.tolist() == [[0]] and abs(v.item() - oracle.cos_sim(q[:1].float(), c[:1].float()).item()) < 1e-3
+    # zero rows in the catalog and a zero query score 0, never NaN
+    c2 = torch.randn(300, 72, generator=g)
+    c2[::7] = 0
+    q2 = torch.randn(4, 72, generator=g)
+    q2[1] = 0
+    v, i = ops.cos_topk(q2.to(dtype).cuda(), c2.to(dtype).cuda(), 20, path=path)
+    assert torch.isfinite(v).all() and (v[1] == 0).all()
+    rv, ri = oracle.cos_topk(q2.to(dtype).float(), c2.to(dtype).float(), 20)
+    err, _ = oracle.compare_topk(v.cpu(), i.cpu(), rv, ri, rtol=tol)
+    assert err <= tol
+    # embedding dim that is not a multiple of 64 (K tail of the tensor path), query count across chunk boundaries
+    items, _ = oracle.synth_clustered(4100, 200, seed=78, n_centres=9)
+    nq = 259 if path == ops.PATH_GEMV else 513
+    queries, _ = oracle.synth_queries_from_items(items, nq, seed=79)
+    v, i = ops.cos_topk(queries.to(dtype).cuda(), items.to(dtype).cuda(), 12, path=path)
+    rv, ri = oracle.cos_topk(queries.to(dtype).float(), items.to(dtype).float(), 12)
+    _check_topk(v, i, rv, ri, tol)
+    # empty query batch
+    v, i = ops.cos_topk(queries[:0].to(dtype).cuda(), items.to(dtype).cuda(), 12, path=path)
+    assert v.shape == (0, 12) and i.shape == (0, 12)
+
+
+def test_gemm_path_honours_exclusion_mask():
+    items, _ = oracle.synth_clustered(6000, 128, seed=80)
+    queries, _ = oracle.synth_queries_from_items(items, 140, seed=81)
+    rv, ri = oracle.cos_topk(queries, items, 30)
+    mask = torch.zeros(6000, dtype=torch.bool)
+    mask[ri[:, :10].reshape(-1)] = True  # ban every query's ten best rows
+    v, i = ops.cos_topk(queries.cuda(), items.cuda(), 15, exclude_mask=mask.cuda(), path=ops.PATH_GEMM)
+    assert not mask[i.cpu()].any()
+    sims = oracle.cos_sim(queries, items)
+    sims[:, mask] = float("-inf")
+    wv, wi = torch.topk(sims, 15, dim=1)
+    _check_topk(v, i, wv, wi, F32_RTOL)
+
+
 def test_exclusion_mask_and_row_offset():
     items, _ = oracle.synth_clustered(8000, 384, seed=5)
     queries, _ = oracle.synth_queries_from_items(items, 2, seed=6)
