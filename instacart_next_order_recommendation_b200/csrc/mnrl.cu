@@ -117,23 +117,49 @@ __global__ void __launch_bounds__(kMnrlThreads) mnrl_kernel(MnrlArgs g) {
     for (int r = 0; r < TM; ++r) tile_lse[r] = (tile_is_anchor && row0 + r < B) ? g.lse[row0 + r] : 0.f;
   }
 
-  for (int j = warp; j < B; j += kMnrlWarps) {
-    float y[EPL];
-    load_slice<T, NCV>(Y + static_cast<int64_t>(j) * ldy, nvec, lane, y);
-    float yinv;
-    if (MODE == 0) {
-      float ss = 0.f;
+  // JB stream rows per iteration: their loads, dot products and warp reductions are independent chains, so one
+  // warp keeps several L2 round trips and shuffle trees in flight instead of paying each latency in turn
+  constexpr int JB = EPL <= 16 ? 4 : 2;
+  for (int j0 = warp * JB; j0 < B; j0 += kMnrlWarps * JB) {
+    float y[JB][EPL];
+    float yinv[JB], stream_lse[JB];
 #pragma unroll
-      for (int i = 0; i < EPL; ++i) ss = fmaf(y[i], y[i], ss);
-      ss = warp_sum(ss);
-      yinv = 1.0f / fmaxf(sqrtf(ss), kNormEps);
-      if (blockIdx.x == 0 && lane == 0) g.inv_p[j] = yinv;
-    } else {
-      yinv = tile_is_anchor ? g.inv_p[j] : g.inv_a[j];
+    for (int b = 0; b < JB; ++b) {
+      const int j = j0 + b;
+      if (j < B) {
+        load_slice<T, NCV>(Y + static_cast<int64_t>(j) * ldy, nvec, lane, y[b]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) y[b][i] = 0.f;
+      }
+      yinv[b] = 0.f;
+      stream_lse[b] = 0.f;
+      if (MODE == 1 && j < B) {
+        yinv[b] = tile_is_anchor ? g.inv_p[j] : g.inv_a[j];
+        stream_lse[b] = tile_is_anchor ? 0.f : g.lse[j];
+      }
     }
-    float dot[TM];
+    if (MODE == 0) {
+      float ss[JB];
 #pragma unroll
-    for (int r = 0; r < TM; ++r) dot[r] = 0.f;
+      for (int b = 0; b < JB; ++b) {
+        ss[b] = 0.f;
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) ss[b] = fmaf(y[b][i], y[b][i], ss[b]);
+      }
+#pragma unroll
+      for (int b = 0; b < JB; ++b) ss[b] = warp_sum(ss[b]);
+#pragma unroll
+      for (int b = 0; b < JB; ++b) {
+        yinv[b] = 1.0f / fmaxf(sqrtf(ss[b]), kNormEps);
+        if (blockIdx.x == 0 && lane == 0 && j0 + b < B) g.inv_p[j0 + b] = yinv[b];
+      }
+    }
+    float dot[JB][TM];
+#pragma unroll
+    for (int b = 0; b < JB; ++b)
+#pragma unroll
+      for (int r = 0; r < TM; ++r) dot[b][r] = 0.f;
 #pragma unroll
     for (int c = 0; c < NCV; ++c) {
 #pragma unroll
@@ -141,35 +167,44 @@ __global__ void __launch_bounds__(kMnrlThreads) mnrl_kernel(MnrlArgs g) {
 #pragma unroll
         for (int r = 0; r < TM; ++r) {
           const float4 xv = *reinterpret_cast<const float4*>(xt + r * dpad + (c * 32 + lane) * VEC + h * 4);
-          dot[r] = fmaf(xv.x, y[c * VEC + h * 4 + 0], dot[r]);
-          dot[r] = fmaf(xv.y, y[c * VEC + h * 4 + 1], dot[r]);
-          dot[r] = fmaf(xv.z, y[c * VEC + h * 4 + 2], dot[r]);
-          dot[r] = fmaf(xv.w, y[c * VEC + h * 4 + 3], dot[r]);
+#pragma unroll
+          for (int b = 0; b < JB; ++b) {
+            dot[b][r] = fmaf(xv.x, y[b][c * VEC + h * 4 + 0], dot[b][r]);
+            dot[b][r] = fmaf(xv.y, y[b][c * VEC + h * 4 + 1], dot[b][r]);
+            dot[b][r] = fmaf(xv.z, y[b][c * VEC + h * 4 + 2], dot[b][r]);
+            dot[b][r] = fmaf(xv.w, y[b][c * VEC + h * 4 + 3], dot[b][r]);
+          }
         }
       }
     }
 #pragma unroll
-    for (int r = 0; r < TM; ++r) dot[r] = warp_sum(dot[r]);
+    for (int b = 0; b < JB; ++b)
+#pragma unroll
+      for (int r = 0; r < TM; ++r) dot[b][r] = warp_sum(dot[b][r]);
 
-    if (MODE == 0) {
 #pragma unroll
-      for (int r = 0; r < TM; ++r) {
-        const float s = g.scale * dot[r] * yinv;
-        const float mn = fmaxf(m[r], s);
-        l[r] = l[r] * __expf(m[r] - mn) + __expf(s - mn);
-        m[r] = mn;
-        if (j == row0 + r) diag[r] = s;
-      }
-    } else {
-      const float stream_lse = tile_is_anchor ? 0.f : g.lse[j];
+    for (int b = 0; b < JB; ++b) {
+      const int j = j0 + b;
+      if (j >= B) continue;
+      if (MODE == 0) {
 #pragma unroll
-      for (int r = 0; r < TM; ++r) {
-        const float s = g.scale * dot[r] * yinv;
-        const float lse = tile_is_anchor ? tile_lse[r] : stream_lse;
-        float w = __expf(s - lse) - ((j == row0 + r) ? 1.f : 0.f);
-        w *= coef * yinv;  // d/d(x^_r) += w * y_j  (y^_j = y_j * yinv)
+        for (int r = 0; r < TM; ++r) {
+          const float s = g.scale * dot[b][r] * yinv[b];
+          const float mn = fmaxf(m[r], s);
+          l[r] = l[r] * __expf(m[r] - mn) + __expf(s - mn);
+          m[r] = mn;
+          if (j == row0 + r) diag[r] = s;
+        }
+      } else {
 #pragma unroll
-        for (int i = 0; i < EPL; ++i) acc[r][i] = fmaf(w, y[i], acc[r][i]);
+        for (int r = 0; r < TM; ++r) {
+          const float s = g.scale * dot[b][r] * yinv[b];
+          const float lse = tile_is_anchor ? tile_lse[r] : stream_lse[b];
+          float w = __expf(s - lse) - ((j == row0 + r) ? 1.f : 0.f);
+          w *= coef * yinv[b];  // d/d(x^_r) += w * y_j  (y^_j = y_j * yinv)
+#pragma unroll
+          for (int i = 0; i < EPL; ++i) acc[r][i] = fmaf(w, y[b][i], acc[r][i]);
+        }
       }
     }
   }

@@ -224,41 +224,53 @@ def topk_merge(cand_scores: torch.Tensor, cand_ids: torch.Tensor, k_out: int):
     return vals, ids
 
 
+def _fast_rows(t: torch.Tensor) -> torch.Tensor:
+    """_rows() without the checks' cost for the common case: contiguous, 16-byte aligned, D a multiple of 8."""
+    if t.dim() == 2 and t.is_contiguous() and t.shape[1] % 8 == 0 and t.data_ptr() % 16 == 0:
+        return t
+    return _rows(t)
+
+
 def mnrl_forward(anchors: torch.Tensor, positives: torch.Tensor, scale: float):
-    """Returns (loss f32 scalar tensor, saved=(lse, inv_a, inv_p))."""
+    """Returns (loss f32 scalar tensor, saved): saved[0:3B] = lse | inv_a | inv_p, the rest is kernel workspace."""
     _require_cuda("anchors", anchors)
     _require_cuda("positives", positives)
     if anchors.dtype != positives.dtype or anchors.shape != positives.shape:
         raise ValueError("anchors and positives must share dtype and shape [B, D]")
-    a, p = _rows(anchors), _rows(positives)
+    a, p = _fast_rows(anchors), _fast_rows(positives)
     B, D = a.shape
     dev = a.device
     lib = _lib.load()
     loss = torch.empty((), dtype=torch.float32, device=dev)
-    saved = torch.empty(3, B, dtype=torch.float32, device=dev)
+    off = (3 * B + 63) // 64 * 64  # workspace starts 256-byte aligned behind the three saved vectors
+    saved = torch.empty(off + B + 128, dtype=torch.float32, device=dev)
+    base = saved.data_ptr()
     with _on(dev):
-        ws = _workspace(lib.icr_mnrl_workspace_bytes(B, D), dev)
         _lib.check(
             lib.icr_mnrl_fwd(a.data_ptr(), _ld(a), p.data_ptr(), _ld(p), B, D, _dtype_code(a), float(scale), loss.data_ptr(),
-                             saved[0].data_ptr(), saved[1].data_ptr(), saved[2].data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev))
+                             base, base + 4 * B, base + 8 * B, base + 4 * off, 4 * (B + 128), _stream(dev))
         )
     return loss, saved
 
 
 def mnrl_backward(anchors: torch.Tensor, positives: torch.Tensor, scale: float, saved: torch.Tensor, grad_out: torch.Tensor):
-    a, p = _rows(anchors), _rows(positives)
+    a, p = _fast_rows(anchors), _fast_rows(positives)
     B, D = a.shape
     dev = a.device
     lib = _lib.load()
-    ga = torch.empty_like(a, memory_format=torch.contiguous_format)
-    gp = torch.empty_like(p, memory_format=torch.contiguous_format)
-    go = grad_out.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
+    grads = torch.empty(2, B, D, dtype=a.dtype, device=dev)
+    go = grad_out
+    if not (go.is_cuda and go.dtype == torch.float32 and go.is_contiguous()):
+        go = go.detach().to(device=dev, dtype=torch.float32).contiguous()
+    base = saved.data_ptr()
+    off = (3 * B + 63) // 64 * 64
+    gbytes = B * D * a.element_size()
     with _on(dev):
-        ws = _workspace(lib.icr_mnrl_workspace_bytes(B, D), dev)
         _lib.check(
-            lib.icr_mnrl_bwd(a.data_ptr(), _ld(a), p.data_ptr(), _ld(p), B, D, _dtype_code(a), float(scale), saved[0].data_ptr(),
-                             saved[1].data_ptr(), saved[2].data_ptr(), go.data_ptr(), ga.data_ptr(), D, gp.data_ptr(), D,
-                             ws.data_ptr(), ws.numel(), _stream(dev))
+            lib.icr_mnrl_bwd(a.data_ptr(), _ld(a), p.data_ptr(), _ld(p), B, D, _dtype_code(a), float(scale), base, base + 4 * B,
+                             base + 8 * B, go.data_ptr(), grads.data_ptr(), D, grads.data_ptr() + gbytes, D,
+                             base + 4 * off, 4 * (B + 128), _stream(dev))
         )
+    ga, gp = grads[0], grads[1]
     D0 = anchors.shape[1]
     return (ga[:, :D0], gp[:, :D0]) if D0 != D else (ga, gp)
