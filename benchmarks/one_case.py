@@ -15,6 +15,8 @@ CASES = {
     "c4q1": (1_250_000, 768, 1, 100, torch.bfloat16),
     "c5": (4_000_000, 384, 4096, 100, torch.bfloat16),
     "c2bf16": (49_688, 384, 10_000, 100, torch.bfloat16),
+    "c2": (49_688, 384, 10_000, 100, torch.float32),
+    "c1q4": (49_688, 384, 4, 10, torch.float32),
 }
 
 if __name__ == "__main__":

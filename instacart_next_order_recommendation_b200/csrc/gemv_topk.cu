@@ -24,12 +24,34 @@ namespace icr {
 
 constexpr int kGemvThreads = 256;  // compute threads of either kernel
 constexpr int kGemvWarps = kGemvThreads / 32;
-constexpr int kGemvCand = 1024;  // candidate keys per query held in shared memory
 constexpr int kGemvUnroll = 3;   // 16-byte vectors per lane per row kept in flight (direct-load kernel)
 constexpr int kMergeSel = 256;   // >= ICR_MAX_K: output buffer of the in-kernel merge
-constexpr int kSlabRows = 8;     // rows per ring slot
 constexpr int kMaxSlots = 16;
 constexpr int kRingThreads = kGemvThreads + 32;  // + the producer warp
+
+#ifdef ICR_TRACE  // development builds only (ICR_NVCC_DEFS=-DICR_TRACE): per-CTA globaltimer stamps of the ring kernel
+__device__ unsigned long long g_trace[296 * 8];
+#define ICR_STAMP(i)                                                      \
+  do {                                                                    \
+    if ((threadIdx.x & 255) == 0 && threadIdx.x < 256) {                  \
+      unsigned long long t_;                                              \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));              \
+      g_trace[blockIdx.x * 8 + (i)] = t_;                                 \
+    }                                                                     \
+  } while (0)
+__device__ unsigned long long g_trace_merge[8];
+#define ICR_MSTAMP(i)                                                     \
+  do {                                                                    \
+    if (threadIdx.x == 0) {                                               \
+      unsigned long long t_;                                              \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));              \
+      g_trace_merge[i] = t_;                                              \
+    }                                                                     \
+  } while (0)
+#else
+#define ICR_STAMP(i) do {} while (0)
+#define ICR_MSTAMP(i) do {} while (0)
+#endif
 
 struct GemvArgs {
   const void* cat;
@@ -60,71 +82,69 @@ __device__ __forceinline__ void compute_sync() {
   else __syncthreads();
 }
 
-template <bool NAMED>
-__device__ __forceinline__ void compute_bitonic_sort_desc(uint64_t* keys, int n, int tid) {
-  compute_sync<NAMED>();
-  for (int size = 2; size <= n; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int t = tid; t < (n >> 1); t += kGemvThreads) {
-        const int lo = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
-        const int hi = lo + stride;
-        const bool desc = ((lo & size) == 0);
-        const uint64_t a = keys[lo], b = keys[hi];
-        if ((a < b) == desc) {
-          keys[lo] = b;
-          keys[hi] = a;
-        }
-      }
-      compute_sync<NAMED>();
-    }
-  }
-}
-
 // shared-memory carve-up common to both kernels (after `prefix` bytes used by the ring)
 template <int QT>
 struct GemvSmem {
-  uint64_t* cand;       // [QT][kGemvCand]
+  // candidate keys per query held in shared memory (>= k + the rows scored between two threshold refreshes)
+  static constexpr int CAND = QT == 1 ? 1024 : (QT <= 3 ? 768 : 512);
+  uint64_t* cand;       // [QT][CAND]
+  uint64_t* sel;        // [QT][kMergeSel]  selection output (threshold refresh, merge fallback)
   float* qs;            // [QT][dpad]
   int* ncand;           // [QT]
   float* tau;           // [QT]
-  int* list_cnt;        // [512]   merge: per-CTA list lengths
-  uint64_t* sel;        // [kMergeSel] merge fallback
-  unsigned int* hist;   // [kHsBins]   merge fallback
-  int* misc;            // [4]
+  int* list_cnt;        // [512]   merge: per-query floor slots and counters
+  unsigned int* hist;   // [QT][kHsBins]
   __device__ GemvSmem(unsigned char* base, int dpad) {
     cand = reinterpret_cast<uint64_t*>(base);
-    sel = cand + QT * kGemvCand;
-    qs = reinterpret_cast<float*>(sel + kMergeSel);
+    sel = cand + QT * CAND;
+    qs = reinterpret_cast<float*>(sel + QT * kMergeSel);
     ncand = reinterpret_cast<int*>(qs + QT * dpad);
     tau = reinterpret_cast<float*>(ncand + QT);
     list_cnt = reinterpret_cast<int*>(tau + QT);
     hist = reinterpret_cast<unsigned int*>(list_cnt + 512);
-    misc = reinterpret_cast<int*>(hist + kHsBins);
   }
   static size_t bytes(int D) {
-    return static_cast<size_t>(QT) * kGemvCand * 8 + kMergeSel * 8 + static_cast<size_t>(QT) * D * 4 + QT * 8 + 512 * 4 + kHsBins * 4 + 16;
+    return static_cast<size_t>(QT) * (CAND * 8 + kMergeSel * 8 + kHsBins * 4 + 8) + static_cast<size_t>(QT) * D * 4 + 512 * 4 + 16;
   }
 };
 
 // ---- stage the L2-normalised queries in shared memory (fp32) ----------------------------------------
+// One warp per query; the row is fetched with 16-byte loads issued back to back (one memory round trip: this
+// sits on the critical path of a batch-1 request, before the first FMA).
 template <typename T, int QT>
 __device__ __forceinline__ void stage_queries(const GemvArgs& a, float* qs, int dpad, int nq, int warp, int lane) {
+  constexpr int VEC = Elem<T>::VEC;
+  constexpr int U = 4;
+  const int nvec = dpad / VEC;
   const T* qg = static_cast<const T*>(a.q);
   for (int t = warp; t < QT; t += kGemvWarps) {
+    float* dst = qs + t * dpad;
     if (t < nq) {
-      const T* qrow = qg + static_cast<int64_t>(a.q0 + t) * a.ldq;
+      const uint4* qrow = reinterpret_cast<const uint4*>(qg + static_cast<int64_t>(a.q0 + t) * a.ldq);
       float ss = 0.f;
-      for (int e = lane; e < dpad; e += 32) {
-        const float f = Elem<T>::to_f32(qrow[e]);
-        qs[t * dpad + e] = f;
-        ss = fmaf(f, f, ss);
+      for (int vb = lane; vb < nvec; vb += 32 * U) {
+        uint4 x[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) x[u] = (vb + 32 * u < nvec) ? __ldg(qrow + vb + 32 * u) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (vb + 32 * u < nvec) {
+            float f[VEC];
+            Elem<T>::unpack(x[u], f);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+              dst[(vb + 32 * u) * VEC + i] = f[i];
+              ss = fmaf(f[i], f[i], ss);
+            }
+          }
+        }
       }
       ss = warp_sum(ss);
       const float inv = 1.0f / fmaxf(sqrtf(ss), kNormEps);
       __syncwarp();
-      for (int e = lane; e < dpad; e += 32) qs[t * dpad + e] *= inv;
+      for (int e = lane; e < dpad; e += 32) dst[e] *= inv;
     } else {
-      for (int e = lane; e < dpad; e += 32) qs[t * dpad + e] = 0.f;
+      for (int e = lane; e < dpad; e += 32) dst[e] = 0.f;
     }
   }
 }
@@ -176,36 +196,60 @@ __device__ __forceinline__ void reduce_and_append(float (&acc)[RB * (QT + 1)], c
     const float score = acc[0] * (1.0f / fmaxf(sqrtf(ss), kNormEps));
     if (!excluded && score > sm.tau[t]) {
       const int pos = atomicAdd(&sm.ncand[t], 1);
-      if (pos < kGemvCand) sm.cand[t * kGemvCand + pos] = make_key(score, static_cast<uint32_t>(row));
+      if (pos < GemvSmem<QT>::CAND) sm.cand[t * GemvSmem<QT>::CAND + pos] = make_key(score, static_cast<uint32_t>(row));
     }
   }
 }
 
-// if a list could overflow during the next block of rows (or at the end), keep its k best and raise tau
+// If a list could overflow during the next block of rows (or at the end), keep its k best and raise tau.
+// One warp per query (QT <= 7 < 8 warps), histogram selection instead of a sort: no CTA-wide barrier inside, and
+// every query of the pass is handled at the same time. The final lists are sorted (k keys only) for the merge.
 template <int QT, bool NAMED>
-__device__ __forceinline__ void refresh_thresholds(const GemvArgs& a, GemvSmem<QT>& sm, int nq, bool last, int block_rows, int tid) {
-  for (int t = 0; t < nq; ++t) {
-    const int n = min(sm.ncand[t], kGemvCand);
-    if (last || n > kGemvCand - block_rows) {
-      uint64_t* keys = sm.cand + t * kGemvCand;
-      const int P = next_pow2(n < 2 ? 2 : n);
-      for (int i = n + tid; i < P; i += kGemvThreads) keys[i] = 0ull;
-      compute_bitonic_sort_desc<NAMED>(keys, P, tid);
-      if (tid == 0) {
-        const int kept = min(n, a.k);
-        sm.ncand[t] = kept;
-        sm.tau[t] = (kept >= a.k) ? key_score(keys[a.k - 1]) : -INFINITY;
+__device__ __forceinline__ void refresh_thresholds(const GemvArgs& a, GemvSmem<QT>& sm, int nq, bool last, int block_rows, int tid,
+                                                   bool early = false) {
+  constexpr int CAND = GemvSmem<QT>::CAND;
+  const int warp = tid >> 5, lane = tid & 31;
+  if (warp < nq) {
+    const int t = warp;
+    const int n = min(sm.ncand[t], CAND);
+    if (last || n > CAND - block_rows || (early && n >= 2 * a.k + 32)) {
+      uint64_t* keys = sm.cand + t * CAND;
+      uint64_t* sel = sm.sel + t * kMergeSel;
+      int kept = min(n, a.k);
+      uint64_t kth = ~0ull;
+      if (n <= 64 || n <= a.k) {  // short list: order it by rank counting
+        warp_rank_sort_desc(keys, n, sel, kept, lane);
+        for (int i = lane; i < kept; i += 32) keys[i] = sel[i];
+        if (kept > 0) kth = sel[kept - 1];
+      } else {
+        warp_select_topk(keys, n, a.k, sel, sm.hist + t * kHsBins, lane);  // k best, unordered
+        __syncwarp();
+        if (last) {  // the merge wants sorted lists
+          warp_rank_sort_desc(sel, kept, keys, kept, lane);
+          kth = keys[kept - 1];
+        } else {
+          for (int i = lane; i < kept; i += 32) {
+            keys[i] = sel[i];
+            kth = sel[i] < kth ? sel[i] : kth;
+          }
+          kth = warp_min_u64(kth);
+        }
       }
-      compute_sync<NAMED>();
+      if (lane == 0) {
+        sm.ncand[t] = kept;
+        sm.tau[t] = (kept >= a.k) ? key_score(kth) : -INFINITY;
+      }
     }
   }
+  compute_sync<NAMED>();
 }
 
 // Merge of the G per-CTA lists of query t by a group of GT threads (gtid = index in the group); LISTS * GT >= G.
 template <int QT, int GT, int LISTS, typename Sync>
 __device__ __forceinline__ void merge_query(const GemvArgs& a, GemvSmem<QT>& sm, int t, int gtid, Sync sync) {
+  constexpr int kGemvCand = GemvSmem<QT>::CAND;
   const int k = a.k, G = gridDim.x, lane = gtid & 31;
-  uint64_t* buf = sm.cand + t * kGemvCand;  // heads first, then the gathered candidates
+  uint64_t* buf = sm.cand + t * GemvSmem<QT>::CAND;  // heads first, then the gathered candidates
   uint64_t* floor_slot = reinterpret_cast<uint64_t*>(sm.list_cnt) + t;
   int* counter = sm.list_cnt + 64 + t;
   const int64_t slot0 = static_cast<int64_t>(a.q0 + t) * G;
@@ -228,10 +272,12 @@ __device__ __forceinline__ void merge_query(const GemvArgs& a, GemvSmem<QT>& sm,
     *floor_slot = 0ull;  // stays 0 when fewer than k lists are non-empty
   }
   sync();
+  ICR_MSTAMP(1);
 #pragma unroll
   for (int j = 0; j < LISTS; ++j) {
     if (my_head[j] != 0ull) {
       int rank = 0;
+#pragma unroll 8
       for (int i = 0; i < G; ++i) rank += (buf[i] > my_head[j]) ? 1 : 0;
       if (rank == k - 1) *floor_slot = my_head[j];
     }
@@ -239,27 +285,43 @@ __device__ __forceinline__ void merge_query(const GemvArgs& a, GemvSmem<QT>& sm,
   sync();
   const uint64_t head_floor = *floor_slot;
   sync();  // everyone has read the floor and is done with the heads in `buf`
+  ICR_MSTAMP(2);
+  // Lists are sorted, so the entries of a list that reach the floor form a prefix: each qualifying list (at most k
+  // of them) is walked by its thread in chunks of 4 independent loads until an entry falls below the floor.
 #pragma unroll
   for (int j = 0; j < LISTS; ++j) {
-    if (my_head[j] != 0ull && my_head[j] >= head_floor) {  // at most k lists qualify
+    if (my_head[j] != 0ull && my_head[j] >= head_floor) {
       const uint64_t* list = a.part_keys + (slot0 + gtid + j * GT) * k;
-      uint64_t key = my_head[j];
-      for (int i = 0;;) {
+      {
         const int pos = atomicAdd(counter, 1);
-        if (pos < kGemvCand) buf[pos] = key;
-        if (++i >= my_cnt[j]) break;
-        key = __ldcg(list + i);
-        if (key < head_floor) break;
+        if (pos < kGemvCand) buf[pos] = my_head[j];
+      }
+      bool more = true;
+      for (int i = 1; more && i < my_cnt[j]; i += 4) {
+        uint64_t key[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) key[u] = (i + u < my_cnt[j]) ? __ldcg(list + i + u) : 0ull;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (more && key[u] != 0ull && key[u] >= head_floor) {
+            const int pos = atomicAdd(counter, 1);
+            if (pos < kGemvCand) buf[pos] = key[u];
+          } else {
+            more = false;
+          }
+        }
       }
     }
   }
   sync();
+  ICR_MSTAMP(3);
   int n = *counter;
   const int64_t qo = static_cast<int64_t>(a.q0 + t) * k;
   if (n <= kGemvCand) {
     for (int i = gtid; i < n; i += GT) {
       const uint64_t key = buf[i];
       int rank = 0;
+#pragma unroll 8
       for (int j = 0; j < n; ++j) rank += (buf[j] > key) ? 1 : 0;
       if (rank < k) {
         a.out_scores[qo + rank] = key_score(key);
@@ -271,21 +333,16 @@ __device__ __forceinline__ void merge_query(const GemvArgs& a, GemvSmem<QT>& sm,
       a.out_ids[qo + i] = -1;
     }
   } else if (gtid < 32) {
-    // overflow (possible only for k > 32): exact streaming merge by one warp, list by list. With several queries in
-    // flight the fallback buffers are shared, so it is serialised through a spin lock on shared memory.
-    int* lock = sm.misc + 2;
-    if (lane == 0) {
-      while (atomicCAS(lock, 0, 1) != 0) {
-      }
-    }
-    __syncwarp();
+    // overflow (possible only for k > 32): exact streaming merge by one warp, list by list
+    uint64_t* sel = sm.sel + t * kMergeSel;
+    unsigned int* hist = sm.hist + t * kHsBins;
     n = 0;
     for (int c = 0; c < G; ++c) {
       const int cnt = __ldcg(a.part_cnt + slot0 + c);
       if (cnt == 0) continue;
       if (n + cnt > kGemvCand) {
-        warp_select_topk(buf, n, k, sm.sel, sm.hist, lane);
-        for (int i = lane; i < k; i += 32) buf[i] = sm.sel[i];
+        warp_select_topk(buf, n, k, sel, hist, lane);
+        for (int i = lane; i < k; i += 32) buf[i] = sel[i];
         n = k;
         __syncwarp();
       }
@@ -295,25 +352,21 @@ __device__ __forceinline__ void merge_query(const GemvArgs& a, GemvSmem<QT>& sm,
     }
     int kept = n;
     if (n > k) {
-      warp_select_topk(buf, n, k, sm.sel, sm.hist, lane);
+      warp_select_topk(buf, n, k, sel, hist, lane);
       kept = k;
     } else {
-      for (int i = lane; i < n; i += 32) sm.sel[i] = buf[i];
+      for (int i = lane; i < n; i += 32) sel[i] = buf[i];
     }
     __syncwarp();
     const int P = next_pow2(kept < 2 ? 2 : kept);
-    for (int i = kept + lane; i < P; i += 32) sm.sel[i] = 0ull;
-    warp_bitonic_sort_desc(sm.sel, P, lane);
+    for (int i = kept + lane; i < P; i += 32) sel[i] = 0ull;
+    warp_bitonic_sort_desc(sel, P, lane);
     for (int i = lane; i < k; i += 32) {
       const bool ok = i < kept;
-      a.out_scores[qo + i] = ok ? key_score(sm.sel[i]) : -INFINITY;
-      a.out_ids[qo + i] = ok ? static_cast<int64_t>(key_row(sm.sel[i])) + a.id_offset : -1;
+      a.out_scores[qo + i] = ok ? key_score(sel[i]) : -INFINITY;
+      a.out_ids[qo + i] = ok ? static_cast<int64_t>(key_row(sel[i])) + a.id_offset : -1;
     }
     __syncwarp();
-    if (lane == 0) {
-      __threadfence_block();
-      atomicExch(lock, 0);
-    }
   }
 }
 
@@ -325,20 +378,23 @@ __device__ __forceinline__ void emit_and_merge(const GemvArgs& a, GemvSmem<QT>& 
   for (int t = 0; t < nq; ++t) {
     const int n = has_rows ? sm.ncand[t] : 0;
     const int64_t slot = static_cast<int64_t>(a.q0 + t) * G + blockIdx.x;
-    for (int i = tid; i < n; i += kGemvThreads) a.part_keys[slot * k + i] = sm.cand[t * kGemvCand + i];
+    for (int i = tid; i < n; i += kGemvThreads) a.part_keys[slot * k + i] = sm.cand[t * GemvSmem<QT>::CAND + i];
     if (tid == 0) a.part_cnt[slot] = n;
   }
   if (a.out_scores == nullptr) return;  // the caller merges the per-CTA lists with a separate select launch
 
-  __threadfence();
+  // the barrier orders the CTA's list writes before thread 0's fence, which publishes them device-wide (cumulativity)
   compute_sync<NAMED>();
+  int* is_last = sm.list_cnt + 128;
   if (tid == 0) {
-    sm.misc[0] = (atomicAdd(a.done_counter, 1u) == static_cast<unsigned int>(G) - 1u) ? 1 : 0;
-    sm.misc[2] = 0;  // lock of the merge's overflow fallback
+    __threadfence();
+    *is_last = (atomicAdd(a.done_counter, 1u) == static_cast<unsigned int>(G) - 1u) ? 1 : 0;
   }
   compute_sync<NAMED>();
-  if (!sm.misc[0]) return;
+  ICR_STAMP(6);
+  if (!*is_last) return;
   __threadfence();
+  ICR_MSTAMP(0);
 
   // Every per-CTA list is sorted, so the k best list HEADS are k distinct keys >= head_floor (the k-th largest
   // head) and no key below head_floor can be among the k best overall: typically ~2k of the G*k keys survive.
@@ -347,10 +403,14 @@ __device__ __forceinline__ void emit_and_merge(const GemvArgs& a, GemvSmem<QT>& 
   // queries: one warp each, side by side.
   if (nq == 1) {
     merge_query<QT, kGemvThreads, 2>(a, sm, 0, tid, [] { compute_sync<NAMED>(); });
+  } else if (nq <= 4) {  // two warps per query, each pair on its own named barrier
+    const int t = warp >> 1;
+    if (t < nq) merge_query<QT, 64, 5>(a, sm, t, tid & 63, [t] { ptx::named_sync(2 + t, 64); });
   } else if (warp < nq) {
     merge_query<QT, 32, 10>(a, sm, warp, lane, [] { __syncwarp(); });
   }
   compute_sync<NAMED>();
+  ICR_MSTAMP(4);
   if (tid == 0) *a.done_counter = 0u;  // ready for the next launch that shares this workspace
 }
 
@@ -417,7 +477,8 @@ __global__ void __launch_bounds__(kGemvThreads) gemv_topk_kernel(GemvArgs a) {
 template <typename T, int QT>
 __global__ void __launch_bounds__(kRingThreads, 1) gemv_ring_kernel(GemvArgs a) {
   constexpr int VEC = Elem<T>::VEC;
-  constexpr int RB = (QT == 7) ? 4 : 8;  // rows reduced together (V = RB * (QT + 1) <= 32)
+  constexpr int RB = (QT == 7) ? 4 : 8;  // rows reduced together (V = RB * (QT + 1) <= 32) = rows per ring slot
+  constexpr int kSlabRows = RB;
   constexpr int V = RB * (QT + 1);
   extern __shared__ __align__(128) unsigned char ring_smem_raw[];
   const int nvec = a.D / VEC;
@@ -435,6 +496,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) gemv_ring_kernel(GemvArgs a) 
   const int64_t row_end = min(a.N, row_begin + a.rows_per_cta);
   const int nb = row_begin < row_end ? static_cast<int>((row_end - row_begin + kSlabRows - 1) / kSlabRows) : 0;
 
+  ICR_STAMP(0);
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) {
       ptx::mbar_init(ptx::smem_u32(&full_bar[s]), 1);
@@ -443,6 +505,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) gemv_ring_kernel(GemvArgs a) 
     ptx::mbar_fence_init();
   }
   __syncthreads();  // the only CTA-wide barrier: the producer warp never joins another one
+  ICR_STAMP(1);
 
   if (warp == kGemvWarps) {
     // ================= producer: the whole ring is in flight before the first FMA =================
@@ -470,6 +533,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) gemv_ring_kernel(GemvArgs a) 
     sm.tau[tid] = -INFINITY;
   }
   compute_sync<true>();
+  ICR_STAMP(2);
 
   const int iters = (nb + kGemvWarps - 1) / kGemvWarps;
   constexpr int kItersPerRefresh = 4;
@@ -480,10 +544,11 @@ __global__ void __launch_bounds__(kRingThreads, 1) gemv_ring_kernel(GemvArgs a) 
       const int slot = b % NS;
       const uint32_t parity = static_cast<uint32_t>(b / NS) & 1u;
       ptx::mbar_wait(ptx::smem_u32(&full_bar[slot]), parity);
+      if (it == 0) ICR_STAMP(3);
       const unsigned char* slab = ring + static_cast<size_t>(slot) * slot_bytes;
       const int64_t r0 = row_begin + static_cast<int64_t>(b) * kSlabRows;
-#pragma unroll
-      for (int g = 0; g < kSlabRows / RB; ++g) {
+      {
+        constexpr int g = 0;
         float acc[V];
 #pragma unroll
         for (int i = 0; i < V; ++i) acc[i] = 0.f;
@@ -501,16 +566,21 @@ __global__ void __launch_bounds__(kRingThreads, 1) gemv_ring_kernel(GemvArgs a) 
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&empty_bar[slot]));
     }
-    if ((it + 1) % kItersPerRefresh == 0 || it + 1 == iters) {
+    // early thresholds (as soon as a list holds 2k + 32 keys) keep the final list short: the selection at the end
+    // of the stream is on the critical path of a request, the ones in the middle hide behind the ring
+    if ((it + 1) % kItersPerRefresh == 0 || it + 1 == iters || it == 0) {
       compute_sync<true>();
-      refresh_thresholds<QT, true>(a, sm, nq, it + 1 == iters, kBlockRows, tid);
+      if (it + 1 == iters) ICR_STAMP(4);
+      refresh_thresholds<QT, true>(a, sm, nq, it + 1 == iters, kBlockRows, tid, true);
     }
   }
   if (iters == 0) {
     compute_sync<true>();
     refresh_thresholds<QT, true>(a, sm, nq, true, kBlockRows, tid);
   }
+  ICR_STAMP(5);
   emit_and_merge<QT, true>(a, sm, nq, row_begin < row_end, tid);
+  ICR_STAMP(7);
 }
 
 // ---- host side --------------------------------------------------------------------------------------------
@@ -534,7 +604,7 @@ static int launch_direct(const GemvArgs& a, int grid, cudaStream_t st) {
 template <typename T, int QT>
 static int ring_slots_for(int D) {
   const size_t fixed = GemvSmem<QT>::bytes(D) + 2 * kMaxSlots * sizeof(uint64_t) + 128;
-  const size_t slot = static_cast<size_t>(kSlabRows) * D * sizeof(T);
+  const size_t slot = static_cast<size_t>(QT == 7 ? 4 : 8) * D * sizeof(T);
   if (fixed + kGemvWarps * slot > kSmemBudget) return 0;
   const size_t n = (kSmemBudget - fixed) / slot;
   // A multiple of the consumer-warp count, so that every slot is only ever consumed by ONE warp (batch b goes to
@@ -546,7 +616,7 @@ static int ring_slots_for(int D) {
 template <typename T, int QT>
 static int launch_ring(GemvArgs a, int grid, cudaStream_t st) {
   a.ring_slots = ring_slots_for<T, QT>(a.D);
-  const size_t smem = static_cast<size_t>(a.ring_slots) * kSlabRows * a.D * sizeof(T) + 2 * kMaxSlots * sizeof(uint64_t) + GemvSmem<QT>::bytes(a.D) + 128;
+  const size_t smem = static_cast<size_t>(a.ring_slots) * (QT == 7 ? 4 : 8) * a.D * sizeof(T) + 2 * kMaxSlots * sizeof(uint64_t) + GemvSmem<QT>::bytes(a.D) + 128;
   static thread_local size_t configured = 0;
   if (smem > configured) {
     ICR_CUDA_CHECK(cudaFuncSetAttribute(gemv_ring_kernel<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -569,8 +639,8 @@ static bool ring_ok(int64_t ldc, int D, int dtype, int qt) {
   int slots;
   if (dtype == ICR_F32) slots = qt == 1 ? ring_slots_for<float, 1>(D) : (qt == 3 ? ring_slots_for<float, 3>(D) : ring_slots_for<float, 7>(D));
   else slots = qt == 1 ? ring_slots_for<__nv_bfloat16, 1>(D) : (qt == 3 ? ring_slots_for<__nv_bfloat16, 3>(D) : ring_slots_for<__nv_bfloat16, 7>(D));
-  // measured at C1 size: with one slot per warp (no load/compute overlap inside a warp) the ring still wins for
-  // 1-3 queries per pass but loses to the direct kernel for 4-7, whose FMA work per slab is larger
+  // one slot per warp (no load/compute overlap inside a warp) still wins for 1-3 queries per pass; 4-7 queries
+  // (4-row slabs) want two slots per warp
   return qt == 7 ? slots >= 2 * kGemvWarps : slots >= kGemvWarps;
 }
 
@@ -628,3 +698,12 @@ int launch_gemv_topk(const void* cat, int64_t N, int64_t ldc, int D, int dtype, 
 }
 
 }  // namespace icr
+
+#ifdef ICR_TRACE
+extern "C" int icr_debug_read_trace(unsigned long long* out, int n) {
+  return static_cast<int>(cudaMemcpyFromSymbol(out, icr::g_trace, sizeof(unsigned long long) * n));
+}
+extern "C" int icr_debug_read_merge_trace(unsigned long long* out) {
+  return static_cast<int>(cudaMemcpyFromSymbol(out, icr::g_trace_merge, sizeof(unsigned long long) * 8));
+}
+#endif

@@ -139,14 +139,12 @@ __global__ void __launch_bounds__(kHsWarps * 32) select_hist_kernel(HistSelectAr
     if (lane == 0) a.tau_out[q] = (kept >= k) ? key_score(mn) : -INFINITY;
   }
   if (a.out_scores) {
-    const int P = next_pow2(kept < 2 ? 2 : kept);
-    for (int i = kept + lane; i < P; i += 32) sel[i] = 0ull;
-    warp_bitonic_sort_desc(sel, P, lane);
+    warp_rank_sort_desc(sel, kept, buf, kept, lane);  // buf is free again: sorted output order
     const float scale = a.out_scale * (a.out_qscale ? a.out_qscale[q] : 1.0f);
     for (int i = lane; i < k; i += 32) {
       const bool ok = i < kept;
-      a.out_scores[q * k + i] = ok ? key_score(sel[i]) * scale : -INFINITY;
-      a.out_ids[q * k + i] = ok ? static_cast<int64_t>(key_row(sel[i])) + a.id_offset : -1;
+      a.out_scores[q * k + i] = ok ? key_score(buf[i]) * scale : -INFINITY;
+      a.out_ids[q * k + i] = ok ? static_cast<int64_t>(key_row(buf[i])) + a.id_offset : -1;
     }
   }
 }

@@ -25,6 +25,33 @@ __device__ __forceinline__ uint64_t warp_max_u64(uint64_t v) {
   return v;
 }
 
+// out[r] = the key of rank r (0 = largest) among in[0..n), for r < kout. Keys are distinct; `in` and `out` must not
+// overlap. Rank counting: every lane compares its own keys (four at a time) against all n keys read as shared-memory
+// broadcasts - n*n/32 comparisons but no barriers, no divergent stores and full ILP, which beats a bitonic network
+// in shared memory for the list lengths met here (n <= a few hundred).
+__device__ __forceinline__ void warp_rank_sort_desc(const uint64_t* in, int n, uint64_t* out, int kout, int lane) {
+  __syncwarp();
+  for (int base = lane; base < n; base += 128) {
+    uint64_t my[4];
+    int rank[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      my[u] = (base + 32 * u < n) ? in[base + 32 * u] : ~0ull;
+      rank[u] = 0;
+    }
+#pragma unroll 4
+    for (int j = 0; j < n; ++j) {
+      const uint64_t kj = in[j];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) rank[u] += (kj > my[u]) ? 1 : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (base + 32 * u < n && rank[u] < kout) out[rank[u]] = my[u];
+  }
+  __syncwarp();
+}
+
 // Moves the k largest of buf[0..n) to sel[0..k) (unordered). n > k on entry. Destroys buf.
 __device__ __forceinline__ void warp_select_topk(uint64_t* buf, int n, int k, uint64_t* sel, unsigned int* hist, int lane) {
   int need = k, nsel = 0, len = n;
@@ -106,11 +133,8 @@ __device__ __forceinline__ void warp_select_topk(uint64_t* buf, int n, int k, ui
       __syncwarp();
       return;
     }
-    if (nb <= 64) {
-      for (int i = nb + lane; i < 64; i += 32) buf[i] = 0ull;
-      warp_bitonic_sort_desc(buf, 64, lane);
-      for (int i = lane; i < need; i += 32) sel[nsel + i] = buf[i];
-      __syncwarp();
+    if (nb <= 128) {
+      warp_rank_sort_desc(buf, nb, sel + nsel, need, lane);
       return;
     }
     len = nb;  // refine inside the boundary bin (its key range is 256x narrower)
