@@ -195,6 +195,19 @@ __device__ __forceinline__ int chunk_first_tile(const GemmArgs& g, int c) {
   return g.tile_begin + static_cast<int>(static_cast<int64_t>(c) * (g.tile_end - g.tile_begin) / g.chunks);
 }
 
+__device__ __forceinline__ uint32_t order_bits_canonical(float s) {  // s must not be -0.0
+  const uint32_t b = __float_as_uint(s);
+  return b ^ (static_cast<uint32_t>(static_cast<int32_t>(b) >> 31) | 0x80000000u);
+}
+// segment ("raw") key <-> ordered key
+__device__ __forceinline__ uint64_t canonical_key(uint64_t raw) {
+  const float f = __uint_as_float(static_cast<uint32_t>(raw >> 32)) + 0.0f;  // -0.0 -> +0.0: equal scores, equal keys
+  return (static_cast<uint64_t>(order_bits_canonical(f)) << 32) | (raw & 0xFFFFFFFFull);
+}
+__device__ __forceinline__ uint64_t raw_key(uint64_t key) {
+  return (static_cast<uint64_t>(__float_as_uint(unorder_bits(static_cast<uint32_t>(key >> 32)))) << 32) | (key & 0xFFFFFFFFull);
+}
+
 struct SegState {
   uint64_t* seg;    // this thread's candidate segment (global)
   int cnt;
@@ -212,10 +225,10 @@ __device__ __forceinline__ void compact_full_segments(SegState& s, uint64_t* scr
     uint64_t* seg = reinterpret_cast<uint64_t*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(s.seg), L));
     const int n = __shfl_sync(kFull, s.cnt, L);
     __syncwarp();
-    for (int i = lane; i < cap; i += 32) scratch[i] = (i < n) ? __ldcg(seg + i) : 0ull;
+    for (int i = lane; i < cap; i += 32) scratch[i] = (i < n) ? canonical_key(__ldcg(seg + i)) : 0ull;
     warp_bitonic_sort_desc(scratch, cap, lane);
     const int kept = n < k ? n : k;
-    for (int i = lane; i < kept; i += 32) seg[i] = scratch[i];
+    for (int i = lane; i < kept; i += 32) seg[i] = raw_key(scratch[i]);
     const uint32_t t_new = (n >= k) ? static_cast<uint32_t>(scratch[k - 1] >> 32) : 0u;
     if (lane == L) {
       s.cnt = kept;
@@ -225,53 +238,93 @@ __device__ __forceinline__ void compact_full_segments(SegState& s, uint64_t* scr
   }
 }
 
-__device__ __forceinline__ uint32_t order_bits_canonical(float s) {  // s must not be -0.0
-  const uint32_t b = __float_as_uint(s);
-  return b ^ (static_cast<uint32_t>(static_cast<int32_t>(b) >> 31) | 0x80000000u);
-}
-
-// predicated append of key (ob, ~row): no branch, so a warp whose lanes disagree pays nothing extra
-__device__ __forceinline__ void append_if(SegState& s, uint32_t ob, uint32_t nrow) {
+// predicated append of a raw key (score bits, ~row): no branch, so a warp whose lanes disagree pays nothing extra
+__device__ __forceinline__ void append_if(SegState& s, float sc, float tau_f, uint32_t nrow) {
   uint32_t inc;
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "setp.gt.u32 p, %2, %3;\n"
-      "@p st.global.v2.u32 [%1], {%4, %2};\n"
+      "setp.gt.f32 p, %2, %3;\n"
+      "@p st.global.v2.u32 [%1], {%4, %5};\n"
       "selp.u32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(inc)
-      : "l"(s.seg + s.cnt), "r"(ob), "r"(s.tau_ob), "r"(nrow)
+      : "l"(s.seg + s.cnt), "f"(sc), "f"(tau_f), "r"(nrow), "r"(__float_as_uint(sc))
       : "memory");
   s.cnt += static_cast<int>(inc);
 }
 
 // Filter 32 accumulator columns (catalog rows rbase .. rbase+31) of this thread's query.
-// Keys carry the score in "raw" units — the accumulator itself (plane path) or accumulator * catalog inverse
-// norm (bf16 path); the per-query positive factor (2^-16, or the query's inverse norm) does not change the
-// order within a query and is applied once, to the k final scores, by the select kernel.
+// Segments hold RAW keys: (accumulator-unit score bits, ~row); the select kernel turns them into ordered keys when
+// it gathers them. Scores are in "raw" units - the accumulator itself (plane path) or accumulator * catalog inverse
+// norm (bf16 path); the per-query positive factor (2^-16, or the query's inverse norm) does not change the order
+// within a query and is applied once, to the k final scores, by the select kernel.
+// cmax / cmin: largest / smallest catalog inverse norm of these 32 rows (bf16 path).
 template <bool BF16>
-__device__ __forceinline__ void filter32(const uint32_t (&r)[32], SegState& s, const float* cinv32, int rbase, bool fast, int N,
-                                         const uint8_t* mask) {
+__device__ __forceinline__ void filter32(const uint32_t (&r)[32], SegState& s, const float* cinv32, float cmax, float cmin, int rbase,
+                                         bool fast, int N, const uint8_t* mask) {
+  const float tau_f = unorder_bits(s.tau_ob);  // NaN for dead lanes: every comparison below is false
   if (fast) {
-    // Survivors are rare once the threshold has converged (k / rows-seen per score), so scores are screened 8 at a
-    // time: one max tree + one warp vote (~1-2 instructions per score); only a group in which SOME lane has a
-    // survivor runs the predicated appends (~10 per score). The vote keeps the branch warp-uniform.
-    const float tau_f = unorder_bits(s.tau_ob);  // NaN for dead lanes: every comparison below is false
+    // Survivors are rare once the threshold has converged (k / rows-seen per score), so the 32 accumulators are
+    // screened together: one max tree + one warp vote (~1.1 instructions per score; the bf16 path bounds the scaled
+    // maximum with the block's extreme inverse norms instead of scaling 32 scores). Only when SOME lane of the warp
+    // has a survivor are the scores scaled and appended - with positions from a prefix sum over the 32 predicates,
+    // so the 32 predicated stores are independent of each other (no serial counter chain).
+    float m[16];
 #pragma unroll
-    for (int g8 = 0; g8 < 4; ++g8) {
-      float sc[8];
+    for (int j = 0; j < 16; ++j) m[j] = fmaxf(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int c = g8 * 8 + j;
-        sc[j] = BF16 ? __uint_as_float(r[c]) * cinv32[c] : __uint_as_float(r[c]);
+    for (int w = 8; w > 0; w >>= 1)
+#pragma unroll
+      for (int j = 0; j < w; ++j) m[j] = fmaxf(m[j], m[j + w]);
+    const float bound = BF16 ? fmaxf(m[0] * cmax, m[0] * cmin) : m[0];
+    if (__any_sync(kFull, bound > tau_f)) {
+      float sc[32];
+      if (BF16) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 ci = *reinterpret_cast<const float4*>(cinv32 + j);
+          sc[j] = __uint_as_float(r[j]) * ci.x;
+          sc[j + 1] = __uint_as_float(r[j + 1]) * ci.y;
+          sc[j + 2] = __uint_as_float(r[j + 2]) * ci.z;
+          sc[j + 3] = __uint_as_float(r[j + 3]) * ci.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sc[j] = __uint_as_float(r[j]);
       }
-      const float m = fmaxf(fmaxf(fmaxf(sc[0], sc[1]), fmaxf(sc[2], sc[3])), fmaxf(fmaxf(sc[4], sc[5]), fmaxf(sc[6], sc[7])));
-      if (__any_sync(kFull, m > tau_f)) {
+      int off[33];
+      off[0] = s.cnt;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)  // + 0.0 turns -0.0 into +0.0 so that equal scores have equal keys
-          append_if(s, order_bits_canonical(sc[j] + 0.0f), ~static_cast<uint32_t>(rbase + g8 * 8 + j));
+      for (int g = 0; g < 4; ++g) {  // prefix sums: depth 3 inside a group of 8, one add between groups
+        int inc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) inc[j] = (sc[g * 8 + j] > tau_f) ? 1 : 0;
+        const int s01 = inc[0] + inc[1], s23 = inc[2] + inc[3], s45 = inc[4] + inc[5], s67 = inc[6] + inc[7];
+        const int b = off[g * 8];
+        off[g * 8 + 1] = b + inc[0];
+        off[g * 8 + 2] = b + s01;
+        off[g * 8 + 3] = b + s01 + inc[2];
+        const int b4 = b + s01 + s23;
+        off[g * 8 + 4] = b4;
+        off[g * 8 + 5] = b4 + inc[4];
+        off[g * 8 + 6] = b4 + s45;
+        off[g * 8 + 7] = b4 + s45 + inc[6];
+        off[g * 8 + 8] = b4 + s45 + s67;
       }
+      const uint32_t nrow0 = ~static_cast<uint32_t>(rbase);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.gt.f32 p, %1, %2;\n"
+            "@p st.global.v2.u32 [%0], {%3, %4};\n"
+            "}\n" ::"l"(s.seg + off[j]),
+            "f"(sc[j]), "f"(tau_f), "r"(nrow0 - j), "r"(__float_as_uint(sc[j]))
+            : "memory");
+      }
+      s.cnt = off[32];
     }
   } else {
     // last (partial) tile of the catalog, or an exclusion mask: rows are checked one by one
@@ -279,10 +332,8 @@ __device__ __forceinline__ void filter32(const uint32_t (&r)[32], SegState& s, c
     for (int j = 0; j < 32; ++j) {
       const int row = rbase + j;
       if (row < N && !(mask && mask[row])) {
-        float sc;
-        if (BF16) sc = fmaf(__uint_as_float(r[j]), cinv32[j], 0.0f);
-        else sc = __uint_as_float(r[j]) + 0.0f;
-        append_if(s, order_bits_canonical(sc), ~static_cast<uint32_t>(row));
+        const float sc = BF16 ? __uint_as_float(r[j]) * cinv32[j] : __uint_as_float(r[j]);
+        append_if(s, sc, tau_f, ~static_cast<uint32_t>(row));
       }
     }
   }
@@ -495,10 +546,23 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const bool vec_ok = dense && (g.dense_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.dense_out) & 15) == 0);
       for (int tile = t0; tile < t1; ++tile) {
         const int row0 = tile * BN + half * kEpiCols;
+        float cmax_l = 1.f, cmin_l = 1.f;  // lane u: extremes of the inverse norms of 32-row block u
         if (BF16) {
-          // stage this warp's 128 catalog inverse norms once per tile (read back as shared-memory broadcasts)
+          // stage this warp's catalog inverse norms once per tile (read back as shared-memory broadcasts), with
+          // the extremes of every 32-row block for the screening bound
+          static_assert(kEpiCols / 32 <= 32, "one lane per 32-row block");
           __syncwarp();
-          for (int i = lane; i < kEpiCols; i += 32) cinv_s[i] = (row0 + i < g.N) ? __ldg(g.cinv + row0 + i) : 0.f;
+#pragma unroll
+          for (int u = 0; u < kEpiCols / 32; ++u) {
+            const int i = u * 32 + lane;
+            const float ci = (row0 + i < g.N) ? __ldg(g.cinv + row0 + i) : 0.f;
+            cinv_s[i] = ci;
+            const float mx = warp_max(ci), mn = -warp_max(-ci);
+            if (lane == u) {
+              cmax_l = mx;
+              cmin_l = mn;
+            }
+          }
           __syncwarp();
         }
         mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
@@ -516,7 +580,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             if (live) dense_store32<BF16>(ra, out_q + row0 + cb * 32, qscale, cinv_s + cb * 32, g.N - (row0 + cb * 32), vec_ok);
           } else {
             compact_full_segments(s, scratch, cap, g.k, lane);
-            filter32<BF16>(ra, s, cinv_s + cb * 32, row0 + cb * 32, fast, g.N, g.mask);
+            filter32<BF16>(ra, s, cinv_s + cb * 32, __shfl_sync(kFull, cmax_l, cb), __shfl_sync(kFull, cmin_l, cb), row0 + cb * 32, fast,
+                           g.N, g.mask);
           }
           tmem_ld_wait(rb);
           if (cb + 2 < kEpiCols / 32) tmem_ld32(taddr + (cb + 2) * 32, ra);
@@ -524,7 +589,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             if (live) dense_store32<BF16>(rb, out_q + row0 + (cb + 1) * 32, qscale, cinv_s + (cb + 1) * 32, g.N - (row0 + (cb + 1) * 32), vec_ok);
           } else {
             compact_full_segments(s, scratch, cap, g.k, lane);
-            filter32<BF16>(rb, s, cinv_s + (cb + 1) * 32, row0 + (cb + 1) * 32, fast, g.N, g.mask);
+            filter32<BF16>(rb, s, cinv_s + (cb + 1) * 32, __shfl_sync(kFull, cmax_l, cb + 1), __shfl_sync(kFull, cmin_l, cb + 1),
+                           row0 + (cb + 1) * 32, fast, g.N, g.mask);
           }
         }
         tc_fence_before();

@@ -38,7 +38,13 @@ struct HistSelectArgs {
   int64_t Q;
   float out_scale;          // final score = key score * out_scale * (out_qscale ? out_qscale[q] : 1)
   const float* out_qscale;  // [Q] or null
+  int raw_keys;             // segments hold (score bits, ~row) as the GEMM epilogue writes them; carry keys are ordered
 };
+
+__device__ __forceinline__ uint64_t canonical_from_raw(uint64_t raw) {
+  const float f = __uint_as_float(static_cast<uint32_t>(raw >> 32));
+  return (static_cast<uint64_t>(order_bits(f)) << 32) | (raw & 0xFFFFFFFFull);
+}
 
 struct HsSmem {
   uint64_t buf[kHsWarps][kHsCap];
@@ -110,7 +116,7 @@ __global__ void __launch_bounds__(kHsWarps * 32) select_hist_kernel(HistSelectAr
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const int i = i0 + u * 32 + lane;
-          if (i < take) buf[n + i] = v[u];
+          if (i < take) buf[n + i] = a.raw_keys ? canonical_from_raw(v[u]) : v[u];
         }
       }
       n += take;
@@ -177,6 +183,7 @@ int launch_select_hist(const uint64_t* seg_keys, const int* seg_cnt, int64_t Q, 
   a.Q = Q;
   a.out_scale = out_scale;
   a.out_qscale = out_qscale;
+  a.raw_keys = 1;  // the only producer of segments is the GEMM epilogue
   const unsigned grid = static_cast<unsigned>((Q + kHsWarps - 1) / kHsWarps);
   select_hist_kernel<<<grid, kHsWarps * 32, sizeof(HsSmem), st>>>(a);
   ICR_LAUNCH_CHECK();
