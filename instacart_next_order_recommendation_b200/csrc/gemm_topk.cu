@@ -50,9 +50,19 @@ constexpr int kSegCapMax = 512;      // candidate keys per (query, chunk, column
 #ifndef ICR_EPI_WARPS
 #define ICR_EPI_WARPS 4
 #endif
-constexpr int kEpiWarps = ICR_EPI_WARPS;  // 4 or 8
-constexpr int kEpiHalves = kEpiWarps / 4;    // column groups of a tile, one per set of four epilogue warps
-constexpr int kEpiCols = BN / kEpiHalves;   // accumulator columns each epilogue warp filters per tile
+// Epilogue warps per CTA, in sets of four (a warp may only read the TMEM lane quarter warp_id % 4); with two sets each
+// filters half of a tile's columns. Measured (profiles/r01_notes.md): the three-term kernel is tensor-bound and does
+// best with four (fewer segments for the select); the one-term kernels are epilogue-latency-bound and want two warps
+// per scheduler.
+#ifndef ICR_EPI_WARPS_F32
+#define ICR_EPI_WARPS_F32 4
+#endif
+#ifndef ICR_EPI_WARPS_BF16
+#define ICR_EPI_WARPS_BF16 8
+#endif
+__host__ __device__ constexpr int epi_warps(int terms) { return terms == 3 ? ICR_EPI_WARPS_F32 : ICR_EPI_WARPS_BF16; }
+constexpr int kEpiWarps = 8;  // upper bound, for buffer sizes
+constexpr int kEpiCols = BN;
 constexpr int kGemmThreads = 128 + kEpiWarps * 32;
 constexpr int kTmemCols = 512;      // two 256-column fp32 accumulators
 constexpr uint32_t kSpinLimit = 1u << 24;
@@ -365,6 +375,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmArgs g) {
   static_assert(!ASTAT || TERMS == 1, "A-stationary is the bf16 variant");
   constexpr bool BF16 = (TERMS == 1);
+  constexpr int EW = epi_warps(TERMS), EH = EW / 4, ECOLS = BN / EH;  // epilogue warps, column groups, columns per warp
   constexpr int kStageTiles = ASTAT ? 1 : ((TERMS == 3) ? 4 : 2);  // B | A_hi A_lo B_hi B_lo | A B
   constexpr int kStageBytes = kStageTiles * kTileBytes;
   constexpr int kAResidentBytes = ASTAT ? kAStatMaxKB * kTileBytes : 0;
@@ -378,7 +389,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   unsigned char* a_resident = smem;                    // ASTAT: kb-th K block of the queries at kb * kTileBytes
   unsigned char* stage_base = smem + kAResidentBytes;
   float* cinv_all = reinterpret_cast<float*>(smem + kRingBytes);                    // 8 warps x 128 floats
-  uint64_t* bars = reinterpret_cast<uint64_t*>(cinv_all + kEpiWarps * kEpiCols);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cinv_all + EW * ECOLS);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kMaxStages;
   uint64_t* tfull_bar = bars + 2 * kMaxStages;
@@ -400,7 +411,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&tfull_bar[a]), 1);   // one multicast tcgen05.commit
-      mbar_init(smem_u32(&tempty_bar[a]), 2 * kEpiWarps);  // the epilogue warps of both CTAs (used in the leader only)
+      mbar_init(smem_u32(&tempty_bar[a]), 2 * EW);  // the epilogue warps of both CTAs (used in the leader only)
     }
     mbar_init(smem_u32(afull_bar), 1);
     mbar_init(smem_u32(aempty_bar), 1);
@@ -521,12 +532,12 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       }
       if (ASTAT) umma_commit_pair(smem_u32(aempty_bar));  // resident queries may be overwritten in both CTAs
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 4 + EW) {
     // ================= epilogue: threshold filter, one query per thread =================
     const int ew = (warp - 4) & 3;   // TMEM lane quarter this warp may read (hardware rule: warp id % 4)
     const int half = (warp - 4) >> 2;  // which 128 accumulator columns of every tile this warp filters
-    uint64_t* scratch = g.compact_scratch + (static_cast<int64_t>(blockIdx.x) * kEpiWarps + (warp - 4)) * kSegCapMax;
-    float* cinv_s = cinv_all + (warp - 4) * kEpiCols;
+    uint64_t* scratch = g.compact_scratch + (static_cast<int64_t>(blockIdx.x) * EW + (warp - 4)) * kSegCapMax;
+    float* cinv_s = cinv_all + (warp - 4) * ECOLS;
     const int cap = g.seg_cap;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -535,7 +546,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const int t0 = chunk_first_tile(g, chunk), t1 = chunk_first_tile(g, chunk + 1);
       const int q = qb * (2 * BM) + static_cast<int>(rank) * BM + ew * 32 + lane;
       const bool live = q < g.Q;
-      const int64_t seg_index = (static_cast<int64_t>(live ? q : 0) * g.chunks + chunk) * kEpiHalves + half;
+      const int64_t seg_index = (static_cast<int64_t>(live ? q : 0) * g.chunks + chunk) * EH + half;
       SegState s;
       s.seg = g.cand + seg_index * cap;
       s.cnt = 0;
@@ -545,15 +556,15 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const float qscale = dense ? g.acc_scale * ((BF16 && live) ? g.qinv[q] : 1.0f) : 0.f;
       const bool vec_ok = dense && (g.dense_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.dense_out) & 15) == 0);
       for (int tile = t0; tile < t1; ++tile) {
-        const int row0 = tile * BN + half * kEpiCols;
+        const int row0 = tile * BN + half * ECOLS;
         float cmax_l = 1.f, cmin_l = 1.f;  // lane u: extremes of the inverse norms of 32-row block u
         if (BF16) {
           // stage this warp's catalog inverse norms once per tile (read back as shared-memory broadcasts), with
           // the extremes of every 32-row block for the screening bound
-          static_assert(kEpiCols / 32 <= 32, "one lane per 32-row block");
+          static_assert(ECOLS / 32 <= 32, "one lane per 32-row block");
           __syncwarp();
 #pragma unroll
-          for (int u = 0; u < kEpiCols / 32; ++u) {
+          for (int u = 0; u < ECOLS / 32; ++u) {
             const int i = u * 32 + lane;
             const float ci = (row0 + i < g.N) ? __ldg(g.cinv + row0 + i) : 0.f;
             cinv_s[i] = ci;
@@ -567,12 +578,12 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         }
         mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * BN + half * kEpiCols);
-        const bool fast = (row0 + kEpiCols <= g.N) && (g.mask == nullptr);
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * BN + half * ECOLS);
+        const bool fast = (row0 + ECOLS <= g.N) && (g.mask == nullptr);
         uint32_t ra[32], rb[32];
         tmem_ld32(taddr, ra);
 #pragma unroll 1
-        for (int cb = 0; cb < kEpiCols / 32; cb += 2) {
+        for (int cb = 0; cb < ECOLS / 32; cb += 2) {
           // the next 32 columns are in flight while the current 32 are filtered
           tmem_ld_wait(ra);
           tmem_ld32(taddr + (cb + 1) * 32, rb);
@@ -584,7 +595,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                            g.N, g.mask);
           }
           tmem_ld_wait(rb);
-          if (cb + 2 < kEpiCols / 32) tmem_ld32(taddr + (cb + 2) * 32, ra);
+          if (cb + 2 < ECOLS / 32) tmem_ld32(taddr + (cb + 2) * 32, ra);
           if (dense) {
             if (live) dense_store32<BF16>(rb, out_q + row0 + (cb + 1) * 32, qscale, cinv_s + (cb + 1) * 32, g.N - (row0 + (cb + 1) * 32), vec_ok);
           } else {
@@ -750,8 +761,9 @@ static GemmWs gemm_ws_layout(int64_t Q, int64_t N, int64_t D, int dtype, int k, 
     w.carry_cnt[i] = take(static_cast<size_t>(Q) * 4);
   }
   w.seg_cap = seg_cap_for(k);
-  w.cand = take(static_cast<size_t>(Q) * maxc * kEpiHalves * w.seg_cap * 8);
-  w.cand_cnt = take(static_cast<size_t>(Q) * maxc * kEpiHalves * 4);
+  const int halves = epi_warps(dtype == ICR_F32 ? 3 : 1) / 4;
+  w.cand = take(static_cast<size_t>(Q) * maxc * halves * w.seg_cap * 8);
+  w.cand_cnt = take(static_cast<size_t>(Q) * maxc * halves * 4);
   w.scratch = take(static_cast<size_t>(kNumSMs) * kEpiWarps * kSegCapMax * 8);  // in-kernel compaction scratch
   w.total = off + 1024;
   return w;
@@ -857,14 +869,15 @@ int launch_gemm_topk(const void* queries, int64_t Q, int64_t ldq, const void* ca
     const int pairs = items < kNumSMs / 2 ? items : kNumSMs / 2;
     const int grid = 2 * pairs;  // whole CTA pairs (cluster dims 2x1x1)
     profile_begin(kKernelGemm, terms, st);
-    if (which == 0) gemm_topk_kernel<3, false, false><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(map_a, map_b, g);
-    if (which == 1) gemm_topk_kernel<1, false, false><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(map_a, map_b, g);
-    if (which == 2) gemm_topk_kernel<1, true, false><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(map_a, map_b, g);
+    const int threads = 128 + epi_warps(terms) * 32;
+    if (which == 0) gemm_topk_kernel<3, false, false><<<grid, threads, kGemmSmemBytes, st>>>(map_a, map_b, g);
+    if (which == 1) gemm_topk_kernel<1, false, false><<<grid, threads, kGemmSmemBytes, st>>>(map_a, map_b, g);
+    if (which == 2) gemm_topk_kernel<1, true, false><<<grid, threads, kGemmSmemBytes, st>>>(map_a, map_b, g);
     profile_end(st);
     ICR_LAUNCH_CHECK();
     const bool last = (p == np - 1);
     const int cur = p & 1, prev = cur ^ 1;
-    rc = launch_select_hist(g.cand, g.cand_cnt, Q, g.chunks * kEpiHalves, g.seg_cap, g.seg_cap,
+    rc = launch_select_hist(g.cand, g.cand_cnt, Q, g.chunks * (epi_warps(terms) / 4), g.seg_cap, g.seg_cap,
                        p > 0 ? reinterpret_cast<uint64_t*>(base + L.carry[prev]) : nullptr,
                        p > 0 ? reinterpret_cast<int*>(base + L.carry_cnt[prev]) : nullptr,
                        last ? nullptr : reinterpret_cast<uint64_t*>(base + L.carry[cur]),
@@ -949,9 +962,10 @@ int launch_gemm_dense(const void* a, int64_t Qa, int64_t lda, const void* b, int
   const int items = qblocks * chunks;
   const int grid = 2 * (items < npairs ? items : npairs);
   profile_begin(kKernelGemm, which == 0 ? 3 : 1, st);
-  if (which == 0) gemm_topk_kernel<3, false, true><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(map_a, map_b, g);
-  if (which == 1) gemm_topk_kernel<1, false, true><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(map_a, map_b, g);
-  if (which == 2) gemm_topk_kernel<1, true, true><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(map_a, map_b, g);
+  const int threads = 128 + epi_warps(which == 0 ? 3 : 1) * 32;
+  if (which == 0) gemm_topk_kernel<3, false, true><<<grid, threads, kGemmSmemBytes, st>>>(map_a, map_b, g);
+  if (which == 1) gemm_topk_kernel<1, false, true><<<grid, threads, kGemmSmemBytes, st>>>(map_a, map_b, g);
+  if (which == 2) gemm_topk_kernel<1, true, true><<<grid, threads, kGemmSmemBytes, st>>>(map_a, map_b, g);
   profile_end(st);
   ICR_LAUNCH_CHECK();
   return ICR_OK;
