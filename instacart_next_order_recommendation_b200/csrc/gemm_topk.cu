@@ -166,6 +166,18 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
                "h"(static_cast<uint16_t>(3))
                : "memory");
 }
+// one lane of a converged warp (warp-uniform predicate)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -467,11 +479,19 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         }
       }
     }
-  } else if (warp == 1 && lane == 0 && rank == 0) {
+  } else if (warp == 1 && rank == 0) {
     // ================= MMA issuer (leader CTA only) =================
+    // The WHOLE warp walks the loop and one elected lane issues: descriptors, barrier addresses and loop state are
+    // then warp-uniform values (uniform registers), not per-thread values that must be moved into uniform
+    // registers before every tcgen05 instruction. With a single-lane branch that traffic made the issue loop,
+    // not the tensor pipe, the limit of the one-term kernels (4 MMAs per stage): profiles/r01_notes.md.
     // instruction descriptor: D=f32, A/B = f16 or bf16, K-major both, N=256, M=256 (two CTAs x 128)
     const uint32_t fmt = BF16 ? 1u : 0u;
     const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(BN >> 3) << 17) | (static_cast<uint32_t>((2 * BM) >> 4) << 24);
+    // descriptors differ only in the 16-byte-unit start address (shared memory is < 256 KB: no carry out of the field)
+    const uint64_t a_res0 = smem_desc_sw128(smem_u32(a_resident));
+    const uint64_t st0 = smem_desc_sw128(smem_u32(stage_base));
+    constexpr uint64_t kTileUnits = kTileBytes >> 4, kStageUnits = kStageBytes >> 4;
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -491,46 +511,51 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(smem_u32(&full_bar[stage]), phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(stage_base + stage * kStageBytes);
-          if (ASTAT) {
-            const uint64_t adesc = smem_desc_sw128(smem_u32(a_resident + kb * kTileBytes)), bdesc = smem_desc_sw128(sa);
+          const uint64_t sd = st0 + static_cast<uint64_t>(stage) * kStageUnits;
+          if (elect_one()) {
+            if (ASTAT) {
+              const uint64_t adesc = a_res0 + static_cast<uint64_t>(kb) * kTileUnits, bdesc = sd;
 #pragma unroll
-            for (int k4 = 0; k4 < BK / 16; ++k4) {
-              const uint64_t o = static_cast<uint64_t>(k4 * 2);
-              umma_f16_pair(d_tmem, adesc + o, bdesc + o, idesc, (kb | k4) != 0 ? 1u : 0u);
-            }
-          } else if (TERMS == 3) {
-            const uint64_t a_hi = smem_desc_sw128(sa), a_lo = smem_desc_sw128(sa + kTileBytes);
-            const uint64_t b_hi = smem_desc_sw128(sa + 2 * kTileBytes), b_lo = smem_desc_sw128(sa + 3 * kTileBytes);
+              for (int k4 = 0; k4 < BK / 16; ++k4) {
+                // advancing 16 elements (32 bytes) along K inside the swizzle atom = +2 in the 16-byte address field
+                const uint64_t o = static_cast<uint64_t>(k4 * 2);
+                umma_f16_pair(d_tmem, adesc + o, bdesc + o, idesc, (kb | k4) != 0 ? 1u : 0u);
+              }
+            } else if (TERMS == 3) {
+              const uint64_t a_hi = sd, a_lo = sd + kTileUnits, b_hi = sd + 2 * kTileUnits, b_lo = sd + 3 * kTileUnits;
 #pragma unroll
-            for (int k4 = 0; k4 < BK / 16; ++k4) {
-              // advancing 16 elements (32 bytes) along K inside the swizzle atom = +2 in the 16-byte address field
-              const uint64_t o = static_cast<uint64_t>(k4 * 2);
-              umma_f16_pair(d_tmem, a_hi + o, b_hi + o, idesc, (kb | k4) != 0 ? 1u : 0u);
-              umma_f16_pair(d_tmem, a_hi + o, b_lo + o, idesc, 1u);
-              umma_f16_pair(d_tmem, a_lo + o, b_hi + o, idesc, 1u);
-            }
-          } else {
-            const uint64_t adesc = smem_desc_sw128(sa), bdesc = smem_desc_sw128(sa + kTileBytes);
+              for (int k4 = 0; k4 < BK / 16; ++k4) {
+                const uint64_t o = static_cast<uint64_t>(k4 * 2);
+                umma_f16_pair(d_tmem, a_hi + o, b_hi + o, idesc, (kb | k4) != 0 ? 1u : 0u);
+                umma_f16_pair(d_tmem, a_hi + o, b_lo + o, idesc, 1u);
+                umma_f16_pair(d_tmem, a_lo + o, b_hi + o, idesc, 1u);
+              }
+            } else {
+              const uint64_t adesc = sd, bdesc = sd + kTileUnits;
 #pragma unroll
-            for (int k4 = 0; k4 < BK / 16; ++k4) {
-              const uint64_t o = static_cast<uint64_t>(k4 * 2);
-              umma_f16_pair(d_tmem, adesc + o, bdesc + o, idesc, (kb | k4) != 0 ? 1u : 0u);
+              for (int k4 = 0; k4 < BK / 16; ++k4) {
+                const uint64_t o = static_cast<uint64_t>(k4 * 2);
+                umma_f16_pair(d_tmem, adesc + o, bdesc + o, idesc, (kb | k4) != 0 ? 1u : 0u);
+              }
             }
+            umma_commit_pair(smem_u32(&empty_bar[stage]));  // frees the stage in both CTAs when these MMAs have read it
+            if (kb == KB - 1) umma_commit_pair(smem_u32(&tfull_bar[acc]));  // accumulator complete -> both epilogues
           }
-          umma_commit_pair(smem_u32(&empty_bar[stage]));  // frees the stage in both CTAs when these MMAs have read it
+          __syncwarp();
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit_pair(smem_u32(&tfull_bar[acc]));  // accumulator complete -> both epilogues
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
         }
       }
-      if (ASTAT) umma_commit_pair(smem_u32(aempty_bar));  // resident queries may be overwritten in both CTAs
+      if (ASTAT) {
+        if (elect_one()) umma_commit_pair(smem_u32(aempty_bar));  // resident queries may be overwritten in both CTAs
+        __syncwarp();
+      }
     }
   } else if (warp >= 4 && warp < 4 + EW) {
     // ================= epilogue: threshold filter, one query per thread =================
