@@ -17,6 +17,8 @@ CASES = {
     "c2bf16": (49_688, 384, 10_000, 100, torch.bfloat16),
     "c2": (49_688, 384, 10_000, 100, torch.float32),
     "c1q4": (49_688, 384, 4, 10, torch.float32),
+    "c4q16": (1_250_000, 768, 16, 100, torch.bfloat16),
+    "c1q32": (49_688, 384, 32, 10, torch.float32),
 }
 
 if __name__ == "__main__":

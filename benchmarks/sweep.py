@@ -145,7 +145,7 @@ def main():
             topk_case("C1 batch-1 top-10 (L2-warm)", 49_688, 384, 1, 10, dt, iters=50, cold=False)
             topk_case("C1 batch-1 top-10, CUDA graph", 49_688, 384, 1, 10, dt, iters=50, cold=True, graph=True)
             topk_case("C1 batch-1 top-10, CUDA graph (L2-warm)", 49_688, 384, 1, 10, dt, iters=50, cold=False, graph=True)
-        for Q in (2, 4, 7):
+        for Q in (2, 4, 7, 8, 16, 32, 64, 128, 256):
             topk_case(f"C1-size batch-{Q} top-10", 49_688, 384, Q, 10, f32, iters=30)
     if on("c2"):
         topk_case("C2 IR eval fp32", 49_688, 384, 10_000, 100, f32, eager=True)

@@ -88,6 +88,7 @@ struct GemmArgs {
   float* dense_out;          // K2' mode: write every score to dense_out[q * dense_ld + row] instead of filtering
   int64_t dense_ld;
   uint64_t* compact_scratch; // [gridDim.x][kEpiWarps][kSegCapMax] global scratch of the (rare) in-kernel compaction
+  int qpad;                  // swapped kernel: queries rounded up to a multiple of 32 (the MMA's N)
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -650,6 +651,258 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   }
 }
 
+
+// =====================================================================================================
+// K2s: "swapped" kernel for small query batches (Q <= 256 and the queries fit in ~half of shared memory).
+//
+// Below the ridge (Q < ~256) the path is HBM-bound, but with queries on the MMA's M axis every catalog tile costs
+// a full M=256 MMA whatever Q is, and half of the ring re-streams the same queries from L2. Here the roles are
+// swapped: the CATALOG tile is the M operand (256 rows per pair, 128 per CTA), the QUERIES are the N operand
+// (N = Q rounded up to 32), loaded once and resident in shared memory. MMA time scales with Q, the whole ring
+// carries catalog bytes only, and the epilogue sees 128 x Q scores per CTA and tile instead of 128 x 256.
+// Epilogue thread = catalog row (TMEM lane); per-query thresholds live in shared memory; survivors go to the
+// (query, chunk, CTA) segment through a shared-memory counter. Same phases, segments and select as K2.
+// =====================================================================================================
+constexpr int kSwapMaxStages = 12;
+constexpr int kSwapThreads = 256;  // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 epilogue
+constexpr int kSwapResidentMax = 64 * 1024;  // leaves >= 8 catalog stages: measured, a 5-stage ring loses to K2
+
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+template <int TERMS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSwapThreads, 1)
+gemm_swap_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_c, const GemmArgs g) {
+  constexpr bool BF16 = (TERMS == 1);
+  constexpr int CT = (TERMS == 3) ? 2 : 1;  // catalog tiles per stage: hi | lo plane
+  constexpr int kStageBytes = CT * kTileBytes;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int KB = g.kb_per_term;
+  const int QH = g.qpad >> 1;              // query rows held by each CTA of the pair
+  const int qtile_bytes = QH * 128;        // one 64-element K block of them (multiple of 2 KB)
+  const int res_bytes = CT * KB * qtile_bytes;
+  int stages = (kRingBytes - res_bytes) / kStageBytes;
+  if (stages > kSwapMaxStages) stages = kSwapMaxStages;
+  unsigned char* q_res = smem;  // block (plane * KB + kb) at q_res + block * qtile_bytes
+  unsigned char* stage_base = smem + res_bytes;
+  float* tau_s = reinterpret_cast<float*>(smem + kRingBytes);  // [256] per-query thresholds (raw units)
+  int* cnt_s = reinterpret_cast<int*>(tau_s + 256);             // [256] keys in this CTA's segment of each query
+  int* flag_s = cnt_s + 256;                                    // [4]   some segment is close to its capacity
+  uint64_t* bars = reinterpret_cast<uint64_t*>(flag_s + 4);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kSwapMaxStages;
+  uint64_t* tfull_bar = bars + 2 * kSwapMaxStages;
+  uint64_t* tempty_bar = bars + 2 * kSwapMaxStages + 2;
+  uint64_t* qfull_bar = bars + 2 * kSwapMaxStages + 4;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kSwapMaxStages + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int items = g.chunks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&tfull_bar[a]), 1);
+      mbar_init(smem_u32(&tempty_bar[a]), 2 * 4);  // four epilogue warps in each CTA
+    }
+    mbar_init(smem_u32(qfull_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_q) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_c) : "memory");
+  }
+  if (warp == 2) tmem_alloc_pair(smem_u32(tmem_ptr), kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0 && lane == 0) {
+    // ================= TMA producer =================
+    const uint32_t qb = smem_u32(qfull_bar);
+    if (rank == 0) mbar_expect_tx(qb, 2 * res_bytes);
+    for (int pl = 0; pl < CT; ++pl)
+      for (int kb = 0; kb < KB; ++kb)
+        tma_load_2d_pair(smem_u32(q_res + (pl * KB + kb) * qtile_bytes), &tma_q, pl * g.plane_stride + kb * BK, static_cast<int>(rank) * QH, qb);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int w = pair; w < items; w += npairs) {
+      const int t0 = chunk_first_tile(g, w), t1 = chunk_first_tile(g, w + 1);
+      for (int tile = t0; tile < t1; ++tile) {
+        const int crow = tile * BN + static_cast<int>(rank) * BNH;
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          if (rank == 0) mbar_expect_tx(fb, 2 * kStageBytes);
+          const uint32_t sa = smem_u32(stage_base + stage * kStageBytes);
+          tma_load_2d_pair(sa, &tma_c, kb * BK, crow, fb);
+          if (TERMS == 3) tma_load_2d_pair(sa + kTileBytes, &tma_c, g.plane_stride + kb * BK, crow, fb);
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && rank == 0) {
+    // ================= MMA issuer: whole warp walks the loop, one elected lane issues =================
+    const uint32_t fmt = BF16 ? 1u : 0u;
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(g.qpad >> 3) << 17) | (static_cast<uint32_t>(BN >> 4) << 24);
+    const uint64_t qd0 = smem_desc_sw128(smem_u32(q_res));
+    const uint64_t cd0 = smem_desc_sw128(smem_u32(stage_base));
+    constexpr uint64_t kTileUnits = kTileBytes >> 4, kStageUnits = kStageBytes >> 4;
+    const uint64_t qunits = static_cast<uint64_t>(qtile_bytes >> 4);
+    mbar_wait(smem_u32(qfull_bar), 0);
+    tc_fence_after();
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int w = pair; w < items; w += npairs) {
+      const int t0 = chunk_first_tile(g, w), t1 = chunk_first_tile(g, w + 1);
+      for (int tile = t0; tile < t1; ++tile) {
+        mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * 256);
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          tc_fence_after();
+          const uint64_t c_hi = cd0 + static_cast<uint64_t>(stage) * kStageUnits;
+          const uint64_t q_hi = qd0 + static_cast<uint64_t>(kb) * qunits;
+          if (elect_one()) {
+#pragma unroll
+            for (int k4 = 0; k4 < BK / 16; ++k4) {
+              const uint64_t o = static_cast<uint64_t>(k4 * 2);
+              umma_f16_pair(d_tmem, c_hi + o, q_hi + o, idesc, (kb | k4) != 0 ? 1u : 0u);
+              if (TERMS == 3) {
+                const uint64_t c_lo = c_hi + kTileUnits, q_lo = q_hi + static_cast<uint64_t>(KB) * qunits;
+                umma_f16_pair(d_tmem, c_hi + o, q_lo + o, idesc, 1u);
+                umma_f16_pair(d_tmem, c_lo + o, q_hi + o, idesc, 1u);
+              }
+            }
+            umma_commit_pair(smem_u32(&empty_bar[stage]));
+            if (kb == KB - 1) umma_commit_pair(smem_u32(&tfull_bar[acc]));
+          }
+          __syncwarp();
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue: thread = catalog row, columns = queries =================
+    const int ew = warp & 3, et = threadIdx.x - 128;
+    const int cap = g.seg_cap;
+    uint64_t* scratch = g.compact_scratch + (static_cast<int64_t>(blockIdx.x) * kEpiWarps + ew) * kSegCapMax;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int w = pair; w < items; w += npairs) {
+      const int t0 = chunk_first_tile(g, w), t1 = chunk_first_tile(g, w + 1);
+      const int64_t seg0 = static_cast<int64_t>(w) * 2 + rank;  // + q * chunks * 2
+      for (int j = et; j < 256; j += 128) {
+        tau_s[j] = j < g.Q ? g.tau[j] : INFINITY;
+        cnt_s[j] = 0;
+      }
+      if (et == 0) flag_s[0] = 0;
+      epi_sync();
+      for (int tile = t0; tile < t1; ++tile) {
+        const int row = tile * BN + static_cast<int>(rank) * BNH + ew * 32 + lane;
+        const bool valid = row < g.N && !(g.mask && g.mask[row]);
+        const float cinv_r = BF16 ? (row < g.N ? __ldg(g.cinv + row) : 0.f) : 1.0f;
+        const uint32_t nrow = ~static_cast<uint32_t>(row);
+        mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * 256);
+        for (int jb = 0; jb < g.qpad; jb += 32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + jb, r);
+          tmem_ld_wait(r);
+          float sc[32];
+          unsigned m = 0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 t4 = *reinterpret_cast<const float4*>(tau_s + jb + j);  // broadcast reads
+            sc[j] = __uint_as_float(r[j]) * cinv_r;
+            sc[j + 1] = __uint_as_float(r[j + 1]) * cinv_r;
+            sc[j + 2] = __uint_as_float(r[j + 2]) * cinv_r;
+            sc[j + 3] = __uint_as_float(r[j + 3]) * cinv_r;
+            m |= (sc[j] > t4.x ? 1u : 0u) << j;
+            m |= (sc[j + 1] > t4.y ? 1u : 0u) << (j + 1);
+            m |= (sc[j + 2] > t4.z ? 1u : 0u) << (j + 2);
+            m |= (sc[j + 3] > t4.w ? 1u : 0u) << (j + 3);
+          }
+          if (!valid) m = 0;
+          if (__any_sync(kFull, m != 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (m & (1u << j)) {
+                const int q = jb + j;
+                const int pos = atomicAdd(&cnt_s[q], 1);
+                if (pos < cap) {
+                  uint64_t* seg = g.cand + (static_cast<int64_t>(q) * g.chunks * 2 + seg0) * cap;
+                  seg[pos] = (static_cast<uint64_t>(__float_as_uint(sc[j])) << 32) | nrow;
+                }
+                if (pos >= cap - 129) flag_s[0] = 1;
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(smem_u32(&tempty_bar[acc]), 0);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+        // A tile adds at most 128 keys per query to this CTA's segments: any segment that could overflow during
+        // the next tile is cut back to its k best now, which also raises that query's threshold in this CTA.
+        epi_sync();
+        if (flag_s[0]) {
+          for (int q = ew; q < g.Q; q += 4) {
+            const int n = min(cnt_s[q], cap);
+            if (n > cap - 128) {
+              uint64_t* seg = g.cand + (static_cast<int64_t>(q) * g.chunks * 2 + seg0) * cap;
+              for (int i = lane; i < cap; i += 32) scratch[i] = (i < n) ? canonical_key(__ldcg(seg + i)) : 0ull;
+              warp_bitonic_sort_desc(scratch, cap, lane);
+              const int kept = n < g.k ? n : g.k;
+              for (int i = lane; i < kept; i += 32) seg[i] = raw_key(scratch[i]);
+              if (lane == 0) {
+                cnt_s[q] = kept;
+                if (n >= g.k) tau_s[q] = fmaxf(tau_s[q], unorder_bits(static_cast<uint32_t>(scratch[g.k - 1] >> 32)));
+              }
+              __syncwarp();
+            }
+          }
+          epi_sync();
+          if (et == 0) flag_s[0] = 0;
+          epi_sync();
+        }
+      }
+      for (int j = et; j < g.Q; j += 128) g.cand_cnt[static_cast<int64_t>(j) * g.chunks * 2 + seg0] = min(cnt_s[j], cap);
+      epi_sync();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, kTmemCols);
+  }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------
 int launch_row_inv_norms(const void* x, int64_t rows, int64_t dim, int64_t ld, int dtype, float* inv, cudaStream_t st);
 int launch_split_planes(const float* x, int64_t rows, int64_t dim, int64_t ld, uint16_t* planes, cudaStream_t st);
@@ -667,6 +920,18 @@ constexpr size_t kGemmSmemBytes = static_cast<size_t>(kRingBytes) + kEpiWarps * 
                                   (2 * kMaxStages + 6) * sizeof(uint64_t) + 16 + 1024;
 static int seg_cap_for(int k) { return k <= 128 ? 256 : kSegCapMax; }
 static_assert(kGemmSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
+constexpr size_t kSwapSmemBytes = static_cast<size_t>(kRingBytes) + 2 * 256 * 4 + 16 + (2 * kSwapMaxStages + 6) * sizeof(uint64_t) + 16 + 1024;
+static_assert(kSwapSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
+
+// the swapped kernel applies when one block of queries is small enough to stay resident next to a useful ring
+static bool swap_applies(int64_t Q, int64_t D, int dtype) {
+  static const bool disabled = getenv("ICR_NO_SWAP") != nullptr;  // A/B switch for benchmarks
+  if (disabled || Q > 256) return false;
+  const int64_t qpad = (Q + 31) / 32 * 32;
+  const int64_t kb = (D + BK - 1) / BK;
+  const int64_t res = (dtype == ICR_F32 ? 2 : 1) * kb * (qpad / 2) * 128;
+  return res <= kSwapResidentMax;
+}
 constexpr int kNumSMs = 148;
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -685,7 +950,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // 2-D map over a row-major [rows, cols] matrix of 16-bit elements, box = [128 rows, 64 cols], 128B swizzle
-static int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld_elems, bool bf16) {
+static int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld_elems, bool bf16, int box_rows = 128) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point unavailable");
@@ -693,7 +958,7 @@ static int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols
   }
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld_elems) * 2};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), 128u};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   const CUresult r = enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims,
                          strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -712,12 +977,17 @@ struct Phase {
 
 // Phases of geometrically growing tile ranges. tau after a phase is the exact k-th score of all rows seen,
 // so a phase that multiplies the rows seen by g admits ~k*ln(g) (at most ~k*(g-1)) survivors per query.
-static int plan_phases(int64_t N, int qblocks, int k, Phase* out, int max_phases) {
+// swapped kernel: its epilogue work is small (128 x Q scores per tile), so it affords denser survivors in exchange
+// for fewer phases - every phase costs a launch of the GEMM and of the select (~25 us for a small batch)
+static int plan_phases(int64_t N, int qblocks, int k, Phase* out, int max_phases, bool swap) {
   const int T = static_cast<int>((N + BN - 1) / BN);
-  const int growth = 8;
+  static const int swap_growth = getenv("ICR_SWAP_GROWTH") ? atoi(getenv("ICR_SWAP_GROWTH")) : 32;  // tuning hook
+  const int growth = swap ? swap_growth : 8;
   const int npairs = kNumSMs / 2;
   int first = (2 * k + BN - 1) / BN;
   if (first < 2) first = 2;
+  static const int swap_first = getenv("ICR_SWAP_FIRST") ? atoi(getenv("ICR_SWAP_FIRST")) : 8;  // tuning hook
+  if (swap && first < swap_first) first = swap_first;
   int n = 0, begin = 0, end = first < T ? first : T;
   while (begin < T && n < max_phases) {
     if (n == max_phases - 1) end = T;
@@ -765,7 +1035,7 @@ static GemmWs gemm_ws_layout(int64_t Q, int64_t N, int64_t D, int dtype, int k, 
   GemmWs w{};
   const int qblocks = static_cast<int>((Q + 2 * BM - 1) / (2 * BM));
   Phase ph[kMaxPhases];
-  const int np = plan_phases(N, qblocks, k, ph, kMaxPhases);
+  const int np = plan_phases(N, qblocks, k, ph, kMaxPhases, swap_applies(Q, D, dtype));
   int maxc = 1;
   for (int i = 0; i < np; ++i) maxc = ph[i].chunks > maxc ? ph[i].chunks : maxc;
   w.max_chunks = maxc;
@@ -786,7 +1056,7 @@ static GemmWs gemm_ws_layout(int64_t Q, int64_t N, int64_t D, int dtype, int k, 
     w.carry_cnt[i] = take(static_cast<size_t>(Q) * 4);
   }
   w.seg_cap = seg_cap_for(k);
-  const int halves = epi_warps(dtype == ICR_F32 ? 3 : 1) / 4;
+  const int halves = swap_applies(Q, D, dtype) ? 2 : epi_warps(dtype == ICR_F32 ? 3 : 1) / 4;
   w.cand = take(static_cast<size_t>(Q) * maxc * halves * w.seg_cap * 8);
   w.cand_cnt = take(static_cast<size_t>(Q) * maxc * halves * 4);
   w.scratch = take(static_cast<size_t>(kNumSMs) * kEpiWarps * kSegCapMax * 8);  // in-kernel compaction scratch
@@ -870,11 +1140,21 @@ int launch_gemm_topk(const void* queries, int64_t Q, int64_t ldq, const void* ca
     g.qinv = qinv;
     g.cinv = cinv;
   }
-  // kernel variant: 0 = fp16 planes (3 terms), 1 = bf16 streaming both operands, 2 = bf16 with resident queries
-  static thread_local bool attr_set[3] = {false, false, false};
-  const int which = terms == 3 ? 0 : (g.kb_per_term <= kAStatMaxKB ? 2 : 1);
+  // kernel variant: 0 = fp16 planes (3 terms), 1 = bf16 streaming both operands, 2 = bf16 with resident queries,
+  // 3 / 4 = swapped kernel (small batches) on planes / bf16
+  static thread_local bool attr_set[5] = {false, false, false, false, false};
+  const bool swap = swap_applies(Q, D, dtype);
+  const int which = swap ? (terms == 3 ? 3 : 4) : (terms == 3 ? 0 : (g.kb_per_term <= kAStatMaxKB ? 2 : 1));
+  if (swap) {
+    g.qpad = static_cast<int>((Q + 31) / 32 * 32);
+    if (terms == 3) rc = make_map(&map_a, base + L.q_planes, Q, 2 * dp, 2 * dp, false, g.qpad / 2);
+    else rc = make_map(&map_a, queries, Q, D, ldq, true, g.qpad / 2);
+    if (rc) return rc;
+  }
   if (!attr_set[which]) {
     const int smem = static_cast<int>(kGemmSmemBytes);
+    if (which == 3) ICR_CUDA_CHECK(cudaFuncSetAttribute(gemm_swap_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSwapSmemBytes)));
+    if (which == 4) ICR_CUDA_CHECK(cudaFuncSetAttribute(gemm_swap_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSwapSmemBytes)));
     if (which == 0) ICR_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_kernel<3, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     if (which == 1) ICR_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_kernel<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     if (which == 2) ICR_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_kernel<1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -885,7 +1165,7 @@ int launch_gemm_topk(const void* queries, int64_t Q, int64_t ldq, const void* ca
   ICR_LAUNCH_CHECK();
 
   Phase ph[kMaxPhases];
-  const int np = plan_phases(N, qblocks, k, ph, kMaxPhases);
+  const int np = plan_phases(N, qblocks, k, ph, kMaxPhases, swap);
   for (int p = 0; p < np; ++p) {
     g.tile_begin = ph[p].tile_begin;
     g.tile_end = ph[p].tile_end;
@@ -898,11 +1178,13 @@ int launch_gemm_topk(const void* queries, int64_t Q, int64_t ldq, const void* ca
     if (which == 0) gemm_topk_kernel<3, false, false><<<grid, threads, kGemmSmemBytes, st>>>(map_a, map_b, g);
     if (which == 1) gemm_topk_kernel<1, false, false><<<grid, threads, kGemmSmemBytes, st>>>(map_a, map_b, g);
     if (which == 2) gemm_topk_kernel<1, true, false><<<grid, threads, kGemmSmemBytes, st>>>(map_a, map_b, g);
+    if (which == 3) gemm_swap_kernel<3><<<grid, kSwapThreads, kSwapSmemBytes, st>>>(map_a, map_b, g);
+    if (which == 4) gemm_swap_kernel<1><<<grid, kSwapThreads, kSwapSmemBytes, st>>>(map_a, map_b, g);
     profile_end(st);
     ICR_LAUNCH_CHECK();
     const bool last = (p == np - 1);
     const int cur = p & 1, prev = cur ^ 1;
-    rc = launch_select_hist(g.cand, g.cand_cnt, Q, g.chunks * (epi_warps(terms) / 4), g.seg_cap, g.seg_cap,
+    rc = launch_select_hist(g.cand, g.cand_cnt, Q, g.chunks * (swap ? 2 : epi_warps(terms) / 4), g.seg_cap, g.seg_cap,
                        p > 0 ? reinterpret_cast<uint64_t*>(base + L.carry[prev]) : nullptr,
                        p > 0 ? reinterpret_cast<int*>(base + L.carry_cnt[prev]) : nullptr,
                        last ? nullptr : reinterpret_cast<uint64_t*>(base + L.carry[cur]),

@@ -19,6 +19,7 @@ namespace icr {
 constexpr int kHsWarps = 4;       // queries per CTA (11 KB of shared memory each: 5 CTAs = 20 warps per SM)
 constexpr int kHsCap = 1024;      // keys buffered per query at once
 constexpr int kHsSel = 256;       // >= ICR_MAX_K
+constexpr int kHsPref = 448;      // segments per gather round: the prefix array (+1) is overlaid on sel[] (512 ints)
 
 struct HistSelectArgs {
   const uint64_t* seg_keys;  // [Q][nseg][seg_stride]
@@ -50,7 +51,6 @@ struct HsSmem {
   uint64_t buf[kHsWarps][kHsCap];
   uint64_t sel[kHsWarps][kHsSel];
   unsigned int hist[kHsWarps][kHsBins];
-  int pref[kHsWarps][33];
 };
 
 __global__ void __launch_bounds__(kHsWarps * 32) select_hist_kernel(HistSelectArgs a) {
@@ -62,7 +62,6 @@ __global__ void __launch_bounds__(kHsWarps * 32) select_hist_kernel(HistSelectAr
   uint64_t* buf = sm.buf[warp];
   uint64_t* sel = sm.sel[warp];
   unsigned int* hist = sm.hist[warp];
-  int* pref = sm.pref[warp];
   const int k = a.k;
   const int cap = min(a.seg_cap, a.seg_stride);
 
@@ -72,27 +71,47 @@ __global__ void __launch_bounds__(kHsWarps * 32) select_hist_kernel(HistSelectAr
     for (int i = lane; i < n; i += 32) buf[i] = a.carry_in[q * k + i];
   }
   const uint64_t* qbase = a.seg_keys + q * a.nseg * static_cast<int64_t>(a.seg_stride);
-  for (int g0 = 0; g0 < a.nseg; g0 += 32) {
-    const int s_mine = g0 + lane;
-    const int my_cnt = (s_mine < a.nseg) ? min(a.seg_cnt[q * a.nseg + s_mine], cap) : 0;
-    int incl = my_cnt;
+  // Segment lengths of up to kHsPref segments are fetched at once (independent loads) and prefix-summed in shared
+  // memory, then the keys are gathered by flat index (binary search for the segment): a small batch may have
+  // hundreds of short segments per query (one per chunk and CTA), and walking them 32 at a time made the gather
+  // a chain of dependent memory round trips. The prefix array lives in `sel`, which is idle until the selection.
+  int* pref = reinterpret_cast<int*>(sel);
+  for (int g0 = 0; g0 < a.nseg; g0 += kHsPref) {
+    const int ng = min(kHsPref, a.nseg - g0);
+    int top = 1;
+    while (top * 2 <= ng) top *= 2;  // first step of the binary search
+    int done = 0, total = 0;
+    bool have_pref = false;
+    do {
+      if (!have_pref) {
+        __syncwarp();
+#pragma unroll 4
+        for (int i = lane; i < ng; i += 32) pref[i] = min(__ldg(a.seg_cnt + q * a.nseg + g0 + i), cap);
+        __syncwarp();
+        int carry = 0;
+        for (int b0 = 0; b0 < ng; b0 += 32) {
+          const int v = (b0 + lane < ng) ? pref[b0 + lane] : 0;
+          int incl = v;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(kFull, incl, o);
-      if (lane >= o) incl += v;
-    }
-    const int total = __shfl_sync(kFull, incl, 31);
-    __syncwarp();
-    pref[lane] = incl - my_cnt;
-    if (lane == 31) pref[32] = total;
-    __syncwarp();
-    int done = 0;
-    while (done < total) {
-      if (kHsCap - n < 32) {  // buffer full: keep the k best and go on
+          for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += u;
+          }
+          if (b0 + lane < ng) pref[b0 + lane] = carry + incl - v;
+          carry += __shfl_sync(kFull, incl, 31);
+        }
+        if (lane == 0) pref[ng] = carry;
+        total = carry;
+        have_pref = true;
+        __syncwarp();
+      }
+      if (done >= total) break;
+      if (kHsCap - n < 32) {  // buffer full: keep the k best and go on (the selection overwrites the prefix array)
         warp_select_topk(buf, n, k, sel, hist, lane);
         for (int i = lane; i < k; i += 32) buf[i] = sel[i];
         n = k;
-        __syncwarp();
+        have_pref = false;
+        continue;
       }
       const int take = min(kHsCap - n, total - done);
       // 8 independent global loads per lane in flight before the first shared-memory store: the gather is
@@ -105,12 +124,11 @@ __global__ void __launch_bounds__(kHsWarps * 32) select_hist_kernel(HistSelectAr
           v[u] = 0ull;
           if (i < take) {
             const int idx = done + i;
-            // segment holding flat index idx: largest s with pref[s] <= idx (binary search over 32 entries)
-            int s = 0;
-#pragma unroll
-            for (int step = 16; step > 0; step >>= 1)
-              if (pref[s + step] <= idx) s += step;
-            v[u] = __ldcs(qbase + static_cast<int64_t>(g0 + s) * a.seg_stride + (idx - pref[s]));
+            // segment holding flat index idx: largest s with pref[s] <= idx
+            int sg = 0;
+            for (int step = top; step > 0; step >>= 1)
+              if (sg + step < ng && pref[sg + step] <= idx) sg += step;
+            v[u] = __ldcs(qbase + static_cast<int64_t>(g0 + sg) * a.seg_stride + (idx - pref[sg]));
           }
         }
 #pragma unroll
@@ -122,7 +140,7 @@ __global__ void __launch_bounds__(kHsWarps * 32) select_hist_kernel(HistSelectAr
       n += take;
       done += take;
       __syncwarp();
-    }
+    } while (done < total);
   }
   __syncwarp();
   int kept = n;
@@ -151,6 +169,238 @@ __global__ void __launch_bounds__(kHsWarps * 32) select_hist_kernel(HistSelectAr
       const bool ok = i < kept;
       a.out_scores[q * k + i] = ok ? key_score(buf[i]) * scale : -INFINITY;
       a.out_ids[q * k + i] = ok ? static_cast<int64_t>(key_row(buf[i])) + a.id_offset : -1;
+    }
+  }
+}
+
+// ---- block-per-query variant for small batches --------------------------------------------------------------
+// With a few dozen queries the warp-per-query kernel leaves the GPU idle while each warp walks thousands of keys on
+// its own (the swapped GEMM kernel produces one short segment per chunk and CTA: hundreds per query). Here a CTA of
+// 256 threads owns a query: block-wide gather, block-wide histogram partition down to <= 1024 keys, then one warp
+// finishes with warp_select_topk. Same inputs, outputs and exactness as select_hist_kernel.
+constexpr int kBsThreads = 256;
+constexpr int kBsCap = 6144;    // keys buffered per query at once (two buffers: 96 KB)
+constexpr int kBsPref = 1024;   // segments per gather round
+
+struct BsSmem {
+  uint64_t buf[kBsCap];
+  uint64_t bnd[kBsCap];
+  uint64_t sel[kHsSel];
+  uint64_t red[2 * (kBsThreads / 32)];
+  unsigned int hist[kHsBins];
+  int pref[kBsPref + 1];
+  int misc[8];
+};
+
+// k largest of cur[0..n) -> sm.sel[0..k) (unordered); n > k. `cur` is sm.buf; sm.bnd is scratch.
+__device__ __forceinline__ void block_select_topk(BsSmem& sm, int n, int k, int tid) {
+  const int warp = tid >> 5, lane = tid & 31;
+  uint64_t* cur = sm.buf;
+  uint64_t* other = sm.bnd;
+  int need = k, nsel = 0, len = n;
+  for (;;) {
+    if (len <= 1024) {
+      if (warp == 0) {
+        if (need == len) {
+          for (int i = lane; i < len; i += 32) sm.sel[nsel + i] = cur[i];
+        } else {
+          warp_select_topk(cur, len, need, sm.sel + nsel, sm.hist, lane);
+        }
+      }
+      __syncthreads();
+      return;
+    }
+    uint64_t mn = ~0ull, mx = 0ull;
+    for (int i = tid; i < len; i += kBsThreads) {
+      const uint64_t key = cur[i];
+      mn = key < mn ? key : mn;
+      mx = key > mx ? key : mx;
+    }
+    mn = warp_min_u64(mn);
+    mx = warp_max_u64(mx);
+    if (lane == 0) {
+      sm.red[warp] = mn;
+      sm.red[kBsThreads / 32 + warp] = mx;
+    }
+    if (tid < kHsBins) sm.hist[tid] = 0u;
+    __syncthreads();
+    mn = sm.red[0];
+    mx = sm.red[kBsThreads / 32];
+#pragma unroll
+    for (int w = 1; w < kBsThreads / 32; ++w) {
+      mn = sm.red[w] < mn ? sm.red[w] : mn;
+      mx = sm.red[kBsThreads / 32 + w] > mx ? sm.red[kBsThreads / 32 + w] : mx;
+    }
+    const uint64_t range = mx - mn;
+    const int bits = 64 - __clzll(static_cast<long long>(range | 1ull));
+    const int shift = bits > 8 ? bits - 8 : 0;
+    for (int i = tid; i < len; i += kBsThreads) atomicAdd(&sm.hist[255 - static_cast<int>((cur[i] - mn) >> shift)], 1u);
+    __syncthreads();
+    if (warp == 0) {  // cumulative counts from the top bin: lane L owns t in [8L, 8L+8)
+      unsigned int local[8], lsum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        local[j] = sm.hist[lane * 8 + j];
+        lsum += local[j];
+      }
+      unsigned int incl = lsum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int v = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += v;
+      }
+      unsigned int c = incl - lsum;
+      if (c < static_cast<unsigned int>(need) && static_cast<unsigned int>(need) <= incl) {
+        int t_star = -1;
+        unsigned int above = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (t_star < 0 && c + local[j] >= static_cast<unsigned int>(need)) {
+            t_star = lane * 8 + j;
+            above = c;
+          }
+          c += local[j];
+        }
+        sm.misc[0] = 255 - t_star;
+        sm.misc[1] = static_cast<int>(above);
+      }
+      if (lane == 0) {
+        sm.misc[2] = nsel;
+        sm.misc[3] = 0;
+      }
+    }
+    __syncthreads();
+    const int b_star = sm.misc[0];
+    for (int i = tid; i < len; i += kBsThreads) {
+      const uint64_t key = cur[i];
+      const int bin = static_cast<int>((key - mn) >> shift);
+      if (bin > b_star) sm.sel[atomicAdd(&sm.misc[2], 1)] = key;
+      else if (bin == b_star) other[atomicAdd(&sm.misc[3], 1)] = key;
+    }
+    __syncthreads();
+    nsel = sm.misc[2];
+    need -= sm.misc[1];
+    const int nb = sm.misc[3];
+    __syncthreads();  // misc is rewritten in the next round
+    if (need == nb) {
+      for (int i = tid; i < nb; i += kBsThreads) sm.sel[nsel + i] = other[i];
+      __syncthreads();
+      return;
+    }
+    uint64_t* t = cur;
+    cur = other;
+    other = t;
+    len = nb;
+    if (cur != sm.buf && len <= 1024) {  // the warp-level finish works in place on `cur`; keep it simple: move back
+      for (int i = tid; i < len; i += kBsThreads) sm.buf[i] = cur[i];
+      __syncthreads();
+      cur = sm.buf;
+      other = sm.bnd;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kBsThreads) select_block_kernel(HistSelectArgs a) {
+  extern __shared__ __align__(16) unsigned char bs_raw[];
+  BsSmem& sm = *reinterpret_cast<BsSmem*>(bs_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t q = blockIdx.x;
+  const int k = a.k;
+  const int cap = min(a.seg_cap, a.seg_stride);
+  int n = 0;
+  if (a.carry_in) {
+    n = min(a.carry_cnt_in[q], k);
+    for (int i = tid; i < n; i += kBsThreads) sm.buf[i] = a.carry_in[q * k + i];
+  }
+  const uint64_t* qbase = a.seg_keys + q * a.nseg * static_cast<int64_t>(a.seg_stride);
+  for (int g0 = 0; g0 < a.nseg; g0 += kBsPref) {
+    const int ng = min(kBsPref, a.nseg - g0);
+    int top = 1;
+    while (top * 2 <= ng) top *= 2;
+    __syncthreads();
+    for (int i = tid; i < ng; i += kBsThreads) sm.pref[i] = min(__ldg(a.seg_cnt + q * a.nseg + g0 + i), cap);
+    __syncthreads();
+    if (warp == 0) {
+      int carry = 0;
+      for (int b0 = 0; b0 < ng; b0 += 32) {
+        const int v = (b0 + lane < ng) ? sm.pref[b0 + lane] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int u = __shfl_up_sync(kFull, incl, o);
+          if (lane >= o) incl += u;
+        }
+        if (b0 + lane < ng) sm.pref[b0 + lane] = carry + incl - v;
+        carry += __shfl_sync(kFull, incl, 31);
+      }
+      if (lane == 0) sm.pref[ng] = carry;
+    }
+    __syncthreads();
+    const int total = sm.pref[ng];
+    int done = 0;
+    while (done < total) {
+      if (kBsCap - n < kBsThreads) {  // buffer full: keep the k best and go on
+        block_select_topk(sm, n, k, tid);
+        for (int i = tid; i < k; i += kBsThreads) sm.buf[i] = sm.sel[i];
+        n = k;
+        __syncthreads();
+      }
+      const int take = min(kBsCap - n, total - done);
+      for (int i0 = 0; i0 < take; i0 += kBsThreads * 4) {
+        uint64_t v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * kBsThreads + tid;
+          v[u] = 0ull;
+          if (i < take) {
+            const int idx = done + i;
+            int sg = 0;
+            for (int step = top; step > 0; step >>= 1)
+              if (sg + step < ng && sm.pref[sg + step] <= idx) sg += step;
+            v[u] = __ldcs(qbase + static_cast<int64_t>(g0 + sg) * a.seg_stride + (idx - sm.pref[sg]));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * kBsThreads + tid;
+          if (i < take) sm.buf[n + i] = a.raw_keys ? canonical_from_raw(v[u]) : v[u];
+        }
+      }
+      n += take;
+      done += take;
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  int kept = n;
+  if (n > k) {
+    block_select_topk(sm, n, k, tid);
+    kept = k;
+  } else {
+    for (int i = tid; i < n; i += kBsThreads) sm.sel[i] = sm.buf[i];
+    __syncthreads();
+  }
+  if (a.carry_out) {
+    for (int i = tid; i < kept; i += kBsThreads) a.carry_out[q * k + i] = sm.sel[i];
+    if (tid == 0) a.carry_cnt_out[q] = kept;
+  }
+  // every thread ranks one selected key (kept <= 256): the minimum is the new threshold, the ranks the output order
+  const bool mine = tid < kept;
+  const uint64_t key = mine ? sm.sel[tid] : 0ull;
+  int rank = 0;
+  if (mine)
+    for (int j = 0; j < kept; ++j) rank += (sm.sel[j] > key) ? 1 : 0;
+  if (a.tau_out && mine && rank == kept - 1) a.tau_out[q] = (kept >= k) ? key_score(key) : -INFINITY;
+  if (a.tau_out && kept == 0 && tid == 0) a.tau_out[q] = -INFINITY;
+  if (a.out_scores) {
+    const float scale = a.out_scale * (a.out_qscale ? a.out_qscale[q] : 1.0f);
+    if (mine) {
+      a.out_scores[q * k + rank] = key_score(key) * scale;
+      a.out_ids[q * k + rank] = static_cast<int64_t>(key_row(key)) + a.id_offset;
+    }
+    for (int i = kept + tid; i < k; i += kBsThreads) {
+      a.out_scores[q * k + i] = -INFINITY;
+      a.out_ids[q * k + i] = -1;
     }
   }
 }
@@ -184,6 +434,17 @@ int launch_select_hist(const uint64_t* seg_keys, const int* seg_cnt, int64_t Q, 
   a.out_scale = out_scale;
   a.out_qscale = out_qscale;
   a.raw_keys = 1;  // the only producer of segments is the GEMM epilogue
+  static const int block_max_q = getenv("ICR_SELECT_BLOCK_MAXQ") ? atoi(getenv("ICR_SELECT_BLOCK_MAXQ")) : 512;  // tuning hook
+  if (Q <= block_max_q) {
+    static thread_local bool battr_set = false;
+    if (!battr_set) {
+      ICR_CUDA_CHECK(cudaFuncSetAttribute(select_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(BsSmem))));
+      battr_set = true;
+    }
+    select_block_kernel<<<static_cast<unsigned>(Q), kBsThreads, sizeof(BsSmem), st>>>(a);
+    ICR_LAUNCH_CHECK();
+    return ICR_OK;
+  }
   const unsigned grid = static_cast<unsigned>((Q + kHsWarps - 1) / kHsWarps);
   select_hist_kernel<<<grid, kHsWarps * 32, sizeof(HsSmem), st>>>(a);
   ICR_LAUNCH_CHECK();
