@@ -205,7 +205,13 @@ int icr_split_f16_planes(const float* x, int64_t rows, int64_t dim, int64_t ld, 
 static int resolve_path(int path, int64_t Q, int64_t N, int64_t D, int dtype, int k, const uint8_t* mask) {
   if (path == ICR_PATH_GEMV || path == ICR_PATH_GEMM) return path;
   // small batches are HBM-bound GEMVs; larger ones are tensor-core work
-  const int gemv_max_q = (dtype == ICR_F32) ? 7 : 3;
+  int gemv_max_q = (dtype == ICR_F32) ? 7 : 3;
+  // The tensor-core pipeline costs ~55 us of launches and selects on top of its stream, but streams a large catalog
+  // closer to the HBM rate than the multi-query GEMV passes (measured, profiles/r01_notes.md): crossover ~256 MB
+  // for 4-7 queries, ~640 MB for 2-3.
+  const double cat_bytes = static_cast<double>(N) * static_cast<double>(D) * (dtype == ICR_F32 ? 4.0 : 2.0);
+  if (cat_bytes >= 256e6 && gemv_max_q > 3) gemv_max_q = 3;
+  if (cat_bytes >= 640e6) gemv_max_q = 1;
   if (Q > gemv_max_q && gemm_topk_supported(Q, N, D, dtype, k, mask)) return ICR_PATH_GEMM;
   return ICR_PATH_GEMV;
 }

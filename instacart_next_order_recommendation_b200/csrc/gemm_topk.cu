@@ -89,6 +89,7 @@ struct GemmArgs {
   int64_t dense_ld;
   uint64_t* compact_scratch; // [gridDim.x][kEpiWarps][kSegCapMax] global scratch of the (rare) in-kernel compaction
   int qpad;                  // swapped kernel: queries rounded up to a multiple of 32 (the MMA's N)
+  int dense_raw;             // dense mode stores raw-unit scores (no per-query factor): first phase of the top-k path
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -248,8 +249,9 @@ __device__ __forceinline__ void compact_full_segments(SegState& s, uint64_t* scr
     uint64_t* seg = reinterpret_cast<uint64_t*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(s.seg), L));
     const int n = __shfl_sync(kFull, s.cnt, L);
     __syncwarp();
-    for (int i = lane; i < cap; i += 32) scratch[i] = (i < n) ? canonical_key(__ldcg(seg + i)) : 0ull;
-    warp_bitonic_sort_desc(scratch, cap, lane);
+    const int P = cap <= 256 ? 256 : kSegCapMax;  // power of two for the sorting network
+    for (int i = lane; i < P; i += 32) scratch[i] = (i < n) ? canonical_key(__ldcg(seg + i)) : 0ull;
+    warp_bitonic_sort_desc(scratch, P, lane);
     const int kept = n < k ? n : k;
     for (int i = lane; i < kept; i += 32) seg[i] = raw_key(scratch[i]);
     const uint32_t t_new = (n >= k) ? static_cast<uint32_t>(scratch[k - 1] >> 32) : 0u;
@@ -579,7 +581,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       constexpr bool dense = DENSE;  // compile-time: the top-k instantiation keeps its register budget
       s.tau_ob = (live && !dense) ? order_bits(g.tau[q]) : 0xFFFFFFFFu;
       float* out_q = dense ? g.dense_out + static_cast<int64_t>(live ? q : 0) * g.dense_ld : nullptr;
-      const float qscale = dense ? g.acc_scale * ((BF16 && live) ? g.qinv[q] : 1.0f) : 0.f;
+      const float qscale = dense ? (g.dense_raw ? 1.0f : g.acc_scale * ((BF16 && live) ? g.qinv[q] : 1.0f)) : 0.f;
       const bool vec_ok = dense && (g.dense_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.dense_out) & 15) == 0);
       for (int tile = t0; tile < t1; ++tile) {
         const int row0 = tile * BN + half * ECOLS;
@@ -873,8 +875,9 @@ gemm_swap_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
             const int n = min(cnt_s[q], cap);
             if (n > cap - 128) {
               uint64_t* seg = g.cand + (static_cast<int64_t>(q) * g.chunks * 2 + seg0) * cap;
-              for (int i = lane; i < cap; i += 32) scratch[i] = (i < n) ? canonical_key(__ldcg(seg + i)) : 0ull;
-              warp_bitonic_sort_desc(scratch, cap, lane);
+              const int P = cap <= 256 ? 256 : kSegCapMax;
+              for (int i = lane; i < P; i += 32) scratch[i] = (i < n) ? canonical_key(__ldcg(seg + i)) : 0ull;
+              warp_bitonic_sort_desc(scratch, P, lane);
               const int kept = n < g.k ? n : g.k;
               for (int i = lane; i < kept; i += 32) seg[i] = raw_key(scratch[i]);
               if (lane == 0) {
@@ -910,7 +913,8 @@ size_t select_scratch_bytes(int64_t Q, int nseg, int seg_cap, int k);
 int launch_select_hist(const uint64_t* seg_keys, const int* seg_cnt, int64_t Q, int nseg, int seg_stride, int seg_cap,
                        const uint64_t* carry_in, const int* carry_cnt_in, uint64_t* carry_out, int* carry_cnt_out, float* tau_out,
                        float* out_scores, int64_t* out_ids, int64_t id_offset, int k, float out_scale, const float* out_qscale,
-                       cudaStream_t st);
+                       cudaStream_t st, const float* dense = nullptr, int64_t dense_ld = 0, int dense_rows = 0,
+                       const uint8_t* mask = nullptr);
 int launch_select(const uint64_t* seg_keys, const int* seg_cnt, int64_t Q, int nseg, int seg_stride, int seg_cap,
                   const uint64_t* carry_in, const int* carry_cnt_in, uint64_t* carry_out, int* carry_cnt_out,
                   float* tau_out, float* out_scores, int64_t* out_ids, int64_t id_offset, int k, void* scratch,
@@ -918,7 +922,9 @@ int launch_select(const uint64_t* seg_keys, const int* seg_cnt, int64_t Q, int n
 
 constexpr size_t kGemmSmemBytes = static_cast<size_t>(kRingBytes) + kEpiWarps * kEpiCols * sizeof(float) +
                                   (2 * kMaxStages + 6) * sizeof(uint64_t) + 16 + 1024;
-static int seg_cap_for(int k) { return k <= 128 ? 256 : kSegCapMax; }
+// 256 + 32: a whole 256-row tile of a first phase (threshold -inf, every row survives) fits without tripping the
+// in-kernel cut-back, whose margin is 32 keys
+static int seg_cap_for(int k) { return k <= 128 ? 288 : kSegCapMax; }
 static_assert(kGemmSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
 constexpr size_t kSwapSmemBytes = static_cast<size_t>(kRingBytes) + 2 * 256 * 4 + 16 + (2 * kSwapMaxStages + 6) * sizeof(uint64_t) + 16 + 1024;
 static_assert(kSwapSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
@@ -979,16 +985,22 @@ struct Phase {
 // so a phase that multiplies the rows seen by g admits ~k*ln(g) (at most ~k*(g-1)) survivors per query.
 // swapped kernel: its epilogue work is small (128 x Q scores per tile), so it affords denser survivors in exchange
 // for fewer phases - every phase costs a launch of the GEMM and of the select (~25 us for a small batch)
-static int plan_phases(int64_t N, int qblocks, int k, Phase* out, int max_phases, bool swap) {
+static int plan_phases(int64_t N, int qblocks, int k, Phase* out, int max_phases, bool swap, int begin0 = 0) {
   const int T = static_cast<int>((N + BN - 1) / BN);
   static const int swap_growth = getenv("ICR_SWAP_GROWTH") ? atoi(getenv("ICR_SWAP_GROWTH")) : 32;  // tuning hook
   const int growth = swap ? swap_growth : 8;
   const int npairs = kNumSMs / 2;
+  static const int k2_first = getenv("ICR_K2_FIRST") ? atoi(getenv("ICR_K2_FIRST")) : 4;  // tuning hook
   int first = (2 * k + BN - 1) / BN;
-  if (first < 2) first = 2;
+  if (first < k2_first) first = k2_first;
   static const int swap_first = getenv("ICR_SWAP_FIRST") ? atoi(getenv("ICR_SWAP_FIRST")) : 8;  // tuning hook
   if (swap && first < swap_first) first = swap_first;
   int n = 0, begin = 0, end = first < T ? first : T;
+  if (begin0 > 0) {  // rows of tiles [0, begin0) were scored densely: the sparse phases start behind them
+    begin = begin0;
+    const int64_t next = static_cast<int64_t>(begin0) * growth;
+    end = next < T ? static_cast<int>(next) : T;
+  }
   while (begin < T && n < max_phases) {
     if (n == max_phases - 1) end = T;
     const int tiles = end - begin;
@@ -997,7 +1009,7 @@ static int plan_phases(int64_t N, int qblocks, int k, Phase* out, int max_phases
     // ~(growth-1)*k survivors per query, spread over 2*chunks segments, kept under a quarter of the capacity
     const int cap = seg_cap_for(k);
     int chunks = (2 * npairs + qblocks - 1) / qblocks;
-    const int by_load = n == 0 ? (tiles * BN + cap - 1) / cap : ((growth - 1) * k + cap / 2 - 1) / (cap / 2);
+    const int by_load = (n == 0 && begin0 == 0) ? (tiles * BN + cap - 1) / cap : ((growth - 1) * k + cap / 2 - 1) / (cap / 2);
     if (chunks < by_load) chunks = by_load;
     if (chunks > tiles) chunks = tiles;
     if (chunks < 1) chunks = 1;
@@ -1025,9 +1037,35 @@ static int plan_phases(int64_t N, int qblocks, int k, Phase* out, int max_phases
 }
 
 constexpr int kMaxPhases = 16;
+constexpr int kDense0Tiles = 4;  // rows 0..1023 are scored densely in the first phase of the (non-swapped) top-k path
+
+// launches the DENSE instantiation `which` (0 planes, 1 bf16 streaming, 2 bf16 resident queries)
+static int launch_dense_variant(int which, int grid, const CUtensorMap& map_a, const CUtensorMap& map_b, const GemmArgs& g, cudaStream_t st) {
+  static thread_local bool attr_set[3] = {false, false, false};
+  if (!attr_set[which]) {
+    const int smem = static_cast<int>(kGemmSmemBytes);
+    if (which == 0) ICR_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_kernel<3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (which == 1) ICR_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_kernel<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (which == 2) ICR_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_kernel<1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set[which] = true;
+  }
+  profile_begin(kKernelGemm, which == 0 ? 3 : 1, st);
+  const int threads = 128 + epi_warps(which == 0 ? 3 : 1) * 32;
+  if (which == 0) gemm_topk_kernel<3, false, true><<<grid, threads, kGemmSmemBytes, st>>>(map_a, map_b, g);
+  if (which == 1) gemm_topk_kernel<1, false, true><<<grid, threads, kGemmSmemBytes, st>>>(map_a, map_b, g);
+  if (which == 2) gemm_topk_kernel<1, true, true><<<grid, threads, kGemmSmemBytes, st>>>(map_a, map_b, g);
+  profile_end(st);
+  ICR_LAUNCH_CHECK();
+  return ICR_OK;
+}
+
+static bool dense0_applies(int64_t Q, int64_t D, int dtype) {
+  static const bool disabled = getenv("ICR_NO_DENSE0") != nullptr;  // A/B switch for benchmarks
+  return !disabled && !swap_applies(Q, D, dtype);
+}
 
 struct GemmWs {
-  size_t q_planes, c_planes, qinv, cinv, tau, carry[2], carry_cnt[2], cand, cand_cnt, scratch, total;
+  size_t q_planes, c_planes, qinv, cinv, tau, carry[2], carry_cnt[2], cand, cand_cnt, scratch, dense0, total;
   int max_chunks, seg_cap;
 };
 
@@ -1035,7 +1073,8 @@ static GemmWs gemm_ws_layout(int64_t Q, int64_t N, int64_t D, int dtype, int k, 
   GemmWs w{};
   const int qblocks = static_cast<int>((Q + 2 * BM - 1) / (2 * BM));
   Phase ph[kMaxPhases];
-  const int np = plan_phases(N, qblocks, k, ph, kMaxPhases, swap_applies(Q, D, dtype));
+  const bool dense0 = dense0_applies(Q, D, dtype);
+  const int np = plan_phases(N, qblocks, k, ph, kMaxPhases, swap_applies(Q, D, dtype), dense0 ? kDense0Tiles : 0);
   int maxc = 1;
   for (int i = 0; i < np; ++i) maxc = ph[i].chunks > maxc ? ph[i].chunks : maxc;
   w.max_chunks = maxc;
@@ -1060,6 +1099,7 @@ static GemmWs gemm_ws_layout(int64_t Q, int64_t N, int64_t D, int dtype, int k, 
   w.cand = take(static_cast<size_t>(Q) * maxc * halves * w.seg_cap * 8);
   w.cand_cnt = take(static_cast<size_t>(Q) * maxc * halves * 4);
   w.scratch = take(static_cast<size_t>(kNumSMs) * kEpiWarps * kSegCapMax * 8);  // in-kernel compaction scratch
+  w.dense0 = take(dense0 ? static_cast<size_t>(Q) * kDense0Tiles * BN * 4 : 0);
   w.total = off + 1024;
   return w;
 }
@@ -1164,12 +1204,43 @@ int launch_gemm_topk(const void* queries, int64_t Q, int64_t ldq, const void* ca
   fill_f32_kernel<<<static_cast<unsigned>((Q + 255) / 256), 256, 0, st>>>(const_cast<float*>(g.tau), Q, -INFINITY);
   ICR_LAUNCH_CHECK();
 
+  // ---- first phase, dense: rows of the first kDense0Tiles tiles have no threshold to beat yet, so every score would
+  // be appended through uncoalesced 8-byte stores (measured: 27 us per tile). They are written as a dense [Q, 1024]
+  // score matrix instead (full 128-byte lines) and the select builds its keys from that.
   Phase ph[kMaxPhases];
-  const int np = plan_phases(N, qblocks, k, ph, kMaxPhases, swap);
-  for (int p = 0; p < np; ++p) {
-    g.tile_begin = ph[p].tile_begin;
-    g.tile_end = ph[p].tile_end;
-    g.chunks = ph[p].chunks;
+  const int T = static_cast<int>((N + BN - 1) / BN);
+  const bool dense0 = dense0_applies(Q, D, dtype);
+  int done_phases = 0;
+  if (dense0) {
+    const int T0 = T < kDense0Tiles ? T : kDense0Tiles;
+    float* d0 = reinterpret_cast<float*>(base + L.dense0);
+    GemmArgs gd = g;
+    gd.tile_begin = 0;
+    gd.tile_end = T0;
+    gd.chunks = T0;
+    gd.dense_out = d0;
+    gd.dense_ld = static_cast<int64_t>(kDense0Tiles) * BN;
+    gd.dense_raw = 1;
+    const int items = qblocks * T0;
+    const int pairs = items < kNumSMs / 2 ? items : kNumSMs / 2;
+    if ((rc = launch_dense_variant(which, 2 * pairs, map_a, map_b, gd, st))) return rc;
+    const bool last = (T0 >= T);
+    const int rows0 = static_cast<int>(N < static_cast<int64_t>(T0) * BN ? N : static_cast<int64_t>(T0) * BN);
+    rc = launch_select_hist(g.cand, g.cand_cnt, Q, 0, g.seg_cap, g.seg_cap, nullptr, nullptr,
+                            last ? nullptr : reinterpret_cast<uint64_t*>(base + L.carry[0]),
+                            last ? nullptr : reinterpret_cast<int*>(base + L.carry_cnt[0]), last ? nullptr : const_cast<float*>(g.tau),
+                            last ? out_scores : nullptr, last ? out_ids : nullptr, row_offset, k, g.acc_scale, g.qinv, st, d0, gd.dense_ld,
+                            rows0, mask);
+    if (rc) return rc;
+    if (last) return ICR_OK;
+    done_phases = 1;
+  }
+  const int np = plan_phases(N, qblocks, k, ph, kMaxPhases, swap, dense0 ? kDense0Tiles : 0);
+  for (int pp = 0; pp < np; ++pp) {
+    const int p = pp + done_phases;  // index for the carry ping-pong
+    g.tile_begin = ph[pp].tile_begin;
+    g.tile_end = ph[pp].tile_end;
+    g.chunks = ph[pp].chunks;
     const int items = qblocks * g.chunks;
     const int pairs = items < kNumSMs / 2 ? items : kNumSMs / 2;
     const int grid = 2 * pairs;  // whole CTA pairs (cluster dims 2x1x1)
@@ -1182,7 +1253,7 @@ int launch_gemm_topk(const void* queries, int64_t Q, int64_t ldq, const void* ca
     if (which == 4) gemm_swap_kernel<1><<<grid, kSwapThreads, kSwapSmemBytes, st>>>(map_a, map_b, g);
     profile_end(st);
     ICR_LAUNCH_CHECK();
-    const bool last = (p == np - 1);
+    const bool last = (pp == np - 1);
     const int cur = p & 1, prev = cur ^ 1;
     rc = launch_select_hist(g.cand, g.cand_cnt, Q, g.chunks * (swap ? 2 : epi_warps(terms) / 4), g.seg_cap, g.seg_cap,
                        p > 0 ? reinterpret_cast<uint64_t*>(base + L.carry[prev]) : nullptr,
@@ -1258,24 +1329,9 @@ int launch_gemm_dense(const void* a, int64_t Qa, int64_t lda, const void* b, int
   if (chunks > tiles) chunks = tiles;
   if (chunks < 1) chunks = 1;
   g.chunks = chunks;
-  static thread_local bool attr_set[3] = {false, false, false};
-  if (!attr_set[which]) {
-    const int smem = static_cast<int>(kGemmSmemBytes);
-    if (which == 0) ICR_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_kernel<3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    if (which == 1) ICR_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_kernel<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    if (which == 2) ICR_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_kernel<1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set[which] = true;
-  }
   const int items = qblocks * chunks;
   const int grid = 2 * (items < npairs ? items : npairs);
-  profile_begin(kKernelGemm, which == 0 ? 3 : 1, st);
-  const int threads = 128 + epi_warps(which == 0 ? 3 : 1) * 32;
-  if (which == 0) gemm_topk_kernel<3, false, true><<<grid, threads, kGemmSmemBytes, st>>>(map_a, map_b, g);
-  if (which == 1) gemm_topk_kernel<1, false, true><<<grid, threads, kGemmSmemBytes, st>>>(map_a, map_b, g);
-  if (which == 2) gemm_topk_kernel<1, true, true><<<grid, threads, kGemmSmemBytes, st>>>(map_a, map_b, g);
-  profile_end(st);
-  ICR_LAUNCH_CHECK();
-  return ICR_OK;
+  return launch_dense_variant(which, grid, map_a, map_b, g, st);
 }
 
 }  // namespace icr

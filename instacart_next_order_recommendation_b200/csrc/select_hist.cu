@@ -40,6 +40,12 @@ struct HistSelectArgs {
   float out_scale;          // final score = key score * out_scale * (out_qscale ? out_qscale[q] : 1)
   const float* out_qscale;  // [Q] or null
   int raw_keys;             // segments hold (score bits, ~row) as the GEMM epilogue writes them; carry keys are ordered
+  // dense front end (first phase of K2): instead of segments, row q of a [Q][dense_ld] score matrix holds the raw
+  // scores of catalog rows 0 .. dense_rows-1; rows flagged in `mask` are skipped
+  const float* dense;
+  int64_t dense_ld;
+  int dense_rows;
+  const uint8_t* mask;
 };
 
 __device__ __forceinline__ uint64_t canonical_from_raw(uint64_t raw) {
@@ -69,6 +75,32 @@ __global__ void __launch_bounds__(kHsWarps * 32) select_hist_kernel(HistSelectAr
   if (a.carry_in) {
     n = min(a.carry_cnt_in[q], k);
     for (int i = lane; i < n; i += 32) buf[i] = a.carry_in[q * k + i];
+  }
+  if (a.dense) {
+    const float* row = a.dense + q * a.dense_ld;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int base = 0; base < a.dense_rows; base += 32 * 8) {
+      if (kHsCap - n < 32 * 8) {  // buffer full: keep the k best and go on
+        warp_select_topk(buf, n, k, sel, hist, lane);
+        for (int i = lane; i < k; i += 32) buf[i] = sel[i];
+        n = k;
+        __syncwarp();
+      }
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int r = base + u * 32 + lane;
+        v[u] = (r < a.dense_rows) ? __ldcs(row + r) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int r = base + u * 32 + lane;
+        const bool ok = r < a.dense_rows && !(a.mask && a.mask[r]);
+        const unsigned m = __ballot_sync(kFull, ok);
+        if (ok) buf[n + __popc(m & lt)] = make_key(v[u], static_cast<uint32_t>(r));
+        n += __popc(m);
+      }
+    }
   }
   const uint64_t* qbase = a.seg_keys + q * a.nseg * static_cast<int64_t>(a.seg_stride);
   // Segment lengths of up to kHsPref segments are fetched at once (independent loads) and prefix-summed in shared
@@ -312,6 +344,40 @@ __global__ void __launch_bounds__(kBsThreads) select_block_kernel(HistSelectArgs
     n = min(a.carry_cnt_in[q], k);
     for (int i = tid; i < n; i += kBsThreads) sm.buf[i] = a.carry_in[q * k + i];
   }
+  if (a.dense) {
+    const float* row = a.dense + q * a.dense_ld;
+    const unsigned lt = (1u << lane) - 1u;
+    __syncthreads();
+    for (int base = 0; base < a.dense_rows; base += kBsThreads * 4) {
+      if (kBsCap - n < kBsThreads * 4) {
+        block_select_topk(sm, n, k, tid);
+        for (int i = tid; i < k; i += kBsThreads) sm.buf[i] = sm.sel[i];
+        n = k;
+        __syncthreads();
+      }
+      if (tid == 0) sm.misc[4] = n;
+      __syncthreads();
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = base + u * kBsThreads + tid;
+        v[u] = (r < a.dense_rows) ? __ldcs(row + r) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = base + u * kBsThreads + tid;
+        const bool ok = r < a.dense_rows && !(a.mask && a.mask[r]);
+        const unsigned m = __ballot_sync(kFull, ok);
+        int wbase = 0;
+        if (lane == 0 && m) wbase = atomicAdd(&sm.misc[4], __popc(m));
+        wbase = __shfl_sync(kFull, wbase, 0);
+        if (ok) sm.buf[wbase + __popc(m & lt)] = make_key(v[u], static_cast<uint32_t>(r));
+      }
+      __syncthreads();
+      n = sm.misc[4];
+      __syncthreads();
+    }
+  }
   const uint64_t* qbase = a.seg_keys + q * a.nseg * static_cast<int64_t>(a.seg_stride);
   for (int g0 = 0; g0 < a.nseg; g0 += kBsPref) {
     const int ng = min(kBsPref, a.nseg - g0);
@@ -408,7 +474,7 @@ __global__ void __launch_bounds__(kBsThreads) select_block_kernel(HistSelectArgs
 int launch_select_hist(const uint64_t* seg_keys, const int* seg_cnt, int64_t Q, int nseg, int seg_stride, int seg_cap,
                        const uint64_t* carry_in, const int* carry_cnt_in, uint64_t* carry_out, int* carry_cnt_out, float* tau_out,
                        float* out_scores, int64_t* out_ids, int64_t id_offset, int k, float out_scale, const float* out_qscale,
-                       cudaStream_t st) {
+                       cudaStream_t st, const float* dense, int64_t dense_ld, int dense_rows, const uint8_t* mask) {
   if (Q == 0) return ICR_OK;
   static thread_local bool attr_set = false;
   if (!attr_set) {
@@ -434,6 +500,10 @@ int launch_select_hist(const uint64_t* seg_keys, const int* seg_cnt, int64_t Q, 
   a.out_scale = out_scale;
   a.out_qscale = out_qscale;
   a.raw_keys = 1;  // the only producer of segments is the GEMM epilogue
+  a.dense = dense;
+  a.dense_ld = dense_ld;
+  a.dense_rows = dense_rows;
+  a.mask = mask;
   static const int block_max_q = getenv("ICR_SELECT_BLOCK_MAXQ") ? atoi(getenv("ICR_SELECT_BLOCK_MAXQ")) : 512;  // tuning hook
   if (Q <= block_max_q) {
     static thread_local bool battr_set = false;
