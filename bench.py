@@ -235,7 +235,14 @@ def main():
         roof = {"bound": "hbm", "achieved": bytes_per_launch / (kt["ms_per_launch"] * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s"}
         roof["note"] = f"catalog bytes per GEMV launch (L2-resident after the first pass); peak = {peaks['source']} HBM copy"
     roof["frac"] = roof["achieved"] / roof["peak"]
-    roof["traffic"] = None
+    roof["traffic"] = None  # bytes per launch from the committed ncu --set full capture of this workload, if there is one
+    try:
+        cap = json.loads((ROOT / "profiles" / "r01_kernel_traffic.json").read_text())[kt["kernel"]][args.dtype]["launch_bytes"]
+        if args.path == "auto" and world >= 1:
+            roof["traffic"] = sum(cap) / len(cap)
+            roof["traffic_note"] = "mean DRAM bytes (read+write) per launch of this kernel, ncu --set full, profiles/r01_kernel_traffic.json"
+    except (OSError, KeyError, ValueError):
+        pass
     roof["kernel"] = kt["kernel"]
     roof["kernel_ms_per_step"] = kt["ms_per_step"]
     roof["kernel_launches_per_step"] = kt["launches_per_step"]
