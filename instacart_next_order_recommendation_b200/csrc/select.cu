@@ -190,37 +190,4 @@ int launch_select(const uint64_t* seg_keys, const int* seg_cnt, int64_t Q, int n
   }
 }
 
-// ---- K4: merge of G shard lists given as separate (score, id) arrays ----------------------------
-__global__ void __launch_bounds__(kSelectThreads) merge_lists_kernel(const float* __restrict__ cs, const int64_t* __restrict__ ci,
-                                                                     int64_t Q, int G, int k_in, int k_out,
-                                                                     float* __restrict__ os, int64_t* __restrict__ oi) {
-  __shared__ uint64_t keys[kSortCap];
-  const int64_t q = blockIdx.x;
-  const int total = G * k_in;
-  for (int t = threadIdx.x; t < total; t += blockDim.x) {
-    const int g = t / k_in, i = t - g * k_in;
-    const int64_t off = (static_cast<int64_t>(g) * Q + q) * k_in + i;
-    const int64_t id = ci[off];
-    keys[t] = (id >= 0) ? make_key(cs[off], static_cast<uint32_t>(id)) : 0ull;
-  }
-  const int valid = sort_and_truncate(keys, total, k_out);
-  for (int i = threadIdx.x; i < k_out; i += blockDim.x) {
-    const bool ok = i < valid;
-    os[q * k_out + i] = ok ? key_score(keys[i]) : -INFINITY;
-    oi[q * k_out + i] = ok ? static_cast<int64_t>(key_row(keys[i])) : -1;
-  }
-}
-
-int launch_merge_lists(const float* cs, const int64_t* ci, int64_t Q, int G, int k_in, int k_out, float* os, int64_t* oi,
-                       cudaStream_t st) {
-  if (Q == 0) return ICR_OK;
-  if (static_cast<int64_t>(G) * k_in > kSortCap) {
-    set_error("topk_merge: G*k_in = %lld exceeds %d", static_cast<long long>(G) * k_in, kSortCap);
-    return ICR_ERR_ARG;
-  }
-  merge_lists_kernel<<<static_cast<unsigned>(Q), kSelectThreads, 0, st>>>(cs, ci, Q, G, k_in, k_out, os, oi);
-  ICR_LAUNCH_CHECK();
-  return ICR_OK;
-}
-
 }  // namespace icr

@@ -46,7 +46,31 @@ struct HistSelectArgs {
   int64_t dense_ld;
   int dense_rows;
   const uint8_t* mask;
+  // list front end (K4 shard merge): G lists of list_k (score, id) pairs per query, laid out [G][Q][list_k]; id < 0 = empty
+  const float* list_scores;
+  const int64_t* list_ids;
+  int list_g, list_k;
 };
+
+// flat candidate t of query q from the dense matrix or the shard lists -> key; false if there is none
+__device__ __forceinline__ bool front_fetch(const HistSelectArgs& a, int64_t q, int t, int count, uint64_t& key) {
+  key = 0ull;
+  if (t >= count) return false;
+  if (a.dense) {
+    if (a.mask && a.mask[t]) return false;
+    key = make_key(__ldcs(a.dense + q * a.dense_ld + t), static_cast<uint32_t>(t));
+    return true;
+  }
+  const int g = t / a.list_k, i = t - g * a.list_k;
+  const int64_t off = (static_cast<int64_t>(g) * a.Q + q) * a.list_k + i;
+  const int64_t id = __ldcs(a.list_ids + off);
+  if (id < 0) return false;
+  key = make_key(__ldcs(a.list_scores + off), static_cast<uint32_t>(id));
+  return true;
+}
+__device__ __forceinline__ int front_count(const HistSelectArgs& a) {
+  return a.dense ? a.dense_rows : (a.list_scores ? a.list_g * a.list_k : 0);
+}
 
 __device__ __forceinline__ uint64_t canonical_from_raw(uint64_t raw) {
   const float f = __uint_as_float(static_cast<uint32_t>(raw >> 32));
@@ -76,28 +100,23 @@ __global__ void __launch_bounds__(kHsWarps * 32) select_hist_kernel(HistSelectAr
     n = min(a.carry_cnt_in[q], k);
     for (int i = lane; i < n; i += 32) buf[i] = a.carry_in[q * k + i];
   }
-  if (a.dense) {
-    const float* row = a.dense + q * a.dense_ld;
+  if (const int count = front_count(a)) {
     const unsigned lt = (1u << lane) - 1u;
-    for (int base = 0; base < a.dense_rows; base += 32 * 8) {
+    for (int base = 0; base < count; base += 32 * 8) {
       if (kHsCap - n < 32 * 8) {  // buffer full: keep the k best and go on
         warp_select_topk(buf, n, k, sel, hist, lane);
         for (int i = lane; i < k; i += 32) buf[i] = sel[i];
         n = k;
         __syncwarp();
       }
-      float v[8];
+      uint64_t key[8];
+      bool ok[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) ok[u] = front_fetch(a, q, base + u * 32 + lane, count, key[u]);
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        const int r = base + u * 32 + lane;
-        v[u] = (r < a.dense_rows) ? __ldcs(row + r) : 0.f;
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int r = base + u * 32 + lane;
-        const bool ok = r < a.dense_rows && !(a.mask && a.mask[r]);
-        const unsigned m = __ballot_sync(kFull, ok);
-        if (ok) buf[n + __popc(m & lt)] = make_key(v[u], static_cast<uint32_t>(r));
+        const unsigned m = __ballot_sync(kFull, ok[u]);
+        if (ok[u]) buf[n + __popc(m & lt)] = key[u];
         n += __popc(m);
       }
     }
@@ -344,11 +363,10 @@ __global__ void __launch_bounds__(kBsThreads) select_block_kernel(HistSelectArgs
     n = min(a.carry_cnt_in[q], k);
     for (int i = tid; i < n; i += kBsThreads) sm.buf[i] = a.carry_in[q * k + i];
   }
-  if (a.dense) {
-    const float* row = a.dense + q * a.dense_ld;
+  if (const int count = front_count(a)) {
     const unsigned lt = (1u << lane) - 1u;
     __syncthreads();
-    for (int base = 0; base < a.dense_rows; base += kBsThreads * 4) {
+    for (int base = 0; base < count; base += kBsThreads * 4) {
       if (kBsCap - n < kBsThreads * 4) {
         block_select_topk(sm, n, k, tid);
         for (int i = tid; i < k; i += kBsThreads) sm.buf[i] = sm.sel[i];
@@ -357,21 +375,17 @@ __global__ void __launch_bounds__(kBsThreads) select_block_kernel(HistSelectArgs
       }
       if (tid == 0) sm.misc[4] = n;
       __syncthreads();
-      float v[4];
+      uint64_t key[4];
+      bool ok[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) ok[u] = front_fetch(a, q, base + u * kBsThreads + tid, count, key[u]);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int r = base + u * kBsThreads + tid;
-        v[u] = (r < a.dense_rows) ? __ldcs(row + r) : 0.f;
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int r = base + u * kBsThreads + tid;
-        const bool ok = r < a.dense_rows && !(a.mask && a.mask[r]);
-        const unsigned m = __ballot_sync(kFull, ok);
+        const unsigned m = __ballot_sync(kFull, ok[u]);
         int wbase = 0;
         if (lane == 0 && m) wbase = atomicAdd(&sm.misc[4], __popc(m));
         wbase = __shfl_sync(kFull, wbase, 0);
-        if (ok) sm.buf[wbase + __popc(m & lt)] = make_key(v[u], static_cast<uint32_t>(r));
+        if (ok[u]) sm.buf[wbase + __popc(m & lt)] = key[u];
       }
       __syncthreads();
       n = sm.misc[4];
@@ -471,16 +485,30 @@ __global__ void __launch_bounds__(kBsThreads) select_block_kernel(HistSelectArgs
   }
 }
 
+static int run_select(const HistSelectArgs& a, int64_t Q, cudaStream_t st);
+
+// K4: merge of G shard lists of k_in (score, id) pairs per query, [G][Q][k_in] -> sorted top k_out per query
+int launch_merge_lists(const float* cs, const int64_t* ci, int64_t Q, int G, int k_in, int k_out, float* os, int64_t* oi,
+                       cudaStream_t st) {
+  if (Q == 0) return ICR_OK;
+  HistSelectArgs a{};
+  a.k = k_out;
+  a.Q = Q;
+  a.out_scores = os;
+  a.out_ids = oi;
+  a.out_scale = 1.0f;
+  a.list_scores = cs;
+  a.list_ids = ci;
+  a.list_g = G;
+  a.list_k = k_in;
+  return run_select(a, Q, st);
+}
+
 int launch_select_hist(const uint64_t* seg_keys, const int* seg_cnt, int64_t Q, int nseg, int seg_stride, int seg_cap,
                        const uint64_t* carry_in, const int* carry_cnt_in, uint64_t* carry_out, int* carry_cnt_out, float* tau_out,
                        float* out_scores, int64_t* out_ids, int64_t id_offset, int k, float out_scale, const float* out_qscale,
                        cudaStream_t st, const float* dense, int64_t dense_ld, int dense_rows, const uint8_t* mask) {
   if (Q == 0) return ICR_OK;
-  static thread_local bool attr_set = false;
-  if (!attr_set) {
-    ICR_CUDA_CHECK(cudaFuncSetAttribute(select_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(HsSmem))));
-    attr_set = true;
-  }
   HistSelectArgs a{};
   a.seg_keys = seg_keys;
   a.seg_cnt = seg_cnt;
@@ -504,6 +532,15 @@ int launch_select_hist(const uint64_t* seg_keys, const int* seg_cnt, int64_t Q, 
   a.dense_ld = dense_ld;
   a.dense_rows = dense_rows;
   a.mask = mask;
+  return run_select(a, Q, st);
+}
+
+static int run_select(const HistSelectArgs& a, int64_t Q, cudaStream_t st) {
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    ICR_CUDA_CHECK(cudaFuncSetAttribute(select_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(HsSmem))));
+    attr_set = true;
+  }
   static const int block_max_q = getenv("ICR_SELECT_BLOCK_MAXQ") ? atoi(getenv("ICR_SELECT_BLOCK_MAXQ")) : 512;  // tuning hook
   if (Q <= block_max_q) {
     static thread_local bool battr_set = false;
