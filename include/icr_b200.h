@@ -158,6 +158,40 @@ int icr_mnrl_bwd(const void* a, int64_t lda, const void* p, int64_t ldp,
                  void* grad_a, int64_t ldga, void* grad_p, int64_t ldgp,
                  void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * IR metric arithmetic over the retrieved ids (the evaluator's host tail, on the device).
+ * Stands in for the per-query Python loops of sentence-transformers'
+ * InformationRetrievalEvaluator.compute_metrics (evaluator built at
+ * src/training/train_sbert.py:197-202, key read at :220) and of the in-tree
+ * src/baselines/metrics.py:13-176 (compute_ir_metrics), whose NDCG / AP normalisers differ:
+ * the *_RETRIEVED kinds follow metrics.py (:112-119 ideal ordering of the retrieved
+ * relevances; :66-72 AP / min(|relevant|, |ranked|)).
+ *
+ *   ids         [Q, K] i64 (row stride ld_ids), best first, id < 0 = no result (K <= ICR_MAX_K)
+ *   rel_offsets [Q+1] i64, rel_rows[rel_offsets[q] : rel_offsets[q+1]] = the relevant catalog
+ *               rows of query q that exist in the catalog, ASCENDING
+ *   n_relevant  [Q] i32 = len(relevant_docs[qid]) (may exceed the segment length when a
+ *               relevant id is not in the catalog); a query with 0 scores 0 on every metric
+ *   kinds, ks   HOST arrays of M metric kinds / cut-offs (copied into the launch parameters)
+ *   per_query   [Q, M] f64 out: metric m of query q
+ *   means       [M] f64 out: mean over the Q queries, summed in a fixed order
+ * ------------------------------------------------------------------------------------- */
+typedef enum {
+  ICR_METRIC_ACCURACY = 0,
+  ICR_METRIC_PRECISION = 1,
+  ICR_METRIC_RECALL = 2,
+  ICR_METRIC_MRR = 3,
+  ICR_METRIC_NDCG = 4,           /* IDCG = min(n_relevant, k) ones (sentence-transformers) */
+  ICR_METRIC_MAP = 5,            /* AP / min(k, n_relevant)   (sentence-transformers)      */
+  ICR_METRIC_NDCG_RETRIEVED = 6, /* IDCG = the retrieved hits moved to the front (metrics.py:112-119) */
+  ICR_METRIC_MAP_RETRIEVED = 7   /* AP / min(n_relevant, #retrieved in the first k) (metrics.py:66-72) */
+} icr_metric_kind;
+#define ICR_MAX_METRICS 32
+int icr_ir_metrics(const int64_t* ids, int64_t Q, int K, int64_t ld_ids,
+                   const int64_t* rel_offsets, const int64_t* rel_rows, const int32_t* n_relevant,
+                   const int32_t* kinds, const int32_t* ks, int M,
+                   double* per_query, double* means, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

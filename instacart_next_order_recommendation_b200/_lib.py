@@ -57,6 +57,10 @@ SIGNATURES = {
         [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
          c_void_p, c_size_t, c_void_p],
     ),
+    "icr_ir_metrics": (
+        c_int,
+        [c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p],
+    ),
     "icr_mnrl_bwd": (
         c_int,
         [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -80,6 +80,9 @@ static bool dense_use_gemm(int64_t Qa, int64_t Nb, int64_t D, int dtype) {
 }
 
 int launch_mnrl_dispatch(const MnrlArgs& g, int dtype, bool bwd, cudaStream_t st);
+int launch_ir_metrics(const int64_t* ids, int64_t Q, int K, int64_t ld, const int64_t* rel_offsets, const int64_t* rel_rows,
+                      const int32_t* n_relevant, const int32_t* kinds, const int32_t* ks, int M, double* per_query, double* means,
+                      cudaStream_t st);
 
 static int elem_size(int dtype) { return dtype == ICR_F32 ? 4 : 2; }
 static int vec_elems(int dtype) { return dtype == ICR_F32 ? 4 : 8; }
@@ -432,6 +435,31 @@ int icr_mnrl_bwd(const void* a, int64_t lda, const void* p, int64_t ldp, int64_t
   g.ldga = ldga;
   g.ldgp = ldgp;
   return launch_mnrl_dispatch(g, dtype, true, static_cast<cudaStream_t>(stream));
+}
+
+int icr_ir_metrics(const int64_t* ids, int64_t Q, int K, int64_t ld_ids, const int64_t* rel_offsets, const int64_t* rel_rows,
+                   const int32_t* n_relevant, const int32_t* kinds, const int32_t* ks, int M, double* per_query, double* means,
+                   void* stream) {
+  g_launches = 0;
+  if (Q < 0 || K < 1 || K > ICR_MAX_K || ld_ids < K || M < 1 || M > ICR_MAX_METRICS || !kinds || !ks) {
+    set_error("ir_metrics: bad arguments Q=%lld K=%d ld=%lld M=%d (K <= %d, M <= %d)", (long long)Q, K, (long long)ld_ids, M, ICR_MAX_K,
+              ICR_MAX_METRICS);
+    return ICR_ERR_ARG;
+  }
+  for (int m = 0; m < M; ++m) {
+    if (kinds[m] < ICR_METRIC_ACCURACY || kinds[m] > ICR_METRIC_MAP_RETRIEVED || ks[m] < 1) {
+      set_error("ir_metrics: metric %d has kind %d, k %d", m, kinds[m], ks[m]);
+      return ICR_ERR_ARG;
+    }
+  }
+  if (!means || (Q > 0 && (!ids || !rel_offsets || !n_relevant || !per_query))) {
+    set_error("ir_metrics: null pointer");
+    return ICR_ERR_ARG;
+  }
+  int rc;
+  if ((rc = check_device())) return rc;
+  return launch_ir_metrics(ids, Q, K, ld_ids, rel_offsets, rel_rows, n_relevant, kinds, ks, M, per_query, means,
+                           static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

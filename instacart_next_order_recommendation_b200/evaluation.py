@@ -12,7 +12,10 @@ Two consumers of the reference are served:
   whose only consumer (src/baselines/metrics.py:150-165) reads ranks <= 100, scored with the
   metric definitions of src/baselines/metrics.py:13-176.
 
-Metric arithmetic is vectorised numpy over the [Q, k] id matrix (integer/host work).
+Metric arithmetic runs on the device too (``icr_ir_metrics``: one warp per query over the [Q, k]
+id matrix), so an evaluation moves M floats to the host instead of Q x k ids
+plus Python loops. ``compute_metrics_from_ids`` / ``compute_ir_metrics`` keep the same arithmetic
+for id matrices / string rankings that already live on the host.
 """
 
 from __future__ import annotations
@@ -23,6 +26,7 @@ from typing import Callable
 import numpy as np
 import torch
 
+from . import ops
 from .similarity import cos_topk, to_device_matrix
 
 logger = logging.getLogger(__name__)
@@ -35,18 +39,25 @@ def _encode(model, texts: list[str], batch_size: int, show_progress_bar: bool):
         return model.encode(texts, batch_size=batch_size, show_progress_bar=show_progress_bar)
 
 
-def topk_ids(query_emb, corpus_emb, k: int, *, query_chunk: int = 16384):
-    """Sorted top-k (scores f32 [Q,k], corpus rows int64 [Q,k]) as host numpy arrays."""
+def topk_ids_device(query_emb, corpus_emb, k: int, *, query_chunk: int = 16384):
+    """Sorted top-k (scores f32 [Q,k], corpus rows int64 [Q,k]) as device tensors."""
     c = to_device_matrix(corpus_emb)
     q = to_device_matrix(query_emb, device=c.device)
     k = min(k, c.shape[0])
-    vals, ids = [], []
+    if q.shape[0] <= query_chunk:
+        return cos_topk(q, c, k)
+    vals = torch.empty(q.shape[0], k, dtype=torch.float32, device=c.device)
+    ids = torch.empty(q.shape[0], k, dtype=torch.int64, device=c.device)
     for s in range(0, q.shape[0], query_chunk):
         v, i = cos_topk(q[s : s + query_chunk], c, k)
-        vals.append(v)
-        ids.append(i)
-    v = torch.cat(vals) if vals else torch.empty(0, k)
-    i = torch.cat(ids) if ids else torch.empty(0, k, dtype=torch.int64)
+        vals[s : s + query_chunk] = v
+        ids[s : s + query_chunk] = i
+    return vals, ids
+
+
+def topk_ids(query_emb, corpus_emb, k: int, *, query_chunk: int = 16384):
+    """Sorted top-k (scores f32 [Q,k], corpus rows int64 [Q,k]) as host numpy arrays."""
+    v, i = topk_ids_device(query_emb, corpus_emb, k, query_chunk=query_chunk)
     return v.cpu().numpy(), i.cpu().numpy()
 
 
@@ -98,6 +109,16 @@ class InformationRetrievalEvaluator:
         row_of = {cid: i for i, cid in enumerate(self.corpus_ids)}
         self._relevant_rows = [np.fromiter((row_of[d] for d in relevant_docs[qid] if d in row_of), dtype=np.int64) for qid in self.queries_ids]
         self._n_relevant = np.array([len(relevant_docs[qid]) for qid in self.queries_ids], dtype=np.float64)
+        # the same metric list in the kernel's (kind, k) form, in the order compute_metrics_from_ids emits its keys
+        self._metric_specs = (
+            [(f"accuracy@{k}", ops.METRIC_ACCURACY, k) for k in self.accuracy_at_k]
+            + [(f"precision@{k}", ops.METRIC_PRECISION, k) for k in self.precision_recall_at_k]
+            + [(f"recall@{k}", ops.METRIC_RECALL, k) for k in self.precision_recall_at_k]
+            + [(f"mrr@{k}", ops.METRIC_MRR, k) for k in self.mrr_at_k]
+            + [(f"ndcg@{k}", ops.METRIC_NDCG, k) for k in self.ndcg_at_k]
+            + [(f"map@{k}", ops.METRIC_MAP, k) for k in self.map_at_k]
+        )
+        self._tables: dict = {}  # device -> RelevanceTable
 
     def __call__(self, model, output_path: str | None = None, epoch: int = -1, steps: int = -1, *args, **kwargs) -> dict[str, float]:
         query_emb = _encode(model, self.queries, self.batch_size, self.show_progress_bar)
@@ -109,8 +130,26 @@ class InformationRetrievalEvaluator:
         return out
 
     def compute_metrics_from_embeddings(self, query_emb, corpus_emb) -> dict[str, float]:
-        _, ids = topk_ids(query_emb, corpus_emb, self.max_k)
-        return self.compute_metrics_from_ids(ids)
+        """Fused top-k, then the metric kernel over the device-resident id matrix; one small device->host read."""
+        _, ids = topk_ids_device(query_emb, corpus_emb, self.max_k)
+        return self.compute_metrics_on_device(ids)
+
+    def relevance_table(self, device) -> ops.RelevanceTable:
+        device = torch.device(device)
+        if device not in self._tables:
+            self._tables[device] = ops.RelevanceTable(self._relevant_rows, self._n_relevant.astype(np.int32), device=device)
+        return self._tables[device]
+
+    def compute_metrics_on_device(self, ids: torch.Tensor) -> dict[str, float]:
+        """ids: CUDA int64 [Q, >=1] retrieved corpus rows, best first (-1 = none), as cos_topk returns them."""
+        if ids.shape[0] == 0 or not self._metric_specs:
+            return {name: 0.0 for name, _, _ in self._metric_specs}
+        out: dict[str, float] = {}
+        for s0 in range(0, len(self._metric_specs), ops.MAX_METRICS):
+            specs = self._metric_specs[s0 : s0 + ops.MAX_METRICS]
+            means, _ = ops.ir_metrics(ids, self.relevance_table(ids.device), [(kind, k) for _, kind, k in specs])
+            out.update({name: float(v) for (name, _, _), v in zip(specs, means.tolist())})
+        return out
 
     def compute_metrics_from_ids(self, ids: np.ndarray) -> dict[str, float]:
         """ids: [Q, >=max_k] retrieved corpus rows, best first (-1 = none)."""
@@ -164,6 +203,35 @@ def rank_all(query_embeddings, corpus_embeddings, query_ids: list[str], product_
     """
     _, ids = topk_ids(query_embeddings, corpus_embeddings, limit)
     return {qid: [product_ids[j] for j in ids[i] if j >= 0] for i, qid in enumerate(query_ids)}
+
+
+BASELINE_METRICS = (
+    ("accuracy_at_1", ops.METRIC_ACCURACY, 1), ("accuracy_at_3", ops.METRIC_ACCURACY, 3), ("accuracy_at_5", ops.METRIC_ACCURACY, 5),
+    ("accuracy_at_10", ops.METRIC_ACCURACY, 10), ("recall_at_10", ops.METRIC_RECALL, 10), ("mrr_at_10", ops.METRIC_MRR, 10),
+    ("ndcg_at_10", ops.METRIC_NDCG_RETRIEVED, 10), ("map_at_100", ops.METRIC_MAP_RETRIEVED, 100),
+)
+
+
+def evaluate_rankings(query_embeddings, corpus_embeddings, query_ids: list[str], product_ids: list[str],
+                      relevant_docs: dict[str, set[str]], limit: int = 100) -> dict[str, float]:
+    """``compute_ir_metrics(rank_all(...), relevant_docs)`` without leaving the device.
+
+    Same numbers as ranking every query (content_based.py:38-64) and scoring the rankings with
+    src/baselines/metrics.py:122-176, but the [Q, 100] ids feed the metric kernel directly instead of
+    becoming Q Python lists of product-id strings. Queries without relevant docs are skipped (metrics.py:137).
+    """
+    keep = [i for i, q in enumerate(query_ids) if q in relevant_docs and relevant_docs[q]]
+    if not keep:
+        return {name: 0.0 for name, _, _ in BASELINE_METRICS}
+    row_of = {pid: i for i, pid in enumerate(product_ids)}
+    q = to_device_matrix(query_embeddings)
+    if len(keep) != len(query_ids):
+        q = q[torch.as_tensor(keep, device=q.device)]
+    _, ids = topk_ids_device(q, corpus_embeddings, limit)
+    rel = [relevant_docs[query_ids[i]] for i in keep]
+    table = ops.RelevanceTable([[row_of[d] for d in r if d in row_of] for r in rel], [len(r) for r in rel], device=ids.device)
+    means, _ = ops.ir_metrics(ids, table, [(kind, k) for _, kind, k in BASELINE_METRICS])
+    return {name: float(v) for (name, _, _), v in zip(BASELINE_METRICS, means.tolist())}
 
 
 def compute_ir_metrics(query_rankings: dict[str, list[str]], relevant_docs: dict[str, set[str]]) -> dict[str, float]:

@@ -224,6 +224,61 @@ def topk_merge(cand_scores: torch.Tensor, cand_ids: torch.Tensor, k_out: int):
     return vals, ids
 
 
+# metric kinds of include/icr_b200.h (icr_metric_kind)
+METRIC_ACCURACY, METRIC_PRECISION, METRIC_RECALL, METRIC_MRR, METRIC_NDCG, METRIC_MAP, METRIC_NDCG_RETRIEVED, METRIC_MAP_RETRIEVED = range(8)
+MAX_METRICS = 32
+
+
+class RelevanceTable:
+    """relevant_docs in the form the metric kernel reads: per query an ascending run of catalog rows (CSR) + |relevant|."""
+
+    def __init__(self, relevant_rows, n_relevant=None, device=None):
+        import numpy as np
+
+        runs = [np.unique(np.asarray(r, dtype=np.int64)) for r in relevant_rows]
+        offsets = np.zeros(len(runs) + 1, dtype=np.int64)
+        if runs:
+            np.cumsum([len(r) for r in runs], out=offsets[1:])
+        flat = np.concatenate(runs) if runs else np.zeros(0, np.int64)
+        nrel = np.asarray([len(r) for r in runs] if n_relevant is None else n_relevant, dtype=np.int32)
+        if nrel.shape != (len(runs),):
+            raise ValueError("n_relevant must have one entry per query")
+        self.n_queries = len(runs)
+        self.offsets = torch.from_numpy(offsets).to(device)
+        self.rows = torch.from_numpy(flat if flat.size else np.zeros(1, np.int64)).to(device)
+        self.n_relevant = torch.from_numpy(nrel if nrel.size else np.zeros(1, np.int32)).to(device)
+
+
+def ir_metrics(ids: torch.Tensor, table: RelevanceTable, metrics: list[tuple[int, int]]):
+    """(means f64 [M], per_query f64 [Q, M]) of the (kind, k) metrics over the retrieved-id matrix `ids` [Q, K]."""
+    import ctypes
+
+    _require_cuda("ids", ids)
+    if ids.dim() != 2 or ids.dtype != torch.int64:
+        raise ValueError("ids must be an int64 [Q, K] matrix (the second output of cos_topk)")
+    if ids.stride(1) != 1:
+        ids = ids.contiguous()
+    Q, K = ids.shape
+    if Q != table.n_queries:
+        raise ValueError(f"{Q} id rows but the relevance table holds {table.n_queries} queries")
+    if table.offsets.device != ids.device:
+        raise ValueError("relevance table and ids live on different devices")
+    M = len(metrics)
+    kinds = (ctypes.c_int32 * max(M, 1))(*[int(m[0]) for m in metrics])
+    ks = (ctypes.c_int32 * max(M, 1))(*[int(m[1]) for m in metrics])
+    dev = ids.device
+    per_query = torch.empty(Q, max(M, 1), dtype=torch.float64, device=dev)
+    means = torch.empty(max(M, 1), dtype=torch.float64, device=dev)
+    lib = _lib.load()
+    with _on(dev):
+        _lib.check(
+            lib.icr_ir_metrics(ids.data_ptr(), Q, K, ids.stride(0) if Q > 1 else K, table.offsets.data_ptr(), table.rows.data_ptr(),
+                               table.n_relevant.data_ptr(), ctypes.addressof(kinds), ctypes.addressof(ks), M, per_query.data_ptr(),
+                               means.data_ptr(), _stream(dev))
+        )
+    return means, per_query
+
+
 def _fast_rows(t: torch.Tensor) -> torch.Tensor:
     """_rows() without the checks' cost for the common case: contiguous, 16-byte aligned, D a multiple of 8."""
     if t.dim() == 2 and t.is_contiguous() and t.shape[1] % 8 == 0 and t.data_ptr() % 16 == 0:

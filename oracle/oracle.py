@@ -224,6 +224,62 @@ def ir_metrics(query_rankings: dict[str, list[str]], relevant_docs: dict[str, se
 
 
 # --------------------------------------------------------------------------------------
+# a6: InformationRetrievalEvaluator.compute_metrics (ST 5.2.2, restated from the published
+#     algorithm — "parity unpinned", see the header; evaluator built at train_sbert.py:197-202).
+#     Loop form, per query in order: accuracy@k (any hit in the first k), precision@k = hits/k,
+#     recall@k = hits/|relevant|, MRR@k = 1/rank of the first hit, NDCG@k = DCG/DCG([1]*|relevant|)
+#     with discount 1/log2(rank+1), MAP@k = sum of precision at each hit / min(k, |relevant|).
+#     `ranked` holds catalog rows (ints), best first; entries < 0 mean "no result".
+# --------------------------------------------------------------------------------------
+
+
+def st_ir_metrics(ranked: Sequence[Sequence[int]], relevant: Sequence[set], n_relevant: Sequence[int] | None = None,
+                  accuracy_at_k=(1, 3, 5, 10), precision_recall_at_k=(1, 3, 5, 10), mrr_at_k=(10,), ndcg_at_k=(10,), map_at_k=(100,),
+                  per_query: bool = False):
+    n = len(ranked)
+    nrel = [len(r) for r in relevant] if n_relevant is None else list(n_relevant)
+    names = ([f"accuracy@{k}" for k in accuracy_at_k] + [f"precision@{k}" for k in precision_recall_at_k]
+             + [f"recall@{k}" for k in precision_recall_at_k] + [f"mrr@{k}" for k in mrr_at_k] + [f"ndcg@{k}" for k in ndcg_at_k]
+             + [f"map@{k}" for k in map_at_k])
+    rows = []
+    for rk, rel, nr in zip(ranked, relevant, nrel):
+        rk = [r for r in rk if r >= 0]
+        vals = {}
+        for k in accuracy_at_k:
+            vals[f"accuracy@{k}"] = 1.0 if any(r in rel for r in rk[:k]) else 0.0
+        for k in precision_recall_at_k:
+            c = sum(1 for r in rk[:k] if r in rel)
+            vals[f"precision@{k}"] = c / k
+            vals[f"recall@{k}"] = c / nr
+        for k in mrr_at_k:
+            vals[f"mrr@{k}"] = 0.0
+            for j, r in enumerate(rk[:k]):
+                if r in rel:
+                    vals[f"mrr@{k}"] = 1.0 / (j + 1)
+                    break
+        for k in ndcg_at_k:
+            dcg = 0.0
+            for j, r in enumerate(rk[:k]):
+                if r in rel:
+                    dcg += 1.0 / math.log2(j + 2)
+            idcg = 0.0
+            for j in range(min(nr, k)):
+                idcg += 1.0 / math.log2(j + 2)
+            vals[f"ndcg@{k}"] = dcg / idcg
+        for k in map_at_k:
+            hits, sp = 0, 0.0
+            for j, r in enumerate(rk[:k]):
+                if r in rel:
+                    hits += 1
+                    sp += hits / (j + 1)
+            vals[f"map@{k}"] = sp / min(k, nr)
+        rows.append([vals[m] for m in names])
+    arr = np.asarray(rows, dtype=np.float64).reshape(n, len(names))
+    means = {m: (float(arr[:, i].sum() / n) if n else 0.0) for i, m in enumerate(names)}
+    return (means, arr) if per_query else means
+
+
+# --------------------------------------------------------------------------------------
 # a5: MultipleNegativesRankingLoss.forward (ST 5.2.2, restated; built at train_sbert.py:182-185)
 #     scores = cos_sim(anchors, candidates) * scale ; CrossEntropyLoss()(scores, arange(B))
 # --------------------------------------------------------------------------------------

@@ -303,6 +303,77 @@ def test_ir_evaluator_and_rank_all_against_oracle(golden_dir):
         assert out[f"order-recommendation_cosine_{k}"] == pytest.approx(val, abs=1e-12)
 
 
+def _random_rankings(rng, Q, K, n_corpus, short_rows=True):
+    ids = np.stack([rng.permutation(n_corpus)[:K] for _ in range(Q)]).astype(np.int64)
+    relevant = [set(int(x) for x in rng.choice(n_corpus, size=rng.integers(1, 15), replace=False)) for _ in range(Q)]
+    for q in range(0, Q, 3):  # plant hits near the top so that every metric is exercised
+        ids[q, rng.integers(0, min(10, K))] = next(iter(relevant[q]))
+    if short_rows:
+        for q in range(1, Q, 7):  # rows with fewer than K results end in -1
+            ids[q, rng.integers(0, K):] = -1
+    # |relevant| may count documents that are not in the catalog
+    n_rel = [len(r) + (int(rng.integers(0, 3)) if q % 5 == 0 else 0) for q, r in enumerate(relevant)]
+    return ids, relevant, n_rel
+
+
+@pytest.mark.parametrize("Q,K,n_corpus", [(257, 100, 500), (40, 37, 300), (1, 10, 50), (1000, 256, 5000), (9, 1, 20)])
+def test_ir_metric_kernel_vs_oracle_loops(Q, K, n_corpus):
+    """icr_ir_metrics == the evaluator's per-query loops (oracle.st_ir_metrics), per query and in the mean."""
+    rng = np.random.default_rng(Q * 1000 + K)
+    ids, relevant, n_rel = _random_rankings(rng, Q, K, n_corpus)
+    specs = ([(ops.METRIC_ACCURACY, k) for k in (1, 3, 5, 10)] + [(ops.METRIC_PRECISION, k) for k in (1, 3, 5, 10)]
+             + [(ops.METRIC_RECALL, k) for k in (1, 3, 5, 10)] + [(ops.METRIC_MRR, 10), (ops.METRIC_NDCG, 10), (ops.METRIC_MAP, 100)])
+    table = ops.RelevanceTable([sorted(r) for r in relevant], n_rel, device="cuda")
+    means, per_query = ops.ir_metrics(torch.from_numpy(ids).cuda(), table, specs)
+    want_means, want_pq = oracle.st_ir_metrics([list(r) for r in ids], relevant, n_rel, per_query=True)
+    np.testing.assert_allclose(per_query.cpu().numpy(), want_pq, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(means.cpu().numpy(), np.array(list(want_means.values())), rtol=0, atol=1e-12)
+
+
+def test_ir_metric_kernel_baseline_flavour_vs_reference_metrics(golden_dir):
+    """The *_RETRIEVED kinds equal src/baselines/metrics.py (pinned by the reference's own outputs in metrics_golden.json)."""
+    from instacart_next_order_recommendation_b200 import evaluation
+
+    gold = json.loads((golden_dir / "metrics_golden.json").read_text())
+    cases = [(gold["rank_all_top100"], gold["relevant"], gold["metrics"])] + [(c["rankings"], c["relevant"], c["metrics"]) for c in gold["extra"]]
+    specs = [(kind, k) for _, kind, k in evaluation.BASELINE_METRICS]
+    for rankings, relevant, want in cases:
+        qids = [q for q in rankings if relevant.get(q)]
+        if not qids:
+            continue
+        pids = sorted({p for q in qids for p in rankings[q]} | {p for q in qids for p in relevant[q]})
+        row_of = {p: i for i, p in enumerate(pids)}
+        K = max(1, min(100, max(len(rankings[q]) for q in qids)))
+        ids = np.full((len(qids), K), -1, dtype=np.int64)
+        for r, q in enumerate(qids):
+            top = rankings[q][:K]
+            ids[r, : len(top)] = [row_of[p] for p in top]
+        table = ops.RelevanceTable([[row_of[p] for p in relevant[q]] for q in qids], [len(set(relevant[q])) for q in qids], device="cuda")
+        means, _ = ops.ir_metrics(torch.from_numpy(ids).cuda(), table, specs)
+        for (name, _, _), v in zip(evaluation.BASELINE_METRICS, means.tolist()):
+            assert v == pytest.approx(want[name], abs=1e-12), name
+    # and the fused consumer: embeddings in, the reference's metric dict out
+    z = np.load(golden_dir / "embeddings_small.npz")
+    pids = [str(p) for p in z["product_ids"]]
+    qids = list(gold["rank_all_top100"].keys())
+    m = evaluation.evaluate_rankings(z["queries"], z["items"], qids, pids, {k: set(v) for k, v in gold["relevant"].items()})
+    for key, val in gold["metrics"].items():
+        assert m[key] == pytest.approx(val, abs=1e-12), key
+
+
+def test_ir_metric_kernel_argument_errors():
+    table = ops.RelevanceTable([[1, 2]], device="cuda")
+    ids = torch.zeros(1, 10, dtype=torch.int64, device="cuda")
+    with pytest.raises(ValueError):
+        ops.ir_metrics(ids, table, [(99, 10)])
+    with pytest.raises(ValueError):
+        ops.ir_metrics(ids, table, [(ops.METRIC_MRR, 0)])
+    with pytest.raises(ValueError):
+        ops.ir_metrics(torch.zeros(2, 10, dtype=torch.int64, device="cuda"), table, [(ops.METRIC_MRR, 10)])
+    with pytest.raises(RuntimeError):
+        ops.ir_metrics(ids.cpu(), table, [(ops.METRIC_MRR, 10)])
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("B,D,scale", [(256, 384, 20.0), (64, 384, 30.0), (37, 768, 20.0), (8, 64, 20.0), (1024, 384, 20.0)])
 def test_mnrl_forward_backward_vs_autograd(dtype, B, D, scale):

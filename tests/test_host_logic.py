@@ -123,42 +123,6 @@ def test_compute_ir_metrics_matches_reference_code(golden_dir):
             assert m[key] == pytest.approx(val, abs=1e-12), key
 
 
-def _st_style_metrics(ranked_rows, relevant_rows_sets, ks_acc, ks_pr, k_mrr, k_ndcg, k_map):
-    """Loop restatement of sentence-transformers' evaluator arithmetic for the vectorised version."""
-    import math
-
-    out = {}
-    n = len(ranked_rows)
-    for k in ks_acc:
-        out[f"accuracy@{k}"] = sum(any(r in rel for r in rk[:k]) for rk, rel in zip(ranked_rows, relevant_rows_sets)) / n
-    for k in ks_pr:
-        out[f"precision@{k}"] = sum(sum(r in rel for r in rk[:k]) / k for rk, rel in zip(ranked_rows, relevant_rows_sets)) / n
-        out[f"recall@{k}"] = sum(sum(r in rel for r in rk[:k]) / len(rel) for rk, rel in zip(ranked_rows, relevant_rows_sets)) / n
-    mrr = 0.0
-    for rk, rel in zip(ranked_rows, relevant_rows_sets):
-        for j, r in enumerate(rk[:k_mrr]):
-            if r in rel:
-                mrr += 1 / (j + 1)
-                break
-    out[f"mrr@{k_mrr}"] = mrr / n
-    nd = 0.0
-    for rk, rel in zip(ranked_rows, relevant_rows_sets):
-        dcg = sum((1.0 if r in rel else 0.0) / math.log2(j + 2) for j, r in enumerate(rk[:k_ndcg]))
-        idcg = sum(1.0 / math.log2(j + 2) for j in range(min(len(rel), k_ndcg)))
-        nd += dcg / idcg
-    out[f"ndcg@{k_ndcg}"] = nd / n
-    mp = 0.0
-    for rk, rel in zip(ranked_rows, relevant_rows_sets):
-        hits, s = 0, 0.0
-        for j, r in enumerate(rk[:k_map]):
-            if r in rel:
-                hits += 1
-                s += hits / (j + 1)
-        mp += s / min(k_map, len(rel))
-    out[f"map@{k_map}"] = mp / n
-    return out
-
-
 def test_evaluator_metric_arithmetic_and_keys():
     rng = np.random.default_rng(5)
     n_corpus, n_q = 500, 40
@@ -175,7 +139,9 @@ def test_evaluator_metric_arithmetic_and_keys():
         ids[r, rng.integers(0, 10)] = int(next(iter(relevant[qid]))[1:])
     got = ev.compute_metrics_from_ids(ids)
     rel_rows = [{int(d[1:]) for d in relevant[q]} for q in ev.queries_ids]
-    want = _st_style_metrics([list(r) for r in ids], rel_rows, [1, 3, 5, 10], [1, 3, 5, 10], 10, 10, 100)
+    from oracle import oracle
+
+    want = oracle.st_ir_metrics([list(r) for r in ids], rel_rows)
     assert set(got) == set(want)
     for k in want:
         assert got[k] == pytest.approx(want[k], abs=1e-12), k
