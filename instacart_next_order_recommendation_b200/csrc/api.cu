@@ -80,6 +80,10 @@ static bool dense_use_gemm(int64_t Qa, int64_t Nb, int64_t D, int dtype) {
 }
 
 int launch_mnrl_dispatch(const MnrlArgs& g, int dtype, bool bwd, cudaStream_t st);
+// tensor-core MNRL (mnrl_tc.cu)
+bool mnrl_tc_applies(int64_t B, int64_t D);
+size_t mnrl_tc_workspace_bytes(int64_t B, int64_t D);
+int launch_mnrl_tc(const MnrlArgs& m, int dtype, bool bwd, void* ws, size_t ws_bytes, cudaStream_t st);
 int launch_ir_metrics(const int64_t* ids, int64_t Q, int K, int64_t ld, const int64_t* rel_offsets, const int64_t* rel_rows,
                       const int32_t* n_relevant, const int32_t* kinds, const int32_t* ks, int M, double* per_query, double* means,
                       cudaStream_t st);
@@ -360,7 +364,7 @@ int icr_topk_merge(const float* cand_scores, const int64_t* cand_ids, int64_t Q,
 }
 
 size_t icr_mnrl_workspace_bytes(int64_t B, int64_t D) {
-  (void)D;
+  if (B > 0 && D > 0 && mnrl_tc_applies(B, D)) return mnrl_tc_workspace_bytes(B, D);
   return align_up(static_cast<size_t>(B > 0 ? B : 0) * sizeof(float), 256) + 256;
 }
 
@@ -404,6 +408,7 @@ int icr_mnrl_fwd(const void* a, int64_t lda, const void* p, int64_t ldp, int64_t
   g.counter = static_cast<unsigned int*>(workspace);
   g.row_loss = reinterpret_cast<float*>(static_cast<char*>(workspace) + 256);
   g.loss = loss;
+  if (mnrl_tc_applies(B, D)) return launch_mnrl_tc(g, dtype, false, workspace, workspace_bytes, st);
   ICR_CUDA_CHECK(cudaMemsetAsync(g.counter, 0, sizeof(unsigned int), st));
   return launch_mnrl_dispatch(g, dtype, false, st);
 }
@@ -434,6 +439,7 @@ int icr_mnrl_bwd(const void* a, int64_t lda, const void* p, int64_t ldp, int64_t
   g.grad_p = grad_p;
   g.ldga = ldga;
   g.ldgp = ldgp;
+  if (mnrl_tc_applies(B, D)) return launch_mnrl_tc(g, dtype, true, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
   return launch_mnrl_dispatch(g, dtype, true, static_cast<cudaStream_t>(stream));
 }
 

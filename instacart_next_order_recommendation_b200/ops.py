@@ -287,7 +287,7 @@ def _fast_rows(t: torch.Tensor) -> torch.Tensor:
 
 
 def mnrl_forward(anchors: torch.Tensor, positives: torch.Tensor, scale: float):
-    """Returns (loss f32 scalar tensor, saved): saved[0:3B] = lse | inv_a | inv_p, the rest is kernel workspace."""
+    """Returns (loss f32 scalar tensor, saved): saved = lse | inv_a | inv_p, B floats each."""
     _require_cuda("anchors", anchors)
     _require_cuda("positives", positives)
     if anchors.dtype != positives.dtype or anchors.shape != positives.shape:
@@ -297,13 +297,13 @@ def mnrl_forward(anchors: torch.Tensor, positives: torch.Tensor, scale: float):
     dev = a.device
     lib = _lib.load()
     loss = torch.empty((), dtype=torch.float32, device=dev)
-    off = (3 * B + 63) // 64 * 64  # workspace starts 256-byte aligned behind the three saved vectors
-    saved = torch.empty(off + B + 128, dtype=torch.float32, device=dev)
+    saved = torch.empty(3 * B, dtype=torch.float32, device=dev)  # lse | inv_a | inv_p
     base = saved.data_ptr()
     with _on(dev):
+        ws = _workspace(lib.icr_mnrl_workspace_bytes(B, D), dev)
         _lib.check(
             lib.icr_mnrl_fwd(a.data_ptr(), _ld(a), p.data_ptr(), _ld(p), B, D, _dtype_code(a), float(scale), loss.data_ptr(),
-                             base, base + 4 * B, base + 8 * B, base + 4 * off, 4 * (B + 128), _stream(dev))
+                             base, base + 4 * B, base + 8 * B, ws.data_ptr(), ws.numel(), _stream(dev))
         )
     return loss, saved
 
@@ -318,13 +318,13 @@ def mnrl_backward(anchors: torch.Tensor, positives: torch.Tensor, scale: float, 
     if not (go.is_cuda and go.dtype == torch.float32 and go.is_contiguous()):
         go = go.detach().to(device=dev, dtype=torch.float32).contiguous()
     base = saved.data_ptr()
-    off = (3 * B + 63) // 64 * 64
     gbytes = B * D * a.element_size()
     with _on(dev):
+        ws = _workspace(lib.icr_mnrl_workspace_bytes(B, D), dev)
         _lib.check(
             lib.icr_mnrl_bwd(a.data_ptr(), _ld(a), p.data_ptr(), _ld(p), B, D, _dtype_code(a), float(scale), base, base + 4 * B,
                              base + 8 * B, go.data_ptr(), grads.data_ptr(), D, grads.data_ptr() + gbytes, D,
-                             base + 4 * off, 4 * (B + 128), _stream(dev))
+                             ws.data_ptr(), ws.numel(), _stream(dev))
         )
     ga, gp = grads[0], grads[1]
     D0 = anchors.shape[1]

@@ -375,7 +375,8 @@ def test_ir_metric_kernel_argument_errors():
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("B,D,scale", [(256, 384, 20.0), (64, 384, 30.0), (37, 768, 20.0), (8, 64, 20.0), (1024, 384, 20.0)])
+@pytest.mark.parametrize("B,D,scale", [(256, 384, 20.0), (64, 384, 30.0), (37, 768, 20.0), (8, 64, 20.0), (1024, 384, 20.0),
+                                       (130, 384, 20.0), (288, 384, 20.0), (384, 384, 20.0), (512, 384, 30.0), (1000, 128, 30.0), (300, 768, 20.0), (2048, 384, 20.0), (4096, 64, 20.0)])
 def test_mnrl_forward_backward_vs_autograd(dtype, B, D, scale):
     g = torch.Generator().manual_seed(2024)
     items, _ = oracle.synth_clustered(B, D, seed=2024, n_centres=12)
@@ -392,6 +393,43 @@ def test_mnrl_forward_backward_vs_autograd(dtype, B, D, scale):
     tol = MNRL_ATOL if dtype == torch.float32 else MNRL_ATOL + 2 ** -8 * rga.abs().max().item() * 1.7  # bf16 output rounding
     assert (ad.grad.float().cpu() - 1.7 * rga).abs().max() <= tol
     assert (pd.grad.float().cpu() - 1.7 * rgp).abs().max() <= tol
+    # gradients shrink like 1/B, so the absolute bound alone says little for large batches: also bound the error
+    # relative to the largest gradient entry (fp16 operands of the gradient products: 2^-11 per element)
+    rel = 2e-3 if dtype == torch.float32 else 2e-3 + 2 ** -8
+    assert (ad.grad.float().cpu() - 1.7 * rga).abs().max() <= rel * 1.7 * rga.abs().max()
+    assert (pd.grad.float().cpu() - 1.7 * rgp).abs().max() <= rel * 1.7 * rgp.abs().max()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_mnrl_tensor_path_equals_cuda_core_path(dtype, monkeypatch):
+    """The two MNRL kernel families (mnrl.cu / mnrl_tc.cu) agree on the same batch (subprocess: the switch is read once)."""
+    import subprocess
+    import sys
+
+    code = (
+        "import sys, torch; sys.path.insert(0, '.');"
+        "import instacart_next_order_recommendation_b200 as icr;"
+        f"dt = torch.{str(dtype).split('.')[-1]};"
+        "g = torch.Generator().manual_seed(7);"
+        "a = torch.randn(192, 384, generator=g).to(dt).cuda().requires_grad_(True);"
+        "p = (torch.randn(192, 384, generator=g) * 3).to(dt).cuda().requires_grad_(True);"
+        "l = icr.mnrl_loss(a, p, 20.0); l.backward();"
+        "torch.save((l.detach().cpu(), a.grad.float().cpu(), p.grad.float().cpu()), sys.argv[1])"
+    )
+    import os
+    import tempfile
+
+    outs = {}
+    for path in ("tc", "simt"):
+        with tempfile.NamedTemporaryFile(suffix=".pt") as f:
+            env = dict(os.environ, ICR_MNRL_PATH=path)
+            subprocess.run([sys.executable, "-c", code, f.name], check=True, env=env, cwd=str(__import__("pathlib").Path(__file__).resolve().parents[1]))
+            outs[path] = torch.load(f.name)
+    (l1, ga1, gp1), (l2, ga2, gp2) = outs["tc"], outs["simt"]
+    assert abs(l1.item() - l2.item()) <= 2e-5
+    tol = 2e-3 if dtype == torch.float32 else 2e-3 + 2 ** -7
+    assert (ga1 - ga2).abs().max() <= tol * ga2.abs().max()
+    assert (gp1 - gp2).abs().max() <= tol * gp2.abs().max()
 
 
 def test_mnrl_known_answers_and_module_interface():
