@@ -74,6 +74,13 @@ int icr_split_f16_planes(const float* x, int64_t rows, int64_t dim, int64_t ld,
                          uint16_t* planes, void* stream);
 int64_t icr_planes_row_elems(int64_t dim); /* = 2 * round_up(dim, 64) */
 
+/* Catalog upload helper: fp32 rows as the reference stores them on disk (embeddings.npy,
+ * src/inference/serve_recommendations.py:127) -> the HBM-resident form: ICR_F32 or ICR_BF16
+ * (round to nearest even), optionally L2-normalised first (x / max(||x||, 1e-12), the reference
+ * normalises at encode time, :195-200). x and out are device pointers; dim % 4 == 0. */
+int icr_convert_rows(const float* x, int64_t rows, int64_t dim, int64_t ldx,
+                     void* out, int64_t ldo, int out_dtype, int normalize, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Fused cosine top-k  ==  torch.topk(cos_sim(queries, catalog), k, dim=1, sorted=True)
  * with ties broken by the lower catalog row.

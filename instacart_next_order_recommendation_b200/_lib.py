@@ -38,6 +38,7 @@ SIGNATURES = {
     "icr_row_inv_norms": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "icr_split_f16_planes": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
     "icr_planes_row_elems": (c_int64, [c_int64]),
+    "icr_convert_rows": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "icr_cos_topk_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int]),
     "icr_cos_topk": (
         c_int,

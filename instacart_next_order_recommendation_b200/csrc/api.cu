@@ -51,6 +51,8 @@ void profile_end(cudaStream_t st) {
 // kernels' host launchers (defined in the other translation units)
 int launch_row_inv_norms(const void* x, int64_t rows, int64_t dim, int64_t ld, int dtype, float* inv, cudaStream_t st);
 int launch_split_planes(const float* x, int64_t rows, int64_t dim, int64_t ld, uint16_t* planes, cudaStream_t st);
+int launch_convert_rows(const float* x, int64_t rows, int64_t dim, int64_t ldx, void* out, int64_t ldo, int out_dtype, int normalize,
+                        cudaStream_t st);
 int gemv_grid(int64_t N);
 int launch_gemv_topk(const void* cat, int64_t N, int64_t ldc, int D, int dtype, const void* q, int64_t ldq, int Q,
                      const uint8_t* mask, int k, uint64_t* part_keys, int* part_cnt, int grid, float* out_scores, int64_t* out_ids,
@@ -441,6 +443,24 @@ int icr_mnrl_bwd(const void* a, int64_t lda, const void* p, int64_t ldp, int64_t
   g.ldgp = ldgp;
   if (mnrl_tc_applies(B, D)) return launch_mnrl_tc(g, dtype, true, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
   return launch_mnrl_dispatch(g, dtype, true, static_cast<cudaStream_t>(stream));
+}
+
+int icr_convert_rows(const float* x, int64_t rows, int64_t dim, int64_t ldx, void* out, int64_t ldo, int out_dtype, int normalize,
+                     void* stream) {
+  g_launches = 0;
+  int rc = check_matrix("convert_rows.x", x, rows, dim, ldx, ICR_F32);
+  if (rc) return rc;
+  if (out_dtype != ICR_F32 && out_dtype != ICR_BF16) {
+    set_error("convert_rows: unsupported output dtype %d", out_dtype);
+    return ICR_ERR_DTYPE;
+  }
+  const int64_t osz = out_dtype == ICR_F32 ? 4 : 2;
+  if (rows > 0 && (!out || ldo < dim || (reinterpret_cast<uintptr_t>(out) & 15) || (ldo * osz) % 8 != 0)) {
+    set_error("convert_rows: output must be non-null, 16-byte aligned, row stride >= dim and a multiple of 8 bytes");
+    return ICR_ERR_ALIGN;
+  }
+  if ((rc = check_device())) return rc;
+  return launch_convert_rows(x, rows, dim, ldx, out, ldo, out_dtype, normalize ? 1 : 0, static_cast<cudaStream_t>(stream));
 }
 
 int icr_ir_metrics(const int64_t* ids, int64_t Q, int K, int64_t ld_ids, const int64_t* rel_offsets, const int64_t* rel_rows,

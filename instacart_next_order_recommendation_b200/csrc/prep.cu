@@ -3,6 +3,11 @@
 
 namespace icr {
 
+__device__ __forceinline__ float4 ldg_stream_f4(const float* p) {
+  const uint4 v = ldg_stream(p);
+  return make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
+}
+
 // one warp per row; 128-bit loads; inv = 1 / max(||x||, eps)   (torch F.normalize semantics)
 template <typename T>
 __global__ void __launch_bounds__(256) row_inv_norms_kernel(const T* __restrict__ x, int64_t rows, int64_t dim, int64_t ld,
@@ -78,6 +83,62 @@ int launch_split_planes(const float* x, int64_t rows, int64_t dim, int64_t ld, u
   const int64_t want = (rows + 7) / 8;
   const int blocks = static_cast<int>(want < 148 * 16 ? want : 148 * 16);
   split_f16_planes_kernel<<<blocks, 256, 0, st>>>(x, rows, dim, ld, reinterpret_cast<__half*>(planes), dim_pad);
+  ICR_LAUNCH_CHECK();
+  return ICR_OK;
+}
+
+// Catalog upload: fp32 rows as stored on disk -> the resident form (fp32 or bf16), optionally L2-normalised first.
+// One warp per row, 128-bit loads; bf16 rounding is round-to-nearest-even (what torch's .to(bfloat16) does).
+template <typename OUT>
+__global__ void __launch_bounds__(256) convert_rows_kernel(const float* __restrict__ x, int64_t rows, int64_t dim, int64_t ldx,
+                                                           OUT* __restrict__ out, int64_t ldo, int normalize) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const int nvec = static_cast<int>(dim / 4);
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    const float* row = x + r * ldx;
+    float inv = 1.0f;
+    if (normalize) {
+      float ss = 0.f;
+      for (int v = lane; v < nvec; v += 32) {
+        const float4 f = *reinterpret_cast<const float4*>(row + 4 * v);
+        ss = fmaf(f.x, f.x, fmaf(f.y, f.y, fmaf(f.z, f.z, fmaf(f.w, f.w, ss))));
+      }
+      ss = warp_sum(ss);
+      inv = 1.0f / fmaxf(sqrtf(ss), kNormEps);
+    }
+    OUT* dst = out + r * ldo;
+    for (int v = lane; v < nvec; v += 32) {
+      float4 f = ldg_stream_f4(row + 4 * v);
+      if (normalize) {
+        f.x *= inv;
+        f.y *= inv;
+        f.z *= inv;
+        f.w *= inv;
+      }
+      if (sizeof(OUT) == 4) {
+        *reinterpret_cast<float4*>(dst + 4 * v) = f;
+      } else {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(f.x, f.y), hi = __floats2bfloat162_rn(f.z, f.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(dst + 4 * v) = pk;
+      }
+    }
+  }
+}
+
+int launch_convert_rows(const float* x, int64_t rows, int64_t dim, int64_t ldx, void* out, int64_t ldo, int out_dtype, int normalize,
+                        cudaStream_t st) {
+  if (rows == 0) return ICR_OK;
+  const int64_t want = (rows + 7) / 8;
+  const int blocks = static_cast<int>(want < 148 * 16 ? want : 148 * 16);
+  if (out_dtype == ICR_F32)
+    convert_rows_kernel<float><<<blocks, 256, 0, st>>>(x, rows, dim, ldx, static_cast<float*>(out), ldo, normalize);
+  else
+    convert_rows_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(x, rows, dim, ldx, static_cast<__nv_bfloat16*>(out), ldo, normalize);
   ICR_LAUNCH_CHECK();
   return ICR_OK;
 }

@@ -8,6 +8,12 @@
         embeddings.npy  float32 [N, D]
         product_ids.json
 
+``EmbeddingIndex.open`` memory-maps the same file instead of reading it, ``save_bf16_sidecar`` /
+``open_bf16_sidecar`` add an optional ``embeddings.bf16.bin`` next to it (half the bytes on disk and
+over PCIe, valid only while the manifest-validated ``embeddings.npy`` it was made from is unchanged),
+and ``DeviceCatalog.from_index`` streams either one into HBM chunk by chunk through pinned staging
+buffers — for a whole catalog or for one rank's row block of a sharded one.
+
 ``DeviceCatalog`` is what the kernels read: the same rows resident in HBM (fp32, or bf16
 on request), plus — for fp32 — the fp16 (hi|lo) operand planes of the tensor-core path,
 built once at load instead of re-normalising the catalog on every request as
@@ -33,6 +39,7 @@ INDEX_SUBDIR = ".embedding_index"
 MANIFEST_FILENAME = "manifest.json"
 EMBEDDINGS_FILENAME = "embeddings.npy"
 PRODUCT_IDS_FILENAME = "product_ids.json"
+BF16_SIDECAR_FILENAME = "embeddings.bf16.bin"  # raw bfloat16 [N, D], row-major, no header (shape comes from embeddings.npy)
 
 
 class EmbeddingIndex:
@@ -77,6 +84,59 @@ class EmbeddingIndex:
             return None
         return embeddings
 
+    def _valid_manifest(self) -> bool:
+        try:
+            meta = json.loads((self._dir / MANIFEST_FILENAME).read_text())
+        except (OSError, json.JSONDecodeError):
+            return False
+        if meta.get("corpus_path") != str(self.corpus_path) or meta.get("model_dir") != str(self.model_dir):
+            return False
+        mtime = self._corpus_mtime()
+        return mtime is not None and meta.get("corpus_mtime") == mtime
+
+    def open(self, product_ids: list[str]) -> np.ndarray | None:
+        """Like ``load`` (same validity rules) but memory-maps embeddings.npy read-only instead of reading it."""
+        if not self._valid_manifest():
+            return None
+        try:
+            embeddings = np.load(self._dir / EMBEDDINGS_FILENAME, mmap_mode="r")
+            cached_ids = json.loads((self._dir / PRODUCT_IDS_FILENAME).read_text())
+        except (OSError, ValueError):
+            return None
+        if cached_ids != product_ids or len(embeddings) != len(product_ids):
+            return None
+        return embeddings
+
+    def save_bf16_sidecar(self, *, normalize: bool = False) -> Path:
+        """Write embeddings.bf16.bin from the index's embeddings.npy (rows optionally L2-normalised, then rounded to
+        nearest-even bfloat16). Host-side file conversion, chunked; the index itself is not touched."""
+        emb = np.load(self._dir / EMBEDDINGS_FILENAME, mmap_mode="r")
+        path = self._dir / BF16_SIDECAR_FILENAME
+        tmp = path.with_suffix(".tmp")
+        with open(tmp, "wb") as f:
+            for s0 in range(0, emb.shape[0], 1 << 16):
+                t = torch.from_numpy(np.array(emb[s0 : s0 + (1 << 16)], dtype=np.float32))
+                if normalize:
+                    t = torch.nn.functional.normalize(t, p=2, dim=1, eps=1e-12)
+                f.write(t.to(torch.bfloat16).view(torch.int16).numpy().tobytes())
+        tmp.replace(path)
+        return path
+
+    def open_bf16_sidecar(self, product_ids: list[str], _emb: np.ndarray | None = None) -> np.ndarray | None:
+        """uint16 memmap [N, D] of the sidecar's bfloat16 bit patterns, or None unless the index itself is valid for
+        `product_ids`, and the sidecar is as large as embeddings.npy says and not older than it."""
+        emb = _emb if _emb is not None else self.open(product_ids)  # _emb: the caller has just validated the index
+        if emb is None or emb.ndim != 2:
+            return None
+        side, base = self._dir / BF16_SIDECAR_FILENAME, self._dir / EMBEDDINGS_FILENAME
+        try:
+            st_side, st_base = side.stat(), base.stat()
+        except OSError:
+            return None
+        if st_side.st_size != emb.shape[0] * emb.shape[1] * 2 or st_side.st_mtime < st_base.st_mtime:
+            return None
+        return np.memmap(side, dtype=np.uint16, mode="r", shape=emb.shape)
+
     def save(self, product_ids: list[str], embeddings: np.ndarray) -> None:
         self._dir.mkdir(parents=True, exist_ok=True)
         mtime = self._corpus_mtime()
@@ -115,6 +175,28 @@ class DeviceCatalog:
         self.inv_norms: torch.Tensor | None = None
         if dtype == torch.bfloat16 and self.rows.shape[0] > 0:
             self.inv_norms = ops.row_inv_norms(self.rows)
+
+    @classmethod
+    def from_index(cls, index: "EmbeddingIndex", product_ids: list[str], *, dtype: torch.dtype = torch.float32,
+                   device: torch.device | None = None, rows: tuple[int, int] | None = None, normalize: bool = False,
+                   use_sidecar: bool = True, chunk_rows: int = 1 << 15, row_offset: int | None = None) -> "DeviceCatalog | None":
+        """Stream a validated on-disk index (or the row block `rows` = [lo, hi) of it) into HBM.
+
+        None if the index is missing or stale (the caller re-encodes, as the reference does,
+        serve_recommendations.py:183-204). With dtype bfloat16 a valid ``embeddings.bf16.bin`` sidecar is uploaded
+        as is (half the bytes); otherwise the fp32 rows go up chunk by chunk and ``icr_convert_rows`` writes the
+        resident form. ``row_offset`` defaults to lo, so a row-sharded catalog returns global ids.
+        """
+        emb = index.open(product_ids)
+        if emb is None:
+            return None
+        dev = device if device is not None else default_device()
+        lo, hi = (0, emb.shape[0]) if rows is None else (max(0, int(rows[0])), min(emb.shape[0], int(rows[1])))
+        hi = max(lo, hi)
+        side = index.open_bf16_sidecar(product_ids, _emb=emb) if (use_sidecar and dtype == torch.bfloat16 and not normalize) else None
+        resident = upload_rows(side if side is not None else emb, lo, hi, device=dev, dtype=dtype, normalize=normalize,
+                               chunk_rows=chunk_rows, source_is_bf16_bits=side is not None)
+        return cls(resident, device=dev, dtype=dtype, row_offset=lo if row_offset is None else row_offset)
 
     @property
     def device(self) -> torch.device:
@@ -233,3 +315,85 @@ class DeviceCatalog:
         if k < 1:
             return (torch.empty(q.shape[0], 0, device=self.device), torch.empty(q.shape[0], 0, dtype=torch.int64, device=self.device))
         return ops.cos_topk(q, self.rows, k, cat_planes=self.planes, cat_inv_norms=self.inv_norms, exclude_mask=exclude_mask, row_offset=self.row_offset, path=path)
+
+
+def chunk_spans(lo: int, hi: int, chunk_rows: int) -> list[tuple[int, int]]:
+    """[lo, hi) cut into consecutive spans of at most chunk_rows rows."""
+    chunk_rows = max(1, int(chunk_rows))
+    return [(s, min(hi, s + chunk_rows)) for s in range(lo, hi, chunk_rows)]
+
+
+_PINNED: dict = {}  # (slot, element size) -> pinned byte buffer, kept between loads (cudaHostAlloc costs tens of ms)
+_COPY_THREADS = 4
+_copy_pool = None
+
+
+def _pinned_stage(slot: int, rows: int, cols: int, dtype: torch.dtype) -> torch.Tensor:
+    need = rows * cols * torch.empty((), dtype=dtype).element_size()
+    buf = _PINNED.get(slot)
+    if buf is None or buf.numel() < need:
+        buf = torch.empty(need, dtype=torch.uint8).pin_memory()
+        _PINNED[slot] = buf
+    return buf[:need].view(dtype).view(rows, cols)
+
+
+def _host_copy(dst: np.ndarray, src: np.ndarray) -> None:
+    """dst[:] = src with a few threads: numpy releases the GIL while copying, and one core moves only ~8 GB/s out of
+    the page cache — less than the PCIe link the staging buffer feeds."""
+    global _copy_pool
+    n = dst.shape[0]
+    if n < 4096:
+        np.copyto(dst, src, casting="same_kind")
+        return
+    if _copy_pool is None:
+        from concurrent.futures import ThreadPoolExecutor
+
+        _copy_pool = ThreadPoolExecutor(_COPY_THREADS)
+    step = -(-n // _COPY_THREADS)
+    list(_copy_pool.map(lambda s: np.copyto(dst[s : s + step], src[s : s + step], casting="same_kind"), range(0, n, step)))
+
+
+def upload_rows(src: np.ndarray, lo: int, hi: int, *, device: torch.device, dtype: torch.dtype, normalize: bool = False,
+                chunk_rows: int = 1 << 15, source_is_bf16_bits: bool = False) -> torch.Tensor:
+    """Rows [lo, hi) of a host (typically memory-mapped) matrix -> a device tensor [hi-lo, D] of `dtype`.
+
+    Two pinned staging buffers alternate: while chunk i crosses PCIe (and is converted by ``icr_convert_rows`` on
+    the same side stream), the host copies chunk i+1 out of the page cache into the other buffer. fp32 -> fp32
+    without normalisation lands directly in the destination; bf16 bit patterns from the sidecar likewise.
+    """
+    n, D = hi - lo, int(src.shape[1])
+    out = torch.empty(n, D, dtype=dtype, device=device)
+    if n == 0:
+        return out
+    if source_is_bf16_bits and (dtype != torch.bfloat16 or normalize):
+        raise ValueError("the bf16 sidecar can only be uploaded as an un-normalised bfloat16 catalog")
+    direct = source_is_bf16_bits or (dtype == torch.float32 and not normalize)
+    if not direct and D % 4:
+        raise ValueError("icr_convert_rows needs an embedding dim that is a multiple of 4")
+    stage_dtype = torch.int16 if source_is_bf16_bits else torch.float32
+    np_dtype = np.uint16 if source_is_bf16_bits else np.float32
+    chunk_rows = min(max(1, int(chunk_rows)), n)
+    pinned = [_pinned_stage(b, chunk_rows, D, stage_dtype) for b in range(2)]
+    staged = None if direct else [torch.empty(chunk_rows, D, dtype=torch.float32, device=device) for _ in range(2)]
+    free = [torch.cuda.Event(), torch.cuda.Event()]  # recorded when the buffer pair's last consumer has run
+    side = torch.cuda.Stream(device)
+    side.wait_stream(torch.cuda.current_stream(device))
+    dst_bits = out.view(torch.int16) if source_is_bf16_bits else None
+    for i, (s0, s1) in enumerate(chunk_spans(lo, hi, chunk_rows)):
+        b, m = i & 1, s1 - s0
+        if i >= 2:
+            free[b].synchronize()
+        host = pinned[b][:m]
+        _host_copy(host.numpy().view(np_dtype), src[s0:s1])
+        with torch.cuda.stream(side):
+            if direct:
+                (dst_bits if source_is_bf16_bits else out)[s0 - lo : s1 - lo].copy_(host, non_blocking=True)
+            else:
+                staged[b][:m].copy_(host, non_blocking=True)
+                ops.convert_rows(staged[b][:m], out[s0 - lo : s1 - lo], normalize=normalize)
+            free[b].record(side)
+    torch.cuda.current_stream(device).wait_stream(side)
+    for t in staged or ():
+        t.record_stream(side)  # allocated on the current stream, last used on the side stream
+    side.synchronize()  # the staging buffers are reused by the next load
+    return out

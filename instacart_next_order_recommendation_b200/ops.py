@@ -126,6 +126,19 @@ def split_f16_planes(x: torch.Tensor) -> torch.Tensor:
     return planes
 
 
+def convert_rows(x: torch.Tensor, out: torch.Tensor, *, normalize: bool = False) -> torch.Tensor:
+    """fp32 device rows -> `out` (float32 or bfloat16 device rows of the same shape), optionally L2-normalised first."""
+    _require_cuda("x", x)
+    _require_cuda("out", out)
+    if x.dtype != torch.float32 or x.dim() != 2 or out.shape != x.shape or x.stride(1) != 1 or out.stride(1) != 1:
+        raise ValueError("convert_rows expects float32 [rows, dim] input and an output of the same shape, both contiguous in dim")
+    lib = _lib.load()
+    with _on(x.device):
+        _lib.check(lib.icr_convert_rows(x.data_ptr(), x.shape[0], x.shape[1], _ld(x), out.data_ptr(), _ld(out), _dtype_code(out), int(normalize),
+                                        _stream(x.device)))
+    return out
+
+
 def cos_topk(
     queries: torch.Tensor,
     catalog: torch.Tensor,

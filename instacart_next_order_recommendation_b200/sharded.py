@@ -77,6 +77,23 @@ class ShardedCatalog:
         lo, hi = shard_bounds(len(embeddings), ws, rk)
         return cls(embeddings[lo:hi], row_offset=lo, total_rows=len(embeddings), group=group, **kw)
 
+    @classmethod
+    def from_index(cls, index, product_ids: list[str], *, group=None, dtype: torch.dtype = torch.float32,
+                   device: torch.device | None = None, **load_kw) -> "ShardedCatalog | None":
+        """Every rank streams only ITS row block of a validated on-disk index into HBM (``DeviceCatalog.from_index``)."""
+        ws = dist.get_world_size(group) if dist.is_initialized() else 1
+        rk = dist.get_rank(group) if dist.is_initialized() else 0
+        lo, hi = shard_bounds(len(product_ids), ws, rk)
+        local = DeviceCatalog.from_index(index, product_ids, dtype=dtype, device=device, rows=(lo, hi), **load_kw)
+        if local is None:
+            return None
+        self = cls.__new__(cls)
+        self.group, self.world_size, self.rank = group, ws, rk
+        self.total_rows, self.row_offset = len(product_ids), lo
+        self._local_topk = self._merge = None
+        self.local, self.n_local, self.device = local, len(local), local.device
+        return self
+
     def local_topk(self, queries, k: int):
         """[Q,k] candidates of this shard with GLOBAL ids; short shards pad with (-inf, -1)."""
         kk = min(k, self.n_local)

@@ -303,6 +303,51 @@ def test_ir_evaluator_and_rank_all_against_oracle(golden_dir):
         assert out[f"order-recommendation_cosine_{k}"] == pytest.approx(val, abs=1e-12)
 
 
+def _index_on_disk(tmp_path, n, d, seed=3):
+    from instacart_next_order_recommendation_b200.index import EmbeddingIndex
+
+    corpus = tmp_path / "eval_corpus.json"
+    corpus.write_text("{}")
+    ids = [str(i) for i in range(n)]
+    emb = oracle.synth_unnormalised(n, d, seed=seed).numpy()
+    idx = EmbeddingIndex(corpus, "fake-model")
+    idx.save(ids, emb)
+    return idx, ids, emb
+
+
+@pytest.mark.parametrize("chunk_rows", [1 << 17, 1000, 37])
+def test_catalog_streamed_from_index_equals_catalog_from_memory(tmp_path, chunk_rows):
+    """DeviceCatalog.from_index (memmap -> pinned staging -> HBM, icr_convert_rows) holds bit-identical rows."""
+    idx, ids, emb = _index_on_disk(tmp_path, 5003, 384)
+    t = torch.from_numpy(emb)
+    cat = icr.DeviceCatalog.from_index(idx, ids, chunk_rows=chunk_rows)
+    assert torch.equal(cat.rows.cpu(), t) and cat.row_offset == 0
+    bf = icr.DeviceCatalog.from_index(idx, ids, dtype=torch.bfloat16, chunk_rows=chunk_rows)
+    assert torch.equal(bf.rows.cpu(), t.to(torch.bfloat16))
+    # a row block of a sharded catalog: global ids through row_offset
+    part = icr.DeviceCatalog.from_index(idx, ids, rows=(1200, 3100), chunk_rows=chunk_rows)
+    assert torch.equal(part.rows.cpu(), t[1200:3100]) and part.row_offset == 1200
+    # pre-normalised upload: rows are x / max(|x|, eps) (one rounding apart from torch's at most)
+    nrm = icr.DeviceCatalog.from_index(idx, ids, normalize=True, chunk_rows=chunk_rows)
+    ref = torch.nn.functional.normalize(t, dim=1)
+    assert (nrm.rows.cpu() - ref).abs().max() <= 2e-7
+    # the bf16 sidecar is uploaded as is and gives the same resident bytes as converting on the device
+    idx.save_bf16_sidecar()
+    side = icr.DeviceCatalog.from_index(idx, ids, dtype=torch.bfloat16, chunk_rows=chunk_rows)
+    assert torch.equal(side.rows.cpu(), t.to(torch.bfloat16))
+    # stale index -> None, like EmbeddingIndex.load
+    assert icr.DeviceCatalog.from_index(idx, ids[:-1]) is None
+    # and the streamed catalog answers like the in-memory one
+    queries = oracle.synth_unnormalised(9, 384, seed=11)
+    v, i = cat.topk(queries.cuda(), 100)
+    rv, ri = oracle.cos_topk(queries, t, 100)
+    _check_topk(v, i, rv, ri, F32_RTOL)
+    sh = icr.ShardedCatalog.from_index(idx, ids, dtype=torch.bfloat16)
+    v, i = sh.topk(queries.cuda().to(torch.bfloat16), 50)
+    rv, ri = oracle.cos_topk(queries.to(torch.bfloat16).float(), t.to(torch.bfloat16).float(), 50)
+    _check_topk(v, i, rv, ri, BF16_RTOL)
+
+
 def _random_rankings(rng, Q, K, n_corpus, short_rows=True):
     ids = np.stack([rng.permutation(n_corpus)[:K] for _ in range(Q)]).astype(np.int64)
     relevant = [set(int(x) for x in rng.choice(n_corpus, size=rng.integers(1, 15), replace=False)) for _ in range(Q)]

@@ -111,6 +111,44 @@ def test_embedding_index_is_byte_compatible_with_the_reference(golden_dir, tmp_p
     assert EmbeddingIndex(corpus, "other-model").load(ids) is None
 
 
+def test_index_memmap_and_bf16_sidecar_rules(tmp_path):
+    from instacart_next_order_recommendation_b200.index import chunk_spans
+
+    corpus = tmp_path / "eval_corpus.json"
+    corpus.write_text("{}")
+    ids = [str(i) for i in range(300)]
+    emb = np.random.default_rng(0).standard_normal((300, 24)).astype(np.float32)
+    idx = EmbeddingIndex(corpus, "fake-model")
+    assert idx.open(ids) is None and idx.open_bf16_sidecar(ids) is None  # nothing on disk yet
+    idx.save(ids, emb)
+    mm = idx.open(ids)
+    assert isinstance(mm, np.memmap) and not mm.flags.writeable
+    np.testing.assert_array_equal(mm, idx.load(ids))
+    assert idx.open(ids[:-1]) is None  # same invalidation rules as load()
+    assert idx.open_bf16_sidecar(ids) is None  # no sidecar yet
+    idx.save_bf16_sidecar()
+    side = idx.open_bf16_sidecar(ids)
+    want = torch.from_numpy(emb).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
+    np.testing.assert_array_equal(side, want)
+    # a sidecar of the wrong size, or older than embeddings.npy, is ignored; so is any sidecar of a stale index
+    import os
+
+    p = idx.directory / "embeddings.bf16.bin"
+    p.write_bytes(p.read_bytes()[:-2])
+    assert idx.open_bf16_sidecar(ids) is None
+    idx.save_bf16_sidecar(normalize=True)
+    side_n = idx.open_bf16_sidecar(ids)
+    want_n = torch.nn.functional.normalize(torch.from_numpy(emb), dim=1).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
+    np.testing.assert_array_equal(side_n, want_n)
+    old = (idx.directory / "embeddings.npy").stat().st_mtime - 100
+    os.utime(p, (old, old))
+    assert idx.open_bf16_sidecar(ids) is None
+    idx.save_bf16_sidecar()
+    os.utime(corpus, (1_700_000_123, 1_700_000_123))
+    assert idx.open(ids) is None and idx.open_bf16_sidecar(ids) is None
+    assert chunk_spans(3, 10, 4) == [(3, 7), (7, 10)] and chunk_spans(5, 5, 4) == [] and chunk_spans(0, 4, 4) == [(0, 4)]
+
+
 def test_compute_ir_metrics_matches_reference_code(golden_dir):
     gold = json.loads((golden_dir / "metrics_golden.json").read_text())
     rel = {k: set(v) for k, v in gold["relevant"].items()}
