@@ -295,30 +295,45 @@ def bench_sharded(icr, dist, dev, rank, world, args, tdtype):
     for s0 in range(0, shard_rows, 1 << 20):  # generated shard by shard on the device (seed + rank), 1M rows at a time
         s1 = min(shard_rows, s0 + (1 << 20))
         rows[s0:s1] = torch.nn.functional.normalize(torch.randn(s1 - s0, D, device=dev, generator=g), dim=1).to(torch.bfloat16)
-    cat = icr.ShardedCatalog(rows, row_offset=lo, total_rows=total_rows, dtype=torch.bfloat16)
+    cat = icr.ShardedCatalog(rows, row_offset=lo, total_rows=total_rows, dtype=torch.bfloat16, exchange="peer")
+    cat_nccl = icr.ShardedCatalog.__new__(icr.ShardedCatalog)  # same resident shard, NCCL all-gather instead of the peer-memory kernel
+    cat_nccl.__dict__.update(cat.__dict__)
+    cat_nccl.exchange, cat_nccl._peer = "nccl", None
     g2 = torch.Generator(device=dev).manual_seed(QUERY_SEED)
     q = torch.nn.functional.normalize(torch.randn(Q, D, device=dev, generator=g2), dim=1).to(torch.bfloat16)
-    for _ in range(2):
-        cat.topk(q, k)
     steps = 5
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    dist.barrier()
-    torch.cuda.synchronize()
-    ev0.record()
-    for _ in range(steps):
-        v, i = cat.topk(q, k)
-    ev1.record()
-    dist.barrier()
-    torch.cuda.synchronize()
-    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = t.item() / steps
+
+    def run(c, qq, n):
+        for _ in range(2):
+            c.topk(qq, k)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(n):
+            out = c.topk(qq, k)
+        ev1.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item() / n, out
+
+    ms_nccl, (v0, i0) = run(cat_nccl, q, steps)
+    ms, (v, i) = run(cat, q, steps)
+    same = bool(torch.equal(v, v0) and torch.equal(i, i0))
+    small = {}
+    for qs in (1, 64):  # request-sized batches: the exchange is a visible share of the call
+        a, _ = run(cat_nccl, q[:qs], 20)
+        b, _ = run(cat, q[:qs], 20)
+        small[f"Q{qs}"] = {"nccl_ms": a, "peer_ms": b}
     flops = 2.0 * Q * shard_rows * D  # per GPU
     peaks = _peaks()
     return {"workload": f"C5: {total_rows} x {D} bf16 catalog row-sharded over {world} GPUs ({shard_rows} rows each), {Q}-query batches, top-{k}, "
-                        "NCCL all-gather of candidates + device merge",
+                        "candidates exchanged over NVLink peer memory + device merge",
             "value": Q / (ms * 1e-3), "unit": "queries/s", "scaling": "weak (catalog rows grow with GPUs)", "ms_per_step": ms, "steps": steps,
-            "exchange_bytes_per_rank": Q * k * 16, "tflops_per_gpu": flops / (ms * 1e-3) / 1e12,
+            "exchange": "icr_peer_exchange: NVLink peer-memory push + flags (one kernel), then device merge", "exchange_bytes_per_rank": Q * k * 12,
+            "nccl_all_gather_ms_per_step": ms_nccl, "peer_equals_nccl": same, "small_batches": small, "tflops_per_gpu": flops / (ms * 1e-3) / 1e12,
             "frac_of_bf16_peak": flops / (ms * 1e-3) / 1e12 / peaks["bf16_tflops"], "ids_in_range": bool(((i >= 0) & (i < total_rows)).all().item())}
 
 

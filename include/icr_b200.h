@@ -146,6 +146,24 @@ int icr_topk_merge(const float* cand_scores, const int64_t* cand_ids,
                    void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Shard-candidate exchange over NVLink peer memory (K4x): the all-gather of every rank's
+ * icr_cos_topk output without NCCL. No reference counterpart (the reference is single-GPU).
+ * The host allocates one symmetric buffer of icr_peer_buffer_bytes() per rank, zero-filled,
+ * mapped into every peer (e.g. torch.distributed._symmetric_memory), and passes the world's
+ * buffer addresses AS SEEN FROM THIS PROCESS in `peer_buffers` (HOST array, index = rank).
+ * `epoch` is the 1-based count of exchange calls on this buffer, identical on all ranks.
+ *   scores [n] f32, ids [n] i64: this rank's candidates (n = Q * k <= n_max)
+ * On return (stream order) the local buffer holds scores [world][n] at *scores_off and
+ * ids [world][n] at *ids_off (byte offsets from the local buffer's base), the inputs
+ * icr_topk_merge expects with G = world. Every rank must make the same call.
+ * ------------------------------------------------------------------------------------- */
+#define ICR_MAX_PEERS 16
+size_t icr_peer_buffer_bytes(int64_t n_max, int world);
+int icr_peer_exchange(const float* scores, const int64_t* ids, int64_t n, int rank, int world,
+                      const uint64_t* peer_buffers, uint32_t epoch, int64_t n_max,
+                      size_t* scores_off, size_t* ids_off, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * MultipleNegativesRankingLoss (sentence-transformers; constructed at
  * src/training/train_sbert.py:182-185):
  *   loss = mean_i CE( scale * cos_sim(A, P)[i, :], i )

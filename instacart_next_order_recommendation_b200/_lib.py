@@ -8,7 +8,7 @@ every compute entry point raises.
 from __future__ import annotations
 
 import ctypes
-from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
+from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_uint32, c_void_p
 from pathlib import Path
 
 LIB_PATH = Path(__file__).resolve().parent / "lib" / "libicr_b200.so"
@@ -52,6 +52,8 @@ SIGNATURES = {
     ),
     "icr_topk_merge_workspace_bytes": (c_size_t, [c_int64, c_int, c_int, c_int]),
     "icr_topk_merge": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "icr_peer_buffer_bytes": (c_size_t, [c_int64, c_int]),
+    "icr_peer_exchange": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_uint32, c_int64, c_void_p, c_void_p, c_void_p]),
     "icr_mnrl_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "icr_mnrl_fwd": (
         c_int,

@@ -53,6 +53,9 @@ int launch_row_inv_norms(const void* x, int64_t rows, int64_t dim, int64_t ld, i
 int launch_split_planes(const float* x, int64_t rows, int64_t dim, int64_t ld, uint16_t* planes, cudaStream_t st);
 int launch_convert_rows(const float* x, int64_t rows, int64_t dim, int64_t ldx, void* out, int64_t ldo, int out_dtype, int normalize,
                         cudaStream_t st);
+void peer_layout(int64_t n_max, int world, uint32_t epoch, size_t* scores_off, size_t* ids_off, size_t* total);
+int launch_peer_exchange(const float* scores, const int64_t* ids, int64_t n, int rank, int world, const uint64_t* peer_buffers, uint32_t epoch,
+                         int64_t n_max, cudaStream_t st);
 int gemv_grid(int64_t N);
 int launch_gemv_topk(const void* cat, int64_t N, int64_t ldc, int D, int dtype, const void* q, int64_t ldq, int Q,
                      const uint8_t* mask, int k, uint64_t* part_keys, int* part_cnt, int grid, float* out_scores, int64_t* out_ids,
@@ -461,6 +464,37 @@ int icr_convert_rows(const float* x, int64_t rows, int64_t dim, int64_t ldx, voi
   }
   if ((rc = check_device())) return rc;
   return launch_convert_rows(x, rows, dim, ldx, out, ldo, out_dtype, normalize ? 1 : 0, static_cast<cudaStream_t>(stream));
+}
+
+size_t icr_peer_buffer_bytes(int64_t n_max, int world) {
+  size_t total = 0;
+  if (n_max < 0 || world < 1) return 0;
+  peer_layout(n_max, world, 0, nullptr, nullptr, &total);
+  return total;
+}
+
+int icr_peer_exchange(const float* scores, const int64_t* ids, int64_t n, int rank, int world, const uint64_t* peer_buffers, uint32_t epoch,
+                      int64_t n_max, size_t* scores_off, size_t* ids_off, void* stream) {
+  g_launches = 0;
+  if (world < 1 || world > ICR_MAX_PEERS || rank < 0 || rank >= world || n < 0 || n > n_max || !peer_buffers || epoch == 0) {
+    set_error("peer_exchange: bad arguments n=%lld n_max=%lld rank=%d world=%d (<= %d) epoch=%u", (long long)n, (long long)n_max, rank, world,
+              ICR_MAX_PEERS, epoch);
+    return ICR_ERR_ARG;
+  }
+  for (int p = 0; p < world; ++p) {
+    if (peer_buffers[p] == 0 || (peer_buffers[p] & 255)) {
+      set_error("peer_exchange: buffer of rank %d is null or not 256-byte aligned", p);
+      return ICR_ERR_ALIGN;
+    }
+  }
+  if (n > 0 && (!scores || !ids || (reinterpret_cast<uintptr_t>(scores) & 3) || (reinterpret_cast<uintptr_t>(ids) & 7))) {
+    set_error("peer_exchange: null or misaligned candidates");
+    return ICR_ERR_ARG;
+  }
+  int rc;
+  if ((rc = check_device())) return rc;
+  peer_layout(n_max, world, epoch, scores_off, ids_off, nullptr);
+  return launch_peer_exchange(scores, ids, n, rank, world, peer_buffers, epoch, n_max, static_cast<cudaStream_t>(stream));
 }
 
 int icr_ir_metrics(const int64_t* ids, int64_t Q, int K, int64_t ld_ids, const int64_t* rel_offsets, const int64_t* rel_rows,

@@ -15,7 +15,7 @@ from typing import Callable
 import torch
 import torch.distributed as dist
 
-from . import ops
+from . import _lib, ops
 from .index import DeviceCatalog
 
 
@@ -37,8 +37,64 @@ def unpack_candidates(buf: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
     return scores.contiguous(), buf[:, 1].contiguous()
 
 
+class PeerExchange:
+    """All-gather of [Q, k] candidates through NVLink peer memory (``icr_peer_exchange``) instead of NCCL.
+
+    PyTorch's symmetric memory is the plumbing: it allocates one buffer per rank and maps every rank's buffer into
+    every process; the exchange itself is one kernel of ours per call (peer stores + system-scope flags). Collective:
+    every rank of `group` constructs it and calls ``all_gather`` with the same shapes in the same order.
+    """
+
+    def __init__(self, group: dist.ProcessGroup | None, device: torch.device, max_candidates: int):
+        import torch.distributed._symmetric_memory as symm
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.world_size = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        if self.world_size > 16:
+            raise ValueError("peer exchange supports up to 16 ranks (one NVLink domain)")
+        self.device = torch.device(device)
+        self.n_max = int(max_candidates)
+        lib = _lib.load()
+        nbytes = lib.icr_peer_buffer_bytes(self.n_max, self.world_size)
+        with torch.cuda.device(self.device):
+            self.buf = symm.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self.buf.zero_()
+            self.handle = symm.rendezvous(self.buf, self.group)
+        import ctypes
+
+        self._ptrs = (ctypes.c_uint64 * self.world_size)(*[int(p) for p in self.handle.buffer_ptrs])
+        self.epoch = 0
+        torch.cuda.synchronize(self.device)
+        dist.barrier(self.group)  # every buffer is zeroed before anyone's first push can land in it
+
+    def all_gather(self, vals: torch.Tensor, ids: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+        """vals f32 [Q,k], ids i64 [Q,k] -> (scores [G,Q,k], ids [G,Q,k]): views of this rank's buffer, valid until the
+        call after next."""
+        import ctypes
+
+        vals, ids = vals.contiguous(), ids.contiguous()
+        n = vals.numel()
+        if n > self.n_max or vals.dtype != torch.float32 or ids.dtype != torch.int64 or ids.numel() != n:
+            raise ValueError(f"peer exchange sized for {self.n_max} f32/i64 candidates per rank, got {n}")
+        self.epoch += 1
+        so, io = ctypes.c_size_t(0), ctypes.c_size_t(0)
+        lib = _lib.load()
+        with ops._on(self.device):
+            _lib.check(lib.icr_peer_exchange(vals.data_ptr(), ids.data_ptr(), n, self.rank, self.world_size, ctypes.addressof(self._ptrs),
+                                             self.epoch, self.n_max, ctypes.addressof(so), ctypes.addressof(io), ops._stream(self.device)))
+        G = self.world_size
+        scores = self.buf[so.value : so.value + G * n * 4].view(torch.float32).view(G, *vals.shape)
+        gids = self.buf[io.value : io.value + G * n * 8].view(torch.int64).view(G, *ids.shape)
+        return scores, gids
+
+
 class ShardedCatalog:
-    """This rank's block of a row-sharded catalog plus the exchange + merge step."""
+    """This rank's block of a row-sharded catalog plus the exchange + merge step.
+
+    ``exchange="nccl"`` (default) all-gathers the packed candidates with NCCL; ``exchange="peer"`` pushes them
+    straight into the peers' buffers over NVLink with ``icr_peer_exchange`` (one kernel, no NCCL launch) — same result.
+    """
 
     def __init__(
         self,
@@ -49,9 +105,14 @@ class ShardedCatalog:
         group: dist.ProcessGroup | None = None,
         dtype: torch.dtype = torch.float32,
         device: torch.device | None = None,
+        exchange: str = "nccl",
         _local_topk: Callable | None = None,
         _merge: Callable | None = None,
     ):
+        if exchange not in ("nccl", "peer"):
+            raise ValueError("exchange must be 'nccl' or 'peer'")
+        self.exchange = exchange
+        self._peer: PeerExchange | None = None
         self.group = group
         self.world_size = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -79,7 +140,7 @@ class ShardedCatalog:
 
     @classmethod
     def from_index(cls, index, product_ids: list[str], *, group=None, dtype: torch.dtype = torch.float32,
-                   device: torch.device | None = None, **load_kw) -> "ShardedCatalog | None":
+                   device: torch.device | None = None, exchange: str = "nccl", **load_kw) -> "ShardedCatalog | None":
         """Every rank streams only ITS row block of a validated on-disk index into HBM (``DeviceCatalog.from_index``)."""
         ws = dist.get_world_size(group) if dist.is_initialized() else 1
         rk = dist.get_rank(group) if dist.is_initialized() else 0
@@ -88,6 +149,7 @@ class ShardedCatalog:
         if local is None:
             return None
         self = cls.__new__(cls)
+        self.exchange, self._peer = exchange, None
         self.group, self.world_size, self.rank = group, ws, rk
         self.total_rows, self.row_offset = len(product_ids), lo
         self._local_topk = self._merge = None
@@ -117,6 +179,11 @@ class ShardedCatalog:
         vals, ids = self.local_topk(queries, k)
         if self.world_size == 1:
             return vals, ids
+        if self.exchange == "peer":
+            if self._peer is None or self._peer.n_max < vals.numel():
+                self._peer = PeerExchange(self.group, self.device, max(vals.numel(), 1 << 16))
+            scores, gids = self._peer.all_gather(vals, ids)
+            return ops.topk_merge(scores, gids, k)
         mine = pack_candidates(vals, ids)
         # output concatenated along dim 0 (the layout every backend's all_gather_into_tensor accepts)
         gathered = torch.empty((self.world_size * mine.shape[0], *mine.shape[1:]), dtype=mine.dtype, device=mine.device)

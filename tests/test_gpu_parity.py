@@ -607,3 +607,20 @@ def test_full_size_properties_c2_shape():
     sample = torch.arange(0, Q, 97, device="cuda")
     rv, ri = oracle.cos_topk(queries[sample].cpu(), items.cpu(), k)
     _check_topk(v[sample], i[sample], rv, ri, F32_RTOL)
+
+
+def test_peer_memory_exchange_equals_nccl_all_gather():
+    """icr_peer_exchange (NVLink peer stores + flags) gathers the same candidates as the NCCL all-gather: 2 ranks."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs on one box (run under gpurun --gpus 2)")
+    root = Path(__file__).resolve().parents[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29517",
+           str(root / "benchmarks" / "peer_exchange_case.py"), "100000"]
+    out = subprocess.run(cmd, cwd=str(root), capture_output=True, text=True, timeout=600, env=dict(os.environ))
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "PEER_EXCHANGE_OK" in out.stdout, out.stdout[-2000:]
