@@ -104,7 +104,15 @@ def _cpu_reference_qps(sample_queries: int, budget_s: float, threads: int | None
         if time.perf_counter() - t0 > budget_s:
             break
     dt = time.perf_counter() - t0
-    return done / dt, done, torch.get_num_threads()
+    # best case for the CPU: operands converted and normalised once, outside the timed region
+    cn = torch.nn.functional.normalize(items, dim=1).t().contiguous()
+    qn = torch.nn.functional.normalize(queries, dim=1)
+    done2, t1 = 0, time.perf_counter()
+    while done2 < sample_queries and time.perf_counter() - t1 < budget_s / 2:
+        torch.topk(torch.mm(qn[done2 : done2 + 500], cn), C2["k"], dim=1, largest=True, sorted=False)
+        done2 += min(500, sample_queries - done2)
+    best = done2 / (time.perf_counter() - t1)
+    return done / dt, done, torch.get_num_threads(), best
 
 
 def run_reference(args, rank: int):
@@ -272,9 +280,11 @@ def main():
     if sharded is not None:
         line["sharded"] = sharded
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        qps, nq, cores = _cpu_reference_qps(sample_queries=4000, budget_s=15.0)
+        qps, nq, cores, best = _cpu_reference_qps(sample_queries=4000, budget_s=15.0)
         line["cpu_baseline"] = {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "host_cpus": os.cpu_count(),
-                                "sample": f"{nq} of the 10,000 queries against the full catalog: oracle port of cos_sim + torch.topk(100), torch CPU"}
+                                "sample": f"{nq} of the 10,000 queries against the full catalog: oracle port of cos_sim + torch.topk(100), torch CPU "
+                                          "(as called: both operands re-normalised per 500-query call)",
+                                "best_case_value": best, "best_case": "operands pre-normalised once, mm + topk only"}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
