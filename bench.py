@@ -198,7 +198,7 @@ def main():
         return catalog.topk(queries_dev, k, path=path)
 
     def step_e2e():
-        # public host-to-host API: pinned queries -> H2D -> fused top-k -> D2H of (scores, ids), chunks pipelined on 2 streams
+        # public host-to-host API: pinned queries -> H2D -> fused top-k -> D2H of (scores, ids), pieces pipelined on 2 streams
         catalog.topk_host(queries_host, k, out=(out_v_host, out_i_host), path=path)
 
     def barrier():
@@ -270,7 +270,7 @@ def main():
                    "multi_gpu": "catalog replica + own query batch per rank (no data-path collective)" if world > 1 else "single GPU",
                    "l2": "512 MiB buffer zeroed between timed iterations (L2 flush)", "seeds": [CATALOG_SEED, QUERY_SEED]},
         "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": Q * D * 4, "d2h_bytes_per_step": Q * k * 12,
-                "note": "DeviceCatalog.topk_host: pinned-host fp32 queries in, (scores f32, ids i64) out to pinned host, 2 chunks pipelined "
+                "note": "DeviceCatalog.topk_host: pinned-host fp32 queries in, (scores f32, ids i64) out to pinned host, 3 pieces (20/60/20 %) pipelined "
                         "over 2 streams; catalog resident in HBM as the reference keeps its index in memory"},
         "gpu_launches": launches_per_step * args.steps,
         "roofline": roof,

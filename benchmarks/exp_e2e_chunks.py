@@ -9,14 +9,16 @@ cat = icr.DeviceCatalog(items)
 qh = torch.nn.functional.normalize(torch.randn(Q, D, generator=torch.Generator().manual_seed(1)), dim=1).pin_memory()
 ov = torch.empty(Q, k).pin_memory(); oi = torch.empty(Q, k, dtype=torch.int64).pin_memory()
 flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
-for nch in (1, 2, 3, 4, 6, 8):
-    for _ in range(3): cat.topk_host(qh, k, out=(ov, oi), n_chunks=nch)
+cases = [dict(n_chunks=n) for n in (1, 2, 3, 4)] + [dict(splits=s) for s in ([3000, 7000], [7000, 3000], [2000, 5000, 3000], [2000, 6000, 2000], [1500, 3500, 3500, 1500], [1024, 4096, 3856, 1024], [4000, 4000, 2000])]
+for kw in cases:
+    nch = kw
+    for _ in range(3): cat.topk_host(qh, k, out=(ov, oi), **kw)
     torch.cuda.synchronize()
     ts = []
     for _ in range(10):
         flush.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); cat.topk_host(qh, k, out=(ov, oi), n_chunks=nch); b.record(); torch.cuda.synchronize()
+        a.record(); cat.topk_host(qh, k, out=(ov, oi), **kw); b.record(); torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))
     ts.sort()
-    print(f"n_chunks={nch}: median {ts[5]:.3f} ms  min {ts[0]:.3f} ms  -> {Q / ts[5] / 1e3:.2f} M q/s", flush=True)
+    print(f"{nch}: median {ts[5]:.3f} ms  min {ts[0]:.3f} ms  -> {Q / ts[5] / 1e3:.2f} M q/s", flush=True)

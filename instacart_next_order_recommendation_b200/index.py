@@ -263,12 +263,14 @@ class DeviceCatalog:
         return (vals.clone(), ids.clone()) if copy else (vals, ids)
 
     def topk_host(self, queries: torch.Tensor, k: int, *, out: tuple[torch.Tensor, torch.Tensor] | None = None,
-                  n_chunks: int = 2, path: int = ops.PATH_AUTO):
+                  n_chunks: int | None = None, path: int = ops.PATH_AUTO, splits: list[int] | None = None):
         """Host-to-host top-k: CPU query matrix in, CPU (values [Q,k] f32, ids [Q,k] i64) out.
 
-        The batch is cut into `n_chunks` pieces that go round-robin over two side streams, each doing
-        H2D copy -> fused top-k -> D2H copy, so the copies of one piece overlap the kernels of another
-        (the B200 has separate copy engines for each direction). Pass pinned tensors (and pinned `out`)
+        The batch is cut into pieces that go round-robin over two side streams, each doing H2D copy -> fused top-k
+        -> D2H copy, so the copies of one piece overlap the kernels of another (the B200 has separate copy engines
+        for each direction). Default cut for large batches: 20 % / 60 % / 20 % — the kernels themselves do not overlap,
+        so what is exposed is the first piece's upload and the last piece's download, and short end pieces shrink
+        both (measured on C2: 1.21 ms against 1.29 ms for two halves and 1.50 ms unpipelined). Pass pinned tensors (and pinned `out`)
         for truly asynchronous copies. Returns after enqueueing; the current stream waits on the side
         streams, so `torch.cuda.current_stream().synchronize()` makes the outputs valid.
         """
@@ -286,14 +288,26 @@ class DeviceCatalog:
         if not hasattr(self, "_side_streams"):
             self._side_streams = [torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)]
         cur = torch.cuda.current_stream(self.device)
-        n_chunks = max(1, min(n_chunks, (Q + 255) // 256))
-        per = -(-Q // n_chunks)
+        if splits is None and n_chunks is None:
+            if Q >= 2048:
+                splits = [Q // 5, Q - 2 * (Q // 5), Q // 5]
+            else:
+                n_chunks = 2
+        if splits is None:
+            n_chunks = max(1, min(n_chunks, (Q + 255) // 256))
+            per = -(-Q // n_chunks)
+            bounds = [(c * per, min(Q, (c + 1) * per)) for c in range(n_chunks)]
+        else:  # explicit piece sizes (a short first piece starts the kernels sooner, a short last one shortens the D2H tail)
+            edges = [0]
+            for n in splits:
+                edges.append(min(Q, edges[-1] + int(n)))
+            edges[-1] = Q
+            bounds = list(zip(edges[:-1], edges[1:]))
         start = torch.cuda.Event()
         start.record(cur)
-        for c in range(n_chunks):
-            lo, hi = c * per, min(Q, (c + 1) * per)
+        for c, (lo, hi) in enumerate(bounds):
             if lo >= hi:
-                break
+                continue
             st = self._side_streams[c % 2]
             st.wait_event(start)
             with torch.cuda.stream(st):
