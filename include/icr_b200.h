@@ -183,6 +183,25 @@ int icr_mnrl_bwd(const void* a, int64_t lda, const void* p, int64_t ldp,
                  void* grad_a, int64_t ldga, void* grad_p, int64_t ldgp,
                  void* workspace, size_t workspace_bytes, void* stream);
 
+/* Rectangular form for cross-device in-batch negatives (sentence-transformers'
+ * gather_across_devices=True; not enabled by the reference, src/training/train_sbert.py:184-185):
+ * B local anchors against Bc >= B candidates (the positives of all ranks, gathered), the positive
+ * of anchor i at candidate i + label_offset (= rank * B).
+ *   loss = mean_i CE( scale * cos_sim(A, C)[i, :], i + label_offset )
+ * grad_c [Bc, D] is this rank's contribution to every candidate's gradient (the host
+ * reduce-scatters it). Tensor-core path only: D % 8 == 0. */
+size_t icr_mnrl_rect_workspace_bytes(int64_t B, int64_t Bc, int64_t D);
+int icr_mnrl_fwd_rect(const void* a, int64_t lda, const void* c, int64_t ldc,
+                      int64_t B, int64_t Bc, int64_t label_offset, int64_t D, int dtype, float scale,
+                      float* loss, float* lse, float* inv_a, float* inv_c,
+                      void* workspace, size_t workspace_bytes, void* stream);
+int icr_mnrl_bwd_rect(const void* a, int64_t lda, const void* c, int64_t ldc,
+                      int64_t B, int64_t Bc, int64_t label_offset, int64_t D, int dtype, float scale,
+                      const float* lse, const float* inv_a, const float* inv_c,
+                      const float* grad_out,
+                      void* grad_a, int64_t ldga, void* grad_c, int64_t ldgc,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * IR metric arithmetic over the retrieved ids (the evaluator's host tail, on the device).
  * Stands in for the per-query Python loops of sentence-transformers'

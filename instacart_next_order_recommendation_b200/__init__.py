@@ -9,7 +9,7 @@ point does, and raises otherwise (there is no CPU fallback).
 
 from .evaluation import InformationRetrievalEvaluator, compute_ir_metrics, rank_all
 from .index import DeviceCatalog, EmbeddingIndex
-from .losses import MultipleNegativesRankingLoss, mnrl_loss
+from .losses import MultipleNegativesRankingLoss, mnrl_loss, mnrl_loss_gathered
 from .recommender import MonitoredRecommender, RecommendationMetrics, Recommender
 from .sharded import ShardedCatalog, shard_bounds
 from .similarity import cos_sim, cos_topk

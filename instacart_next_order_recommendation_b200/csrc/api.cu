@@ -86,8 +86,8 @@ static bool dense_use_gemm(int64_t Qa, int64_t Nb, int64_t D, int dtype) {
 
 int launch_mnrl_dispatch(const MnrlArgs& g, int dtype, bool bwd, cudaStream_t st);
 // tensor-core MNRL (mnrl_tc.cu)
-bool mnrl_tc_applies(int64_t B, int64_t D);
-size_t mnrl_tc_workspace_bytes(int64_t B, int64_t D);
+bool mnrl_tc_applies(int64_t B, int64_t Bc, int64_t D);
+size_t mnrl_tc_workspace_bytes(int64_t B, int64_t Bc, int64_t D);
 int launch_mnrl_tc(const MnrlArgs& m, int dtype, bool bwd, void* ws, size_t ws_bytes, cudaStream_t st);
 int launch_ir_metrics(const int64_t* ids, int64_t Q, int K, int64_t ld, const int64_t* rel_offsets, const int64_t* rel_rows,
                       const int32_t* n_relevant, const int32_t* kinds, const int32_t* ks, int M, double* per_query, double* means,
@@ -369,7 +369,7 @@ int icr_topk_merge(const float* cand_scores, const int64_t* cand_ids, int64_t Q,
 }
 
 size_t icr_mnrl_workspace_bytes(int64_t B, int64_t D) {
-  if (B > 0 && D > 0 && mnrl_tc_applies(B, D)) return mnrl_tc_workspace_bytes(B, D);
+  if (B > 0 && D > 0 && mnrl_tc_applies(B, B, D)) return mnrl_tc_workspace_bytes(B, B, D);
   return align_up(static_cast<size_t>(B > 0 ? B : 0) * sizeof(float), 256) + 256;
 }
 
@@ -404,7 +404,7 @@ int icr_mnrl_fwd(const void* a, int64_t lda, const void* p, int64_t ldp, int64_t
   g.p = p;
   g.lda = lda;
   g.ldp = ldp;
-  g.B = static_cast<int>(B);
+  g.B = g.Bc = static_cast<int>(B);
   g.D = static_cast<int>(D);
   g.scale = scale;
   g.lse = lse;
@@ -413,7 +413,7 @@ int icr_mnrl_fwd(const void* a, int64_t lda, const void* p, int64_t ldp, int64_t
   g.counter = static_cast<unsigned int*>(workspace);
   g.row_loss = reinterpret_cast<float*>(static_cast<char*>(workspace) + 256);
   g.loss = loss;
-  if (mnrl_tc_applies(B, D)) return launch_mnrl_tc(g, dtype, false, workspace, workspace_bytes, st);
+  if (mnrl_tc_applies(B, B, D)) return launch_mnrl_tc(g, dtype, false, workspace, workspace_bytes, st);
   ICR_CUDA_CHECK(cudaMemsetAsync(g.counter, 0, sizeof(unsigned int), st));
   return launch_mnrl_dispatch(g, dtype, false, st);
 }
@@ -433,7 +433,7 @@ int icr_mnrl_bwd(const void* a, int64_t lda, const void* p, int64_t ldp, int64_t
   g.p = p;
   g.lda = lda;
   g.ldp = ldp;
-  g.B = static_cast<int>(B);
+  g.B = g.Bc = static_cast<int>(B);
   g.D = static_cast<int>(D);
   g.scale = scale;
   g.lse = const_cast<float*>(lse);
@@ -444,7 +444,7 @@ int icr_mnrl_bwd(const void* a, int64_t lda, const void* p, int64_t ldp, int64_t
   g.grad_p = grad_p;
   g.ldga = ldga;
   g.ldgp = ldgp;
-  if (mnrl_tc_applies(B, D)) return launch_mnrl_tc(g, dtype, true, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+  if (mnrl_tc_applies(B, B, D)) return launch_mnrl_tc(g, dtype, true, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
   return launch_mnrl_dispatch(g, dtype, true, static_cast<cudaStream_t>(stream));
 }
 
@@ -520,6 +520,86 @@ int icr_ir_metrics(const int64_t* ids, int64_t Q, int K, int64_t ld_ids, const i
   if ((rc = check_device())) return rc;
   return launch_ir_metrics(ids, Q, K, ld_ids, rel_offsets, rel_rows, n_relevant, kinds, ks, M, per_query, means,
                            static_cast<cudaStream_t>(stream));
+}
+
+// ---- rectangular form: B anchors against Bc >= B candidates, the positive of anchor i at column i + label_offset ----
+size_t icr_mnrl_rect_workspace_bytes(int64_t B, int64_t Bc, int64_t D) {
+  if (B < 1 || Bc < 1 || D < 1) return 0;
+  return mnrl_tc_workspace_bytes(B, Bc, D);
+}
+
+static int mnrl_rect_common(const void* a, int64_t lda, const void* c, int64_t ldc, int64_t B, int64_t Bc, int64_t label_offset, int64_t D,
+                            int dtype, void* workspace, size_t workspace_bytes) {
+  int rc;
+  if ((rc = check_matrix("mnrl.anchors", a, B, D, lda, dtype))) return rc;
+  if ((rc = check_matrix("mnrl.candidates", c, Bc, D, ldc, dtype))) return rc;
+  if (B < 1 || Bc < 2 || label_offset < 0 || label_offset + B > Bc || D % 8 != 0 || D > 4096 || B > 65536 || Bc > (1 << 20)) {
+    set_error("mnrl (rectangular): need 1 <= B <= 65536, label_offset + B <= Bc <= 2^20, D %% 8 == 0, D <= 4096; got B=%lld Bc=%lld offset=%lld D=%lld",
+              (long long)B, (long long)Bc, (long long)label_offset, (long long)D);
+    return ICR_ERR_ARG;
+  }
+  if (!workspace || workspace_bytes < icr_mnrl_rect_workspace_bytes(B, Bc, D)) {
+    set_error("mnrl (rectangular): workspace %zu bytes < required %zu", workspace_bytes, icr_mnrl_rect_workspace_bytes(B, Bc, D));
+    return ICR_ERR_WORKSPACE;
+  }
+  return check_device();
+}
+
+int icr_mnrl_fwd_rect(const void* a, int64_t lda, const void* c, int64_t ldc, int64_t B, int64_t Bc, int64_t label_offset, int64_t D, int dtype,
+                      float scale, float* loss, float* lse, float* inv_a, float* inv_c, void* workspace, size_t workspace_bytes, void* stream) {
+  g_launches = 0;
+  int rc = mnrl_rect_common(a, lda, c, ldc, B, Bc, label_offset, D, dtype, workspace, workspace_bytes);
+  if (rc) return rc;
+  if (!loss || !lse || !inv_a || !inv_c) {
+    set_error("mnrl_fwd_rect: null output");
+    return ICR_ERR_ARG;
+  }
+  MnrlArgs g{};
+  g.a = a;
+  g.p = c;
+  g.lda = lda;
+  g.ldp = ldc;
+  g.B = static_cast<int>(B);
+  g.Bc = static_cast<int>(Bc);
+  g.label_off = static_cast<int>(label_offset);
+  g.D = static_cast<int>(D);
+  g.scale = scale;
+  g.lse = lse;
+  g.inv_a = inv_a;
+  g.inv_p = inv_c;
+  g.loss = loss;
+  return launch_mnrl_tc(g, dtype, false, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int icr_mnrl_bwd_rect(const void* a, int64_t lda, const void* c, int64_t ldc, int64_t B, int64_t Bc, int64_t label_offset, int64_t D, int dtype,
+                      float scale, const float* lse, const float* inv_a, const float* inv_c, const float* grad_out, void* grad_a, int64_t ldga,
+                      void* grad_c, int64_t ldgc, void* workspace, size_t workspace_bytes, void* stream) {
+  g_launches = 0;
+  int rc = mnrl_rect_common(a, lda, c, ldc, B, Bc, label_offset, D, dtype, workspace, workspace_bytes);
+  if (rc) return rc;
+  if (!lse || !inv_a || !inv_c || !grad_out || !grad_a || !grad_c || ldga < D || ldgc < D) {
+    set_error("mnrl_bwd_rect: null pointer or bad gradient stride");
+    return ICR_ERR_ARG;
+  }
+  MnrlArgs g{};
+  g.a = a;
+  g.p = c;
+  g.lda = lda;
+  g.ldp = ldc;
+  g.B = static_cast<int>(B);
+  g.Bc = static_cast<int>(Bc);
+  g.label_off = static_cast<int>(label_offset);
+  g.D = static_cast<int>(D);
+  g.scale = scale;
+  g.lse = const_cast<float*>(lse);
+  g.inv_a = const_cast<float*>(inv_a);
+  g.inv_p = const_cast<float*>(inv_c);
+  g.grad_out = grad_out;
+  g.grad_a = grad_a;
+  g.grad_p = grad_c;
+  g.ldga = ldga;
+  g.ldgp = ldgc;
+  return launch_mnrl_tc(g, dtype, true, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -200,6 +200,8 @@ struct MnrlArgs {
   const void* p;
   int64_t lda, ldp;
   int B, D;
+  int Bc;         // candidates: B, or G*B when positives were gathered across devices (tensor path only)
+  int label_off;  // the positive of anchor i is candidate i + label_off
   float scale;
   // forward outputs / backward inputs
   float* lse;

@@ -38,12 +38,15 @@ constexpr float kLn2 = 0.6931471805599453f;
 enum { MODE_LSE = 0, MODE_G = 1, MODE_MM = 2 };
 
 struct TcArgs {
-  int B, D;
-  int KB;       // 64-element K blocks per MMA term
+  int B, D;     // anchors (rows of the score matrix), embedding dim
+  int Bc;       // candidates (columns): B, or G*B with cross-device negatives
+  int label_off;  // the positive of anchor i is candidate i + label_off (rank * B with gathered candidates)
+  int kb[2];      // 64-element K blocks per MMA term (MM: of product z)
+  int qblocks[2];  // blocks of 256 A-operand rows (MM: of product z)
+  int rows[2];     // MM: live rows of product z's output (B, Bc)
   int plane_stride;  // element offset of the lo plane in a plane row (LSE / G)
-  int qblocks;  // blocks of 256 rows
-  int tiles;    // 256-column tiles over the N extent (B for LSE / G, D for MM)
-  int chunks;   // balanced tile ranges; a work item = (row block, chunk) [x matrix z for MM]
+  int tiles;    // 256-column tiles over the N extent (Bc for LSE / G, D for MM)
+  int chunks;   // balanced tile ranges; a work item = (row block, chunk) [of product z for MM]
   float c2;     // LSE / G: scale * 2^-16 * log2(e): accumulator units -> base-2 logits
   float cnat;   // LSE: scale * 2^-16 (natural-unit logit of the diagonal)
   // LSE outputs
@@ -52,11 +55,11 @@ struct TcArgs {
   float* diag;    // [B] natural-unit diagonal logit
   // G
   const float* lse;  // [B] natural units
-  __half* w;         // [B][ldw]  softmax - I
-  __half* wt;        // [B][ldw]  its transpose
-  int64_t ldw;
+  __half* w;         // [B][ldw]   softmax - I      (ldw = Bc rounded up to 64)
+  __half* wt;        // [Bc][ldwt] its transpose    (ldwt = B rounded up to 64)
+  int64_t ldw, ldwt;
   // MM
-  float* raw;  // [2][B][D] dA^, dP^ before coef and the normalisation Jacobian
+  float* raw[2];  // [B][D] dA^, [Bc][D] dP^ before coef and the normalisation Jacobian
 };
 
 __device__ __forceinline__ int tc_chunk_first(const TcArgs& g, int c) { return static_cast<int>(static_cast<int64_t>(c) * g.tiles / g.chunks); }
@@ -84,9 +87,8 @@ mnrl_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-  const int KB = g.KB;
-  const int per_z = g.qblocks * g.chunks;
-  const int items = (MODE == MODE_MM ? 2 : 1) * per_z;
+  const int items0 = g.qblocks[0] * g.chunks;  // work items of product 0 (the only one for LSE / G)
+  const int items = items0 + (MODE == MODE_MM ? g.qblocks[1] * g.chunks : 0);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -113,9 +115,10 @@ mnrl_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     int stage = 0;
     uint32_t phase = 0;
     for (int w = pair; w < items; w += npairs) {
-      const int z = w / per_z, rem = w - z * per_z;
-      const int chunk = rem / g.qblocks, qb = rem - chunk * g.qblocks;
+      const int z = w >= items0 ? 1 : 0, rem = w - z * items0;
+      const int chunk = rem / g.qblocks[z], qb = rem - chunk * g.qblocks[z];
       const int t0 = tc_chunk_first(g, chunk), t1 = tc_chunk_first(g, chunk + 1);
+      const int KB = g.kb[z];
       const CUtensorMap* ma = (MODE == MODE_MM && z == 1) ? &map_a1 : &map_a0;
       const CUtensorMap* mb = (MODE == MODE_MM && z == 1) ? &map_b1 : &map_b0;
       const int arow = qb * (2 * BM) + static_cast<int>(rank) * BM;
@@ -150,9 +153,10 @@ mnrl_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;
     for (int w = pair; w < items; w += npairs) {
-      const int rem = w % per_z;
-      const int chunk = rem / g.qblocks;
+      const int z = w >= items0 ? 1 : 0, rem = w - z * items0;
+      const int chunk = rem / g.qblocks[z];
       const int t0 = tc_chunk_first(g, chunk), t1 = tc_chunk_first(g, chunk + 1);
+      const int KB = g.kb[z];
       for (int tile = t0; tile < t1; ++tile) {
         mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
         tc_fence_after();
@@ -201,12 +205,13 @@ mnrl_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = pair; w < items; w += npairs) {
-      const int z = w / per_z, rem = w - z * per_z;
-      const int chunk = rem / g.qblocks, qb = rem - chunk * g.qblocks;
+      const int z = w >= items0 ? 1 : 0, rem = w - z * items0;
+      const int chunk = rem / g.qblocks[z], qb = rem - chunk * g.qblocks[z];
       const int t0 = tc_chunk_first(g, chunk), t1 = tc_chunk_first(g, chunk + 1);
       const int row_w = qb * (2 * BM) + static_cast<int>(rank) * BM + ew * 32;  // first row of this warp
       const int row = row_w + lane;
-      const bool live = row < g.B;
+      const bool live = row < (MODE == MODE_MM ? g.rows[z] : g.B);
+      const int pos = row + g.label_off;  // column of this row's positive
       // per-item state
       float m = -INFINITY, l = 0.f, dg = 0.f;
       bool have_diag = false;
@@ -225,14 +230,14 @@ mnrl_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           if (cb + 1 < BN / 2 / 32) tmem_ld32(taddr + (cb + 1) * 32, r[(cb + 1) & 1]);
           const int col0 = col_base + cb * 32;
           if (MODE == MODE_LSE) {
-            if (col0 < g.B) {  // warp-uniform
+            if (col0 < g.Bc) {  // warp-uniform
               float v[32];
               float mx = -INFINITY;
-              const bool full = col0 + 32 <= g.B;
+              const bool full = col0 + 32 <= g.Bc;
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 v[j] = __uint_as_float(cur[j]) * g.c2;
-                if (!full && col0 + j >= g.B) v[j] = -INFINITY;
+                if (!full && col0 + j >= g.Bc) v[j] = -INFINITY;
                 mx = fmaxf(mx, v[j]);
               }
               const float mn = fmaxf(m, mx);
@@ -241,12 +246,14 @@ mnrl_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
               for (int j = 0; j < 32; ++j) sum += exp2f(v[j] - mn);
               l = l * exp2f(m - mn) + sum;
               m = mn;
-              if (col0 == row_w) {  // the 32 x 32 block on the diagonal: lane picks column `lane`
+              if (col0 < row_w + g.label_off + 32 && col0 + 32 > row_w + g.label_off) {  // warp-uniform: the positives of this warp's rows
                 float d = 0.f;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) d = (j == lane) ? __uint_as_float(cur[j]) : d;
-                dg = d * g.cnat;
-                have_diag = true;
+                for (int j = 0; j < 32; ++j) d = (col0 + j == pos) ? __uint_as_float(cur[j]) : d;
+                if (pos >= col0 && pos < col0 + 32) {
+                  dg = d * g.cnat;
+                  have_diag = true;
+                }
               }
             }
           } else if (MODE == MODE_G) {
@@ -255,8 +262,8 @@ mnrl_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 float p = exp2f(__uint_as_float(cur[j]) * g.c2 - lse2);
-                if (col0 + j == row) p -= 1.0f;
-                if (col0 + j >= g.B) p = 0.f;
+                if (col0 + j == pos) p -= 1.0f;
+                if (col0 + j >= g.Bc) p = 0.f;
                 h[j] = __float2half_rn(p);
               }
               if (live) {
@@ -266,12 +273,12 @@ mnrl_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                 for (int q4 = 0; q4 < 4; ++q4) dst[q4] = srcv[q4];
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
-                  if (col0 + j < g.B) g.wt[static_cast<int64_t>(col0 + j) * g.ldw + row] = h[j];
+                  if (col0 + j < g.Bc) g.wt[static_cast<int64_t>(col0 + j) * g.ldwt + row] = h[j];
               }
             }
           } else {
             if (live && col0 < g.D) {
-              float* dst = g.raw + (static_cast<int64_t>(z) * g.B + row) * g.D + col0;
+              float* dst = g.raw[z] + static_cast<int64_t>(row) * g.D + col0;
               if (col0 + 32 <= g.D) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
@@ -320,16 +327,18 @@ constexpr int kPrepThreads = kPrepRows * 32;
 
 template <typename T, bool TRANSPOSE>
 __global__ void __launch_bounds__(kPrepThreads) mnrl_tc_prep_kernel(const T* __restrict__ a, int64_t lda, const T* __restrict__ p, int64_t ldp,
-                                                                    int B, int D, int dpad, __half* __restrict__ planes_a,
+                                                                    int Ba, int Bp, int D, int dpad, __half* __restrict__ planes_a,
                                                                     __half* __restrict__ planes_p, float* __restrict__ inv_a,
                                                                     float* __restrict__ inv_p, __half* __restrict__ at, __half* __restrict__ pt,
-                                                                    int64_t ldt, unsigned int* __restrict__ ticket) {
+                                                                    int64_t ldat, int64_t ldpt, unsigned int* __restrict__ ticket) {
   constexpr int VEC = Elem<T>::VEC;
   extern __shared__ __align__(16) unsigned char prep_smem[];
   __half* xs = reinterpret_cast<__half*>(prep_smem);  // [kPrepRows][dpad + 2]
-  const int blocks_per = (B + kPrepRows - 1) / kPrepRows;
-  const bool is_a = static_cast<int>(blockIdx.x) < blocks_per;
-  const int row0 = (is_a ? blockIdx.x : blockIdx.x - blocks_per) * kPrepRows;
+  const int blocks_a = (Ba + kPrepRows - 1) / kPrepRows;
+  const bool is_a = static_cast<int>(blockIdx.x) < blocks_a;
+  const int row0 = (is_a ? blockIdx.x : blockIdx.x - blocks_a) * kPrepRows;
+  const int B = is_a ? Ba : Bp;
+  const int64_t ldt = is_a ? ldat : ldpt;
   const T* X = is_a ? a : p;
   const int64_t ldx = is_a ? lda : ldp;
   __half* planes = is_a ? planes_a : planes_p;
@@ -431,16 +440,17 @@ __global__ void __launch_bounds__(256) mnrl_tc_finish_kernel(const float* __rest
 // ---- backward finish: dx = coef * (dx^ - x^ <x^, dx^>) * inv, warp per row of either matrix ----------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) mnrl_tc_jacobian_kernel(const T* __restrict__ a, int64_t lda, const T* __restrict__ p, int64_t ldp,
-                                                               int B, int D, const float* __restrict__ inv_a, const float* __restrict__ inv_p,
-                                                               const float* __restrict__ raw, const float* __restrict__ grad_out, float scale,
+                                                               int B, int Bc, int D, const float* __restrict__ inv_a, const float* __restrict__ inv_p,
+                                                               const float* __restrict__ raw_a, const float* __restrict__ raw_p,
+                                                               const float* __restrict__ grad_out, float scale,
                                                                T* __restrict__ grad_a, int64_t ldga, T* __restrict__ grad_p, int64_t ldgp) {
   const int lane = threadIdx.x & 31;
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (gw >= 2 * B) return;
+  if (gw >= B + Bc) return;
   const int z = gw >= B ? 1 : 0, row = gw - z * B;
   const T* x = (z ? p : a) + static_cast<int64_t>(row) * (z ? ldp : lda);
   const float inv = z ? inv_p[row] : inv_a[row];
-  const float* dr = raw + (static_cast<int64_t>(z) * B + row) * D;
+  const float* dr = (z ? raw_p : raw_a) + static_cast<int64_t>(row) * D;
   T* out = (z ? grad_p : grad_a) + static_cast<int64_t>(row) * (z ? ldgp : ldga);
   const float coef = grad_out[0] * scale / static_cast<float>(B);
   float pr = 0.f;
@@ -456,25 +466,26 @@ constexpr size_t kTcSmemBytes = static_cast<size_t>(kTcRingBytes) + (2 * kTcMaxS
 static_assert(kTcSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
 
 struct TcWs {
-  size_t planes_a, planes_p, at, pt, w, wt, raw, part_m, part_l, diag, cta_sums, ticket, total;
-  int64_t dpad, ldw;
+  size_t planes_a, planes_p, at, pt, w, wt, raw_a, raw_p, part_m, part_l, diag, cta_sums, ticket, total;
+  int64_t dpad, ldw, ldwt;
   int chunks;
 };
 
-int tc_chunks(int64_t B) {
+int tc_chunks(int64_t B, int64_t Bc) {
   const int qblocks = static_cast<int>((B + 2 * BM - 1) / (2 * BM));
-  const int tiles = static_cast<int>((B + BN - 1) / BN);
+  const int tiles = static_cast<int>((Bc + BN - 1) / BN);
   const int npairs = kNumSMs / 2;
   int chunks = (2 * npairs + qblocks - 1) / qblocks;
   if (chunks > tiles) chunks = tiles;
   return chunks < 1 ? 1 : chunks;
 }
 
-TcWs tc_layout(int64_t B, int64_t D) {
+TcWs tc_layout(int64_t B, int64_t Bc, int64_t D) {
   TcWs w{};
   w.dpad = (D + 63) / 64 * 64;
-  w.ldw = (B + 63) / 64 * 64;
-  w.chunks = tc_chunks(B);
+  w.ldw = (Bc + 63) / 64 * 64;
+  w.ldwt = (B + 63) / 64 * 64;
+  w.chunks = tc_chunks(B, Bc);
   size_t off = 0;
   auto take = [&](size_t bytes) {
     const size_t o = off;
@@ -482,12 +493,13 @@ TcWs tc_layout(int64_t B, int64_t D) {
     return o;
   };
   w.planes_a = take(static_cast<size_t>(B) * 2 * w.dpad * 2);
-  w.planes_p = take(static_cast<size_t>(B) * 2 * w.dpad * 2);
-  w.at = take(static_cast<size_t>(D) * w.ldw * 2);
+  w.planes_p = take(static_cast<size_t>(Bc) * 2 * w.dpad * 2);
+  w.at = take(static_cast<size_t>(D) * w.ldwt * 2);
   w.pt = take(static_cast<size_t>(D) * w.ldw * 2);
   w.w = take(static_cast<size_t>(B) * w.ldw * 2);
-  w.wt = take(static_cast<size_t>(B) * w.ldw * 2);
-  w.raw = take(static_cast<size_t>(2) * B * D * 4);
+  w.wt = take(static_cast<size_t>(Bc) * w.ldwt * 2);
+  w.raw_a = take(static_cast<size_t>(B) * D * 4);
+  w.raw_p = take(static_cast<size_t>(Bc) * D * 4);
   w.part_m = take(static_cast<size_t>(B) * w.chunks * 2 * 4);
   w.part_l = take(static_cast<size_t>(B) * w.chunks * 2 * 4);
   w.diag = take(static_cast<size_t>(B) * 4);
@@ -504,7 +516,7 @@ int launch_tc(const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMap& a
     ICR_CUDA_CHECK(cudaFuncSetAttribute(mnrl_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kTcSmemBytes)));
     attr_set = true;
   }
-  const int items = (MODE == MODE_MM ? 2 : 1) * g.qblocks * g.chunks;
+  const int items = (g.qblocks[0] + (MODE == MODE_MM ? g.qblocks[1] : 0)) * g.chunks;
   const int npairs = kNumSMs / 2;
   const int grid = 2 * (items < npairs ? items : npairs);
   mnrl_tc_kernel<MODE><<<grid, kTcThreads, kTcSmemBytes, st>>>(a0, b0, a1, b1, g);
@@ -514,7 +526,7 @@ int launch_tc(const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMap& a
 
 template <typename T>
 int launch_prep(const MnrlArgs& m, const TcWs& w, char* base, bool transpose, cudaStream_t st) {
-  const int blocks = 2 * ((m.B + kPrepRows - 1) / kPrepRows);
+  const int blocks = (m.B + kPrepRows - 1) / kPrepRows + (m.Bc + kPrepRows - 1) / kPrepRows;
   __half* pa = reinterpret_cast<__half*>(base + w.planes_a);
   __half* pp = reinterpret_cast<__half*>(base + w.planes_p);
   unsigned int* ticket = reinterpret_cast<unsigned int*>(base + w.ticket);
@@ -522,12 +534,12 @@ int launch_prep(const MnrlArgs& m, const TcWs& w, char* base, bool transpose, cu
   if (transpose) {
     const size_t smem = static_cast<size_t>(kPrepRows) * (dpad + 2) * sizeof(__half);
     if (smem > 48 * 1024) ICR_CUDA_CHECK(cudaFuncSetAttribute(mnrl_tc_prep_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    mnrl_tc_prep_kernel<T, true><<<blocks, kPrepThreads, smem, st>>>(static_cast<const T*>(m.a), m.lda, static_cast<const T*>(m.p), m.ldp, m.B, m.D,
-                                                                      dpad, pa, pp, nullptr, nullptr, reinterpret_cast<__half*>(base + w.at),
-                                                                      reinterpret_cast<__half*>(base + w.pt), w.ldw, nullptr);
+    mnrl_tc_prep_kernel<T, true><<<blocks, kPrepThreads, smem, st>>>(static_cast<const T*>(m.a), m.lda, static_cast<const T*>(m.p), m.ldp, m.B, m.Bc,
+                                                                      m.D, dpad, pa, pp, nullptr, nullptr, reinterpret_cast<__half*>(base + w.at),
+                                                                      reinterpret_cast<__half*>(base + w.pt), w.ldwt, w.ldw, nullptr);
   } else {
-    mnrl_tc_prep_kernel<T, false><<<blocks, kPrepThreads, 0, st>>>(static_cast<const T*>(m.a), m.lda, static_cast<const T*>(m.p), m.ldp, m.B, m.D,
-                                                                   dpad, pa, pp, m.inv_a, m.inv_p, nullptr, nullptr, 0, ticket);
+    mnrl_tc_prep_kernel<T, false><<<blocks, kPrepThreads, 0, st>>>(static_cast<const T*>(m.a), m.lda, static_cast<const T*>(m.p), m.ldp, m.B, m.Bc,
+                                                                   m.D, dpad, pa, pp, m.inv_a, m.inv_p, nullptr, nullptr, 0, 0, ticket);
   }
   ICR_LAUNCH_CHECK();
   return ICR_OK;
@@ -540,18 +552,19 @@ int launch_prep(const MnrlArgs& m, const TcWs& w, char* base, bool transpose, cu
 #define ICR_MNRL_TC_MIN_BATCH 288
 #endif
 
-bool mnrl_tc_applies(int64_t B, int64_t D) {
+bool mnrl_tc_applies(int64_t B, int64_t Bc, int64_t D) {
   static const char* force = getenv("ICR_MNRL_PATH");  // "tc" / "simt": A/B switch for benchmarks and tests
-  if (D % 8 != 0 || D > 4096 || B < 2 || B > 65536) return false;
+  if (D % 8 != 0 || D > 4096 || B < 1 || Bc < 2 || B > 65536 || Bc > (1 << 20)) return false;
+  if (Bc != B) return true;  // gathered candidates (cross-device negatives): only this path handles a rectangular score matrix
   if (force && force[0] == 't') return true;
   if (force && force[0] == 's') return false;
   return B >= ICR_MNRL_TC_MIN_BATCH;
 }
 
-size_t mnrl_tc_workspace_bytes(int64_t B, int64_t D) { return tc_layout(B, D).total; }
+size_t mnrl_tc_workspace_bytes(int64_t B, int64_t Bc, int64_t D) { return tc_layout(B, Bc, D).total; }
 
 int launch_mnrl_tc(const MnrlArgs& m, int dtype, bool bwd, void* ws, size_t ws_bytes, cudaStream_t st) {
-  const TcWs w = tc_layout(m.B, m.D);
+  const TcWs w = tc_layout(m.B, m.Bc, m.D);
   if (ws_bytes < w.total) {
     set_error("mnrl (tensor path): workspace %zu bytes < required %zu", ws_bytes, w.total);
     return ICR_ERR_WORKSPACE;
@@ -564,11 +577,14 @@ int launch_mnrl_tc(const MnrlArgs& m, int dtype, bool bwd, void* ws, size_t ws_b
 
   TcArgs g{};
   g.B = m.B;
+  g.Bc = m.Bc;
+  g.label_off = m.label_off;
   g.D = m.D;
-  g.KB = static_cast<int>(w.dpad / BK);
+  g.kb[0] = g.kb[1] = static_cast<int>(w.dpad / BK);
   g.plane_stride = static_cast<int>(w.dpad);
-  g.qblocks = (m.B + 2 * BM - 1) / (2 * BM);
-  g.tiles = (m.B + BN - 1) / BN;
+  g.qblocks[0] = g.qblocks[1] = (m.B + 2 * BM - 1) / (2 * BM);
+  g.rows[0] = g.rows[1] = m.B;
+  g.tiles = (m.Bc + BN - 1) / BN;
   g.chunks = w.chunks;
   g.c2 = m.scale * (1.0f / 65536.0f) * kLog2e;
   g.cnat = m.scale * (1.0f / 65536.0f);
@@ -579,11 +595,13 @@ int launch_mnrl_tc(const MnrlArgs& m, int dtype, bool bwd, void* ws, size_t ws_b
   g.w = reinterpret_cast<__half*>(base + w.w);
   g.wt = reinterpret_cast<__half*>(base + w.wt);
   g.ldw = w.ldw;
-  g.raw = reinterpret_cast<float*>(base + w.raw);
+  g.ldwt = w.ldwt;
+  g.raw[0] = reinterpret_cast<float*>(base + w.raw_a);
+  g.raw[1] = reinterpret_cast<float*>(base + w.raw_p);
 
   CUtensorMap map_a, map_p;
   if ((rc = make_map(&map_a, base + w.planes_a, m.B, 2 * w.dpad, 2 * w.dpad, false))) return rc;
-  if ((rc = make_map(&map_p, base + w.planes_p, m.B, 2 * w.dpad, 2 * w.dpad, false))) return rc;
+  if ((rc = make_map(&map_p, base + w.planes_p, m.Bc, 2 * w.dpad, 2 * w.dpad, false))) return rc;
   if (!bwd) {
     if ((rc = launch_tc<MODE_LSE>(map_a, map_p, map_a, map_p, g, st))) return rc;
     mnrl_tc_finish_kernel<<<(m.B + 255) / 256, 256, 0, st>>>(g.part_m, g.part_l, g.diag, m.B, g.chunks * 2, m.lse,
@@ -593,25 +611,31 @@ int launch_mnrl_tc(const MnrlArgs& m, int dtype, bool bwd, void* ws, size_t ws_b
     return ICR_OK;
   }
   if ((rc = launch_tc<MODE_G>(map_a, map_p, map_a, map_p, g, st))) return rc;
-  // gradient products: dA^ = W P^ (A operand W, B operand P^^T), dP^ = W^T A^ (A operand W^T, B operand A^^T); K = B
+  // gradient products: dA^ [B, D] = W P^ (A operand W [B, Bc], B operand P^^T [D, Bc], K = Bc)
+  //                    dP^ [Bc, D] = W^T A^ (A operand W^T [Bc, B], B operand A^^T [D, B], K = B)
   CUtensorMap map_w, map_wt, map_at, map_pt;
-  if ((rc = make_map(&map_w, base + w.w, m.B, m.B, w.ldw, false))) return rc;
-  if ((rc = make_map(&map_wt, base + w.wt, m.B, m.B, w.ldw, false))) return rc;
-  if ((rc = make_map(&map_at, base + w.at, m.D, m.B, w.ldw, false))) return rc;
-  if ((rc = make_map(&map_pt, base + w.pt, m.D, m.B, w.ldw, false))) return rc;
+  if ((rc = make_map(&map_w, base + w.w, m.B, m.Bc, w.ldw, false))) return rc;
+  if ((rc = make_map(&map_wt, base + w.wt, m.Bc, m.B, w.ldwt, false))) return rc;
+  if ((rc = make_map(&map_at, base + w.at, m.D, m.B, w.ldwt, false))) return rc;
+  if ((rc = make_map(&map_pt, base + w.pt, m.D, m.Bc, w.ldw, false))) return rc;
   TcArgs mm = g;
-  mm.KB = static_cast<int>(w.ldw / BK);
+  mm.kb[0] = static_cast<int>(w.ldw / BK);
+  mm.kb[1] = static_cast<int>(w.ldwt / BK);
+  mm.qblocks[0] = (m.B + 2 * BM - 1) / (2 * BM);
+  mm.qblocks[1] = (m.Bc + 2 * BM - 1) / (2 * BM);
+  mm.rows[0] = m.B;
+  mm.rows[1] = m.Bc;
   mm.tiles = (m.D + BN - 1) / BN;
   mm.chunks = mm.tiles;  // one N tile per work item
   if ((rc = launch_tc<MODE_MM>(map_w, map_pt, map_wt, map_at, mm, st))) return rc;
-  const int jb = (2 * m.B + 7) / 8;
+  const int jb = (m.B + m.Bc + 7) / 8;
   if (dtype == ICR_F32)
-    mnrl_tc_jacobian_kernel<float><<<jb, 256, 0, st>>>(static_cast<const float*>(m.a), m.lda, static_cast<const float*>(m.p), m.ldp, m.B, m.D,
-                                                       m.inv_a, m.inv_p, g.raw, m.grad_out, m.scale, static_cast<float*>(m.grad_a), m.ldga,
-                                                       static_cast<float*>(m.grad_p), m.ldgp);
+    mnrl_tc_jacobian_kernel<float><<<jb, 256, 0, st>>>(static_cast<const float*>(m.a), m.lda, static_cast<const float*>(m.p), m.ldp, m.B, m.Bc,
+                                                       m.D, m.inv_a, m.inv_p, g.raw[0], g.raw[1], m.grad_out, m.scale,
+                                                       static_cast<float*>(m.grad_a), m.ldga, static_cast<float*>(m.grad_p), m.ldgp);
   else
     mnrl_tc_jacobian_kernel<__nv_bfloat16><<<jb, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(m.a), m.lda, static_cast<const __nv_bfloat16*>(m.p),
-                                                               m.ldp, m.B, m.D, m.inv_a, m.inv_p, g.raw, m.grad_out, m.scale,
+                                                               m.ldp, m.B, m.Bc, m.D, m.inv_a, m.inv_p, g.raw[0], g.raw[1], m.grad_out, m.scale,
                                                                static_cast<__nv_bfloat16*>(m.grad_a), m.ldga,
                                                                static_cast<__nv_bfloat16*>(m.grad_p), m.ldgp);
   ICR_LAUNCH_CHECK();

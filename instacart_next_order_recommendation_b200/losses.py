@@ -8,9 +8,10 @@ compatibility; only cosine similarity (the default, and what the reference uses)
 
 from __future__ import annotations
 
-from typing import Any, Iterable
+from typing import Any, Callable, Iterable
 
 import torch
+import torch.distributed as dist
 from torch import nn
 
 from . import ops
@@ -35,6 +36,51 @@ class _FusedMNRL(torch.autograd.Function):
         return ga, gp, None
 
 
+class _FusedMNRLGathered(torch.autograd.Function):
+    """Cross-device in-batch negatives (sentence-transformers' ``gather_across_devices=True``).
+
+    Every rank all-gathers the positives ([G*B, D]), scores its B local anchors against all of them with the
+    rectangular kernels (label of anchor i = rank*B + i) and, in backward, reduce-scatters its [G*B, D] candidate
+    gradient so that each rank ends with the sum over ranks of d loss_r / d (its own positives) — the gradient
+    ``all_gather`` with autograd support produces upstream. `kernels` is a test seam (the gloo tests of this host
+    logic plug a CPU function pair in); product code leaves it None.
+    """
+
+    @staticmethod
+    def forward(ctx, anchors, positives, scale, group, kernels):
+        a, p = anchors.detach(), positives.detach().contiguous()
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        B = p.shape[0]
+        gathered = torch.empty(world * B, p.shape[1], dtype=p.dtype, device=p.device)
+        dist.all_gather_into_tensor(gathered, p, group=group)
+        fwd, _ = kernels if kernels is not None else (ops.mnrl_forward_rect, ops.mnrl_backward_rect)
+        loss, saved = fwd(a, gathered, scale, rank * B)
+        ctx.save_for_backward(a, gathered, saved)
+        ctx.scale, ctx.group, ctx.kernels, ctx.offset, ctx.B = float(scale), group, kernels, rank * B, B
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        a, gathered, saved = ctx.saved_tensors
+        _, bwd = ctx.kernels if ctx.kernels is not None else (ops.mnrl_forward_rect, ops.mnrl_backward_rect)
+        ga, gc = bwd(a, gathered, ctx.scale, ctx.offset, saved, grad_out)
+        gp = torch.empty(ctx.B, gc.shape[1], dtype=gc.dtype, device=gc.device)
+        dist.reduce_scatter_tensor(gp, gc.contiguous(), op=dist.ReduceOp.SUM, group=ctx.group)
+        return ga, gp, None, None, None
+
+
+def mnrl_loss_gathered(anchors: torch.Tensor, positives: torch.Tensor, scale: float = 20.0, group=None,
+                       _kernels: tuple[Callable, Callable] | None = None) -> torch.Tensor:
+    """This rank's MNRL over its anchors against the positives of EVERY rank of `group` (B_eff = G * B candidates)."""
+    if not dist.is_initialized():
+        raise RuntimeError("cross-device negatives need an initialised torch.distributed process group")
+    if anchors.dtype != positives.dtype:
+        positives = positives.to(anchors.dtype)
+    if anchors.dtype not in (torch.float32, torch.bfloat16):
+        anchors, positives = anchors.float(), positives.float()
+    return _FusedMNRLGathered.apply(anchors, positives, scale, group if group is not None else dist.group.WORLD, _kernels)
+
+
 def mnrl_loss(anchors: torch.Tensor, positives: torch.Tensor, scale: float = 20.0) -> torch.Tensor:
     """Functional form on embeddings [B, D] (float32 or bfloat16 CUDA tensors)."""
     if anchors.dtype != positives.dtype:
@@ -51,8 +97,8 @@ class MultipleNegativesRankingLoss(nn.Module):
         self.scale = scale
         if similarity_fct is not None and getattr(similarity_fct, "__name__", "") != "cos_sim":
             raise NotImplementedError("the fused kernel implements cosine similarity (the reference's choice) only")
-        if gather_across_devices:
-            raise NotImplementedError("cross-device negatives are not part of the reference's configuration (train_sbert.py:184-185)")
+        # upstream option; the reference leaves it off (train_sbert.py:184-185). On: negatives come from every rank's batch.
+        self.gather_across_devices = bool(gather_across_devices)
 
     def forward(self, sentence_features: Iterable[dict[str, torch.Tensor]], labels: torch.Tensor | None = None) -> torch.Tensor:
         embeddings = [self.model(f)["sentence_embedding"] for f in sentence_features]
@@ -62,7 +108,9 @@ class MultipleNegativesRankingLoss(nn.Module):
         if len(embeddings) != 2:
             # hard-negative columns would make the candidate matrix [k*B, D]; the reference feeds (anchor, positive) pairs only
             raise NotImplementedError("fused MNRL expects (anchor, positive) pairs, as prepared by src/data/prepare_instacart_sbert.py")
+        if self.gather_across_devices and dist.is_initialized() and dist.get_world_size() > 1:
+            return mnrl_loss_gathered(embeddings[0], embeddings[1], self.scale)
         return mnrl_loss(embeddings[0], embeddings[1], self.scale)
 
     def get_config_dict(self) -> dict[str, Any]:
-        return {"scale": self.scale, "similarity_fct": "cos_sim"}
+        return {"scale": self.scale, "similarity_fct": "cos_sim", "gather_across_devices": self.gather_across_devices}

@@ -342,3 +342,52 @@ def mnrl_backward(anchors: torch.Tensor, positives: torch.Tensor, scale: float, 
     ga, gp = grads[0], grads[1]
     D0 = anchors.shape[1]
     return (ga[:, :D0], gp[:, :D0]) if D0 != D else (ga, gp)
+
+
+def mnrl_forward_rect(anchors: torch.Tensor, candidates: torch.Tensor, scale: float, label_offset: int):
+    """MNRL of B anchors against Bc >= B candidates, the positive of anchor i at candidate i + label_offset.
+    Returns (loss f32 scalar tensor, saved = lse [B] | inv_a [B] | inv_c [Bc])."""
+    _require_cuda("anchors", anchors)
+    _require_cuda("candidates", candidates)
+    if anchors.dtype != candidates.dtype or anchors.dim() != 2 or candidates.dim() != 2 or anchors.shape[1] != candidates.shape[1]:
+        raise ValueError("anchors [B, D] and candidates [Bc, D] must share dtype and embedding dim")
+    a, c = _fast_rows(anchors), _fast_rows(candidates)
+    B, D = a.shape
+    Bc = c.shape[0]
+    dev = a.device
+    lib = _lib.load()
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    saved = torch.empty(2 * B + Bc, dtype=torch.float32, device=dev)
+    base = saved.data_ptr()
+    with _on(dev):
+        ws = _workspace(lib.icr_mnrl_rect_workspace_bytes(B, Bc, D), dev)
+        _lib.check(
+            lib.icr_mnrl_fwd_rect(a.data_ptr(), _ld(a), c.data_ptr(), _ld(c), B, Bc, int(label_offset), D, _dtype_code(a), float(scale),
+                                  loss.data_ptr(), base, base + 4 * B, base + 8 * B, ws.data_ptr(), ws.numel(), _stream(dev))
+        )
+    return loss, saved
+
+
+def mnrl_backward_rect(anchors: torch.Tensor, candidates: torch.Tensor, scale: float, label_offset: int, saved: torch.Tensor,
+                       grad_out: torch.Tensor):
+    """(grad_anchors [B, D], grad_candidates [Bc, D]) of mnrl_forward_rect's loss times grad_out."""
+    a, c = _fast_rows(anchors), _fast_rows(candidates)
+    B, D = a.shape
+    Bc = c.shape[0]
+    dev = a.device
+    lib = _lib.load()
+    ga = torch.empty(B, D, dtype=a.dtype, device=dev)
+    gc = torch.empty(Bc, D, dtype=a.dtype, device=dev)
+    go = grad_out
+    if not (go.is_cuda and go.dtype == torch.float32 and go.is_contiguous()):
+        go = go.detach().to(device=dev, dtype=torch.float32).contiguous()
+    base = saved.data_ptr()
+    with _on(dev):
+        ws = _workspace(lib.icr_mnrl_rect_workspace_bytes(B, Bc, D), dev)
+        _lib.check(
+            lib.icr_mnrl_bwd_rect(a.data_ptr(), _ld(a), c.data_ptr(), _ld(c), B, Bc, int(label_offset), D, _dtype_code(a), float(scale),
+                                  base, base + 4 * B, base + 8 * B, go.data_ptr(), ga.data_ptr(), D, gc.data_ptr(), D,
+                                  ws.data_ptr(), ws.numel(), _stream(dev))
+        )
+    D0 = anchors.shape[1]
+    return (ga[:, :D0], gc[:, :D0]) if D0 != D else (ga, gc)

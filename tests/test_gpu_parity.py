@@ -446,6 +446,31 @@ def test_mnrl_forward_backward_vs_autograd(dtype, B, D, scale):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,Bc,off,D,scale", [(64, 512, 128, 384, 20.0), (256, 2048, 1792, 384, 20.0), (48, 96, 48, 128, 30.0),
+                                              (100, 800, 300, 768, 20.0), (8, 16, 0, 64, 20.0), (300, 300, 0, 384, 20.0)])
+def test_mnrl_rectangular_gathered_candidates_vs_autograd(dtype, B, Bc, off, D, scale):
+    """Cross-device negatives: B anchors against Bc gathered candidates, label i + off (icr_mnrl_fwd_rect / bwd_rect)."""
+    g = torch.Generator().manual_seed(B + Bc)
+    cand, _ = oracle.synth_clustered(Bc, D, seed=2025, n_centres=16)
+    cand = cand * (1.0 + 0.5 * torch.rand(Bc, 1, generator=g))
+    a = torch.nn.functional.normalize(cand[off : off + B] + 0.3 * torch.randn(B, D, generator=g), dim=1)
+    a, cand = a.to(dtype), cand.to(dtype)
+    ad, cd = a.cuda(), cand.cuda()
+    loss, saved = ops.mnrl_forward_rect(ad, cd, scale, off)
+    go = torch.tensor(1.3, device="cuda")
+    ga, gc = ops.mnrl_backward_rect(ad, cd, scale, off, saved, go)
+    rl, rga, rgc = oracle.mnrl_rect_loss_and_grads(a.float(), cand.float(), scale, off)
+    assert abs(loss.item() - rl.item()) <= MNRL_ATOL
+    out_round = 0.0 if dtype == torch.float32 else 2 ** -8
+    for got, want in ((ga, rga), (gc, rgc)):
+        err = (got.float().cpu() - 1.3 * want).abs().max().item()
+        assert err <= MNRL_ATOL + out_round * 1.3 * want.abs().max().item()
+        assert err <= (2e-3 + out_round) * 1.3 * want.abs().max().item()
+    with pytest.raises(ValueError):
+        ops.mnrl_forward_rect(ad, cd, scale, Bc - B + 1)  # the positives would fall off the end of the candidates
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_mnrl_tensor_path_equals_cuda_core_path(dtype, monkeypatch):
     """The two MNRL kernel families (mnrl.cu / mnrl_tc.cu) agree on the same batch (subprocess: the switch is read once)."""
     import subprocess
@@ -609,6 +634,42 @@ def test_full_size_properties_c2_shape():
     _check_topk(v[sample], i[sample], rv, ri, F32_RTOL)
 
 
+def test_c2_planted_relevance_recall_and_ndcg_full_size():
+    """BASELINE config 2 end to end at full size: recall@10 / NDCG@10 (and the rest of the evaluator's metrics) from
+    planted relevance, computed by the device pipeline (fused top-100 -> metric kernel) and by the oracle
+    (cos_sim + topk on the CPU -> per-query loops) — identical up to tie swaps, i.e. to ~1e-4 in the mean."""
+    N, D, Q, k = 49688, 384, 10000, 100
+    items, centre_of = oracle.synth_clustered(N, D, seed=1234)
+    queries, src = oracle.synth_queries_from_items(items, Q, seed=4321)
+    src = src.tolist()
+    rng = np.random.default_rng(99)
+    by_centre: dict[int, list[int]] = {}
+    for r, c in enumerate(centre_of.tolist()):
+        by_centre.setdefault(c, []).append(r)
+    relevant = []
+    for q in range(Q):  # the item the query was generated from plus a few of its cluster
+        mates = by_centre[int(centre_of[src[q]])]
+        relevant.append({src[q], *(int(x) for x in rng.choice(mates, size=min(4, len(mates)), replace=False))})
+    v, i = icr.cos_topk(queries.cuda(), items.cuda(), k)
+    table = ops.RelevanceTable([sorted(r) for r in relevant], device="cuda")
+    specs = [(ops.METRIC_RECALL, 10), (ops.METRIC_NDCG, 10), (ops.METRIC_MRR, 10), (ops.METRIC_ACCURACY, 1), (ops.METRIC_MAP, 100)]
+    means, per_query = ops.ir_metrics(i, table, specs)
+    rv, ri = oracle.cos_topk(queries, items, k)
+    want, want_pq = oracle.st_ir_metrics(ri.tolist(), relevant, accuracy_at_k=(1,), precision_recall_at_k=(10,), mrr_at_k=(10,),
+                                         ndcg_at_k=(10,), map_at_k=(100,), per_query=True)
+    got = dict(zip(["recall@10", "ndcg@10", "mrr@10", "accuracy@1", "map@100"], means.tolist()))
+    assert got["recall@10"] > 0.2  # the planted item is found: the numbers are not trivially zero
+    for name, val in got.items():
+        assert val == pytest.approx(want[name], abs=2e-4), name
+    # per query: identical wherever the id lists are identical (they differ only across score ties)
+    same_rows = (i.cpu() == ri).all(dim=1).numpy()
+    assert same_rows.mean() > 0.99
+    cols = {"accuracy@1": 0, "precision@10": 1, "recall@10": 2, "mrr@10": 3, "ndcg@10": 4, "map@100": 5}
+    pq = per_query.cpu().numpy()
+    for j, name in enumerate(["recall@10", "ndcg@10", "mrr@10", "accuracy@1", "map@100"]):
+        np.testing.assert_allclose(pq[same_rows, j], want_pq[same_rows, cols[name]], rtol=0, atol=1e-12)
+
+
 def test_peer_memory_exchange_equals_nccl_all_gather():
     """icr_peer_exchange (NVLink peer stores + flags) gathers the same candidates as the NCCL all-gather: 2 ranks."""
     import os
@@ -624,3 +685,20 @@ def test_peer_memory_exchange_equals_nccl_all_gather():
     out = subprocess.run(cmd, cwd=str(root), capture_output=True, text=True, timeout=600, env=dict(os.environ))
     assert out.returncode == 0, out.stderr[-2000:]
     assert "PEER_EXCHANGE_OK" in out.stdout, out.stdout[-2000:]
+
+
+def test_mnrl_gathered_negatives_two_ranks_nccl():
+    """MultipleNegativesRankingLoss(gather_across_devices=True) on 2 GPUs == the oracle's single-process restatement."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs on one box (run under gpurun --gpus 2)")
+    root = Path(__file__).resolve().parents[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29519",
+           str(root / "benchmarks" / "mnrl_gathered_case.py")]
+    out = subprocess.run(cmd, cwd=str(root), capture_output=True, text=True, timeout=600, env=dict(os.environ))
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "MNRL_GATHERED_OK" in out.stdout, out.stdout[-2000:]

@@ -78,3 +78,52 @@ def test_two_rank_sharded_topk_equals_unsharded(tmp_path):
 
 def test_two_rank_short_shards(tmp_path):
     _run(15, tmp_path)  # fewer rows than k: shards pad with (-inf, -1), k clamps to the catalog size
+
+
+# ---- cross-device negatives for MNRL: all-gather of positives, label offset, reduce-scatter of candidate gradients ----
+
+
+def _oracle_mnrl_fwd(a, cand, scale, offset):
+    from oracle import oracle
+
+    loss, ga, gc = oracle.mnrl_rect_loss_and_grads(a, cand, scale, offset)
+    return loss, torch.cat([ga.flatten(), gc.flatten()])  # "saved": the unscaled gradients
+
+
+def _oracle_mnrl_bwd(a, cand, scale, offset, saved, grad_out):
+    B, D = a.shape
+    ga = saved[: B * D].view(B, D) * grad_out
+    gc = saved[B * D :].view(cand.shape[0], D) * grad_out
+    return ga, gc
+
+
+def _mnrl_worker(rank: int, world: int, port: int, out_dir: str):
+    sys.path.insert(0, str(ROOT))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from instacart_next_order_recommendation_b200.losses import mnrl_loss_gathered
+        from oracle import oracle
+
+        B, D, scale = 6, 16, 20.0
+        g = torch.Generator().manual_seed(5)
+        A = [torch.randn(B, D, generator=g) for _ in range(world)]
+        P = [torch.randn(B, D, generator=g) * 2 for _ in range(world)]
+        a = A[rank].clone().requires_grad_(True)
+        p = P[rank].clone().requires_grad_(True)
+        loss = mnrl_loss_gathered(a, p, scale, _kernels=(_oracle_mnrl_fwd, _oracle_mnrl_bwd))
+        (loss * 0.5).backward()
+        losses, grads_a, grads_p = oracle.mnrl_gathered_reference(A, P, scale)
+        assert abs(loss.item() - losses[rank].item()) < 1e-6
+        assert (a.grad - 0.5 * grads_a[rank]).abs().max() < 1e-6
+        assert (p.grad - 0.5 * grads_p[rank]).abs().max() < 1e-6  # sum over ranks of d loss_r / d P_rank
+        torch.save({"ok": True}, os.path.join(out_dir, f"m{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_mnrl_with_gathered_negatives(tmp_path):
+    port = _free_port()
+    mp.spawn(_mnrl_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "m0.pt").exists() and (tmp_path / "m1.pt").exists()
