@@ -147,6 +147,8 @@ def main():
             topk_case("C1 batch-1 top-10, CUDA graph (L2-warm)", 49_688, 384, 1, 10, dt, iters=50, cold=False, graph=True)
         for Q in (2, 4, 7, 8, 16, 32, 64, 128, 256):
             topk_case(f"C1-size batch-{Q} top-10", 49_688, 384, Q, 10, f32, iters=30)
+        for Q in (16, 64, 256):  # the same calls replayed as one CUDA graph (DeviceCatalog.topk_small): launch gaps removed
+            topk_case(f"C1-size batch-{Q} top-10, CUDA graph", 49_688, 384, Q, 10, f32, iters=30, graph=True)
     if on("c2"):
         topk_case("C2 IR eval fp32", 49_688, 384, 10_000, 100, f32, eager=True)
         topk_case("C2 IR eval bf16", 49_688, 384, 10_000, 100, bf16)

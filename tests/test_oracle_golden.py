@@ -106,3 +106,41 @@ def test_compare_topk_is_tie_tolerant():
     assert mism == 0
     err, mism = oracle.compare_topk(rv, np.array([[5, 7, 8, 1]]), rv, ri, rtol=1e-5)
     assert mism == 1
+
+
+def _c_oracle():
+    """The plain-C restatement (oracle/c_oracle.c), built on demand: an implementation that shares nothing with torch."""
+    import ctypes
+    import subprocess
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parents[1] / "oracle"
+    subprocess.run(["make", "-s", "-C", str(root)], check=True)
+    lib = ctypes.CDLL(str(root / "_build" / "liboracle_c.so"))
+    lib.oc_cos_topk.restype = ctypes.c_int
+    lib.oc_cos_topk.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
+    lib.oc_mnrl_loss.restype = ctypes.c_double
+    lib.oc_mnrl_loss.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_double]
+    return lib
+
+
+def test_torch_oracle_agrees_with_the_plain_c_restatement(golden_dir):
+    lib = _c_oracle()
+    z = np.load(golden_dir / "embeddings_small.npz")
+    items = np.ascontiguousarray(z["items"], dtype=np.float32)
+    queries = np.ascontiguousarray(z["queries"][:40], dtype=np.float32)
+    unnorm = oracle.synth_unnormalised(700, 48, seed=3).numpy()
+    for q, c, k in ((queries, items, 100), (unnorm[:20].copy(), unnorm, 25), (unnorm[:3].copy(), unnorm[:10].copy(), 10)):
+        Q, N, D = q.shape[0], c.shape[0], c.shape[1]
+        sc = np.empty((Q, k), dtype=np.float64)
+        ids = np.empty((Q, k), dtype=np.int64)
+        assert lib.oc_cos_topk(q.ctypes.data, Q, c.ctypes.data, N, D, k, sc.ctypes.data, ids.ctypes.data) == 0
+        v, i = oracle.cos_topk(q, c, k)
+        err, mism = oracle.compare_topk(v, i, torch.from_numpy(sc).float(), torch.from_numpy(ids), rtol=1e-5)
+        assert err < 1e-5 and mism == 0, (err, mism)
+    g = torch.Generator().manual_seed(9)
+    a = torch.randn(33, 48, generator=g).numpy()
+    p = (torch.randn(33, 48, generator=g) * 3).numpy()
+    for scale in (20.0, 30.0):
+        want = lib.oc_mnrl_loss(a.ctypes.data, p.ctypes.data, 33, 48, scale)
+        assert oracle.mnrl_loss(torch.from_numpy(a), torch.from_numpy(p), scale).item() == pytest.approx(want, abs=2e-5)
