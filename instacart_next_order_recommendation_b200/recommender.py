@@ -68,6 +68,10 @@ class Recommender:
             catalog_dtype = torch.bfloat16 if os.getenv("ICR_CATALOG_DTYPE", "fp32").lower() in ("bf16", "bfloat16") else torch.float32
         dev = torch.device(device) if device is not None else None
         self.catalog = DeviceCatalog(self.product_embeddings, device=dev, dtype=catalog_dtype)
+        # ask the encoder for a device tensor so that the query never visits the host between the
+        # encoder and the scoring kernel (the reference takes numpy, serve_recommendations.py:213); encoders that do
+        # not know `convert_to_tensor` (test doubles) keep the reference call.
+        self._query_on_device = os.getenv("ICR_QUERY_ON_DEVICE", "1") != "0"
 
     # ---- loading: same behaviour as the reference ------------------------------------------
     def _load_corpus(self) -> tuple[list[str], list[str]]:
@@ -107,6 +111,11 @@ class Recommender:
 
     # ---- the hot path ----------------------------------------------------------------------
     def _encode_query(self, query: str):
+        if self._query_on_device:
+            try:
+                return self.model.encode([query], normalize_embeddings=True, convert_to_tensor=True)[0]
+            except TypeError:
+                self._query_on_device = False
         return self.model.encode([query], normalize_embeddings=True)[0]
 
     def _rank(self, query_emb, top_k: int, exclude_product_ids: set[str] | None) -> list[tuple[str, float]]:

@@ -271,6 +271,30 @@ def test_recommender_dropin_matches_reference_golden(golden_dir, tmp_path):
     rec2 = icr.Recommender("fake-model", corpus, model=Enc())
     np.testing.assert_array_equal(rec2.product_embeddings, z["items"])
 
+    # an encoder that honours convert_to_tensor hands the query over on the device: same answers
+    class DeviceEnc(Enc):
+        calls = 0
+
+        def encode(self, texts, convert_to_tensor=False, **kw):
+            out = Enc.encode(self, texts, **kw)
+            if convert_to_tensor:
+                DeviceEnc.calls += 1
+                return torch.from_numpy(out).cuda()
+            return out
+
+    class StrictEnc:  # the reference's exact call only: any other keyword is a TypeError
+        def encode(self, texts, batch_size=64, show_progress_bar=False, normalize_embeddings=True):
+            return Enc().encode(texts)
+
+    rec3 = icr.Recommender("fake-model", corpus, model=DeviceEnc())
+    rec4 = icr.Recommender("fake-model", corpus, model=StrictEnc())
+    for case in gold["cases"][:20]:
+        args = dict(top_k=case["top_k"], exclude_product_ids=set(case["exclude"]))
+        want = rec2.recommend(f"q:{case['q']}", **args)
+        assert rec3.recommend(f"q:{case['q']}", **args) == want
+        assert rec4.recommend(f"q:{case['q']}", **args) == want
+    assert DeviceEnc.calls >= 20 and rec4._query_on_device is False
+
 
 def test_ir_evaluator_and_rank_all_against_oracle(golden_dir):
     z = np.load(golden_dir / "embeddings_small.npz")
