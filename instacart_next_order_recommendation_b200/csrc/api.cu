@@ -59,7 +59,7 @@ int launch_peer_exchange(const float* scores, const int64_t* ids, int64_t n, int
 int gemv_grid(int64_t N);
 int launch_gemv_topk(const void* cat, int64_t N, int64_t ldc, int D, int dtype, const void* q, int64_t ldq, int Q,
                      const uint8_t* mask, int k, uint64_t* part_keys, int* part_cnt, int grid, float* out_scores, int64_t* out_ids,
-                     int64_t id_offset, unsigned int* done_counter, cudaStream_t st);
+                     int64_t id_offset, unsigned int* done_counter, cudaStream_t st, const float* cat_inv);
 size_t select_scratch_bytes(int64_t Q, int nseg, int seg_cap, int k);
 int launch_select(const uint64_t* seg_keys, const int* seg_cnt, int64_t Q, int nseg, int seg_stride, int seg_cap,
                   const uint64_t* carry_in, const int* carry_cnt_in, uint64_t* carry_out, int* carry_cnt_out,
@@ -224,6 +224,10 @@ static int resolve_path(int path, int64_t Q, int64_t N, int64_t D, int dtype, in
   const double cat_bytes = static_cast<double>(N) * static_cast<double>(D) * (dtype == ICR_F32 ? 4.0 : 2.0);
   if (cat_bytes >= 256e6 && gemv_max_q > 3) gemv_max_q = 3;
   if (cat_bytes >= 640e6) gemv_max_q = 1;
+  // rows shorter than 512 bytes leave the GEMV kernel instruction-bound even for one query (per-row reduction and
+  // threshold test against 256 bytes of FMAs: 20 % of the HBM rate measured at D=128 bf16); the swapped tensor-core
+  // kernel streams such a catalog at 74 % with the query padded to N=32
+  if (cat_bytes >= 640e6 && D * (dtype == ICR_F32 ? 4 : 2) < 512) gemv_max_q = 0;
   if (Q > gemv_max_q && gemm_topk_supported(Q, N, D, dtype, k, mask)) return ICR_PATH_GEMM;
   return ICR_PATH_GEMV;
 }
@@ -305,7 +309,7 @@ int icr_cos_topk(const void* queries, int64_t Q, int64_t ldq, const void* catalo
     const int nq = static_cast<int>(Q - q0 < qc ? Q - q0 : qc);
     const char* qptr = static_cast<const char*>(queries) + q0 * ldq * esz;
     rc = launch_gemv_topk(catalog, N, ldc, static_cast<int>(D), dtype, qptr, ldq, nq, exclude_mask, k, part_keys, part_cnt, grid,
-                          out_scores + q0 * k, out_ids + q0 * k, row_offset, done_counter, st);
+                          out_scores + q0 * k, out_ids + q0 * k, row_offset, done_counter, st, cat_inv_norms);
     if (rc) return rc;
   }
   return ICR_OK;

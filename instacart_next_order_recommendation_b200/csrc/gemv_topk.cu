@@ -26,7 +26,7 @@ constexpr int kGemvThreads = 256;  // compute threads of either kernel
 constexpr int kGemvWarps = kGemvThreads / 32;
 constexpr int kGemvUnroll = 3;   // 16-byte vectors per lane per row kept in flight (direct-load kernel)
 constexpr int kMergeSel = 256;   // >= ICR_MAX_K: output buffer of the in-kernel merge
-constexpr int kMaxSlots = 16;
+constexpr int kMaxSlots = 64;
 constexpr int kRingThreads = kGemvThreads + 32;  // + the producer warp
 
 #ifdef ICR_TRACE  // development builds only (ICR_NVCC_DEFS=-DICR_TRACE): per-CTA globaltimer stamps of the ring kernel
@@ -62,6 +62,7 @@ struct GemvArgs {
   int64_t ldq;
   int Q;
   const uint8_t* mask;  // optional exclusion mask
+  const float* cat_inv;  // optional precomputed 1 / max(|row|, eps) (icr_row_inv_norms): single-query ring kernel skips the norm FMAs
   int k;
   int64_t rows_per_cta;
   uint64_t* part_keys;  // [Q][gridDim.x][k]
@@ -149,9 +150,9 @@ __device__ __forceinline__ void stage_queries(const GemvArgs& a, float* qs, int 
   }
 }
 
-// accumulate one 16-byte vector of RB rows against QT queries (+ the rows' squared norms)
-template <typename T, int RB, int QT>
-__device__ __forceinline__ void fma_vector(const uint4 (&c)[RB], const float* qs, int dpad, int v, float (&acc)[RB * (QT + 1)]) {
+// accumulate one 16-byte vector of RB rows against QT queries (+ the rows' squared norms unless NORMS: precomputed)
+template <typename T, int RB, int QT, bool NORMS = false>
+__device__ __forceinline__ void fma_vector(const uint4 (&c)[RB], const float* qs, int dpad, int v, float (&acc)[RB * (QT + (NORMS ? 0 : 1))]) {
   constexpr int VEC = Elem<T>::VEC;
   float qv[QT][VEC];
 #pragma unroll
@@ -174,26 +175,30 @@ __device__ __forceinline__ void fma_vector(const uint4 (&c)[RB], const float* qs
 #pragma unroll
       for (int i = 0; i < VEC; ++i) acc[t * RB + r] = fmaf(f[i], qv[t][i], acc[t * RB + r]);
     }
+    if (!NORMS) {
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) acc[QT * RB + r] = fmaf(f[i], f[i], acc[QT * RB + r]);
+      for (int i = 0; i < VEC; ++i) acc[QT * RB + r] = fmaf(f[i], f[i], acc[QT * RB + r]);
+    }
   }
 }
 
 // transposing reduction of the RB*(QT+1) partial sums, then threshold test and candidate append
-template <int RB, int QT>
-__device__ __forceinline__ void reduce_and_append(float (&acc)[RB * (QT + 1)], const GemvArgs& a, GemvSmem<QT>& sm, int nq, int64_t r0,
-                                                  int64_t row_limit, int lane) {
-  constexpr int V = RB * (QT + 1);
+// NORMS: lane r (< RB) brings the precomputed inverse norm of row r0 + r in `inv_lane`
+template <int RB, int QT, bool NORMS = false>
+__device__ __forceinline__ void reduce_and_append(float (&acc)[RB * (QT + (NORMS ? 0 : 1))], const GemvArgs& a, GemvSmem<QT>& sm, int nq, int64_t r0,
+                                                  int64_t row_limit, int lane, float inv_lane = 0.f) {
+  constexpr int V = RB * (QT + (NORMS ? 0 : 1));
   constexpr int SH = (V == 32) ? 0 : (V == 16 ? 1 : (V == 8 ? 2 : 3));  // lane -> value index shift
   warp_transpose_reduce<V>(acc, lane);
   const int idx = lane >> SH;  // value index owned by this lane
   const int t = idx / RB, r = idx % RB;
   // squared norm of row r lives in the lane group of index QT*RB + r
-  const float ss = __shfl_sync(kFull, acc[0], (QT * RB + r) << SH);
+  const float ss = NORMS ? 0.f : __shfl_sync(kFull, acc[0], (QT * RB + r) << SH);
+  const float inv = NORMS ? __shfl_sync(kFull, inv_lane, r) : (1.0f / fmaxf(sqrtf(ss), kNormEps));
   const int64_t row = r0 + r;
   if (t < nq && (lane & ((1 << SH) - 1)) == 0 && row < row_limit) {
     const bool excluded = a.mask && a.mask[row];
-    const float score = acc[0] * (1.0f / fmaxf(sqrtf(ss), kNormEps));
+    const float score = acc[0] * inv;
     if (!excluded && score > sm.tau[t]) {
       const int pos = atomicAdd(&sm.ncand[t], 1);
       if (pos < GemvSmem<QT>::CAND) sm.cand[t * GemvSmem<QT>::CAND + pos] = make_key(score, static_cast<uint32_t>(row));
@@ -474,12 +479,13 @@ __global__ void __launch_bounds__(kGemvThreads) gemv_topk_kernel(GemvArgs a) {
 // =====================================================================================================
 // ring kernel: producer warp + bulk async copies into a shared-memory ring, 8 consumer warps
 // =====================================================================================================
-template <typename T, int QT>
+template <typename T, int QT, bool NORMS = false>
 __global__ void __launch_bounds__(kRingThreads, 1) gemv_ring_kernel(GemvArgs a) {
+  static_assert(!NORMS || QT == 1, "precomputed norms: single-query kernel only (V must stay a power of two)");
   constexpr int VEC = Elem<T>::VEC;
   constexpr int RB = (QT == 7) ? 4 : 8;  // rows reduced together (V = RB * (QT + 1) <= 32) = rows per ring slot
   constexpr int kSlabRows = RB;
-  constexpr int V = RB * (QT + 1);
+  constexpr int V = RB * (QT + (NORMS ? 0 : 1));
   extern __shared__ __align__(128) unsigned char ring_smem_raw[];
   const int nvec = a.D / VEC;
   const int dpad = nvec * VEC;
@@ -509,18 +515,28 @@ __global__ void __launch_bounds__(kRingThreads, 1) gemv_ring_kernel(GemvArgs a) 
 
   if (warp == kGemvWarps) {
     // ================= producer: the whole ring is in flight before the first FMA =================
-    if (lane == 0) {
-      const char* src = static_cast<const char*>(a.cat) + row_begin * row_bytes;
-      for (int b = 0; b < nb; ++b) {
-        const int slot = b % NS;
-        const uint32_t parity = static_cast<uint32_t>(b / NS) & 1u;
+    // kProducers lanes issue the copies, lane j those of slabs j, j + kProducers, ...: with 768-byte rows a slab is
+    // 6 KB and one lane's wait / expect / copy loop (~450 cycles per slab) was what held the stream at 58 % of the
+    // HBM rate. NS is a multiple of 8, so the lanes own disjoint slot sets (slot = slab % NS) and every slot still
+    // has exactly one producer and one consumer; slot and parity advance incrementally (no division per slab).
+    constexpr int kProducers = 4;
+    if (lane < kProducers) {
+      const char* src = static_cast<const char*>(a.cat) + row_begin * row_bytes + static_cast<int64_t>(lane) * slot_bytes;
+      const uint32_t last_bytes = static_cast<uint32_t>(row_end - row_begin - static_cast<int64_t>(nb - 1) * kSlabRows) * row_bytes;
+      int slot = lane;  // lane < kProducers <= NS
+      uint32_t parity = 0;
+      for (int b = lane; b < nb; b += kProducers) {
         ptx::mbar_wait(ptx::smem_u32(&empty_bar[slot]), parity ^ 1u);
-        const int64_t r0 = row_begin + static_cast<int64_t>(b) * kSlabRows;
-        const int rows = static_cast<int>(min(static_cast<int64_t>(kSlabRows), row_end - r0));
-        const uint32_t bytes = static_cast<uint32_t>(rows) * row_bytes;
+        const uint32_t bytes = (b == nb - 1) ? last_bytes : static_cast<uint32_t>(slot_bytes);
         const uint32_t fb = ptx::smem_u32(&full_bar[slot]);
         ptx::mbar_expect_tx(fb, bytes);
-        ptx::bulk_g2s(ptx::smem_u32(ring + static_cast<size_t>(slot) * slot_bytes), src + static_cast<int64_t>(b) * slot_bytes, bytes, fb);
+        ptx::bulk_g2s(ptx::smem_u32(ring + static_cast<size_t>(slot) * slot_bytes), src, bytes, fb);
+        src += static_cast<int64_t>(kProducers) * slot_bytes;
+        slot += kProducers;
+        if (slot >= NS) {
+          slot -= NS;
+          parity ^= 1u;
+        }
       }
     }
     return;
@@ -538,11 +554,11 @@ __global__ void __launch_bounds__(kRingThreads, 1) gemv_ring_kernel(GemvArgs a) 
   const int iters = (nb + kGemvWarps - 1) / kGemvWarps;
   constexpr int kItersPerRefresh = 4;
   constexpr int kBlockRows = kItersPerRefresh * kGemvWarps * kSlabRows;
+  int slot = warp;  // slab b = it * 8 + warp lives in slot b % NS; NS is a multiple of 8: advance by 8, wrap, flip the parity
+  uint32_t parity = 0;
   for (int it = 0; it < iters; ++it) {
     const int b = it * kGemvWarps + warp;
     if (b < nb) {
-      const int slot = b % NS;
-      const uint32_t parity = static_cast<uint32_t>(b / NS) & 1u;
       ptx::mbar_wait(ptx::smem_u32(&full_bar[slot]), parity);
       if (it == 0) ICR_STAMP(3);
       const unsigned char* slab = ring + static_cast<size_t>(slot) * slot_bytes;
@@ -552,19 +568,57 @@ __global__ void __launch_bounds__(kRingThreads, 1) gemv_ring_kernel(GemvArgs a) 
         float acc[V];
 #pragma unroll
         for (int i = 0; i < V; ++i) acc[i] = 0.f;
-        for (int v = lane; v < nvec; v += 32) {
+        float inv_lane = 0.f;  // issued before the FMAs: one 32-byte load per slab, its latency hides behind them
+        if (NORMS && lane < RB && r0 + lane < row_end) inv_lane = __ldg(a.cat_inv + r0 + lane);
+        const int nfull = nvec & ~31;  // vectors covered by iterations in which every lane has one
+        for (int v = lane; v < nfull; v += 32) {
           uint4 c[RB];
 #pragma unroll
           for (int r = 0; r < RB; ++r) {
             // rows past the end of the catalog were not copied: stale ring bytes, masked by row_limit below
             c[r] = *reinterpret_cast<const uint4*>(slab + static_cast<size_t>(g * RB + r) * row_bytes + static_cast<size_t>(v) * 16);
           }
-          fma_vector<T, RB, QT>(c, sm.qs, dpad, v, acc);
+          fma_vector<T, RB, QT, NORMS>(c, sm.qs, dpad, v, acc);
         }
-        reduce_and_append<RB, QT>(acc, a, sm, nq, r0 + g * RB, row_end, lane);
+        if (nvec - nfull == 16) {
+          // Half-filled last iteration (768-byte and 256-byte bf16 rows, ...): instead of idling 16 lanes, the two
+          // half-warps split the ROWS of the tail — lanes 0-15 take rows 0,2,4,.., lanes 16-31 rows 1,3,5,.. — and
+          // the partial sums are folded into the full-width accumulators with predicated adds (static indices).
+          constexpr int HB = RB / 2;
+          constexpr int VT = QT + (NORMS ? 0 : 1);
+          const int h = lane >> 4, v = nfull + (lane & 15);
+          uint4 c[HB];
+#pragma unroll
+          for (int i = 0; i < HB; ++i)
+            c[i] = *reinterpret_cast<const uint4*>(slab + static_cast<size_t>(g * RB + 2 * i + h) * row_bytes + static_cast<size_t>(v) * 16);
+          float tacc[HB * VT];
+#pragma unroll
+          for (int i = 0; i < HB * VT; ++i) tacc[i] = 0.f;
+          fma_vector<T, HB, QT, NORMS>(c, sm.qs, dpad, v, tacc);
+#pragma unroll
+          for (int t = 0; t < VT; ++t)
+#pragma unroll
+            for (int i = 0; i < HB; ++i) {
+              acc[t * RB + 2 * i] += h == 0 ? tacc[t * HB + i] : 0.f;
+              acc[t * RB + 2 * i + 1] += h == 1 ? tacc[t * HB + i] : 0.f;
+            }
+        } else if (lane < nvec - nfull) {
+          const int v = nfull + lane;
+          uint4 c[RB];
+#pragma unroll
+          for (int r = 0; r < RB; ++r)
+            c[r] = *reinterpret_cast<const uint4*>(slab + static_cast<size_t>(g * RB + r) * row_bytes + static_cast<size_t>(v) * 16);
+          fma_vector<T, RB, QT, NORMS>(c, sm.qs, dpad, v, acc);
+        }
+        reduce_and_append<RB, QT, NORMS>(acc, a, sm, nq, r0 + g * RB, row_end, lane, inv_lane);
       }
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&empty_bar[slot]));
+      slot += kGemvWarps;
+      if (slot >= NS) {
+        slot -= NS;
+        parity ^= 1u;
+      }
     }
     // early thresholds (as soon as a list holds 2k + 32 keys) keep the final list short: the selection at the end
     // of the stream is on the critical path of a request, the ones in the middle hide behind the ring
@@ -610,20 +664,25 @@ static int ring_slots_for(int D) {
   // A multiple of the consumer-warp count, so that every slot is only ever consumed by ONE warp (batch b goes to
   // warp b % 8 and slot b % NS): a slot shared by two warps would let the later one wait on a phase parity that an
   // mbarrier reports as already complete before the earlier phase has even been filled.
-  return n >= 2 * kGemvWarps ? 2 * kGemvWarps : kGemvWarps;
+  // Short rows make small slabs: what has to stay constant is the BYTES in flight per SM (~190 KB keeps the HBM
+  // pipe full; the 96 KB that 16 slabs of 768-byte rows amount to streamed at 54 % of the HBM rate), so the ring
+  // takes as many slots as fit, in multiples of the warp count.
+  size_t slots = n / kGemvWarps * kGemvWarps;
+  if (slots > static_cast<size_t>(kMaxSlots)) slots = kMaxSlots;
+  return static_cast<int>(slots);
 }
 
-template <typename T, int QT>
+template <typename T, int QT, bool NORMS = false>
 static int launch_ring(GemvArgs a, int grid, cudaStream_t st) {
   a.ring_slots = ring_slots_for<T, QT>(a.D);
   const size_t smem = static_cast<size_t>(a.ring_slots) * (QT == 7 ? 4 : 8) * a.D * sizeof(T) + 2 * kMaxSlots * sizeof(uint64_t) + GemvSmem<QT>::bytes(a.D) + 128;
   static thread_local size_t configured = 0;
   if (smem > configured) {
-    ICR_CUDA_CHECK(cudaFuncSetAttribute(gemv_ring_kernel<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    ICR_CUDA_CHECK((cudaFuncSetAttribute(gemv_ring_kernel<T, QT, NORMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))));
     configured = smem;
   }
   profile_begin(kKernelGemv, 1, st);
-  gemv_ring_kernel<T, QT><<<grid, kRingThreads, smem, st>>>(a);
+  gemv_ring_kernel<T, QT, NORMS><<<grid, kRingThreads, smem, st>>>(a);
   profile_end(st);
   ICR_LAUNCH_CHECK();
   return ICR_OK;
@@ -656,8 +715,9 @@ int gemv_grid(int64_t N) {
 // Runs ceil(Q/7) passes (one for Q <= 7). part_keys/part_cnt sized [Q][grid][k] / [Q][grid].
 int launch_gemv_topk(const void* cat, int64_t N, int64_t ldc, int D, int dtype, const void* q, int64_t ldq, int Q,
                      const uint8_t* mask, int k, uint64_t* part_keys, int* part_cnt, int grid, float* out_scores, int64_t* out_ids,
-                     int64_t id_offset, unsigned int* done_counter, cudaStream_t st) {
+                     int64_t id_offset, unsigned int* done_counter, cudaStream_t st, const float* cat_inv) {
   GemvArgs a{};
+  a.cat_inv = cat_inv;
   a.cat = cat;
   a.N = N;
   a.ldc = ldc;
@@ -683,11 +743,13 @@ int launch_gemv_topk(const void* cat, int64_t N, int64_t ldc, int D, int dtype, 
     a.rows_per_cta = (N + g - 1) / g;
     int rc;
     if (dtype == ICR_F32) {
-      if (qt == 1) rc = ring ? launch_ring<float, 1>(a, g, st) : launch_direct<float, 8, 1>(a, g, st);
+      if (qt == 1) rc = ring ? (cat_inv ? launch_ring<float, 1, true>(a, g, st) : launch_ring<float, 1>(a, g, st)) : launch_direct<float, 8, 1>(a, g, st);
       else if (qt == 3) rc = ring ? launch_ring<float, 3>(a, g, st) : launch_direct<float, 8, 3>(a, g, st);
       else rc = ring ? launch_ring<float, 7>(a, g, st) : launch_direct<float, 4, 7>(a, g, st);
     } else {
-      if (qt == 1) rc = ring ? launch_ring<__nv_bfloat16, 1>(a, g, st) : launch_direct<__nv_bfloat16, 8, 1>(a, g, st);
+      if (qt == 1)
+        rc = ring ? (cat_inv ? launch_ring<__nv_bfloat16, 1, true>(a, g, st) : launch_ring<__nv_bfloat16, 1>(a, g, st))
+                  : launch_direct<__nv_bfloat16, 8, 1>(a, g, st);
       else if (qt == 3) rc = ring ? launch_ring<__nv_bfloat16, 3>(a, g, st) : launch_direct<__nv_bfloat16, 8, 3>(a, g, st);
       else rc = ring ? launch_ring<__nv_bfloat16, 7>(a, g, st) : launch_direct<__nv_bfloat16, 4, 7>(a, g, st);
     }

@@ -86,6 +86,31 @@ def test_isotropic_and_unnormalised_inputs(path):
     _check_topk(v, i, *oracle.cos_topk(un_q, un_c, 50), F32_RTOL)
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("D", [384, 128, 768, 192, 64, 200, 1024])
+@pytest.mark.parametrize("use_norms", [False, True])
+def test_single_query_ring_kernel_row_shapes(dtype, D, use_norms):
+    """K1 for one query across row lengths: full iterations only, a half-filled last iteration (the two half-warps
+    split the tail's rows: 16-byte vector count % 32 == 16), other tails; with the row norms accumulated in the kernel
+    or precomputed (icr_row_inv_norms, as DeviceCatalog passes them for bf16 catalogs). Un-normalised rows."""
+    N = 30011
+    items = oracle.synth_unnormalised(N, D, seed=77).to(dtype)
+    query = oracle.synth_unnormalised(1, D, seed=78).to(dtype)
+    it, qt = items.cuda(), query.cuda()
+    inv = ops.row_inv_norms(it) if use_norms else None
+    mask = torch.zeros(N, dtype=torch.uint8, device="cuda")
+    mask[::17] = 1
+    rv_all = oracle.cos_sim(query.float(), items.float())[0]
+    rtol = F32_RTOL if dtype == torch.float32 else 5e-5
+    for k, m in ((100, None), (10, mask)):
+        v, i = ops.cos_topk(qt, it, k, cat_inv_norms=inv, exclude_mask=m, path=ops.PATH_GEMV, row_offset=5)
+        s = rv_all.clone()
+        if m is not None:
+            s[m.cpu().bool()] = float("-inf")
+        rv, ri = torch.topk(s, k)
+        _check_topk(v, i - 5, rv[None], ri[None], rtol)
+
+
 @pytest.mark.parametrize("path", PATHS)
 @pytest.mark.parametrize("Q,N,D,k", [(1, 40000, 768, 100), (3, 10000, 384, 10), (6, 25000, 768, 100)])
 def test_bf16_topk_vs_fp32_math_on_rounded_inputs(path, Q, N, D, k):
