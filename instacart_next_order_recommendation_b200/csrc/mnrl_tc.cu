@@ -471,13 +471,26 @@ struct TcWs {
   int chunks;
 };
 
+// Work items = (row block, chunk of column tiles) over 74 CTA pairs. The launch takes ceil(items / 74) rounds of the
+// longest item, so the chunk count is chosen to minimise rounds x tiles-per-item (B = 4096: 4 chunks -> 64 items of 4
+// tiles in one round, where ceil(148 / row blocks) = 10 chunks gave 160 items = 3 rounds of 2 tiles for 2.2 rounds of
+// work); on ties fewer, longer items win (their epilogues overlap the next tile's MMAs).
 int tc_chunks(int64_t B, int64_t Bc) {
   const int qblocks = static_cast<int>((B + 2 * BM - 1) / (2 * BM));
   const int tiles = static_cast<int>((Bc + BN - 1) / BN);
   const int npairs = kNumSMs / 2;
-  int chunks = (2 * npairs + qblocks - 1) / qblocks;
-  if (chunks > tiles) chunks = tiles;
-  return chunks < 1 ? 1 : chunks;
+  int best = 1;
+  int64_t best_cost = INT64_MAX;
+  for (int c = 1; c <= tiles; ++c) {
+    const int64_t items = static_cast<int64_t>(qblocks) * c;
+    const int64_t rounds = (items + npairs - 1) / npairs;
+    const int64_t cost = rounds * ((tiles + c - 1) / c);
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = c;
+    }
+  }
+  return best;
 }
 
 TcWs tc_layout(int64_t B, int64_t Bc, int64_t D) {
