@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(256) peer_exchange_kernel(const PeerArgs a) {
     const uint64_t t0 = global_timer_ns();
     // epochs only grow (the host counts calls), so >= also accepts a peer that is already one call ahead
     while (static_cast<int32_t>(ld_acquire_sys(mine) - a.epoch) < 0) {
-      if (global_timer_ns() - t0 > 5000000000ull) __trap();  // a peer that never arrives must abort the launch, not hang the GPU
+      if (global_timer_ns() - t0 > 30000000000ull) __trap();  // a peer that never arrives must abort the launch, not hang the GPU
     }
   }
   __syncthreads();
