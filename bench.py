@@ -165,6 +165,12 @@ def main():
         run_reference(args, rank)
         return
 
+    # stdout carries exactly ONE line, the JSON record: native libraries write there too (NCCL prints its version banner
+    # on the first collective), so file descriptor 1 is pointed at stderr for the run and the record goes to the saved one
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
 
@@ -294,10 +300,11 @@ def main():
                                 "sample": f"{nq} of the 10,000 queries against the full catalog: oracle port of cos_sim + torch.topk(100), torch CPU "
                                           "(as called: both operands re-normalised per 500-query call)",
                                 "best_case_value": best, "best_case": "operands pre-normalised once, mm + topk only"}
-    if rank == 0:
-        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    sys.stdout.flush()
+    if rank == 0:
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
 
 
 def bench_ir_eval(icr, ops, dev, rank, flush):
