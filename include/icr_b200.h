@@ -182,6 +182,13 @@ int icr_mnrl_bwd(const void* a, int64_t lda, const void* p, int64_t ldp,
                  const float* grad_out,
                  void* grad_a, int64_t ldga, void* grad_p, int64_t ldgp,
                  void* workspace, size_t workspace_bytes, void* stream);
+/* Forward and backward in one call: loss plus the gradients for dL/dloss = 1 (a training step always wants both; the
+ * caller multiplies by the incoming gradient). Same outputs as icr_mnrl_fwd followed by icr_mnrl_bwd with grad_out = 1. */
+int icr_mnrl_fwd_bwd(const void* a, int64_t lda, const void* p, int64_t ldp,
+                     int64_t B, int64_t D, int dtype, float scale,
+                     float* loss, float* lse, float* inv_a, float* inv_p,
+                     void* grad_a, int64_t ldga, void* grad_p, int64_t ldgp,
+                     void* workspace, size_t workspace_bytes, void* stream);
 
 /* Rectangular form for cross-device in-batch negatives (sentence-transformers'
  * gather_across_devices=True; not enabled by the reference, src/training/train_sbert.py:184-185):

@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(kMnrlThreads) mnrl_kernel(MnrlArgs g) {
 #pragma unroll
       for (int i = 0; i < EPL; ++i) acc[r][i] = 0.f;
   }
-  const float coef = (MODE == 1) ? g.grad_out[0] * g.scale / static_cast<float>(B) : 0.f;
+  const float coef = (MODE == 1) ? (g.grad_out ? g.grad_out[0] : 1.0f) * g.scale / static_cast<float>(B) : 0.f;  // null: dL/dloss = 1
   float tile_lse[TM];
   if (MODE == 1) {
 #pragma unroll

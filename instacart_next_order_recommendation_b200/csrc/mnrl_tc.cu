@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(256) mnrl_tc_jacobian_kernel(const T* __restri
   const float inv = z ? inv_p[row] : inv_a[row];
   const float* dr = (z ? raw_p : raw_a) + static_cast<int64_t>(row) * D;
   T* out = (z ? grad_p : grad_a) + static_cast<int64_t>(row) * (z ? ldgp : ldga);
-  const float coef = grad_out[0] * scale / static_cast<float>(B);
+  const float coef = (grad_out ? grad_out[0] : 1.0f) * scale / static_cast<float>(B);  // null: dL/dloss = 1
   float pr = 0.f;
   for (int e = lane; e < D; e += 32) pr = fmaf(Elem<T>::to_f32(x[e]) * inv, dr[e], pr);
   pr = warp_sum(pr);
@@ -538,7 +538,7 @@ int launch_tc(const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMap& a
 }
 
 template <typename T>
-int launch_prep(const MnrlArgs& m, const TcWs& w, char* base, bool transpose, cudaStream_t st) {
+int launch_prep(const MnrlArgs& m, const TcWs& w, char* base, bool transpose, bool forward, cudaStream_t st) {
   const int blocks = (m.B + kPrepRows - 1) / kPrepRows + (m.Bc + kPrepRows - 1) / kPrepRows;
   __half* pa = reinterpret_cast<__half*>(base + w.planes_a);
   __half* pp = reinterpret_cast<__half*>(base + w.planes_p);
@@ -548,8 +548,9 @@ int launch_prep(const MnrlArgs& m, const TcWs& w, char* base, bool transpose, cu
     const size_t smem = static_cast<size_t>(kPrepRows) * (dpad + 2) * sizeof(__half);
     if (smem > 48 * 1024) ICR_CUDA_CHECK(cudaFuncSetAttribute(mnrl_tc_prep_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     mnrl_tc_prep_kernel<T, true><<<blocks, kPrepThreads, smem, st>>>(static_cast<const T*>(m.a), m.lda, static_cast<const T*>(m.p), m.ldp, m.B, m.Bc,
-                                                                      m.D, dpad, pa, pp, nullptr, nullptr, reinterpret_cast<__half*>(base + w.at),
-                                                                      reinterpret_cast<__half*>(base + w.pt), w.ldwt, w.ldw, nullptr);
+                                                                      m.D, dpad, pa, pp, forward ? m.inv_a : nullptr, forward ? m.inv_p : nullptr,
+                                                                      reinterpret_cast<__half*>(base + w.at), reinterpret_cast<__half*>(base + w.pt),
+                                                                      w.ldwt, w.ldw, forward ? ticket : nullptr);
   } else {
     mnrl_tc_prep_kernel<T, false><<<blocks, kPrepThreads, 0, st>>>(static_cast<const T*>(m.a), m.lda, static_cast<const T*>(m.p), m.ldp, m.B, m.Bc,
                                                                    m.D, dpad, pa, pp, m.inv_a, m.inv_p, nullptr, nullptr, 0, 0, ticket);
@@ -576,7 +577,9 @@ bool mnrl_tc_applies(int64_t B, int64_t Bc, int64_t D) {
 
 size_t mnrl_tc_workspace_bytes(int64_t B, int64_t Bc, int64_t D) { return tc_layout(B, Bc, D).total; }
 
-int launch_mnrl_tc(const MnrlArgs& m, int dtype, bool bwd, void* ws, size_t ws_bytes, cudaStream_t st) {
+// mode 0: forward; 1: backward (lse / inverse norms are inputs); 2: both in one go (gradients for dL/dloss = grad_out or 1)
+int launch_mnrl_tc(const MnrlArgs& m, int dtype, int mode, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const bool fwd = mode != 1, bwd = mode != 0;
   const TcWs w = tc_layout(m.B, m.Bc, m.D);
   if (ws_bytes < w.total) {
     set_error("mnrl (tensor path): workspace %zu bytes < required %zu", ws_bytes, w.total);
@@ -584,8 +587,8 @@ int launch_mnrl_tc(const MnrlArgs& m, int dtype, bool bwd, void* ws, size_t ws_b
   }
   char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~static_cast<uintptr_t>(1023));
   int rc;
-  if (dtype == ICR_F32) rc = launch_prep<float>(m, w, base, bwd, st);
-  else rc = launch_prep<__nv_bfloat16>(m, w, base, bwd, st);
+  if (dtype == ICR_F32) rc = launch_prep<float>(m, w, base, bwd, fwd, st);
+  else rc = launch_prep<__nv_bfloat16>(m, w, base, bwd, fwd, st);
   if (rc) return rc;
 
   TcArgs g{};
@@ -615,13 +618,13 @@ int launch_mnrl_tc(const MnrlArgs& m, int dtype, bool bwd, void* ws, size_t ws_b
   CUtensorMap map_a, map_p;
   if ((rc = make_map(&map_a, base + w.planes_a, m.B, 2 * w.dpad, 2 * w.dpad, false))) return rc;
   if ((rc = make_map(&map_p, base + w.planes_p, m.Bc, 2 * w.dpad, 2 * w.dpad, false))) return rc;
-  if (!bwd) {
+  if (fwd) {
     if ((rc = launch_tc<MODE_LSE>(map_a, map_p, map_a, map_p, g, st))) return rc;
     mnrl_tc_finish_kernel<<<(m.B + 255) / 256, 256, 0, st>>>(g.part_m, g.part_l, g.diag, m.B, g.chunks * 2, m.lse,
                                                              reinterpret_cast<float*>(base + w.cta_sums),
                                                              reinterpret_cast<unsigned int*>(base + w.ticket), m.loss);
     ICR_LAUNCH_CHECK();
-    return ICR_OK;
+    if (!bwd) return ICR_OK;
   }
   if ((rc = launch_tc<MODE_G>(map_a, map_p, map_a, map_p, g, st))) return rc;
   // gradient products: dA^ [B, D] = W P^ (A operand W [B, Bc], B operand P^^T [D, Bc], K = Bc)

@@ -24,13 +24,24 @@ class _FusedMNRL(torch.autograd.Function):
     def forward(ctx, anchors: torch.Tensor, positives: torch.Tensor, scale: float):
         a = anchors.detach()
         p = positives.detach()
+        ctx.scale = float(scale)
+        ctx.fused = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
+        if ctx.fused:
+            # a training step wants the gradients anyway: one library call computes the loss and d loss / d (A, P) for
+            # dL/dloss = 1 (one prep and one host round trip instead of two); backward() only scales them
+            loss, ga, gp = ops.mnrl_forward_backward(a, p, scale)
+            ctx.save_for_backward(ga, gp)
+            return loss
         loss, saved = ops.mnrl_forward(a, p, scale)
         ctx.save_for_backward(a, p, saved)
-        ctx.scale = float(scale)
         return loss
 
     @staticmethod
     def backward(ctx, grad_out):
+        if ctx.fused:
+            ga, gp = ctx.saved_tensors
+            go = grad_out.to(dtype=torch.float32)
+            return (ga * go).to(ga.dtype), (gp * go).to(gp.dtype), None
         a, p, saved = ctx.saved_tensors
         ga, gp = ops.mnrl_backward(a, p, ctx.scale, saved, grad_out)
         return ga, gp, None

@@ -321,6 +321,32 @@ def mnrl_forward(anchors: torch.Tensor, positives: torch.Tensor, scale: float):
     return loss, saved
 
 
+def mnrl_forward_backward(anchors: torch.Tensor, positives: torch.Tensor, scale: float):
+    """(loss, grad_anchors, grad_positives) with the gradients taken for dL/dloss = 1: one library call for a training step."""
+    _require_cuda("anchors", anchors)
+    _require_cuda("positives", positives)
+    if anchors.dtype != positives.dtype or anchors.shape != positives.shape:
+        raise ValueError("anchors and positives must share dtype and shape [B, D]")
+    a, p = _fast_rows(anchors), _fast_rows(positives)
+    B, D = a.shape
+    dev = a.device
+    lib = _lib.load()
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    saved = torch.empty(3 * B, dtype=torch.float32, device=dev)
+    grads = torch.empty(2, B, D, dtype=a.dtype, device=dev)
+    base = saved.data_ptr()
+    gbytes = B * D * a.element_size()
+    with _on(dev):
+        ws = _workspace(lib.icr_mnrl_workspace_bytes(B, D), dev)
+        _lib.check(
+            lib.icr_mnrl_fwd_bwd(a.data_ptr(), _ld(a), p.data_ptr(), _ld(p), B, D, _dtype_code(a), float(scale), loss.data_ptr(),
+                                 base, base + 4 * B, base + 8 * B, grads.data_ptr(), D, grads.data_ptr() + gbytes, D,
+                                 ws.data_ptr(), ws.numel(), _stream(dev))
+        )
+    D0 = anchors.shape[1]
+    return (loss, grads[0][:, :D0], grads[1][:, :D0]) if D0 != D else (loss, grads[0], grads[1])
+
+
 def mnrl_backward(anchors: torch.Tensor, positives: torch.Tensor, scale: float, saved: torch.Tensor, grad_out: torch.Tensor):
     a, p = _fast_rows(anchors), _fast_rows(positives)
     B, D = a.shape

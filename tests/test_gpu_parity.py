@@ -484,12 +484,13 @@ def test_mnrl_forward_backward_vs_autograd(dtype, B, D, scale):
     rl, rga, rgp = oracle.mnrl_loss_and_grads(a.float(), p.float(), scale)
     assert loss.dtype == torch.float32
     assert abs(loss.item() - rl.item()) <= MNRL_ATOL
-    tol = MNRL_ATOL if dtype == torch.float32 else MNRL_ATOL + 2 ** -8 * rga.abs().max().item() * 1.7  # bf16 output rounding
+    # bf16 gradients are rounded when the step's one library call writes them (for dL/dloss = 1) and again after the scaling by the incoming gradient
+    tol = MNRL_ATOL if dtype == torch.float32 else MNRL_ATOL + 2 ** -7 * rga.abs().max().item() * 1.7
     assert (ad.grad.float().cpu() - 1.7 * rga).abs().max() <= tol
     assert (pd.grad.float().cpu() - 1.7 * rgp).abs().max() <= tol
     # gradients shrink like 1/B, so the absolute bound alone says little for large batches: also bound the error
     # relative to the largest gradient entry (fp16 operands of the gradient products: 2^-11 per element)
-    rel = 2e-3 if dtype == torch.float32 else 2e-3 + 2 ** -8
+    rel = 2e-3 if dtype == torch.float32 else 2e-3 + 2 ** -7
     assert (ad.grad.float().cpu() - 1.7 * rga).abs().max() <= rel * 1.7 * rga.abs().max()
     assert (pd.grad.float().cpu() - 1.7 * rgp).abs().max() <= rel * 1.7 * rgp.abs().max()
 
@@ -521,6 +522,28 @@ def test_mnrl_rectangular_gathered_candidates_vs_autograd(dtype, B, Bc, off, D, 
         assert err <= ((2e-3 if Bc >= 64 else 8e-3) + out_round) * 1.3 * want.abs().max().item()  # fp16 operands, few terms to average over
     with pytest.raises(ValueError):
         ops.mnrl_forward_rect(ad, cd, scale, Bc - B + 1)  # the positives would fall off the end of the candidates
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B", [48, 256, 640])
+def test_mnrl_one_call_step_equals_separate_forward_and_backward(dtype, B):
+    """icr_mnrl_fwd_bwd (what a training step uses) == icr_mnrl_fwd followed by icr_mnrl_bwd with the same dL/dloss,
+    on both kernel families; a loss computed without gradients takes the forward-only entry point."""
+    g = torch.Generator().manual_seed(B)
+    a = torch.randn(B, 384, generator=g).to(dtype).cuda()
+    p = (torch.randn(B, 384, generator=g) * 2).to(dtype).cuda()
+    loss1, ga1, gp1 = ops.mnrl_forward_backward(a, p, 20.0)
+    loss0, saved = ops.mnrl_forward(a, p, 20.0)
+    go = torch.tensor(1.0, device="cuda")
+    ga0, gp0 = ops.mnrl_backward(a, p, 20.0, saved, go)
+    assert abs(loss1.item() - loss0.item()) <= 1e-6
+    tol = 1e-7 if dtype == torch.float32 else 2 ** -8 * ga0.float().abs().max().item()
+    assert (ga1.float() - ga0.float()).abs().max().item() <= tol and (gp1.float() - gp0.float()).abs().max().item() <= tol
+    with torch.no_grad():
+        assert abs(icr.mnrl_loss(a, p, 20.0).item() - loss0.item()) <= 1e-6
+    ar = a.clone().requires_grad_(True)
+    (icr.mnrl_loss(ar, p, 20.0) * 0.25).backward()  # only one side needs a gradient, scaled dL/dloss
+    assert (ar.grad.float() - 0.25 * ga0.float()).abs().max().item() <= tol + 1e-7
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
