@@ -105,6 +105,31 @@ def topk_case(name, N, D, Q, k, dtype, path=ops.PATH_AUTO, iters=20, eager=False
     torch.cuda.empty_cache()
 
 
+def c1_rotating_case(dtype, k=10, copies=6, iters=60):
+    """C1 batch-1 with the catalog HBM-cold but the L2 CLEAN: rotate through `copies` replicas of the catalog (6 x 76 MB
+    fp32 >> the 126 MB L2) instead of zeroing a flush buffer, whose dirty lines have to be written back while the next
+    request streams in (the flush variant charges that write traffic to the request)."""
+    N, D = 49_688, 384
+    rows = unit_rows(N, D, dtype, 1234)
+    cats = [icr.DeviceCatalog(rows.clone(), dtype=dtype) for _ in range(copies)]
+    q = unit_rows(1, D, dtype, 4321)
+    state = {"i": 0}
+
+    def fn():
+        c = cats[state["i"] % copies]
+        state["i"] += 1
+        return c.topk(q, k)
+
+    med, best = time_gpu(fn, iters=iters, warmup=2 * copies, cold=False)
+    esz = 4 if dtype == torch.float32 else 2
+    floor = N * D * esz / HBM
+    record(f"C1 batch-1 top-{k} (HBM-cold, clean L2: {copies} rotating catalog copies)", N=N, D=D, Q=1, k=k, dtype=str(dtype).split(".")[-1],
+           kernel="gemv_topk", ms=med, ms_min=best, qps=1 / (med * 1e-3), kernel_ms=0.0, kernel_launches=1, bound="hbm",
+           roofline_frac_call=floor / (med * 1e-3), roofline_frac_kernel=None, hbm_gbs_kernel=None, tflops_kernel=None, l2="cold, clean")
+    del cats
+    torch.cuda.empty_cache()
+
+
 def mnrl_case(B, D, scale, dtype):
     g = torch.Generator(device=DEV).manual_seed(2024)
     a = torch.randn(B, D, device=DEV, generator=g).to(dtype).requires_grad_(True)
@@ -143,6 +168,7 @@ def main():
             for k in (10, 100):
                 topk_case(f"C1 batch-1 top-{k}", 49_688, 384, 1, k, dt, iters=50, eager=(k == 10), cold=True)
             topk_case("C1 batch-1 top-10 (L2-warm)", 49_688, 384, 1, 10, dt, iters=50, cold=False)
+            c1_rotating_case(dt)
             topk_case("C1 batch-1 top-10, CUDA graph", 49_688, 384, 1, 10, dt, iters=50, cold=True, graph=True)
             topk_case("C1 batch-1 top-10, CUDA graph (L2-warm)", 49_688, 384, 1, 10, dt, iters=50, cold=False, graph=True)
         for Q in (2, 4, 7, 8, 16, 32, 64, 128, 256):
@@ -155,7 +181,7 @@ def main():
         topk_case("C2 real query count", 49_688, 384, 13_120, 100, f32)
     if on("c3"):
         for dt in (bf16, f32):
-            for B in (64, 256, 1024) if args.quick else (64, 256, 1024, 4096):
+            for B in (64, 256, 1024) if args.quick else (64, 256, 1024, 4096, 8192):
                 mnrl_case(B, 384, 20.0, dt)
         mnrl_case(256, 384, 30.0, f32)
     if on("c4"):
