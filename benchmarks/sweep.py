@@ -130,6 +130,24 @@ def c1_rotating_case(dtype, k=10, copies=6, iters=60):
     torch.cuda.empty_cache()
 
 
+def cpu_scaled_case(name, N_full, D, Q, k, N_sample=1_000_000):
+    """The reference's CPU path (oracle port: cos_sim + torch.topk) on a down-scaled catalog, extrapolated linearly in N
+    (C4 / C5 do not fit a CPU run at full size)."""
+    import os
+
+    from oracle import oracle
+
+    items = oracle.synth_isotropic(N_sample, D, 1234)
+    queries = oracle.synth_isotropic(Q, D, 4321)
+    oracle.cos_topk(queries[: min(Q, 8)], items[:10000], k)
+    t0 = time.perf_counter()
+    oracle.cos_topk(queries, items, k, sorted=False)
+    dt = time.perf_counter() - t0
+    scale = N_full / N_sample
+    record(name, cpu_ms_sample=dt * 1e3, N_sample=N_sample, N_full=N_full, D=D, Q_cpu=Q, k=k, cpu_ms_extrapolated=dt * 1e3 * scale,
+           cpu_qps_extrapolated=Q / (dt * scale), threads=torch.get_num_threads(), host_cpus=os.cpu_count())
+
+
 def mnrl_case(B, D, scale, dtype):
     g = torch.Generator(device=DEV).manual_seed(2024)
     a = torch.randn(B, D, device=DEV, generator=g).to(dtype).requires_grad_(True)
@@ -194,6 +212,11 @@ def main():
     if on("c5"):
         topk_case("C5 shard (1/8 of 100M x 384) Q=4096", 12_500_000, 384, 4096, 100, bf16, iters=5)
 
+    if on("cpu"):
+        cpu_scaled_case("C4 on the CPU (1M-row sample of 10M x 768, Q=64)", 10_000_000, 768, 64, 100)
+        cpu_scaled_case("C4 on the CPU (1M-row sample of 10M x 768, Q=1)", 10_000_000, 768, 1, 100)
+        cpu_scaled_case("C5 on the CPU (1M-row sample of 100M x 384, Q=256 of 4096)", 100_000_000, 384, 256, 100)
+
     lines = ["# sweep on one B200 (`benchmarks/sweep.py`)", "", f"peaks: HBM {PEAKS['hbm_gbs']} GB/s, bf16 {PEAKS['bf16_tflops']} TFLOP/s (MEASURED_PEAKS.json)", ""]
     tk = [r for r in ROWS if "qps" in r]
     if tk:
@@ -211,6 +234,11 @@ def main():
         lines += ["", "| config | dtype | scale | ours µs (median / min) | torch eager µs (median / min) | speed-up |", "|---|---|---|---|---|---|"]
         for r in mn:
             lines.append(f"| {r['config']} | {r['dtype']} | {r['scale']} | {r['ours_us']:.1f} / {r['ours_min_us']:.1f} | {r['torch_eager_us']:.1f} / {r['torch_eager_min_us']:.1f} | {r['speedup']:.2f}x |")
+    cp = [r for r in ROWS if "cpu_ms_sample" in r]
+    if cp:
+        lines += ["", "| config | threads | CPU ms on the sample | extrapolated to full N (ms) | extrapolated queries/s |", "|---|---|---|---|---|"]
+        for r in cp:
+            lines.append(f"| {r['config']} | {r['threads']} | {r['cpu_ms_sample']:.0f} | {r['cpu_ms_extrapolated']:.0f} | {r['cpu_qps_extrapolated']:.3g} |")
     Path(args.out).parent.mkdir(parents=True, exist_ok=True)
     Path(args.out).write_text("\n".join(lines) + "\n")
     print("wrote", args.out)
