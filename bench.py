@@ -124,6 +124,12 @@ def run_reference(args, rank: int):
 
     from oracle import oracle
 
+    # all the host threads the process may use: torchrun exports OMP_NUM_THREADS=1 to its workers, which would time a
+    # single-threaded CPU baseline whenever the driver launches this arm with N > 1
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except (AttributeError, OSError):
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
     sample = 500
     items = oracle.synth_isotropic(C2["N"], C2["D"], CATALOG_SEED)
     queries = oracle.synth_isotropic(sample, C2["D"], QUERY_SEED)
