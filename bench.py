@@ -376,9 +376,7 @@ def bench_sharded(icr, dist, dev, rank, world, args, tdtype):
         s1 = min(shard_rows, s0 + (1 << 20))
         rows[s0:s1] = torch.nn.functional.normalize(torch.randn(s1 - s0, D, device=dev, generator=g), dim=1).to(torch.bfloat16)
     cat = icr.ShardedCatalog(rows, row_offset=lo, total_rows=total_rows, dtype=torch.bfloat16, exchange="peer")
-    cat_nccl = icr.ShardedCatalog.__new__(icr.ShardedCatalog)  # same resident shard, NCCL all-gather instead of the peer-memory kernel
-    cat_nccl.__dict__.update(cat.__dict__)
-    cat_nccl.exchange, cat_nccl._peer = "nccl", None
+    cat_nccl = cat.with_exchange("nccl")  # same resident shard, NCCL all-gather instead of the peer-memory kernel
     g2 = torch.Generator(device=dev).manual_seed(QUERY_SEED)
     q = torch.nn.functional.normalize(torch.randn(Q, D, device=dev, generator=g2), dim=1).to(torch.bfloat16)
     steps = 5

@@ -16,7 +16,10 @@
 
 namespace icr {
 
-constexpr int kHsWarps = 4;       // queries per CTA (11 KB of shared memory each: 5 CTAs = 20 warps per SM)
+#ifndef ICR_HS_WARPS
+#define ICR_HS_WARPS 4
+#endif
+constexpr int kHsWarps = ICR_HS_WARPS;  // queries per CTA, 11 KB of shared memory each (tuning: profiles/r01_notes.md)
 constexpr int kHsCap = 1024;      // keys buffered per query at once
 constexpr int kHsSel = 256;       // >= ICR_MAX_K
 constexpr int kHsPref = 448;      // segments per gather round: the prefix array (+1) is overlaid on sel[] (512 ints)

@@ -351,6 +351,15 @@ def _pinned_stage(slot: int, rows: int, cols: int, dtype: torch.dtype) -> torch.
     return buf[:need].view(dtype).view(rows, cols)
 
 
+def release_staging() -> None:
+    """Free the pinned staging buffers and the copy threads kept between loads (they are re-created on demand)."""
+    global _copy_pool
+    _PINNED.clear()
+    if _copy_pool is not None:
+        _copy_pool.shutdown(wait=True)
+        _copy_pool = None
+
+
 def _host_copy(dst: np.ndarray, src: np.ndarray) -> None:
     """dst[:] = src with a few threads: numpy releases the GIL while copying, and one core moves only ~8 GB/s out of
     the page cache — less than the PCIe link the staging buffer feeds."""

@@ -122,7 +122,8 @@ class ShardedCatalog:
         self._local_topk = _local_topk
         self._merge = _merge
         if _local_topk is None:
-            self.local = DeviceCatalog(local_rows, device=device, dtype=dtype, row_offset=row_offset)
+            # an already resident shard (DeviceCatalog.from_index) is taken as is
+            self.local = local_rows if isinstance(local_rows, DeviceCatalog) else DeviceCatalog(local_rows, device=device, dtype=dtype, row_offset=row_offset)
             self.n_local = len(self.local)
             self.device = self.local.device
         else:
@@ -148,13 +149,17 @@ class ShardedCatalog:
         local = DeviceCatalog.from_index(index, product_ids, dtype=dtype, device=device, rows=(lo, hi), **load_kw)
         if local is None:
             return None
-        self = cls.__new__(cls)
-        self.exchange, self._peer = exchange, None
-        self.group, self.world_size, self.rank = group, ws, rk
-        self.total_rows, self.row_offset = len(product_ids), lo
-        self._local_topk = self._merge = None
-        self.local, self.n_local, self.device = local, len(local), local.device
-        return self
+        return cls(local, row_offset=lo, total_rows=len(product_ids), group=group, dtype=dtype, device=device, exchange=exchange)
+
+    def with_exchange(self, exchange: str) -> "ShardedCatalog":
+        """The same resident shard behind the other candidate exchange ("nccl" / "peer"): for A/B measurements."""
+        import copy
+
+        other = copy.copy(self)
+        if exchange not in ("nccl", "peer"):
+            raise ValueError("exchange must be 'nccl' or 'peer'")
+        other.exchange, other._peer = exchange, None
+        return other
 
     def local_topk(self, queries, k: int):
         """[Q,k] candidates of this shard with GLOBAL ids; short shards pad with (-inf, -1)."""
