@@ -184,6 +184,21 @@ def main():
     from instacart_next_order_recommendation_b200 import ops
 
     assert torch.cuda.is_available(), "bench.py needs a B200"
+    if world > 1 and os.environ.get("ICR_BENCH_BIND", "1") != "0":
+        # pin this rank (and the pinned host buffers it allocates next) to the CPUs NVML reports as local to its GPU:
+        # with 8 ranks the end-to-end leg moves ~22 GB/s per rank across PCIe, and remote-socket staging costs bandwidth
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+            cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+            cpus &= os.sched_getaffinity(0)
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+        except Exception:
+            pass
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
