@@ -51,6 +51,10 @@ typedef enum {
   ICR_PATH_GEMV = 1, /* K1: streaming CUDA-core GEMV + fused top-k, small query batches */
   ICR_PATH_GEMM = 2  /* K2: tcgen05/TMEM GEMM + threshold-filter epilogue                */
 } icr_path;
+/* OR-ed into `path`: the workspace is RESIDENT — the caller zero-filled it once and since then only icr_cos_topk calls of
+ * the same shape, on one stream, have used it. The GEMV path then skips re-zeroing its merge counter (the merging CTA
+ * leaves it at zero): one memset less on the latency path of a request. */
+#define ICR_PATH_WS_RESIDENT 0x100
 
 int icr_abi_version(void);
 const char* icr_last_error_string(void);

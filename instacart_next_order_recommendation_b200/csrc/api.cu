@@ -235,6 +235,7 @@ static int resolve_path(int path, int64_t Q, int64_t N, int64_t D, int dtype, in
 }
 
 size_t icr_cos_topk_workspace_bytes(int64_t Q, int64_t N, int64_t D, int dtype, int k, int path, int have_planes) {
+  path &= ~ICR_PATH_WS_RESIDENT;
   if (Q <= 0 || N <= 0 || k <= 0) return 256;
   if (path == ICR_PATH_AUTO) {
     const size_t a = gemv_ws_bytes(Q, N, k);
@@ -268,6 +269,8 @@ int icr_cos_topk(const void* queries, int64_t Q, int64_t ldq, const void* catalo
   if ((rc = check_device())) return rc;
   if (Q == 0) return ICR_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool ws_resident = (path & ICR_PATH_WS_RESIDENT) != 0;
+  path &= ~ICR_PATH_WS_RESIDENT;
   const int p = resolve_path(path, Q, N, D, dtype, k, exclude_mask);
   const size_t need = icr_cos_topk_workspace_bytes(Q, N, D, dtype, k, p, cat_planes != nullptr);
   if (workspace_bytes < need || (need > 256 && !workspace)) {
@@ -306,7 +309,7 @@ int icr_cos_topk(const void* queries, int64_t Q, int64_t ldq, const void* catalo
   unsigned int* done_counter = reinterpret_cast<unsigned int*>(w);
   const size_t esz = elem_size(dtype);
   // the last CTA of every GEMV launch merges the per-CTA lists itself (no select launch on the latency path)
-  ICR_CUDA_CHECK(cudaMemsetAsync(done_counter, 0, sizeof(unsigned int), st));
+  if (!ws_resident) ICR_CUDA_CHECK(cudaMemsetAsync(done_counter, 0, sizeof(unsigned int), st));
   for (int64_t q0 = 0; q0 < Q; q0 += qc) {
     const int nq = static_cast<int>(Q - q0 < qc ? Q - q0 : qc);
     const char* qptr = static_cast<const char*>(queries) + q0 * ldq * esz;

@@ -11,7 +11,7 @@ import contextlib
 import torch
 
 from . import _lib
-from ._lib import ICR_BF16, ICR_F32, MAX_K, PATH_AUTO, PATH_GEMM, PATH_GEMV  # noqa: F401
+from ._lib import ICR_BF16, ICR_F32, MAX_K, PATH_AUTO, PATH_GEMM, PATH_GEMV, PATH_WS_RESIDENT  # noqa: F401
 
 _DTYPES = {torch.float32: ICR_F32, torch.bfloat16: ICR_BF16}
 
@@ -150,6 +150,7 @@ def cos_topk(
     row_offset: int = 0,
     path: int = PATH_AUTO,
     out: tuple[torch.Tensor, torch.Tensor] | None = None,
+    workspace: torch.Tensor | None = None,
 ):
     """(values f32 [Q,k] descending, ids int64 [Q,k]) == torch.topk(cos_sim(q, c), k, dim=1)."""
     _require_cuda("queries", queries)
@@ -182,7 +183,13 @@ def cos_topk(
         vals, ids = out
     with _on(dev):
         need = lib.icr_cos_topk_workspace_bytes(Q, N, D, dt, k, path, int(cat_planes is not None))
-        ws = _workspace(need, dev)
+        if workspace is not None:
+            # resident workspace (zero-filled once by its owner, reused call after call on one stream): no merge-counter memset
+            if workspace.numel() < need or workspace.dtype != torch.uint8 or workspace.device != dev:
+                raise ValueError(f"resident workspace must be a uint8 tensor of >= {need} bytes on {dev}")
+            ws, path = workspace, path | PATH_WS_RESIDENT
+        else:
+            ws = _workspace(need, dev)
         _lib.check(
             lib.icr_cos_topk(
                 queries.data_ptr(), Q, _ld(queries), catalog.data_ptr(), N, _ld(catalog), D, dt, _ptr(cat_planes), _ptr(cat_inv_norms),
