@@ -321,6 +321,30 @@ def test_recommender_dropin_matches_reference_golden(golden_dir, tmp_path):
     assert DeviceEnc.calls >= 20 and rec4._query_on_device is False
 
 
+def test_import_swap_with_cached_host_catalog(monkeypatch):
+    """cos_sim(query_emb, product_embeddings) with the reference's numpy catalog; with
+    ICR_CACHE_HOST_OPERANDS=1 the device copy is reused between requests and refreshed when the array changes."""
+    from instacart_next_order_recommendation_b200 import similarity
+
+    monkeypatch.setenv("ICR_CACHE_HOST_OPERANDS", "1")
+    similarity._HOST_CACHE.clear()
+    items = oracle.synth_clustered(4000, 384, seed=5)[0].numpy()  # 6 MB: above the caching threshold
+    q = oracle.synth_isotropic(1, 384, seed=6).numpy()[0]
+    s1 = icr.cos_sim(q, items)
+    assert len(similarity._HOST_CACHE) == 1
+    dev_copy = next(iter(similarity._HOST_CACHE.values()))[1]
+    s2 = icr.cos_sim(q, items)
+    assert next(iter(similarity._HOST_CACHE.values()))[1] is dev_copy and torch.equal(s1, s2)
+    ref = oracle.cos_sim(q, items)
+    assert (s1.cpu() - ref).abs().max() < 1e-6
+    order = s1[0].argsort(descending=True)  # the reference's next line (serve_recommendations.py:215)
+    assert int(order[0]) == int(ref[0].argmax())
+    items[:] = np.roll(items, 1, axis=0)  # rewritten in place: the sample check notices and uploads again
+    s3 = icr.cos_sim(q, items)
+    assert (s3.cpu() - oracle.cos_sim(q, items)).abs().max() < 1e-6
+    similarity._HOST_CACHE.clear()
+
+
 def test_ir_evaluator_and_rank_all_against_oracle(golden_dir):
     z = np.load(golden_dir / "embeddings_small.npz")
     gold = json.loads((golden_dir / "metrics_golden.json").read_text())
