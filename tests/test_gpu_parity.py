@@ -321,6 +321,24 @@ def test_recommender_dropin_matches_reference_golden(golden_dir, tmp_path):
     assert DeviceEnc.calls >= 20 and rec4._query_on_device is False
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_resident_workspace_skips_the_counter_reset_safely(dtype):
+    """ICR_PATH_WS_RESIDENT: a workspace zero-filled once and reused call after call gives the same answers as a fresh
+    workspace per call (the merging CTA of K1 leaves its counter at zero), for changing queries and batch sizes 1-7."""
+    items = oracle.synth_unnormalised(30000, 384, seed=1).to(dtype).cuda()
+    lib = ops._lib.load()
+    for Q in (1, 3, 7):
+        need = lib.icr_cos_topk_workspace_bytes(Q, 30000, 384, ops._dtype_code(items), 10, ops.PATH_GEMV, 0)
+        ws = torch.zeros(need, dtype=torch.uint8, device="cuda")
+        for rep in range(4):
+            q = oracle.synth_unnormalised(Q, 384, seed=50 + rep).to(dtype).cuda()
+            v0, i0 = ops.cos_topk(q, items, 10, path=ops.PATH_GEMV)
+            v1, i1 = ops.cos_topk(q, items, 10, path=ops.PATH_GEMV, workspace=ws)
+            assert torch.equal(v0, v1) and torch.equal(i0, i1)
+    with pytest.raises(ValueError):
+        ops.cos_topk(q, items, 10, path=ops.PATH_GEMV, workspace=torch.zeros(16, dtype=torch.uint8, device="cuda"))
+
+
 def test_import_swap_with_cached_host_catalog(monkeypatch):
     """cos_sim(query_emb, product_embeddings) with the reference's numpy catalog; with
     ICR_CACHE_HOST_OPERANDS=1 the device copy is reused between requests and refreshed when the array changes."""
