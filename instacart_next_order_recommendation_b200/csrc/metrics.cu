@@ -67,12 +67,20 @@ __global__ void __launch_bounds__(256) ir_metrics_kernel(const MetricArgs g) {
   for (int m = lane; m < g.M; m += 32) {
     const int kind = g.kind[m], k = g.k[m];
     const int kk = k < g.K ? k : g.K;
+    // walk the HITS only (set bits in rank order: the same summation order as the reference's loops over ranks);
+    // counts come from population counts of the masks cut at rank kk
     int cum = 0, len = 0, first = -1;
     double dcg = 0.0, sum_prec = 0.0;
-    for (int r = 0; r < kk; ++r) {
-      const uint32_t bit = 1u << (r & 31);
-      len += (s_valid[wib][r >> 5] & bit) ? 1 : 0;
-      if (s_hit[wib][r >> 5] & bit) {
+#pragma unroll
+    for (int c = 0; c < kMaskWords; ++c) {
+      const int lo_r = c * 32;
+      if (lo_r >= kk) break;
+      const uint32_t cut = (kk - lo_r >= 32) ? 0xffffffffu : ((1u << (kk - lo_r)) - 1u);
+      len += __popc(s_valid[wib][c] & cut);
+      uint32_t h = s_hit[wib][c] & cut;
+      while (h) {
+        const int r = lo_r + __ffs(h) - 1;
+        h &= h - 1;
         ++cum;
         if (first < 0) first = r;
         dcg += 1.0 / log2(static_cast<double>(r + 2));
