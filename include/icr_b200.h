@@ -193,6 +193,10 @@ int icr_mnrl_fwd_bwd(const void* a, int64_t lda, const void* p, int64_t ldp,
                      float* loss, float* lse, float* inv_a, float* inv_p,
                      void* grad_a, int64_t ldga, void* grad_p, int64_t ldgp,
                      void* workspace, size_t workspace_bytes, void* stream);
+/* out = grad * grad_out[0] for the two [n]-element gradients of icr_mnrl_fwd_bwd (n = B * D, contiguous): what
+ * autograd's backward does with the incoming dL/dloss. grad_out is a device scalar. */
+int icr_mnrl_scale_grads(const void* grad_a, const void* grad_p, int64_t n, int dtype, const float* grad_out,
+                         void* out_a, void* out_p, void* stream);
 
 /* Rectangular form for cross-device in-batch negatives (sentence-transformers'
  * gather_across_devices=True; not enabled by the reference, src/training/train_sbert.py:184-185):

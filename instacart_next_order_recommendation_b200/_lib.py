@@ -66,6 +66,7 @@ SIGNATURES = {
         [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
          c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_size_t, c_void_p],
     ),
+    "icr_mnrl_scale_grads": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "icr_mnrl_rect_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "icr_mnrl_fwd_rect": (
         c_int,

@@ -85,6 +85,7 @@ static bool dense_use_gemm(int64_t Qa, int64_t Nb, int64_t D, int dtype) {
 }
 
 int launch_mnrl_dispatch(const MnrlArgs& g, int dtype, bool bwd, cudaStream_t st);
+int launch_scale2(const void* x0, const void* x1, int64_t n, int dtype, const float* s, void* o0, void* o1, cudaStream_t st);
 // tensor-core MNRL (mnrl_tc.cu)
 bool mnrl_tc_applies(int64_t B, int64_t Bc, int64_t D);
 size_t mnrl_tc_workspace_bytes(int64_t B, int64_t Bc, int64_t D);
@@ -567,6 +568,19 @@ int icr_mnrl_fwd_bwd(const void* a, int64_t lda, const void* p, int64_t ldp, int
   ICR_CUDA_CHECK(cudaMemsetAsync(g.counter, 0, sizeof(unsigned int), st));
   if ((rc = launch_mnrl_dispatch(g, dtype, false, st))) return rc;
   return launch_mnrl_dispatch(g, dtype, true, st);
+}
+
+// the autograd glue's only arithmetic: both gradients of icr_mnrl_fwd_bwd times the incoming dL/dloss (a device scalar)
+int icr_mnrl_scale_grads(const void* grad_a, const void* grad_p, int64_t n, int dtype, const float* grad_out, void* out_a, void* out_p,
+                         void* stream) {
+  g_launches = 0;
+  if (n < 0 || (dtype != ICR_F32 && dtype != ICR_BF16) || (n > 0 && (!grad_a || !grad_p || !grad_out || !out_a || !out_p))) {
+    set_error("mnrl_scale_grads: bad arguments (n=%lld dtype=%d)", (long long)n, dtype);
+    return ICR_ERR_ARG;
+  }
+  int rc;
+  if ((rc = check_device())) return rc;
+  return launch_scale2(grad_a, grad_p, n, dtype, grad_out, out_a, out_p, static_cast<cudaStream_t>(stream));
 }
 
 // ---- rectangular form: B anchors against Bc >= B candidates, the positive of anchor i at column i + label_offset ----

@@ -296,6 +296,32 @@ static int launch_mnrl(const MnrlArgs& g, bool bwd, cudaStream_t st) {
   return ICR_OK;
 }
 
+// out[i] = x[i] * s[0] for two equally sized buffers at once (the two gradients of a step scaled by the incoming dL/dloss)
+template <typename T>
+__global__ void __launch_bounds__(256) scale2_kernel(const T* __restrict__ x0, const T* __restrict__ x1, int64_t n, const float* __restrict__ s,
+                                                     T* __restrict__ o0, T* __restrict__ o1) {
+  const float f = s[0];
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    o0[i] = Elem<T>::from_f32(Elem<T>::to_f32(x0[i]) * f);
+    o1[i] = Elem<T>::from_f32(Elem<T>::to_f32(x1[i]) * f);
+  }
+}
+
+int launch_scale2(const void* x0, const void* x1, int64_t n, int dtype, const float* s, void* o0, void* o1, cudaStream_t st) {
+  if (n == 0) return ICR_OK;
+  const int64_t want = (n + 255) / 256;
+  const int blocks = static_cast<int>(want < 148 * 8 ? want : 148 * 8);
+  if (dtype == ICR_F32)
+    scale2_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(x0), static_cast<const float*>(x1), n, s, static_cast<float*>(o0),
+                                                 static_cast<float*>(o1));
+  else
+    scale2_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x0), static_cast<const __nv_bfloat16*>(x1), n, s,
+                                                         static_cast<__nv_bfloat16*>(o0), static_cast<__nv_bfloat16*>(o1));
+  ICR_LAUNCH_CHECK();
+  return ICR_OK;
+}
+
 int launch_mnrl_dispatch(const MnrlArgs& g, int dtype, bool bwd, cudaStream_t st) {
   const int vec = dtype == ICR_F32 ? 4 : 8;
   const int nvec = g.D / vec;

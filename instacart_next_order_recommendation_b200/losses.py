@@ -29,8 +29,9 @@ class _FusedMNRL(torch.autograd.Function):
         if ctx.fused:
             # a training step wants the gradients anyway: one library call computes the loss and d loss / d (A, P) for
             # dL/dloss = 1 (one prep and one host round trip instead of two); backward() only scales them
-            loss, ga, gp = ops.mnrl_forward_backward(a, p, scale)
-            ctx.save_for_backward(ga, gp)
+            loss, grads = ops.mnrl_forward_backward(a, p, scale)
+            ctx.save_for_backward(grads)
+            ctx.dim = a.shape[1]
             return loss
         loss, saved = ops.mnrl_forward(a, p, scale)
         ctx.save_for_backward(a, p, saved)
@@ -39,9 +40,11 @@ class _FusedMNRL(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         if ctx.fused:
-            ga, gp = ctx.saved_tensors
-            go = grad_out.to(dtype=torch.float32)
-            return (ga * go).to(ga.dtype), (gp * go).to(gp.dtype), None
+            (grads,) = ctx.saved_tensors
+            out = ops.mnrl_scale_grads(grads, grad_out)  # the only arithmetic of backward: one launch for both gradients
+            if out.shape[2] != ctx.dim:  # embedding dim was padded to the vector width
+                return out[0][:, : ctx.dim], out[1][:, : ctx.dim], None
+            return out[0], out[1], None
         a, p, saved = ctx.saved_tensors
         ga, gp = ops.mnrl_backward(a, p, ctx.scale, saved, grad_out)
         return ga, gp, None

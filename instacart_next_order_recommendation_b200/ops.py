@@ -350,8 +350,23 @@ def mnrl_forward_backward(anchors: torch.Tensor, positives: torch.Tensor, scale:
                                  base, base + 4 * B, base + 8 * B, grads.data_ptr(), D, grads.data_ptr() + gbytes, D,
                                  ws.data_ptr(), ws.numel(), _stream(dev))
         )
-    D0 = anchors.shape[1]
-    return (loss, grads[0][:, :D0], grads[1][:, :D0]) if D0 != D else (loss, grads[0], grads[1])
+    return loss, grads  # grads[0] = d loss / d anchors, grads[1] = d loss / d positives, [2, B, D (padded)]
+
+
+def mnrl_scale_grads(grads: torch.Tensor, grad_out: torch.Tensor) -> torch.Tensor:
+    """grads * grad_out for the [2, B, D] gradient pair of mnrl_forward_backward, one launch; `grads` is left untouched."""
+    dev = grads.device
+    go = grad_out
+    if not (go.is_cuda and go.dtype == torch.float32 and go.is_contiguous()):
+        go = go.detach().to(device=dev, dtype=torch.float32).contiguous()
+    out = torch.empty_like(grads)
+    half = grads.numel() // 2
+    nbytes = half * grads.element_size()
+    lib = _lib.load()
+    with _on(dev):
+        _lib.check(lib.icr_mnrl_scale_grads(grads.data_ptr(), grads.data_ptr() + nbytes, half, _dtype_code(grads), go.data_ptr(),
+                                            out.data_ptr(), out.data_ptr() + nbytes, _stream(dev)))
+    return out
 
 
 def mnrl_backward(anchors: torch.Tensor, positives: torch.Tensor, scale: float, saved: torch.Tensor, grad_out: torch.Tensor):

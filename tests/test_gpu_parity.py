@@ -574,7 +574,9 @@ def test_mnrl_one_call_step_equals_separate_forward_and_backward(dtype, B):
     g = torch.Generator().manual_seed(B)
     a = torch.randn(B, 384, generator=g).to(dtype).cuda()
     p = (torch.randn(B, 384, generator=g) * 2).to(dtype).cuda()
-    loss1, ga1, gp1 = ops.mnrl_forward_backward(a, p, 20.0)
+    loss1, grads1 = ops.mnrl_forward_backward(a, p, 20.0)
+    ga1, gp1 = grads1[0], grads1[1]
+    assert torch.equal(ops.mnrl_scale_grads(grads1, torch.tensor(0.5, device="cuda")).float(), (grads1.float() * 0.5).to(dtype).float())
     loss0, saved = ops.mnrl_forward(a, p, 20.0)
     go = torch.tensor(1.0, device="cuda")
     ga0, gp0 = ops.mnrl_backward(a, p, 20.0, saved, go)
