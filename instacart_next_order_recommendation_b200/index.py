@@ -164,8 +164,14 @@ class DeviceCatalog:
         if dtype not in (torch.float32, torch.bfloat16):
             raise TypeError("catalog dtype must be float32 or bfloat16")
         dev = device if device is not None else (embeddings.device if isinstance(embeddings, torch.Tensor) and embeddings.is_cuda else default_device())
-        self.rows = to_device_matrix(embeddings, device=dev, dtype=dtype)
-        self.rows = ops._rows(self.rows)
+        rows = to_device_matrix(embeddings, device=dev)  # uploaded in the dtype it has (float64 / float16 become float32)
+        if rows.dtype != dtype:
+            if rows.dtype == torch.float32 and rows.dim() == 2 and rows.shape[1] % 4 == 0 and rows.shape[0] > 0:
+                rows = ops._rows(rows)
+                rows = ops.convert_rows(rows, torch.empty(rows.shape, dtype=dtype, device=dev))  # fp32 -> bf16 on the device (RNE)
+            else:
+                rows = rows.to(dtype)
+        self.rows = ops._rows(rows)
         self.row_offset = int(row_offset)
         self.planes: torch.Tensor | None = None
         if build_planes is None:
