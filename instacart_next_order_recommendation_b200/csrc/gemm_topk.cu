@@ -820,7 +820,8 @@ struct Phase {
 static int plan_phases(int64_t N, int qblocks, int k, Phase* out, int max_phases, bool swap, int begin0 = 0) {
   const int T = static_cast<int>((N + BN - 1) / BN);
   static const int swap_growth = getenv("ICR_SWAP_GROWTH") ? atoi(getenv("ICR_SWAP_GROWTH")) : 32;  // tuning hook
-  const int growth = swap ? swap_growth : 8;
+  static const int k2_growth = getenv("ICR_K2_GROWTH") ? atoi(getenv("ICR_K2_GROWTH")) : 8;  // tuning hook
+  const int growth = swap ? swap_growth : k2_growth;
   const int npairs = kNumSMs / 2;
   static const int k2_first = getenv("ICR_K2_FIRST") ? atoi(getenv("ICR_K2_FIRST")) : 4;  // tuning hook
   int first = (2 * k + BN - 1) / BN;
@@ -869,7 +870,9 @@ static int plan_phases(int64_t N, int qblocks, int k, Phase* out, int max_phases
 }
 
 constexpr int kMaxPhases = 16;
-constexpr int kDense0Tiles = 4;  // rows 0..1023 are scored densely in the first phase of the (non-swapped) top-k path
+// rows 0..1023 (4 tiles) are scored densely in the first phase of the (non-swapped) top-k path; ICR_K2_DENSE0 / ICR_K2_GROWTH:
+// tuning hooks (profiles/r01_notes.md)
+static const int kDense0Tiles = getenv("ICR_K2_DENSE0") ? atoi(getenv("ICR_K2_DENSE0")) : 4;
 
 // launches the DENSE instantiation `which` (0 planes, 1 bf16 streaming, 2 bf16 resident queries)
 static int launch_dense_variant(int which, int grid, const CUtensorMap& map_a, const CUtensorMap& map_b, const GemmArgs& g, cudaStream_t st) {
