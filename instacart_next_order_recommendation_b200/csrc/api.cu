@@ -378,8 +378,16 @@ int icr_topk_merge(const float* cand_scores, const int64_t* cand_ids, int64_t Q,
   return launch_merge_lists(cand_scores, cand_ids, Q, G, k_in, k_out, out_scores, out_ids, static_cast<cudaStream_t>(stream));
 }
 
+// the CUDA-core kernels hold a row slice per lane: D <= 768 (f32) / 1536 (bf16); wider rows take the tensor path at any batch size
+static bool mnrl_use_tc(int64_t B, int64_t D, int dtype) {
+  if (mnrl_tc_applies(B, B, D)) return true;
+  const int64_t simt_max = dtype == ICR_F32 ? 768 : 1536;
+  return D > simt_max && D % 8 == 0 && D <= 4096 && B >= 2;
+}
+
 size_t icr_mnrl_workspace_bytes(int64_t B, int64_t D) {
-  if (B > 0 && D > 0 && mnrl_tc_applies(B, B, D)) return mnrl_tc_workspace_bytes(B, B, D);
+  // sized for either element type: the wider-row rule differs between them, the tensor path's need is the larger one
+  if (B > 0 && D > 0 && (mnrl_use_tc(B, D, ICR_F32) || mnrl_use_tc(B, D, ICR_BF16))) return mnrl_tc_workspace_bytes(B, B, D);
   return align_up(static_cast<size_t>(B > 0 ? B : 0) * sizeof(float), 256) + 256;
 }
 
@@ -423,7 +431,7 @@ int icr_mnrl_fwd(const void* a, int64_t lda, const void* p, int64_t ldp, int64_t
   g.counter = static_cast<unsigned int*>(workspace);
   g.row_loss = reinterpret_cast<float*>(static_cast<char*>(workspace) + 256);
   g.loss = loss;
-  if (mnrl_tc_applies(B, B, D)) return launch_mnrl_tc(g, dtype, 0, workspace, workspace_bytes, st);
+  if (mnrl_use_tc(B, D, dtype)) return launch_mnrl_tc(g, dtype, 0, workspace, workspace_bytes, st);
   ICR_CUDA_CHECK(cudaMemsetAsync(g.counter, 0, sizeof(unsigned int), st));
   return launch_mnrl_dispatch(g, dtype, false, st);
 }
@@ -454,7 +462,7 @@ int icr_mnrl_bwd(const void* a, int64_t lda, const void* p, int64_t ldp, int64_t
   g.grad_p = grad_p;
   g.ldga = ldga;
   g.ldgp = ldgp;
-  if (mnrl_tc_applies(B, B, D)) return launch_mnrl_tc(g, dtype, 1, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+  if (mnrl_use_tc(B, D, dtype)) return launch_mnrl_tc(g, dtype, 1, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
   return launch_mnrl_dispatch(g, dtype, true, static_cast<cudaStream_t>(stream));
 }
 
@@ -562,7 +570,7 @@ int icr_mnrl_fwd_bwd(const void* a, int64_t lda, const void* p, int64_t ldp, int
   g.grad_p = grad_p;
   g.ldga = ldga;
   g.ldgp = ldgp;
-  if (mnrl_tc_applies(B, B, D)) return launch_mnrl_tc(g, dtype, 2, workspace, workspace_bytes, st);
+  if (mnrl_use_tc(B, D, dtype)) return launch_mnrl_tc(g, dtype, 2, workspace, workspace_bytes, st);
   g.counter = static_cast<unsigned int*>(workspace);
   g.row_loss = reinterpret_cast<float*>(static_cast<char*>(workspace) + 256);
   ICR_CUDA_CHECK(cudaMemsetAsync(g.counter, 0, sizeof(unsigned int), st));

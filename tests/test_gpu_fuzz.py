@@ -5,6 +5,8 @@ smaller than k, ring kernels with few slabs per CTA, masks, row offsets, un-norm
 (precomputed norms / planes) and raw tensors, on the GEMV, GEMM and automatically chosen paths.
 """
 
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -37,7 +39,12 @@ def _cases(n, seed, big=False):
     return out
 
 
-@pytest.mark.parametrize("case", _cases(72, 20261018) + [(100 + c[0],) + c[1:] for c in _cases(20, 7, big=True)], ids=lambda c: f"{c[0]}-Q{c[1]}-N{c[2]}-D{c[3]}-k{c[4]}-{str(c[5]).split('.')[-1]}-p{c[6]}-m{int(c[7])}-r{int(c[8])}")
+# ICR_FUZZ_CASES / ICR_FUZZ_SEED widen the search for an occasional long run (defaults keep the suite fast)
+_N_CASES = int(os.environ.get("ICR_FUZZ_CASES", "72"))
+_SEED = int(os.environ.get("ICR_FUZZ_SEED", "20261018"))
+
+
+@pytest.mark.parametrize("case", _cases(_N_CASES, _SEED) + [(10_000 + c[0],) + c[1:] for c in _cases(max(20, _N_CASES // 4), 7 + _SEED % 1000, big=True)], ids=lambda c: f"{c[0]}-Q{c[1]}-N{c[2]}-D{c[3]}-k{c[4]}-{str(c[5]).split('.')[-1]}-p{c[6]}-m{int(c[7])}-r{int(c[8])}")
 def test_random_shape_against_oracle(case):
     i, Q, N, D, k, dtype, path, use_mask, resident = case
     items = oracle.synth_unnormalised(N, D, seed=1000 + i).to(dtype)
@@ -70,3 +77,29 @@ def test_random_shape_against_oracle(case):
     err, mism = oracle.compare_topk(torch.where(live, v, torch.zeros_like(v)), torch.where(live, ids, torch.zeros_like(ids)),
                                     torch.where(live, rv, torch.zeros_like(rv)), torch.where(live, ri, torch.zeros_like(ri)), rtol=rtol)
     assert err <= rtol and mism == 0, (err, mism)
+
+
+def _mnrl_cases(n, seed):
+    rng = np.random.default_rng(seed)
+    return [(i, int(rng.integers(2, 700)), int(rng.choice([8, 64, 72, 128, 200, 384, 520, 768, 1024])), float(rng.choice([10.0, 20.0, 30.0])),
+             torch.float32 if rng.random() < 0.5 else torch.bfloat16) for i in range(n)]
+
+
+@pytest.mark.parametrize("case", _mnrl_cases(int(os.environ.get("ICR_FUZZ_MNRL_CASES", "24")), _SEED), ids=lambda c: f"{c[0]}-B{c[1]}-D{c[2]}-s{c[3]}-{str(c[4]).split('.')[-1]}")
+def test_random_mnrl_step_against_autograd(case):
+    """Random batch sizes (both kernel families: the tensor path starts at B = 288), dims and scales; un-normalised inputs."""
+    i, B, D, scale, dtype = case
+    a = oracle.synth_unnormalised(B, D, seed=3000 + i).to(dtype)
+    p = (0.7 * a.float() + 0.5 * oracle.synth_unnormalised(B, D, seed=4000 + i)).to(dtype)  # positives correlate with their anchors
+    ad, pd = a.cuda().requires_grad_(True), p.cuda().requires_grad_(True)
+    loss = icr.mnrl_loss(ad, pd, scale)
+    loss.backward()
+    rl, rga, rgp = oracle.mnrl_loss_and_grads(a.float(), p.float(), scale)
+    assert abs(loss.item() - rl.item()) <= 1e-4
+    for got, want in ((ad.grad, rga), (pd.grad, rgp)):
+        err = (got.float().cpu() - want).abs().max().item()
+        # 1e-4 absolute is the bar for unit-norm embeddings (gradient entries <= scale / B). Un-normalised rows with small
+        # norms have large gradients (the normalisation Jacobian multiplies by 1 / |x|); the tensor path forms the gradient
+        # products from fp16 operands (2^-11 relative each), so the error is bounded relative to the largest entry.
+        bound = 1e-4 + (1e-3 + (2 ** -7 if dtype == torch.bfloat16 else 0.0)) * want.abs().max().item()
+        assert err <= bound, (err, bound)
