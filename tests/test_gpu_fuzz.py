@@ -103,3 +103,48 @@ def test_random_mnrl_step_against_autograd(case):
         # products from fp16 operands (2^-11 relative each), so the error is bounded relative to the largest entry.
         bound = 1e-4 + (1e-3 + (2 ** -7 if dtype == torch.bfloat16 else 0.0)) * want.abs().max().item()
         assert err <= bound, (err, bound)
+
+
+def _dense_cases(n, seed):
+    rng = np.random.default_rng(seed + 1)
+    return [(i, int(rng.choice([1, 3, 63, 64, 65, 200, 513])), int(rng.choice([1, 5, 1000, 1023, 1024, 1025, 3000, 5001])),
+             int(rng.choice([8, 64, 72, 200, 384, 768, 1000])), torch.float32 if rng.random() < 0.5 else torch.bfloat16) for i in range(n)]
+
+
+@pytest.mark.parametrize("case", _dense_cases(int(os.environ.get("ICR_FUZZ_DENSE_CASES", "16")), _SEED), ids=lambda c: f"{c[0]}-Qa{c[1]}-Nb{c[2]}-D{c[3]}-{str(c[4]).split('.')[-1]}")
+def test_random_dense_cos_sim_against_oracle(case):
+    """cos_sim drop-in across the CUDA-core / tensor-core crossover (64 x 1024), tails on both axes, un-normalised inputs."""
+    i, Qa, Nb, D, dtype = case
+    a = oracle.synth_unnormalised(Qa, D, seed=5000 + i).to(dtype)
+    b = oracle.synth_unnormalised(Nb, D, seed=6000 + i).to(dtype)
+    got = ops.cos_sim_dense(a.cuda(), b.cuda()).cpu()
+    want = oracle.cos_sim(a.float(), b.float())
+    assert got.shape == want.shape and (got - want).abs().max().item() <= (2e-6 if dtype == torch.float32 else 5e-6)
+
+
+def _merge_cases(n, seed):
+    rng = np.random.default_rng(seed + 2)
+    return [(i, int(rng.choice([1, 2, 3, 8, 16])), int(rng.choice([1, 7, 64, 600, 5000])), int(rng.choice([1, 10, 100, 256])), int(rng.choice([1, 10, 100, 256])))
+            for i in range(n)]
+
+
+@pytest.mark.parametrize("case", _merge_cases(int(os.environ.get("ICR_FUZZ_MERGE_CASES", "16")), _SEED), ids=lambda c: f"{c[0]}-G{c[1]}-Q{c[2]}-kin{c[3]}-kout{c[4]}")
+def test_random_shard_merge_against_sort(case):
+    """icr_topk_merge on random shard lists with empty slots and duplicate scores: exact (score desc, id asc) order."""
+    i, G, Q, k_in, k_out = case
+    g = torch.Generator().manual_seed(7000 + i)
+    scores = torch.round(torch.randn(G, Q, k_in, generator=g) * 8) / 8  # coarse grid: plenty of exact ties
+    ids = torch.stack([torch.randperm(G * k_in * 4, generator=g)[: G * k_in].view(G, k_in) for _ in range(Q)], dim=1)  # distinct per query
+    empty = torch.rand(G, Q, k_in, generator=g) < 0.2
+    ids = torch.where(empty, torch.full_like(ids, -1), ids)
+    scores = torch.where(empty, torch.full_like(scores, float("-inf")), scores)
+    v, idx = ops.topk_merge(scores.cuda(), ids.cuda(), k_out)
+    v, idx = v.cpu(), idx.cpu()
+    s2 = scores.permute(1, 0, 2).reshape(Q, G * k_in)
+    i2 = ids.permute(1, 0, 2).reshape(Q, G * k_in)
+    for q in range(min(Q, 50)):
+        live = [(float(s), int(d)) for s, d in zip(s2[q].tolist(), i2[q].tolist()) if d >= 0]
+        live.sort(key=lambda t: (-t[0], t[1]))
+        want = live[:k_out] + [(float("-inf"), -1)] * max(0, k_out - len(live))
+        got = list(zip(v[q].tolist(), idx[q].tolist()))
+        assert got == want, (q, got[:5], want[:5])
