@@ -200,8 +200,13 @@ class DeviceCatalog:
         lo, hi = (0, emb.shape[0]) if rows is None else (max(0, int(rows[0])), min(emb.shape[0], int(rows[1])))
         hi = max(lo, hi)
         side = index.open_bf16_sidecar(product_ids, _emb=emb) if (use_sidecar and dtype == torch.bfloat16 and not normalize) else None
-        resident = upload_rows(side if side is not None else emb, lo, hi, device=dev, dtype=dtype, normalize=normalize,
-                               chunk_rows=chunk_rows, source_is_bf16_bits=side is not None)
+        # icr_convert_rows works on 16-byte vectors: an embedding dim that is not a multiple of 4 goes up as fp32 and is
+        # converted (and padded) by the DeviceCatalog constructor instead
+        odd = side is None and emb.shape[1] % 4 != 0 and (dtype != torch.float32 or normalize)
+        if odd and normalize:
+            raise ValueError("normalize=True needs an embedding dim that is a multiple of 4")
+        resident = upload_rows(side if side is not None else emb, lo, hi, device=dev, dtype=torch.float32 if odd else dtype,
+                               normalize=normalize, chunk_rows=chunk_rows, source_is_bf16_bits=side is not None)
         return cls(resident, device=dev, dtype=dtype, row_offset=lo if row_offset is None else row_offset)
 
     @property

@@ -433,6 +433,15 @@ def test_catalog_streamed_from_index_equals_catalog_from_memory(tmp_path, chunk_
     v, i = cat.topk(queries.cuda(), 100)
     rv, ri = oracle.cos_topk(queries, t, 100)
     _check_topk(v, i, rv, ri, F32_RTOL)
+    # an embedding dim that is not a multiple of 4 (no 16-byte vectors): still loads, fp32 and bf16
+    (tmp_path / "odd").mkdir()
+    idx2, ids2, emb2 = _index_on_disk(tmp_path / "odd", 777, 50)
+    for dt in (torch.float32, torch.bfloat16):
+        c2 = icr.DeviceCatalog.from_index(idx2, ids2, dtype=dt, chunk_rows=chunk_rows)
+        q2 = oracle.synth_unnormalised(3, 50, seed=12)
+        v, i = c2.topk(q2.cuda().to(dt), 20)
+        rv, ri = oracle.cos_topk(q2.to(dt).float(), torch.from_numpy(emb2).to(dt).float(), 20)
+        _check_topk(v, i, rv, ri, F32_RTOL if dt == torch.float32 else BF16_RTOL)
     sh = icr.ShardedCatalog.from_index(idx, ids, dtype=torch.bfloat16)
     v, i = sh.topk(queries.cuda().to(torch.bfloat16), 50)
     rv, ri = oracle.cos_topk(queries.to(torch.bfloat16).float(), t.to(torch.bfloat16).float(), 50)
