@@ -35,7 +35,9 @@ constexpr int kTcMaxStages = 6;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
-enum { MODE_LSE = 0, MODE_G = 1, MODE_MM = 2 };
+// MM3: the gradient products with W and x^^T split into fp16 hi + lo planes (three MMA terms, like the scores): small batches,
+// whose gradient entries are large (coef = scale / B) and would carry ~2^-11 relative from single fp16 operands
+enum { MODE_LSE = 0, MODE_G = 1, MODE_MM = 2, MODE_MM3 = 3, MODE_G3 = 4 };  // G3: G that also writes the lo planes
 
 struct TcArgs {
   int B, D;     // anchors (rows of the score matrix), embedding dim
@@ -45,6 +47,7 @@ struct TcArgs {
   int qblocks[2];  // blocks of 256 A-operand rows (MM: of product z)
   int rows[2];     // MM: live rows of product z's output (B, Bc)
   int plane_stride;  // element offset of the lo plane in a plane row (LSE / G)
+  int mm_stride[2];  // MM3: element offset of the lo plane in the rows of product z's operands (ldw, ldwt)
   int tiles;    // 256-column tiles over the N extent (Bc for LSE / G, D for MM)
   int chunks;   // balanced tile ranges; a work item = (row block, chunk) [of product z for MM]
   float c2;     // LSE / G: scale * 2^-16 * log2(e): accumulator units -> base-2 logits
@@ -69,6 +72,8 @@ template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 mnrl_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_b0,
                const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_b1, const TcArgs g) {
+  constexpr bool IS_MM = MODE == MODE_MM || MODE == MODE_MM3;
+  constexpr bool IS_G = MODE == MODE_G || MODE == MODE_G3, SPLIT = MODE == MODE_G3;
   constexpr int TERMS = MODE == MODE_MM ? 1 : 3;
   constexpr int kStageTiles = TERMS == 3 ? 4 : 2;  // A_hi A_lo B_hi B_lo | A B
   constexpr int kStageBytes = kStageTiles * kTileBytes;
@@ -88,7 +93,7 @@ mnrl_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const int items0 = g.qblocks[0] * g.chunks;  // work items of product 0 (the only one for LSE / G)
-  const int items = items0 + (MODE == MODE_MM ? g.qblocks[1] * g.chunks : 0);
+  const int items = items0 + (IS_MM ? g.qblocks[1] * g.chunks : 0);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -119,8 +124,9 @@ mnrl_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       const int chunk = rem / g.qblocks[z], qb = rem - chunk * g.qblocks[z];
       const int t0 = tc_chunk_first(g, chunk), t1 = tc_chunk_first(g, chunk + 1);
       const int KB = g.kb[z];
-      const CUtensorMap* ma = (MODE == MODE_MM && z == 1) ? &map_a1 : &map_a0;
-      const CUtensorMap* mb = (MODE == MODE_MM && z == 1) ? &map_b1 : &map_b0;
+      const CUtensorMap* ma = (IS_MM && z == 1) ? &map_a1 : &map_a0;
+      const CUtensorMap* mb = (IS_MM && z == 1) ? &map_b1 : &map_b0;
+      const int pstride = IS_MM ? g.mm_stride[z] : g.plane_stride;
       const int arow = qb * (2 * BM) + static_cast<int>(rank) * BM;
       for (int tile = t0; tile < t1; ++tile) {
         const int brow = tile * BN + static_cast<int>(rank) * BNH;
@@ -131,9 +137,9 @@ mnrl_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           const uint32_t sa = smem_u32(smem + stage * kStageBytes);
           if (TERMS == 3) {
             tma_load_2d_pair(sa, ma, kb * BK, arow, fb);
-            tma_load_2d_pair(sa + kTileBytes, ma, g.plane_stride + kb * BK, arow, fb);
+            tma_load_2d_pair(sa + kTileBytes, ma, pstride + kb * BK, arow, fb);
             tma_load_2d_pair(sa + 2 * kTileBytes, mb, kb * BK, brow, fb);
-            tma_load_2d_pair(sa + 3 * kTileBytes, mb, g.plane_stride + kb * BK, brow, fb);
+            tma_load_2d_pair(sa + 3 * kTileBytes, mb, pstride + kb * BK, brow, fb);
           } else {
             tma_load_2d_pair(sa, ma, kb * BK, arow, fb);
             tma_load_2d_pair(sa + kTileBytes, mb, kb * BK, brow, fb);
@@ -210,12 +216,12 @@ mnrl_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       const int t0 = tc_chunk_first(g, chunk), t1 = tc_chunk_first(g, chunk + 1);
       const int row_w = qb * (2 * BM) + static_cast<int>(rank) * BM + ew * 32;  // first row of this warp
       const int row = row_w + lane;
-      const bool live = row < (MODE == MODE_MM ? g.rows[z] : g.B);
+      const bool live = row < (IS_MM ? g.rows[z] : g.B);
       const int pos = row + g.label_off;  // column of this row's positive
       // per-item state
       float m = -INFINITY, l = 0.f, dg = 0.f;
       bool have_diag = false;
-      const float lse2 = (MODE == MODE_G && live) ? g.lse[row] * kLog2e : 0.f;
+      const float lse2 = (IS_G && live) ? g.lse[row] * kLog2e : 0.f;
       for (int tile = t0; tile < t1; ++tile) {
         const int col_base = tile * BN + half * (BN / 2);
         mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
@@ -256,24 +262,35 @@ mnrl_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                 }
               }
             }
-          } else if (MODE == MODE_G) {
+          } else if (IS_G) {
             if (col0 < g.ldw) {  // ldw = B rounded up to 64: a 32-column group is inside or outside as a whole
-              __align__(16) __half h[32];
+              __align__(16) __half h[32], lo[32];
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 float p = exp2f(__uint_as_float(cur[j]) * g.c2 - lse2);
                 if (col0 + j == pos) p -= 1.0f;
                 if (col0 + j >= g.Bc) p = 0.f;
                 h[j] = __float2half_rn(p);
+                if (SPLIT) lo[j] = __float2half_rn(p - __half2float(h[j]));
               }
               if (live) {
-                uint4* dst = reinterpret_cast<uint4*>(g.w + static_cast<int64_t>(row) * g.ldw + col0);
+                const int64_t wld = SPLIT ? 2 * g.ldw : g.ldw, wtld = SPLIT ? 2 * g.ldwt : g.ldwt;
+                uint4* dst = reinterpret_cast<uint4*>(g.w + static_cast<int64_t>(row) * wld + col0);
                 const uint4* srcv = reinterpret_cast<const uint4*>(h);
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4) dst[q4] = srcv[q4];
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
-                  if (col0 + j < g.Bc) g.wt[static_cast<int64_t>(col0 + j) * g.ldwt + row] = h[j];
+                  if (col0 + j < g.Bc) g.wt[static_cast<int64_t>(col0 + j) * wtld + row] = h[j];
+                if (SPLIT) {
+                  uint4* dlo = reinterpret_cast<uint4*>(g.w + static_cast<int64_t>(row) * wld + g.ldw + col0);
+                  const uint4* slo = reinterpret_cast<const uint4*>(lo);
+#pragma unroll
+                  for (int q4 = 0; q4 < 4; ++q4) dlo[q4] = slo[q4];
+#pragma unroll
+                  for (int j = 0; j < 32; ++j)
+                    if (col0 + j < g.Bc) g.wt[static_cast<int64_t>(col0 + j) * wtld + g.ldwt + row] = lo[j];
+                }
               }
             }
           } else {
@@ -330,10 +347,10 @@ __global__ void __launch_bounds__(kPrepThreads) mnrl_tc_prep_kernel(const T* __r
                                                                     int Ba, int Bp, int D, int dpad, __half* __restrict__ planes_a,
                                                                     __half* __restrict__ planes_p, float* __restrict__ inv_a,
                                                                     float* __restrict__ inv_p, __half* __restrict__ at, __half* __restrict__ pt,
-                                                                    int64_t ldat, int64_t ldpt, unsigned int* __restrict__ ticket) {
+                                                                    int64_t ldat, int64_t ldpt, unsigned int* __restrict__ ticket, int split) {
   constexpr int VEC = Elem<T>::VEC;
   extern __shared__ __align__(16) unsigned char prep_smem[];
-  __half* xs = reinterpret_cast<__half*>(prep_smem);  // [kPrepRows][dpad + 2]
+  float* xs = reinterpret_cast<float*>(prep_smem);  // [kPrepRows][dpad + 1] normalised rows (fp32: the split transposes need hi AND lo)
   const int blocks_a = (Ba + kPrepRows - 1) / kPrepRows;
   const bool is_a = static_cast<int>(blockIdx.x) < blocks_a;
   const int row0 = (is_a ? blockIdx.x : blockIdx.x - blocks_a) * kPrepRows;
@@ -345,7 +362,7 @@ __global__ void __launch_bounds__(kPrepThreads) mnrl_tc_prep_kernel(const T* __r
   float* inv_out = is_a ? inv_a : inv_p;
   __half* xt = is_a ? at : pt;
   const int r = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int sld = dpad + 2;
+  const int sld = dpad + 1;
   const int row = row0 + r;
   const int nvec = D / VEC, nvec_pad = dpad / VEC;
   if (blockIdx.x == 0 && threadIdx.x == 0 && ticket) *ticket = 0u;
@@ -377,7 +394,7 @@ __global__ void __launch_bounds__(kPrepThreads) mnrl_tc_prep_kernel(const T* __r
         const float y = f[i] * inv256;
         h[i] = __float2half_rn(y);
         l[i] = __float2half_rn(y - __half2float(h[i]));
-        if (TRANSPOSE && v < nvec) xs[r * sld + v * VEC + i] = __float2half_rn(f[i] * inv);
+        if (TRANSPOSE && v < nvec) xs[r * sld + v * VEC + i] = f[i] * inv;
       }
       if (VEC == 8) {
         *reinterpret_cast<uint4*>(hi + v * VEC) = *reinterpret_cast<const uint4*>(h);
@@ -390,8 +407,15 @@ __global__ void __launch_bounds__(kPrepThreads) mnrl_tc_prep_kernel(const T* __r
   }
   if (TRANSPOSE) {
     __syncthreads();
-    if (row0 + lane < B)
-      for (int d = r; d < D; d += kPrepRows) xt[static_cast<int64_t>(d) * ldt + row0 + lane] = xs[lane * sld + d];
+    if (row0 + lane < B) {
+      const int64_t rowld = split ? 2 * ldt : ldt;  // split: [D][hi plane (ldt) | lo plane (ldt)]
+      for (int d = r; d < D; d += kPrepRows) {
+        const float x = xs[lane * sld + d];
+        const __half h = __float2half_rn(x);
+        xt[static_cast<int64_t>(d) * rowld + row0 + lane] = h;
+        if (split) xt[static_cast<int64_t>(d) * rowld + ldt + row0 + lane] = __float2half_rn(x - __half2float(h));
+      }
+    }
   }
 }
 
@@ -465,10 +489,17 @@ __global__ void __launch_bounds__(256) mnrl_tc_jacobian_kernel(const T* __restri
 constexpr size_t kTcSmemBytes = static_cast<size_t>(kTcRingBytes) + (2 * kTcMaxStages + 4) * sizeof(uint64_t) + 16 + 1024;
 static_assert(kTcSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
 
+// below this many anchors the gradient products use hi + lo planes: gradient entries scale with scale / B, and single fp16
+// operands leave ~2^-11 of the largest entry (B = 32, scale 30: 2e-4 absolute, over the 1e-4 bar; B >= 288: < 5e-5)
+#ifndef ICR_MNRL_TC_SPLIT_BELOW
+#define ICR_MNRL_TC_SPLIT_BELOW 288
+#endif
+
 struct TcWs {
   size_t planes_a, planes_p, at, pt, w, wt, raw_a, raw_p, part_m, part_l, diag, cta_sums, ticket, total;
   int64_t dpad, ldw, ldwt;
   int chunks;
+  int split;  // gradient products with hi + lo planes (at .. wt hold two planes per row and are zero-filled first)
 };
 
 // Work items = (row block, chunk of column tiles) over 74 CTA pairs. The launch takes ceil(items / 74) rounds of the
@@ -499,6 +530,8 @@ TcWs tc_layout(int64_t B, int64_t Bc, int64_t D) {
   w.ldw = (Bc + 63) / 64 * 64;
   w.ldwt = (B + 63) / 64 * 64;
   w.chunks = tc_chunks(B, Bc);
+  w.split = B < ICR_MNRL_TC_SPLIT_BELOW ? 1 : 0;
+  const size_t planes = w.split ? 2 : 1;
   size_t off = 0;
   auto take = [&](size_t bytes) {
     const size_t o = off;
@@ -507,10 +540,10 @@ TcWs tc_layout(int64_t B, int64_t Bc, int64_t D) {
   };
   w.planes_a = take(static_cast<size_t>(B) * 2 * w.dpad * 2);
   w.planes_p = take(static_cast<size_t>(Bc) * 2 * w.dpad * 2);
-  w.at = take(static_cast<size_t>(D) * w.ldwt * 2);
-  w.pt = take(static_cast<size_t>(D) * w.ldw * 2);
-  w.w = take(static_cast<size_t>(B) * w.ldw * 2);
-  w.wt = take(static_cast<size_t>(Bc) * w.ldwt * 2);
+  w.at = take(static_cast<size_t>(D) * w.ldwt * 2 * planes);
+  w.pt = take(static_cast<size_t>(D) * w.ldw * 2 * planes);
+  w.w = take(static_cast<size_t>(B) * w.ldw * 2 * planes);
+  w.wt = take(static_cast<size_t>(Bc) * w.ldwt * 2 * planes);
   w.raw_a = take(static_cast<size_t>(B) * D * 4);
   w.raw_p = take(static_cast<size_t>(Bc) * D * 4);
   w.part_m = take(static_cast<size_t>(B) * w.chunks * 2 * 4);
@@ -529,7 +562,7 @@ int launch_tc(const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMap& a
     ICR_CUDA_CHECK(cudaFuncSetAttribute(mnrl_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kTcSmemBytes)));
     attr_set = true;
   }
-  const int items = (g.qblocks[0] + (MODE == MODE_MM ? g.qblocks[1] : 0)) * g.chunks;
+  const int items = (g.qblocks[0] + ((MODE == MODE_MM || MODE == MODE_MM3) ? g.qblocks[1] : 0)) * g.chunks;
   const int npairs = kNumSMs / 2;
   const int grid = 2 * (items < npairs ? items : npairs);
   mnrl_tc_kernel<MODE><<<grid, kTcThreads, kTcSmemBytes, st>>>(a0, b0, a1, b1, g);
@@ -545,15 +578,15 @@ int launch_prep(const MnrlArgs& m, const TcWs& w, char* base, bool transpose, bo
   unsigned int* ticket = reinterpret_cast<unsigned int*>(base + w.ticket);
   const int dpad = static_cast<int>(w.dpad);
   if (transpose) {
-    const size_t smem = static_cast<size_t>(kPrepRows) * (dpad + 2) * sizeof(__half);
+    const size_t smem = static_cast<size_t>(kPrepRows) * (dpad + 1) * sizeof(float);
     if (smem > 48 * 1024) ICR_CUDA_CHECK(cudaFuncSetAttribute(mnrl_tc_prep_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     mnrl_tc_prep_kernel<T, true><<<blocks, kPrepThreads, smem, st>>>(static_cast<const T*>(m.a), m.lda, static_cast<const T*>(m.p), m.ldp, m.B, m.Bc,
                                                                       m.D, dpad, pa, pp, forward ? m.inv_a : nullptr, forward ? m.inv_p : nullptr,
                                                                       reinterpret_cast<__half*>(base + w.at), reinterpret_cast<__half*>(base + w.pt),
-                                                                      w.ldwt, w.ldw, forward ? ticket : nullptr);
+                                                                      w.ldwt, w.ldw, forward ? ticket : nullptr, w.split);
   } else {
     mnrl_tc_prep_kernel<T, false><<<blocks, kPrepThreads, 0, st>>>(static_cast<const T*>(m.a), m.lda, static_cast<const T*>(m.p), m.ldp, m.B, m.Bc,
-                                                                   m.D, dpad, pa, pp, m.inv_a, m.inv_p, nullptr, nullptr, 0, 0, ticket);
+                                                                   m.D, dpad, pa, pp, m.inv_a, m.inv_p, nullptr, nullptr, 0, 0, ticket, 0);
   }
   ICR_LAUNCH_CHECK();
   return ICR_OK;
@@ -587,6 +620,8 @@ int launch_mnrl_tc(const MnrlArgs& m, int dtype, int mode, void* ws, size_t ws_b
   }
   char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~static_cast<uintptr_t>(1023));
   int rc;
+  // split planes lie INSIDE the tensor maps' bounds (no out-of-bounds zero fill between a hi and a lo plane): padding must be zero
+  if (bwd && w.split) ICR_CUDA_CHECK(cudaMemsetAsync(base + w.at, 0, w.raw_a - w.at, st));
   if (dtype == ICR_F32) rc = launch_prep<float>(m, w, base, bwd, fwd, st);
   else rc = launch_prep<__nv_bfloat16>(m, w, base, bwd, fwd, st);
   if (rc) return rc;
@@ -612,6 +647,8 @@ int launch_mnrl_tc(const MnrlArgs& m, int dtype, int mode, void* ws, size_t ws_b
   g.wt = reinterpret_cast<__half*>(base + w.wt);
   g.ldw = w.ldw;
   g.ldwt = w.ldwt;
+  g.mm_stride[0] = static_cast<int>(w.ldw);
+  g.mm_stride[1] = static_cast<int>(w.ldwt);
   g.raw[0] = reinterpret_cast<float*>(base + w.raw_a);
   g.raw[1] = reinterpret_cast<float*>(base + w.raw_p);
 
@@ -626,14 +663,23 @@ int launch_mnrl_tc(const MnrlArgs& m, int dtype, int mode, void* ws, size_t ws_b
     ICR_LAUNCH_CHECK();
     if (!bwd) return ICR_OK;
   }
-  if ((rc = launch_tc<MODE_G>(map_a, map_p, map_a, map_p, g, st))) return rc;
+  if (w.split) rc = launch_tc<MODE_G3>(map_a, map_p, map_a, map_p, g, st);
+  else rc = launch_tc<MODE_G>(map_a, map_p, map_a, map_p, g, st);
+  if (rc) return rc;
   // gradient products: dA^ [B, D] = W P^ (A operand W [B, Bc], B operand P^^T [D, Bc], K = Bc)
   //                    dP^ [Bc, D] = W^T A^ (A operand W^T [Bc, B], B operand A^^T [D, B], K = B)
   CUtensorMap map_w, map_wt, map_at, map_pt;
-  if ((rc = make_map(&map_w, base + w.w, m.B, m.Bc, w.ldw, false))) return rc;
-  if ((rc = make_map(&map_wt, base + w.wt, m.Bc, m.B, w.ldwt, false))) return rc;
-  if ((rc = make_map(&map_at, base + w.at, m.D, m.B, w.ldwt, false))) return rc;
-  if ((rc = make_map(&map_pt, base + w.pt, m.D, m.Bc, w.ldw, false))) return rc;
+  if (w.split) {  // rows = [hi plane | lo plane], both inside the map
+    if ((rc = make_map(&map_w, base + w.w, m.B, 2 * w.ldw, 2 * w.ldw, false))) return rc;
+    if ((rc = make_map(&map_wt, base + w.wt, m.Bc, 2 * w.ldwt, 2 * w.ldwt, false))) return rc;
+    if ((rc = make_map(&map_at, base + w.at, m.D, 2 * w.ldwt, 2 * w.ldwt, false))) return rc;
+    if ((rc = make_map(&map_pt, base + w.pt, m.D, 2 * w.ldw, 2 * w.ldw, false))) return rc;
+  } else {
+    if ((rc = make_map(&map_w, base + w.w, m.B, m.Bc, w.ldw, false))) return rc;
+    if ((rc = make_map(&map_wt, base + w.wt, m.Bc, m.B, w.ldwt, false))) return rc;
+    if ((rc = make_map(&map_at, base + w.at, m.D, m.B, w.ldwt, false))) return rc;
+    if ((rc = make_map(&map_pt, base + w.pt, m.D, m.Bc, w.ldw, false))) return rc;
+  }
   TcArgs mm = g;
   mm.kb[0] = static_cast<int>(w.ldw / BK);
   mm.kb[1] = static_cast<int>(w.ldwt / BK);
@@ -643,7 +689,9 @@ int launch_mnrl_tc(const MnrlArgs& m, int dtype, int mode, void* ws, size_t ws_b
   mm.rows[1] = m.Bc;
   mm.tiles = (m.D + BN - 1) / BN;
   mm.chunks = mm.tiles;  // one N tile per work item
-  if ((rc = launch_tc<MODE_MM>(map_w, map_pt, map_wt, map_at, mm, st))) return rc;
+  if (w.split) rc = launch_tc<MODE_MM3>(map_w, map_pt, map_wt, map_at, mm, st);
+  else rc = launch_tc<MODE_MM>(map_w, map_pt, map_wt, map_at, mm, st);
+  if (rc) return rc;
   const int jb = (m.B + m.Bc + 7) / 8;
   if (dtype == ICR_F32)
     mnrl_tc_jacobian_kernel<float><<<jb, 256, 0, st>>>(static_cast<const float*>(m.a), m.lda, static_cast<const float*>(m.p), m.ldp, m.B, m.Bc,

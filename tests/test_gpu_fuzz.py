@@ -148,3 +148,31 @@ def test_random_shard_merge_against_sort(case):
         want = live[:k_out] + [(float("-inf"), -1)] * max(0, k_out - len(live))
         got = list(zip(v[q].tolist(), idx[q].tolist()))
         assert got == want, (q, got[:5], want[:5])
+
+
+def _rect_cases(n, seed):
+    rng = np.random.default_rng(seed + 3)
+    out = []
+    for i in range(n):
+        B = int(rng.choice([32, 48, 64, 100, 256, 300]))
+        G = int(rng.choice([1, 2, 3, 8]))
+        out.append((i, B, G * B, int(rng.integers(0, G)) * B, int(rng.choice([64, 128, 384, 768])), float(rng.choice([20.0, 30.0])),
+                    torch.float32 if rng.random() < 0.5 else torch.bfloat16))
+    return out
+
+
+@pytest.mark.parametrize("case", _rect_cases(int(os.environ.get("ICR_FUZZ_RECT_CASES", "12")), _SEED), ids=lambda c: f"{c[0]}-B{c[1]}-Bc{c[2]}-off{c[3]}-D{c[4]}-{str(c[6]).split('.')[-1]}")
+def test_random_gathered_mnrl_against_autograd(case):
+    """Rectangular MNRL (B anchors of rank r against the G*B gathered candidates, labels r*B + i) on unit-norm rows."""
+    i, B, Bc, off, D, scale, dtype = case
+    cand = oracle.synth_clustered(Bc, D, seed=8000 + i, n_centres=10)[0]
+    g = torch.Generator().manual_seed(9000 + i)
+    a = torch.nn.functional.normalize(cand[off : off + B] + 0.4 * torch.randn(B, D, generator=g), dim=1)
+    a, cand = a.to(dtype), cand.to(dtype)
+    loss, saved = ops.mnrl_forward_rect(a.cuda(), cand.cuda(), scale, off)
+    ga, gc = ops.mnrl_backward_rect(a.cuda(), cand.cuda(), scale, off, saved, torch.tensor(1.0, device="cuda"))
+    rl, rga, rgc = oracle.mnrl_rect_loss_and_grads(a.float(), cand.float(), scale, off)
+    assert abs(loss.item() - rl.item()) <= 1e-4
+    for got, want in ((ga, rga), (gc, rgc)):
+        bound = 1e-4 + (2 ** -8 if dtype == torch.bfloat16 else 0.0) * want.abs().max().item()
+        assert (got.float().cpu() - want).abs().max().item() <= bound
