@@ -176,3 +176,21 @@ def test_random_gathered_mnrl_against_autograd(case):
     for got, want in ((ga, rga), (gc, rgc)):
         bound = 1e-4 + (2 ** -8 if dtype == torch.bfloat16 else 0.0) * want.abs().max().item()
         assert (got.float().cpu() - want).abs().max().item() <= bound
+
+
+@pytest.mark.parametrize("Q", [1, 2, 255, 256, 257, 2047, 2048, 2049, 5003])
+def test_host_pipeline_piece_boundaries(Q):
+    """topk_host (pinned host in / out, pieces on two streams) == the device call for batch sizes around its split rules."""
+    items = oracle.synth_clustered(20000, 128, seed=3)[0]
+    cat = icr.DeviceCatalog(items.cuda())
+    q = oracle.synth_isotropic(Q, 128, seed=Q)
+    v, i = cat.topk_host(q.pin_memory(), 10)
+    torch.cuda.synchronize()
+    dv, di = cat.topk(q.cuda(), 10)
+    assert torch.equal(v, dv.cpu()) and torch.equal(i, di.cpu())
+    if Q >= 4:
+        v2, i2 = cat.topk_host(q, 10, splits=[1, Q - 3, 2])  # pageable input, explicit uneven pieces
+        torch.cuda.synchronize()
+        # the 1- and 2-query pieces take the GEMV kernels, the device call the tensor path: equal within the fp32 tolerance
+        err, mism = oracle.compare_topk(v2, i2, dv.cpu(), di.cpu(), rtol=1e-5)
+        assert err <= 1e-5 and mism == 0, (err, mism)
