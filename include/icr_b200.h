@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define ICR_ABI_VERSION 1
+#define ICR_ABI_VERSION 2
 #define ICR_MAX_K 256 /* largest k of one fused top-k call (reference: top_k <= 100, schemas.py:34) */
 
 typedef enum {
@@ -73,10 +73,20 @@ int icr_row_inv_norms(const void* x, int64_t rows, int64_t dim, int64_t ld, int 
 /* fp32 rows -> L2-normalised, scaled by 2^8 and split into an fp16 (hi | lo) pair per row:
  * planes[r, 0:dim] = hi, planes[r, dim_pad:dim_pad+dim] = lo, row stride 2*dim_pad fp16
  * elements, dim_pad = dim rounded up to 64, padding zero-filled. This is the operand
- * format of the fp32-parity tensor-core path (three fp16 MMAs with fp32 accumulation). */
+ * format of the fp32-parity DENSE tensor-core path (icr_cos_sim_dense: three fp16 MMAs with fp32 accumulation builds these
+ * per call); exported for callers that want the planes themselves. */
 int icr_split_f16_planes(const float* x, int64_t rows, int64_t dim, int64_t ld,
                          uint16_t* planes, void* stream);
 int64_t icr_planes_row_elems(int64_t dim); /* = 2 * round_up(dim, 64) */
+
+/* fp32 rows -> the SCREENING operand of the tensor-core top-k path: plane[r, 0:dim] = fp16(256 * x_r / max(||x_r||, 1e-12)),
+ * row stride dim_pad = round_up(dim, 64) fp16 elements, padding zero-filled; inv_norms[r] (optional, may be NULL) as
+ * icr_row_inv_norms. One fp16 MMA term on these planes bounds every cosine to within 2^-10; icr_cos_topk keeps every row
+ * whose screened score lies within twice that of the k-th best and re-scores those few rows exactly in fp32 from the
+ * caller's rows, so the returned scores and ids are those of the fp32 computation. */
+int icr_screen_plane(const float* x, int64_t rows, int64_t dim, int64_t ld,
+                     uint16_t* plane, float* inv_norms, void* stream);
+int64_t icr_screen_plane_row_elems(int64_t dim); /* = round_up(dim, 64) */
 
 /* Catalog upload helper: fp32 rows as the reference stores them on disk (embeddings.npy,
  * src/inference/serve_recommendations.py:127) -> the HBM-resident form: ICR_F32 or ICR_BF16
@@ -95,10 +105,10 @@ int icr_convert_rows(const float* x, int64_t rows, int64_t dim, int64_t ldx,
  *
  *   queries      [Q, D] dtype, row stride ldq
  *   catalog      [N, D] dtype, row stride ldc          (the shard's rows when sharded)
- *   cat_planes   optional (may be NULL): icr_split_f16_planes(catalog); used by the GEMM
- *                path for ICR_F32 catalogs; if NULL it is built in the workspace per call
- *   cat_inv_norms optional (may be NULL): icr_row_inv_norms(catalog); used by the GEMM path
- *                for ICR_BF16 catalogs; if NULL it is computed in the workspace per call
+ *   cat_planes   optional (may be NULL): the plane of icr_screen_plane(catalog), [N, round_up(D, 64)] fp16;
+ *                used by the GEMM path for ICR_F32 catalogs; if NULL it is built in the workspace per call
+ *   cat_inv_norms optional (may be NULL): icr_row_inv_norms(catalog); used by the GEMM path (ICR_BF16: epilogue
+ *                scaling; ICR_F32: exact re-scoring of the screened rows); if NULL it is computed per call
  *   exclude_mask optional (may be NULL): N bytes, non-zero = row never returned
  *                (exclude_product_ids semantics, serve_recommendations.py:216-221)
  *   row_offset   added to every returned id (global numbering of a row shard)

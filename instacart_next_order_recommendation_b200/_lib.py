@@ -17,6 +17,7 @@ ICR_F32, ICR_BF16 = 0, 1
 PATH_AUTO, PATH_GEMV, PATH_GEMM = 0, 1, 2
 PATH_WS_RESIDENT = 0x100  # OR-ed into a path: resident workspace, see include/icr_b200.h
 MAX_K = 256
+ABI_VERSION = 2  # include/icr_b200.h ICR_ABI_VERSION
 
 _STATUS = {
     -1: ("ICR_ERR_ARG", ValueError),
@@ -39,6 +40,8 @@ SIGNATURES = {
     "icr_row_inv_norms": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "icr_split_f16_planes": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
     "icr_planes_row_elems": (c_int64, [c_int64]),
+    "icr_screen_plane": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
+    "icr_screen_plane_row_elems": (c_int64, [c_int64]),
     "icr_convert_rows": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "icr_cos_topk_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int]),
     "icr_cos_topk": (
@@ -111,8 +114,8 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.icr_abi_version() != 1:
-        raise RuntimeError(f"libicr_b200.so ABI version {lib.icr_abi_version()} != 1")
+    if lib.icr_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"libicr_b200.so ABI version {lib.icr_abi_version()} != {ABI_VERSION}: rebuild it (python -m ...build --force)")
     _lib = lib
     return lib
 

@@ -51,6 +51,7 @@ void profile_end(cudaStream_t st) {
 // kernels' host launchers (defined in the other translation units)
 int launch_row_inv_norms(const void* x, int64_t rows, int64_t dim, int64_t ld, int dtype, float* inv, cudaStream_t st);
 int launch_split_planes(const float* x, int64_t rows, int64_t dim, int64_t ld, uint16_t* planes, cudaStream_t st);
+int launch_screen_plane(const float* x, int64_t rows, int64_t dim, int64_t ld, uint16_t* plane, float* inv, cudaStream_t st);
 int launch_convert_rows(const float* x, int64_t rows, int64_t dim, int64_t ldx, void* out, int64_t ldo, int out_dtype, int normalize,
                         cudaStream_t st);
 void peer_layout(int64_t n_max, int world, uint32_t epoch, size_t* scores_off, size_t* ids_off, size_t* total);
@@ -215,6 +216,20 @@ int icr_split_f16_planes(const float* x, int64_t rows, int64_t dim, int64_t ld, 
   return launch_split_planes(x, rows, dim, ld, planes, static_cast<cudaStream_t>(stream));
 }
 
+int64_t icr_screen_plane_row_elems(int64_t dim) { return (dim + 63) / 64 * 64; }
+
+int icr_screen_plane(const float* x, int64_t rows, int64_t dim, int64_t ld, uint16_t* plane, float* inv_norms, void* stream) {
+  g_launches = 0;
+  int rc = check_matrix("screen_plane.x", x, rows, dim, ld, ICR_F32);
+  if (rc) return rc;
+  if ((rc = check_device())) return rc;
+  if (rows > 0 && (!plane || (reinterpret_cast<uintptr_t>(plane) & 127))) {
+    set_error("screen_plane: plane must be non-null and 128-byte aligned");
+    return ICR_ERR_ALIGN;
+  }
+  return launch_screen_plane(x, rows, dim, ld, plane, inv_norms, static_cast<cudaStream_t>(stream));
+}
+
 static int resolve_path(int path, int64_t Q, int64_t N, int64_t D, int dtype, int k, const uint8_t* mask) {
   if (path == ICR_PATH_GEMV || path == ICR_PATH_GEMM) return path;
   // small batches are HBM-bound GEMVs; larger ones are tensor-core work
@@ -373,6 +388,8 @@ int icr_topk_merge(const float* cand_scores, const int64_t* cand_ids, int64_t Q,
     set_error("topk_merge: null pointer");
     return ICR_ERR_ARG;
   }
+  // candidate ids travel in the 32-bit half of the selection keys: the caller (ShardedCatalog) bounds the catalog below 2^32 - 1
+  // rows; ids at or above that would come back truncated, so the contract is stated here and enforced on the host side
   int rc;
   if ((rc = check_device())) return rc;
   return launch_merge_lists(cand_scores, cand_ids, Q, G, k_in, k_out, out_scores, out_ids, static_cast<cudaStream_t>(stream));

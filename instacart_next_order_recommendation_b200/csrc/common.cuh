@@ -39,6 +39,35 @@ constexpr int kKernelGemv = 1, kKernelGemm = 2;
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute of a kernel: each launcher remembers, per host
+// thread, on which devices it has configured its kernel (a thread may serve cuda:0 and then cuda:1).
+struct SmemAttrCache {
+  unsigned long long devmask = 0;
+};
+// the same for launchers whose shared-memory need varies with the problem: remembers the largest size set per device
+struct SmemSizeCache {
+  size_t bytes[64] = {};
+};
+template <typename F>
+inline int ensure_dyn_smem_size(SmemSizeCache& c, F func, size_t bytes) {
+  int dev = 0;
+  ICR_CUDA_CHECK(cudaGetDevice(&dev));
+  const bool tracked = dev >= 0 && dev < 64;
+  if (tracked && bytes <= c.bytes[dev]) return ICR_OK;
+  ICR_CUDA_CHECK(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+  if (tracked) c.bytes[dev] = bytes;
+  return ICR_OK;
+}
+template <typename F>
+inline int ensure_dyn_smem(SmemAttrCache& c, F func, size_t bytes) {
+  int dev = 0;
+  ICR_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && ((c.devmask >> dev) & 1ull)) return ICR_OK;
+  ICR_CUDA_CHECK(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+  if (dev >= 0 && dev < 64) c.devmask |= 1ull << dev;
+  return ICR_OK;
+}
+
 // ---- candidate keys -----------------------------------------------------------------------
 // A candidate is one 64-bit key: high word = order-preserving image of the fp32 score, low
 // word = ~row. Larger key == better candidate: higher score first, lower row on ties. Key 0

@@ -4,6 +4,7 @@
 // plumbing); `peer_base[p]` is rank p's buffer as seen from THIS process. Layout of a buffer:
 //   [0, 256)      uint32 flag[src]: last epoch whose candidates from rank `src` have fully arrived here
 //   [512, 516)    ticket counter of the local push kernel
+//   [768, 772)    status: epoch of a call whose wait for a peer timed out (host-visible; PeerExchange.check raises on it)
 //   [1024, ...)   two slots (epoch parity), each  scores f32 [G][n_max]  |  ids i64 [G][n_max]   (used compactly: [G][n])
 // One kernel per call: the CTAs store this rank's [n] (score, id) candidates into slot `rank` of EVERY peer's buffer with
 // 16-byte stores over NVLink (peers visited starting at rank+1, so the G ranks spread over the switch), fence at system
@@ -13,12 +14,15 @@
 // every peer pushed e+1, which each peer enqueues behind its own merge of epoch e.
 //
 // No reference counterpart (the reference is single-GPU); stands in for the ncclAllGather of §8(e).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace icr {
 
 constexpr int kPeerHeaderBytes = 1024;
 constexpr int kPeerTicketOff = 512;
+constexpr int kPeerStatusOff = 768;  // uint32: epoch of an exchange that gave up waiting for a peer (0 = never)
 
 struct PeerArgs {
   const float* scores;
@@ -28,6 +32,7 @@ struct PeerArgs {
   unsigned char* peer_base[ICR_MAX_PEERS];
   size_t scores_off, ids_off;  // byte offsets of this epoch's slot regions inside a buffer
   uint32_t epoch;
+  uint64_t timeout_ns;  // how long the last CTA waits for the peers' flags
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
@@ -76,7 +81,13 @@ __global__ void __launch_bounds__(256) peer_exchange_kernel(const PeerArgs a) {
     const uint64_t t0 = global_timer_ns();
     // epochs only grow (the host counts calls), so >= also accepts a peer that is already one call ahead
     while (static_cast<int32_t>(ld_acquire_sys(mine) - a.epoch) < 0) {
-      if (global_timer_ns() - t0 > 30000000000ull) __trap();  // a peer that never arrives must abort the launch, not hang the GPU
+      // a peer that never arrives must not hang the GPU for ever: after the limit (ICR_PEER_TIMEOUT_S, default 600 s - a rank may
+      // sit in a debugger, a page-cache miss or GC for minutes, as NCCL tolerates) the status word of the local header is set and
+      // the launch ends; the host reads it at its next synchronisation point and raises (PeerExchange.check)
+      if (global_timer_ns() - t0 > a.timeout_ns) {
+        *reinterpret_cast<volatile uint32_t*>(a.peer_base[a.rank] + kPeerStatusOff) = a.epoch;
+        break;
+      }
     }
   }
   __syncthreads();
@@ -102,6 +113,8 @@ int launch_peer_exchange(const float* scores, const int64_t* ids, int64_t n, int
   for (int p = 0; p < world; ++p) a.peer_base[p] = reinterpret_cast<unsigned char*>(static_cast<uintptr_t>(peer_buffers[p]));
   peer_layout(n_max, world, epoch, &a.scores_off, &a.ids_off, nullptr);
   a.epoch = epoch;
+  static const uint64_t timeout_s = getenv("ICR_PEER_TIMEOUT_S") ? strtoull(getenv("ICR_PEER_TIMEOUT_S"), nullptr, 10) : 600ull;
+  a.timeout_ns = (timeout_s ? timeout_s : 1ull) * 1000000000ull;
   // 12 bytes per candidate to every peer: enough CTAs to keep the links busy for large batches, one for a request
   int64_t ctas = (n * 12 * world + (64 << 10) - 1) / (64 << 10);
   ctas = ctas < 1 ? 1 : (ctas > 64 ? 64 : ctas);

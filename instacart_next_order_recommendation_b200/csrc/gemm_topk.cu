@@ -29,6 +29,7 @@
 // Replaces cos_sim [Q,N] -> torch.topk(100) -> Python heap of sentence-transformers'
 // InformationRetrievalEvaluator (built at reference src/training/train_sbert.py:197-202) and the
 // cos_sim -> np.argsort loops of src/baselines/content_based.py:54-63.
+#include "select_args.cuh"
 #include "tc.cuh"  // BM, BN, BK, tile geometry, PTX wrappers, tensor maps
 
 namespace icr {
@@ -82,6 +83,8 @@ struct GemmArgs {
   uint64_t* compact_scratch; // [gridDim.x][kEpiWarps][kSegCapMax] global scratch of the (rare) in-kernel compaction
   int qpad;                  // swapped kernel: queries rounded up to a multiple of 32 (the MMA's N)
   int dense_raw;             // dense mode stores raw-unit scores (no per-query factor): first phase of the top-k path
+  float band;                // screened scores (MODE 2): tau already sits `band` below the k-th best; 0 = exact scores
+  unsigned int* overflow;    // [Q] screened scores: set when a segment cannot be cut back without losing keys of the band
 };
 
 // chunk c of a phase covers tiles [first(c), first(c+1)): sizes differ by at most one tile
@@ -111,7 +114,8 @@ struct SegState {
 // Any lane whose segment could overflow during the next 32 scores gets it compacted by the whole warp.
 // `scratch` is global memory (L2-resident): this path only runs when the running threshold fails to prune, e.g. a
 // catalog sorted by similarity to the query, so it trades speed for 16-32 KB of shared memory.
-__device__ __forceinline__ void compact_full_segments(SegState& s, uint64_t* scratch, int cap, int k, int lane) {
+__device__ __forceinline__ void compact_full_segments(SegState& s, uint64_t* scratch, int cap, int k, int lane, float band,
+                                                      unsigned int* overflow, int q_lane0) {
   unsigned need = __ballot_sync(kFull, s.cnt > cap - 32);
   while (need) {
     const int L = __ffs(need) - 1;
@@ -122,9 +126,23 @@ __device__ __forceinline__ void compact_full_segments(SegState& s, uint64_t* scr
     const int P = cap <= 256 ? 256 : kSegCapMax;  // power of two for the sorting network
     for (int i = lane; i < P; i += 32) scratch[i] = (i < n) ? canonical_key(__ldcg(seg + i)) : 0ull;
     warp_bitonic_sort_desc(scratch, P, lane);
-    const int kept = n < k ? n : k;
+    int kept = n < k ? n : k;
+    uint32_t t_new = (n >= k) ? static_cast<uint32_t>(scratch[k - 1] >> 32) : 0u;
+    if (band > 0.f && n >= k) {
+      // screened scores: every key within `band` of the segment's k-th best may still belong to the exact top-k
+      t_new = order_bits(unorder_bits(t_new) - band);
+      const uint64_t t_key = static_cast<uint64_t>(t_new) << 32;
+      int c = 0;
+      for (int i = lane; i < n; i += 32) c += (scratch[i] >= t_key) ? 1 : 0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(kFull, c, o);
+      kept = c;
+      if (kept > cap - 64) {  // too many near-ties to carry: this query is ranked exactly over the whole catalog at the end
+        if (lane == 0) overflow[q_lane0 + L] = 1u;
+        kept = k;
+      }
+    }
     for (int i = lane; i < kept; i += 32) seg[i] = raw_key(scratch[i]);
-    const uint32_t t_new = (n >= k) ? static_cast<uint32_t>(scratch[k - 1] >> 32) : 0u;
     if (lane == L) {
       s.cnt = kept;
       s.tau_ob = max(s.tau_ob, t_new);
@@ -251,15 +269,19 @@ __device__ __forceinline__ void dense_store32(const uint32_t (&r)[32], float* ou
   }
 }
 
-// TERMS = 3: fp16 hi/lo planes (fp32 parity); TERMS = 1: raw bf16 rows.
+// MODE = 3: fp16 hi/lo planes, three MMA terms (fp32 parity of every score: the dense K2' path);
+// MODE = 1: raw bf16 rows, one term, inverse norms applied in the epilogue;
+// MODE = 2: one fp16 plane of the normalised fp32 rows, one term: SCREENING scores (select_args.cuh), the survivors
+//           of the whole sweep are re-scored exactly by the last select.
 // ASTAT (bf16, D <= 384): the work item's 128 query rows stay resident in shared memory for all of its catalog
 // tiles ("A-stationary"), so the ring streams catalog tiles only: 31 instead of 62 B/cycle/SM of L2 traffic,
 // which is the difference between L2-bound and tensor-bound for one-term MMAs (profiles/r01_notes.md).
-template <int TERMS, bool ASTAT, bool DENSE>
+template <int MODE, bool ASTAT, bool DENSE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmArgs g) {
-  static_assert(!ASTAT || TERMS == 1, "A-stationary is the bf16 variant");
-  constexpr bool BF16 = (TERMS == 1);
+  constexpr int TERMS = (MODE == 3) ? 3 : 1;
+  static_assert(!ASTAT || TERMS == 1, "A-stationary is a one-term variant");
+  constexpr bool BF16 = (MODE == 1);
   constexpr int EW = epi_warps(TERMS), EH = EW / 4, ECOLS = BN / EH;  // epilogue warps, column groups, columns per warp
   constexpr int kStageTiles = ASTAT ? 1 : ((TERMS == 3) ? 4 : 2);  // B | A_hi A_lo B_hi B_lo | A B
   constexpr int kStageBytes = kStageTiles * kTileBytes;
@@ -488,7 +510,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           if (dense) {
             if (live) dense_store32<BF16>(ra, out_q + row0 + cb * 32, qscale, cinv_s + cb * 32, g.N - (row0 + cb * 32), vec_ok);
           } else {
-            compact_full_segments(s, scratch, cap, g.k, lane);
+            compact_full_segments(s, scratch, cap, g.k, lane, g.band, g.overflow, q - lane);
             filter32<BF16>(ra, s, cinv_s + cb * 32, __shfl_sync(kFull, cmax_l, cb), __shfl_sync(kFull, cmin_l, cb), row0 + cb * 32, fast,
                            g.N, g.mask);
           }
@@ -497,7 +519,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           if (dense) {
             if (live) dense_store32<BF16>(rb, out_q + row0 + (cb + 1) * 32, qscale, cinv_s + (cb + 1) * 32, g.N - (row0 + (cb + 1) * 32), vec_ok);
           } else {
-            compact_full_segments(s, scratch, cap, g.k, lane);
+            compact_full_segments(s, scratch, cap, g.k, lane, g.band, g.overflow, q - lane);
             filter32<BF16>(rb, s, cinv_s + (cb + 1) * 32, __shfl_sync(kFull, cmax_l, cb + 1), __shfl_sync(kFull, cmin_l, cb + 1),
                            row0 + (cb + 1) * 32, fast, g.N, g.mask);
           }
@@ -541,10 +563,11 @@ constexpr int kSwapResidentMax = 64 * 1024;  // leaves >= 8 catalog stages: meas
 
 __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-template <int TERMS>
+template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSwapThreads, 1)
 gemm_swap_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_c, const GemmArgs g) {
-  constexpr bool BF16 = (TERMS == 1);
+  constexpr int TERMS = (MODE == 3) ? 3 : 1;
+  constexpr bool BF16 = (MODE == 1);
   constexpr int CT = (TERMS == 3) ? 2 : 1;  // catalog tiles per stage: hi | lo plane
   constexpr int kStageBytes = CT * kTileBytes;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -748,11 +771,25 @@ gemm_swap_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
               const int P = cap <= 256 ? 256 : kSegCapMax;
               for (int i = lane; i < P; i += 32) scratch[i] = (i < n) ? canonical_key(__ldcg(seg + i)) : 0ull;
               warp_bitonic_sort_desc(scratch, P, lane);
-              const int kept = n < g.k ? n : g.k;
+              int kept = n < g.k ? n : g.k;
+              float t_new = (n >= g.k) ? unorder_bits(static_cast<uint32_t>(scratch[g.k - 1] >> 32)) : -INFINITY;
+              if (g.band > 0.f && n >= g.k) {  // screened scores: keep the whole band below the segment's k-th best
+                t_new -= g.band;
+                const uint64_t t_key = static_cast<uint64_t>(order_bits(t_new)) << 32;
+                int c = 0;
+                for (int i = lane; i < n; i += 32) c += (scratch[i] >= t_key) ? 1 : 0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(kFull, c, o);
+                kept = c;
+                if (kept > cap - 136) {  // no room for another tile (<= 128 keys): exact ranking of this query at the end
+                  if (lane == 0) g.overflow[q] = 1u;
+                  kept = g.k;
+                }
+              }
               for (int i = lane; i < kept; i += 32) seg[i] = raw_key(scratch[i]);
               if (lane == 0) {
                 cnt_s[q] = kept;
-                if (n >= g.k) tau_s[q] = fmaxf(tau_s[q], unorder_bits(static_cast<uint32_t>(scratch[g.k - 1] >> 32)));
+                tau_s[q] = fmaxf(tau_s[q], t_new);
               }
               __syncwarp();
             }
@@ -779,16 +816,7 @@ gemm_swap_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
 // ---- host side ---------------------------------------------------------------------------------------
 int launch_row_inv_norms(const void* x, int64_t rows, int64_t dim, int64_t ld, int dtype, float* inv, cudaStream_t st);
 int launch_split_planes(const float* x, int64_t rows, int64_t dim, int64_t ld, uint16_t* planes, cudaStream_t st);
-size_t select_scratch_bytes(int64_t Q, int nseg, int seg_cap, int k);
-int launch_select_hist(const uint64_t* seg_keys, const int* seg_cnt, int64_t Q, int nseg, int seg_stride, int seg_cap,
-                       const uint64_t* carry_in, const int* carry_cnt_in, uint64_t* carry_out, int* carry_cnt_out, float* tau_out,
-                       float* out_scores, int64_t* out_ids, int64_t id_offset, int k, float out_scale, const float* out_qscale,
-                       cudaStream_t st, const float* dense = nullptr, int64_t dense_ld = 0, int dense_rows = 0,
-                       const uint8_t* mask = nullptr);
-int launch_select(const uint64_t* seg_keys, const int* seg_cnt, int64_t Q, int nseg, int seg_stride, int seg_cap,
-                  const uint64_t* carry_in, const int* carry_cnt_in, uint64_t* carry_out, int* carry_cnt_out,
-                  float* tau_out, float* out_scores, int64_t* out_ids, int64_t id_offset, int k, void* scratch,
-                  size_t scratch_bytes, cudaStream_t st);
+int launch_screen_plane(const float* x, int64_t rows, int64_t dim, int64_t ld, uint16_t* plane, float* inv, cudaStream_t st);
 
 constexpr size_t kGemmSmemBytes = static_cast<size_t>(kRingBytes) + kEpiWarps * kEpiCols * sizeof(float) +
                                   (2 * kMaxStages + 6) * sizeof(uint64_t) + 16 + 1024;
@@ -800,12 +828,26 @@ constexpr size_t kSwapSmemBytes = static_cast<size_t>(kRingBytes) + 2 * 256 * 4 
 static_assert(kSwapSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
 
 // the swapped kernel applies when one block of queries is small enough to stay resident next to a useful ring
+// fp32 catalogs: MODE 2 (one-term screening + exact re-scoring of the survivors) unless ICR_F32_EXACT3 asks for the
+// round-1 path (three MMA terms on hi|lo planes built per call) - kept as an A/B switch for benchmarks and tests
+static bool f32_exact3() {
+  static const bool on = getenv("ICR_F32_EXACT3") != nullptr;
+  return on;
+}
+static int mode_for(int dtype) { return dtype == ICR_BF16 ? 1 : (f32_exact3() ? 3 : 2); }
+// keys carried per query between phases: k exact keys, or k + room for the screening band (select_args.cuh)
+static int carry_cap(int k, int mode) {
+  if (mode != 2) return k;
+  const int kc = k + (k > 32 ? k : 32);
+  return kc < 512 ? kc : 512;
+}
+
 static bool swap_applies(int64_t Q, int64_t D, int dtype) {
   static const bool disabled = getenv("ICR_NO_SWAP") != nullptr;  // A/B switch for benchmarks
   if (disabled || Q > 256) return false;
   const int64_t qpad = (Q + 31) / 32 * 32;
   const int64_t kb = (D + BK - 1) / BK;
-  const int64_t res = (dtype == ICR_F32 ? 2 : 1) * kb * (qpad / 2) * 128;
+  const int64_t res = (mode_for(dtype) == 3 ? 2 : 1) * kb * (qpad / 2) * 128;
   return res <= kSwapResidentMax;
 }
 
@@ -874,21 +916,50 @@ constexpr int kMaxPhases = 16;
 // tuning hooks (profiles/r01_notes.md)
 static const int kDense0Tiles = getenv("ICR_K2_DENSE0") ? atoi(getenv("ICR_K2_DENSE0")) : 4;
 
-// launches the DENSE instantiation `which` (0 planes, 1 bf16 streaming, 2 bf16 resident queries)
-static int launch_dense_variant(int which, int grid, const CUtensorMap& map_a, const CUtensorMap& map_b, const GemmArgs& g, cudaStream_t st) {
-  static thread_local bool attr_set[3] = {false, false, false};
-  if (!attr_set[which]) {
-    const int smem = static_cast<int>(kGemmSmemBytes);
-    if (which == 0) ICR_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_kernel<3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    if (which == 1) ICR_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_kernel<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    if (which == 2) ICR_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_kernel<1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set[which] = true;
-  }
-  profile_begin(kKernelGemm, which == 0 ? 3 : 1, st);
-  const int threads = 128 + epi_warps(which == 0 ? 3 : 1) * 32;
-  if (which == 0) gemm_topk_kernel<3, false, true><<<grid, threads, kGemmSmemBytes, st>>>(map_a, map_b, g);
-  if (which == 1) gemm_topk_kernel<1, false, true><<<grid, threads, kGemmSmemBytes, st>>>(map_a, map_b, g);
-  if (which == 2) gemm_topk_kernel<1, true, true><<<grid, threads, kGemmSmemBytes, st>>>(map_a, map_b, g);
+// kernel variants: 0 = fp16 hi|lo planes (3 terms), 1 = bf16 streaming both operands, 2 = bf16 with resident queries,
+// 3 / 4 = swapped kernel (small batches) on planes / bf16, 5 / 6 = fp16 screen plane streaming / resident queries,
+// 7 = swapped kernel on the screen plane
+static int variant_terms(int which) { return (which == 0 || which == 3) ? 3 : 1; }
+
+#define ICR_GEMM_VARIANTS(X, DENSE)            \
+  X(0, (gemm_topk_kernel<3, false, DENSE>))    \
+  X(1, (gemm_topk_kernel<1, false, DENSE>))    \
+  X(2, (gemm_topk_kernel<1, true, DENSE>))     \
+  X(5, (gemm_topk_kernel<2, false, DENSE>))    \
+  X(6, (gemm_topk_kernel<2, true, DENSE>))
+
+// launches instantiation `which` of the queries-on-M kernel, DENSE (K2' / first phase) or filtering
+template <bool DENSE>
+static int launch_gemm_variant(int which, int grid, const CUtensorMap& map_a, const CUtensorMap& map_b, const GemmArgs& g, cudaStream_t st) {
+  static thread_local SmemAttrCache cache[8];
+  int rc = ICR_OK;
+#define ICR_SET(ID, K) \
+  if (which == ID) rc = ensure_dyn_smem(cache[ID], K, kGemmSmemBytes);
+  ICR_GEMM_VARIANTS(ICR_SET, DENSE)
+#undef ICR_SET
+  if (rc) return rc;
+  profile_begin(kKernelGemm, variant_terms(which), st);
+  const int threads = 128 + epi_warps(variant_terms(which)) * 32;
+#define ICR_RUN(ID, K) \
+  if (which == ID) K<<<grid, threads, kGemmSmemBytes, st>>>(map_a, map_b, g);
+  ICR_GEMM_VARIANTS(ICR_RUN, DENSE)
+#undef ICR_RUN
+  profile_end(st);
+  ICR_LAUNCH_CHECK();
+  return ICR_OK;
+}
+
+static int launch_swap_variant(int which, int grid, const CUtensorMap& map_q, const CUtensorMap& map_c, const GemmArgs& g, cudaStream_t st) {
+  static thread_local SmemAttrCache cache[3];
+  int rc = ICR_OK;
+  if (which == 3) rc = ensure_dyn_smem(cache[0], gemm_swap_kernel<3>, kSwapSmemBytes);
+  if (which == 4) rc = ensure_dyn_smem(cache[1], gemm_swap_kernel<1>, kSwapSmemBytes);
+  if (which == 7) rc = ensure_dyn_smem(cache[2], gemm_swap_kernel<2>, kSwapSmemBytes);
+  if (rc) return rc;
+  profile_begin(kKernelGemm, variant_terms(which), st);
+  if (which == 3) gemm_swap_kernel<3><<<grid, kSwapThreads, kSwapSmemBytes, st>>>(map_q, map_c, g);
+  if (which == 4) gemm_swap_kernel<1><<<grid, kSwapThreads, kSwapSmemBytes, st>>>(map_q, map_c, g);
+  if (which == 7) gemm_swap_kernel<2><<<grid, kSwapThreads, kSwapSmemBytes, st>>>(map_q, map_c, g);
   profile_end(st);
   ICR_LAUNCH_CHECK();
   return ICR_OK;
@@ -900,12 +971,13 @@ static bool dense0_applies(int64_t Q, int64_t D, int dtype) {
 }
 
 struct GemmWs {
-  size_t q_planes, c_planes, qinv, cinv, tau, carry[2], carry_cnt[2], cand, cand_cnt, scratch, dense0, total;
-  int max_chunks, seg_cap;
+  size_t q_planes, c_planes, qinv, cinv, tau, overflow, carry[2], carry_cnt[2], cand, cand_cnt, scratch, dense0, total;
+  int max_chunks, seg_cap, kc;
 };
 
 static GemmWs gemm_ws_layout(int64_t Q, int64_t N, int64_t D, int dtype, int k, int have_planes, int have_cinv) {
   GemmWs w{};
+  const int mode = mode_for(dtype);
   const int qblocks = static_cast<int>((Q + 2 * BM - 1) / (2 * BM));
   Phase ph[kMaxPhases];
   const bool dense0 = dense0_applies(Q, D, dtype);
@@ -913,24 +985,27 @@ static GemmWs gemm_ws_layout(int64_t Q, int64_t N, int64_t D, int dtype, int k, 
   int maxc = 1;
   for (int i = 0; i < np; ++i) maxc = ph[i].chunks > maxc ? ph[i].chunks : maxc;
   w.max_chunks = maxc;
-  const int64_t dp2 = 2 * ((D + 63) / 64 * 64);
+  const int64_t dp = (D + 63) / 64 * 64;
+  const int64_t plane_elems = mode == 3 ? 2 * dp : dp;  // hi|lo planes, or the screen plane
   size_t off = 0;
   auto take = [&](size_t bytes) {
     const size_t o = off;
     off += align_up(bytes, 1024);
     return o;
   };
-  w.q_planes = take(dtype == ICR_F32 ? static_cast<size_t>(Q) * dp2 * 2 : 0);
-  w.c_planes = take((dtype == ICR_F32 && !have_planes) ? static_cast<size_t>(N) * dp2 * 2 : 0);
-  w.qinv = take(dtype == ICR_BF16 ? static_cast<size_t>(Q) * 4 : 0);
-  w.cinv = take((dtype == ICR_BF16 && !have_cinv) ? static_cast<size_t>(N) * 4 : 0);
+  w.q_planes = take(mode != 1 ? static_cast<size_t>(Q) * plane_elems * 2 : 0);
+  w.c_planes = take((mode == 3 || (mode == 2 && !have_planes)) ? static_cast<size_t>(N) * plane_elems * 2 : 0);
+  w.qinv = take(mode != 3 ? static_cast<size_t>(Q) * 4 : 0);
+  w.cinv = take((mode != 3 && !have_cinv) ? static_cast<size_t>(N) * 4 : 0);
   w.tau = take(static_cast<size_t>(Q) * 4);
+  w.overflow = take(static_cast<size_t>(Q) * 4);
+  w.kc = carry_cap(k, mode);
   for (int i = 0; i < 2; ++i) {
-    w.carry[i] = take(static_cast<size_t>(Q) * k * 8);
+    w.carry[i] = take(static_cast<size_t>(Q) * w.kc * 8);
     w.carry_cnt[i] = take(static_cast<size_t>(Q) * 4);
   }
   w.seg_cap = seg_cap_for(k);
-  const int halves = swap_applies(Q, D, dtype) ? 2 : epi_warps(dtype == ICR_F32 ? 3 : 1) / 4;
+  const int halves = swap_applies(Q, D, dtype) ? 2 : epi_warps(mode == 3 ? 3 : 1) / 4;
   w.cand = take(static_cast<size_t>(Q) * maxc * halves * w.seg_cap * 8);
   w.cand_cnt = take(static_cast<size_t>(Q) * maxc * halves * 4);
   w.scratch = take(static_cast<size_t>(kNumSMs) * kEpiWarps * kSegCapMax * 8);  // in-kernel compaction scratch
@@ -948,18 +1023,23 @@ bool gemm_topk_supported(int64_t Q, int64_t N, int64_t D, int dtype, int k, cons
 }
 
 size_t gemm_topk_workspace_bytes(int64_t Q, int64_t N, int64_t D, int dtype, int k, int have_planes) {
-  // sized without cached bf16 inverse norms so that one figure covers both cases
+  // sized without cached inverse norms so that one figure covers both cases
   return gemm_ws_layout(Q, N, D, dtype, k, have_planes, 0).total;
 }
 
-__global__ void fill_f32_kernel(float* p, int64_t n, float v) {
+// tau = -inf (phase 0 admits every row), overflow flags cleared
+__global__ void init_phase_state_kernel(float* tau, unsigned int* overflow, int64_t n) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < n) p[i] = v;
+  if (i < n) {
+    tau[i] = -INFINITY;
+    overflow[i] = 0u;
+  }
 }
 
 int launch_gemm_topk(const void* queries, int64_t Q, int64_t ldq, const void* catalog, int64_t N, int64_t ldc, int64_t D,
                      int dtype, const uint16_t* cat_planes, const float* cat_inv_norms, const uint8_t* mask, int k, int64_t row_offset,
                      float* out_scores, int64_t* out_ids, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int mode = mode_for(dtype);
   const GemmWs L = gemm_ws_layout(Q, N, D, dtype, k, cat_planes != nullptr, cat_inv_norms != nullptr);
   if (ws_bytes < L.total) {
     set_error("gemm_topk: workspace %zu < %zu", ws_bytes, L.total);
@@ -976,27 +1056,72 @@ int launch_gemm_topk(const void* queries, int64_t Q, int64_t ldq, const void* ca
   g.qblocks = qblocks;
   g.mask = mask;
   g.tau = reinterpret_cast<float*>(base + L.tau);
+  g.overflow = reinterpret_cast<unsigned int*>(base + L.overflow);
   g.cand = reinterpret_cast<uint64_t*>(base + L.cand);
   g.cand_cnt = reinterpret_cast<int*>(base + L.cand_cnt);
   g.seg_cap = L.seg_cap;
   g.compact_scratch = reinterpret_cast<uint64_t*>(base + L.scratch);
+  // what every select of this call shares
+  HistSelectArgs sa{};
+  sa.Q = Q;
+  sa.k = k;
+  sa.kc = L.kc;
+  sa.seg_keys = g.cand;
+  sa.seg_cnt = g.cand_cnt;
+  sa.seg_stride = sa.seg_cap = g.seg_cap;
+  sa.id_offset = row_offset;
+  sa.raw_keys = 1;  // the only producer of segments is the GEMM epilogue
   CUtensorMap map_a, map_b;
-  int terms;
-  if (dtype == ICR_F32) {
+  const void* q_operand = queries;  // what the TMA map of the swapped kernel is built over
+  int64_t q_cols = D, q_ld = ldq;
+  if (mode == 3) {
     uint16_t* qp = reinterpret_cast<uint16_t*>(base + L.q_planes);
+    uint16_t* cp = reinterpret_cast<uint16_t*>(base + L.c_planes);
     if ((rc = launch_split_planes(static_cast<const float*>(queries), Q, D, ldq, qp, st))) return rc;
-    const uint16_t* cp = cat_planes;
-    if (!cp) {
-      uint16_t* built = reinterpret_cast<uint16_t*>(base + L.c_planes);
-      if ((rc = launch_split_planes(static_cast<const float*>(catalog), N, D, ldc, built, st))) return rc;
-      cp = built;
-    }
+    if ((rc = launch_split_planes(static_cast<const float*>(catalog), N, D, ldc, cp, st))) return rc;
     if ((rc = make_map(&map_a, qp, Q, 2 * dp, 2 * dp, false))) return rc;
     if ((rc = make_map(&map_b, cp, N, 2 * dp, 2 * dp, false))) return rc;
-    terms = 3;
     g.kb_per_term = static_cast<int>(dp / BK);
     g.plane_stride = static_cast<int>(dp);
     g.acc_scale = 1.0f / 65536.0f;
+    q_operand = qp;
+    q_cols = q_ld = 2 * dp;
+  } else if (mode == 2) {
+    uint16_t* qp = reinterpret_cast<uint16_t*>(base + L.q_planes);
+    float* qinv = reinterpret_cast<float*>(base + L.qinv);
+    if ((rc = launch_screen_plane(static_cast<const float*>(queries), Q, D, ldq, qp, qinv, st))) return rc;
+    const uint16_t* cp = cat_planes;
+    const float* cinv = cat_inv_norms;
+    if (!cp) {
+      uint16_t* built = reinterpret_cast<uint16_t*>(base + L.c_planes);
+      float* built_inv = cinv ? nullptr : reinterpret_cast<float*>(base + L.cinv);
+      if ((rc = launch_screen_plane(static_cast<const float*>(catalog), N, D, ldc, built, built_inv, st))) return rc;
+      cp = built;
+      if (!cinv) cinv = built_inv;
+    } else if (!cinv) {
+      float* built_inv = reinterpret_cast<float*>(base + L.cinv);
+      if ((rc = launch_row_inv_norms(catalog, N, D, ldc, dtype, built_inv, st))) return rc;
+      cinv = built_inv;
+    }
+    if ((rc = make_map(&map_a, qp, Q, dp, dp, false))) return rc;
+    if ((rc = make_map(&map_b, cp, N, dp, dp, false))) return rc;
+    g.kb_per_term = static_cast<int>(dp / BK);
+    g.plane_stride = 0;
+    g.acc_scale = 1.0f / 65536.0f;
+    g.band = kScreenBandRaw;
+    q_operand = qp;
+    q_cols = q_ld = dp;
+    sa.band = kScreenBandRaw;
+    sa.overflow = g.overflow;
+    sa.rs_q = static_cast<const float*>(queries);
+    sa.rs_ldq = ldq;
+    sa.rs_cat = static_cast<const float*>(catalog);
+    sa.rs_ldc = ldc;
+    sa.rs_N = N;
+    sa.rs_D = static_cast<int>(D);
+    sa.rs_qinv = qinv;
+    sa.rs_cinv = cinv;
+    sa.mask = mask;  // the exact ranking of an overflowed query walks the catalog itself
   } else {
     float* qinv = reinterpret_cast<float*>(base + L.qinv);
     if ((rc = launch_row_inv_norms(queries, Q, D, ldq, dtype, qinv, st))) return rc;
@@ -1008,35 +1133,25 @@ int launch_gemm_topk(const void* queries, int64_t Q, int64_t ldq, const void* ca
     }
     if ((rc = make_map(&map_a, queries, Q, D, ldq, true))) return rc;
     if ((rc = make_map(&map_b, catalog, N, D, ldc, true))) return rc;
-    terms = 1;
     g.kb_per_term = static_cast<int>((D + BK - 1) / BK);
     g.plane_stride = 0;
     g.acc_scale = 1.0f;
     g.qinv = qinv;
     g.cinv = cinv;
   }
-  // kernel variant: 0 = fp16 planes (3 terms), 1 = bf16 streaming both operands, 2 = bf16 with resident queries,
-  // 3 / 4 = swapped kernel (small batches) on planes / bf16
-  static thread_local bool attr_set[5] = {false, false, false, false, false};
+  sa.out_scale = g.acc_scale;
+  sa.out_qscale = g.qinv;
+  const int terms = mode == 3 ? 3 : 1;
   const bool swap = swap_applies(Q, D, dtype);
-  const int which = swap ? (terms == 3 ? 3 : 4) : (terms == 3 ? 0 : (g.kb_per_term <= kAStatMaxKB ? 2 : 1));
+  const bool astat = terms == 1 && g.kb_per_term <= kAStatMaxKB;
+  int which;
+  if (swap) which = mode == 3 ? 3 : (mode == 1 ? 4 : 7);
+  else which = mode == 3 ? 0 : (mode == 1 ? (astat ? 2 : 1) : (astat ? 6 : 5));
   if (swap) {
     g.qpad = static_cast<int>((Q + 31) / 32 * 32);
-    if (terms == 3) rc = make_map(&map_a, base + L.q_planes, Q, 2 * dp, 2 * dp, false, g.qpad / 2);
-    else rc = make_map(&map_a, queries, Q, D, ldq, true, g.qpad / 2);
-    if (rc) return rc;
+    if ((rc = make_map(&map_a, q_operand, Q, q_cols, q_ld, mode == 1, g.qpad / 2))) return rc;
   }
-  if (!attr_set[which]) {
-    const int smem = static_cast<int>(kGemmSmemBytes);
-    if (which == 3) ICR_CUDA_CHECK(cudaFuncSetAttribute(gemm_swap_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSwapSmemBytes)));
-    if (which == 4) ICR_CUDA_CHECK(cudaFuncSetAttribute(gemm_swap_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSwapSmemBytes)));
-    if (which == 0) ICR_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_kernel<3, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    if (which == 1) ICR_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_kernel<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    if (which == 2) ICR_CUDA_CHECK(cudaFuncSetAttribute(gemm_topk_kernel<1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set[which] = true;
-  }
-  // tau starts at -inf: phase 0 admits every row
-  fill_f32_kernel<<<static_cast<unsigned>((Q + 255) / 256), 256, 0, st>>>(const_cast<float*>(g.tau), Q, -INFINITY);
+  init_phase_state_kernel<<<static_cast<unsigned>((Q + 255) / 256), 256, 0, st>>>(const_cast<float*>(g.tau), g.overflow, Q);
   ICR_LAUNCH_CHECK();
 
   // ---- first phase, dense: rows of the first kDense0Tiles tiles have no threshold to beat yet, so every score would
@@ -1058,15 +1173,21 @@ int launch_gemm_topk(const void* queries, int64_t Q, int64_t ldq, const void* ca
     gd.dense_raw = 1;
     const int items = qblocks * T0;
     const int pairs = items < kNumSMs / 2 ? items : kNumSMs / 2;
-    if ((rc = launch_dense_variant(which, 2 * pairs, map_a, map_b, gd, st))) return rc;
+    if ((rc = launch_gemm_variant<true>(which, 2 * pairs, map_a, map_b, gd, st))) return rc;
     const bool last = (T0 >= T);
-    const int rows0 = static_cast<int>(N < static_cast<int64_t>(T0) * BN ? N : static_cast<int64_t>(T0) * BN);
-    rc = launch_select_hist(g.cand, g.cand_cnt, Q, 0, g.seg_cap, g.seg_cap, nullptr, nullptr,
-                            last ? nullptr : reinterpret_cast<uint64_t*>(base + L.carry[0]),
-                            last ? nullptr : reinterpret_cast<int*>(base + L.carry_cnt[0]), last ? nullptr : const_cast<float*>(g.tau),
-                            last ? out_scores : nullptr, last ? out_ids : nullptr, row_offset, k, g.acc_scale, g.qinv, st, d0, gd.dense_ld,
-                            rows0, mask);
-    if (rc) return rc;
+    HistSelectArgs s0 = sa;
+    s0.nseg = 0;
+    const bool keep0 = !last || mode == 2;  // a screened search hands its final candidates to the re-scoring kernel through the carry
+    s0.carry_out = keep0 ? reinterpret_cast<uint64_t*>(base + L.carry[0]) : nullptr;
+    s0.carry_cnt_out = keep0 ? reinterpret_cast<int*>(base + L.carry_cnt[0]) : nullptr;
+    s0.tau_out = last ? nullptr : const_cast<float*>(g.tau);
+    s0.out_scores = last ? out_scores : nullptr;
+    s0.out_ids = last ? out_ids : nullptr;
+    s0.dense = d0;
+    s0.dense_ld = gd.dense_ld;
+    s0.dense_rows = static_cast<int>(N < static_cast<int64_t>(T0) * BN ? N : static_cast<int64_t>(T0) * BN);
+    s0.mask = mask;
+    if ((rc = run_select(s0, Q, st))) return rc;
     if (last) return ICR_OK;
     done_phases = 1;
   }
@@ -1079,25 +1200,22 @@ int launch_gemm_topk(const void* queries, int64_t Q, int64_t ldq, const void* ca
     const int items = qblocks * g.chunks;
     const int pairs = items < kNumSMs / 2 ? items : kNumSMs / 2;
     const int grid = 2 * pairs;  // whole CTA pairs (cluster dims 2x1x1)
-    profile_begin(kKernelGemm, terms, st);
-    const int threads = 128 + epi_warps(terms) * 32;
-    if (which == 0) gemm_topk_kernel<3, false, false><<<grid, threads, kGemmSmemBytes, st>>>(map_a, map_b, g);
-    if (which == 1) gemm_topk_kernel<1, false, false><<<grid, threads, kGemmSmemBytes, st>>>(map_a, map_b, g);
-    if (which == 2) gemm_topk_kernel<1, true, false><<<grid, threads, kGemmSmemBytes, st>>>(map_a, map_b, g);
-    if (which == 3) gemm_swap_kernel<3><<<grid, kSwapThreads, kSwapSmemBytes, st>>>(map_a, map_b, g);
-    if (which == 4) gemm_swap_kernel<1><<<grid, kSwapThreads, kSwapSmemBytes, st>>>(map_a, map_b, g);
-    profile_end(st);
-    ICR_LAUNCH_CHECK();
+    if (swap) rc = launch_swap_variant(which, grid, map_a, map_b, g, st);
+    else rc = launch_gemm_variant<false>(which, grid, map_a, map_b, g, st);
+    if (rc) return rc;
     const bool last = (pp == np - 1);
     const int cur = p & 1, prev = cur ^ 1;
-    rc = launch_select_hist(g.cand, g.cand_cnt, Q, g.chunks * (swap ? 2 : epi_warps(terms) / 4), g.seg_cap, g.seg_cap,
-                       p > 0 ? reinterpret_cast<uint64_t*>(base + L.carry[prev]) : nullptr,
-                       p > 0 ? reinterpret_cast<int*>(base + L.carry_cnt[prev]) : nullptr,
-                       last ? nullptr : reinterpret_cast<uint64_t*>(base + L.carry[cur]),
-                       last ? nullptr : reinterpret_cast<int*>(base + L.carry_cnt[cur]),
-                            last ? nullptr : const_cast<float*>(g.tau), last ? out_scores : nullptr, last ? out_ids : nullptr, row_offset,
-                            k, g.acc_scale, g.qinv, st);  // raw key scores -> cosines on the way out
-    if (rc) return rc;
+    HistSelectArgs sp = sa;
+    sp.nseg = g.chunks * (swap ? 2 : epi_warps(terms) / 4);
+    sp.carry_in = p > 0 ? reinterpret_cast<uint64_t*>(base + L.carry[prev]) : nullptr;
+    sp.carry_cnt_in = p > 0 ? reinterpret_cast<int*>(base + L.carry_cnt[prev]) : nullptr;
+    const bool keep = !last || mode == 2;
+    sp.carry_out = keep ? reinterpret_cast<uint64_t*>(base + L.carry[cur]) : nullptr;
+    sp.carry_cnt_out = keep ? reinterpret_cast<int*>(base + L.carry_cnt[cur]) : nullptr;
+    sp.tau_out = last ? nullptr : const_cast<float*>(g.tau);
+    sp.out_scores = last ? out_scores : nullptr;  // raw key scores -> cosines (or exact re-scoring) on the way out
+    sp.out_ids = last ? out_ids : nullptr;
+    if ((rc = run_select(sp, Q, st))) return rc;
   }
   return ICR_OK;
 }
@@ -1166,7 +1284,7 @@ int launch_gemm_dense(const void* a, int64_t Qa, int64_t lda, const void* b, int
   g.chunks = chunks;
   const int items = qblocks * chunks;
   const int grid = 2 * (items < npairs ? items : npairs);
-  return launch_dense_variant(which, grid, map_a, map_b, g, st);
+  return launch_gemm_variant<true>(which, grid, map_a, map_b, g, st);
 }
 
 }  // namespace icr

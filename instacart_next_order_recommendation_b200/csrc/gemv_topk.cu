@@ -643,10 +643,10 @@ constexpr size_t kSmemBudget = 227 * 1024 - 1024;
 template <typename T, int RB, int QT>
 static int launch_direct(const GemvArgs& a, int grid, cudaStream_t st) {
   const size_t smem = GemvSmem<QT>::bytes(a.D);
-  static thread_local size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    ICR_CUDA_CHECK(cudaFuncSetAttribute(gemv_topk_kernel<T, RB, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    configured = smem;
+  static thread_local SmemSizeCache configured;  // per device: a thread may serve several GPUs
+  if (smem > 48 * 1024) {
+    const int rc = ensure_dyn_smem_size(configured, gemv_topk_kernel<T, RB, QT>, smem);
+    if (rc) return rc;
   }
   profile_begin(kKernelGemv, 1, st);
   gemv_topk_kernel<T, RB, QT><<<grid, kGemvThreads, smem, st>>>(a);
@@ -676,10 +676,10 @@ template <typename T, int QT, bool NORMS = false>
 static int launch_ring(GemvArgs a, int grid, cudaStream_t st) {
   a.ring_slots = ring_slots_for<T, QT>(a.D);
   const size_t smem = static_cast<size_t>(a.ring_slots) * (QT == 7 ? 4 : 8) * a.D * sizeof(T) + 2 * kMaxSlots * sizeof(uint64_t) + GemvSmem<QT>::bytes(a.D) + 128;
-  static thread_local size_t configured = 0;
-  if (smem > configured) {
-    ICR_CUDA_CHECK((cudaFuncSetAttribute(gemv_ring_kernel<T, QT, NORMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))));
-    configured = smem;
+  static thread_local SmemSizeCache configured;  // per device
+  {
+    const int rc = ensure_dyn_smem_size(configured, gemv_ring_kernel<T, QT, NORMS>, smem);
+    if (rc) return rc;
   }
   profile_begin(kKernelGemv, 1, st);
   gemv_ring_kernel<T, QT, NORMS><<<grid, kRingThreads, smem, st>>>(a);

@@ -557,10 +557,10 @@ TcWs tc_layout(int64_t B, int64_t Bc, int64_t D) {
 
 template <int MODE>
 int launch_tc(const CUtensorMap& a0, const CUtensorMap& b0, const CUtensorMap& a1, const CUtensorMap& b1, const TcArgs& g, cudaStream_t st) {
-  static thread_local bool attr_set = false;
-  if (!attr_set) {
-    ICR_CUDA_CHECK(cudaFuncSetAttribute(mnrl_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kTcSmemBytes)));
-    attr_set = true;
+  static thread_local SmemAttrCache attr_cache;  // per device
+  {
+    const int rc = ensure_dyn_smem(attr_cache, mnrl_tc_kernel<MODE>, kTcSmemBytes);
+    if (rc) return rc;
   }
   const int items = (g.qblocks[0] + ((MODE == MODE_MM || MODE == MODE_MM3) ? g.qblocks[1] : 0)) * g.chunks;
   const int npairs = kNumSMs / 2;

@@ -64,6 +64,50 @@ __global__ void __launch_bounds__(256) split_f16_planes_kernel(const float* __re
   }
 }
 
+// One warp per row: the SCREENING operand of fp32 catalogs and queries. plane[r] = fp16(256 * x_r / max(|x_r|, eps)),
+// zero-padded to dim_pad; inv[r] = 1 / max(|x_r|, eps) for the exact re-scoring of the few rows that pass the screen.
+// A single fp16 plane carries 11 significant bits per element: the screened score differs from the exact cosine by
+// at most 2^-10 (Cauchy-Schwarz over the two rounding-error vectors), which the caller turns into a safety band.
+__global__ void __launch_bounds__(256) screen_plane_kernel(const float* __restrict__ x, int64_t rows, int64_t dim, int64_t ld,
+                                                           __half* __restrict__ plane, int64_t dim_pad, float* __restrict__ inv_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const int nvec = static_cast<int>(dim / 4), nvec_pad = static_cast<int>(dim_pad / 4);
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    const float* row = x + r * ld;
+    float ss = 0.f;
+    for (int v = lane; v < nvec; v += 32) {
+      const float4 f = ldg_stream_f4(row + 4 * v);
+      ss = fmaf(f.x, f.x, fmaf(f.y, f.y, fmaf(f.z, f.z, fmaf(f.w, f.w, ss))));
+    }
+    ss = warp_sum(ss);
+    const float inv = 1.0f / fmaxf(sqrtf(ss), kNormEps);
+    if (lane == 0 && inv_out) inv_out[r] = inv;
+    const float sc = 256.0f * inv;
+    __half* dst = plane + r * dim_pad;
+    for (int v = lane; v < nvec_pad; v += 32) {
+      float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (v < nvec) f = *reinterpret_cast<const float4*>(row + 4 * v);  // second touch: L1/L2 hit
+      const __half2 a = __floats2half2_rn(f.x * sc, f.y * sc), b = __floats2half2_rn(f.z * sc, f.w * sc);
+      uint2 pk;
+      pk.x = *reinterpret_cast<const uint32_t*>(&a);
+      pk.y = *reinterpret_cast<const uint32_t*>(&b);
+      *reinterpret_cast<uint2*>(dst + 4 * v) = pk;
+    }
+  }
+}
+
+int launch_screen_plane(const float* x, int64_t rows, int64_t dim, int64_t ld, uint16_t* plane, float* inv, cudaStream_t st) {
+  if (rows == 0) return ICR_OK;
+  const int64_t dim_pad = (dim + 63) / 64 * 64;
+  const int64_t want = (rows + 7) / 8;
+  const int blocks = static_cast<int>(want < 148 * 16 ? want : 148 * 16);
+  screen_plane_kernel<<<blocks, 256, 0, st>>>(x, rows, dim, ld, reinterpret_cast<__half*>(plane), dim_pad, inv);
+  ICR_LAUNCH_CHECK();
+  return ICR_OK;
+}
+
 int launch_row_inv_norms(const void* x, int64_t rows, int64_t dim, int64_t ld, int dtype, float* inv, cudaStream_t st) {
   if (rows == 0) return ICR_OK;
   const int threads = 256;

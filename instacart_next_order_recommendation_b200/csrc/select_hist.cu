@@ -12,6 +12,7 @@
 // refinement always terminates. The final phase sorts the k selected keys; earlier phases only need the set
 // and its minimum (the new threshold tau).
 #include "common.cuh"
+#include "select_args.cuh"
 #include "select_warp.cuh"
 
 namespace icr {
@@ -20,40 +21,7 @@ namespace icr {
 #define ICR_HS_WARPS 4
 #endif
 constexpr int kHsWarps = ICR_HS_WARPS;  // queries per CTA, 11 KB of shared memory each (tuning: profiles/r01_notes.md)
-constexpr int kHsCap = 1024;      // keys buffered per query at once
-constexpr int kHsSel = 256;       // >= ICR_MAX_K
-constexpr int kHsPref = 448;      // segments per gather round: the prefix array (+1) is overlaid on sel[] (512 ints)
-
-struct HistSelectArgs {
-  const uint64_t* seg_keys;  // [Q][nseg][seg_stride]
-  const int* seg_cnt;        // [Q][nseg]
-  int nseg;
-  int seg_stride;
-  int seg_cap;
-  const uint64_t* carry_in;  // [Q][k] or null
-  const int* carry_cnt_in;   // [Q]
-  uint64_t* carry_out;       // [Q][k] or null (unsorted set)
-  int* carry_cnt_out;        // [Q]
-  float* tau_out;            // [Q] or null
-  float* out_scores;         // [Q][k] or null (sorted descending)
-  int64_t* out_ids;          // [Q][k]
-  int64_t id_offset;
-  int k;
-  int64_t Q;
-  float out_scale;          // final score = key score * out_scale * (out_qscale ? out_qscale[q] : 1)
-  const float* out_qscale;  // [Q] or null
-  int raw_keys;             // segments hold (score bits, ~row) as the GEMM epilogue writes them; carry keys are ordered
-  // dense front end (first phase of K2): instead of segments, row q of a [Q][dense_ld] score matrix holds the raw
-  // scores of catalog rows 0 .. dense_rows-1; rows flagged in `mask` are skipped
-  const float* dense;
-  int64_t dense_ld;
-  int dense_rows;
-  const uint8_t* mask;
-  // list front end (K4 shard merge): G lists of list_k (score, id) pairs per query, laid out [G][Q][list_k]; id < 0 = empty
-  const float* list_scores;
-  const int64_t* list_ids;
-  int list_g, list_k;
-};
+constexpr int kHsSel = 512;       // >= 2 * ICR_MAX_K: the k results, or k + the band capacity of screened keys
 
 // flat candidate t of query q from the dense matrix or the shard lists -> key; false if there is none
 __device__ __forceinline__ bool front_fetch(const HistSelectArgs& a, int64_t q, int t, int count, uint64_t& key) {
@@ -80,152 +48,797 @@ __device__ __forceinline__ uint64_t canonical_from_raw(uint64_t raw) {
   return (static_cast<uint64_t>(order_bits(f)) << 32) | (raw & 0xFFFFFFFFull);
 }
 
-struct HsSmem {
-  uint64_t buf[kHsWarps][kHsCap];
-  uint64_t sel[kHsWarps][kHsSel];
-  unsigned int hist[kHsWarps][kHsBins];
+
+// ---- exact re-scoring of screened candidates (fp32 catalogs) -------------------------------------------------------
+// cos(q, row) = <q, c_row> * qinv * cinv[row] in fp32 FMAs on the rows as the caller stores them: the arithmetic of the
+// GEMV path (K1), so both paths return the same scores. RB rows are scored at once: RB * NV independent 16-byte loads
+// per lane are in flight before the first FMA (the candidates' rows are scattered over the L2-resident catalog).
+template <int NV, int RB>
+__device__ __forceinline__ void score_rows_fixed(const float* __restrict__ qrow, const float* const (&rows)[RB], float (&acc)[RB], int lane) {
+  float4 qv[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) qv[v] = __ldg(reinterpret_cast<const float4*>(qrow) + v * 32 + lane);
+  float4 c[RB][NV];
+#pragma unroll
+  for (int u = 0; u < RB; ++u)
+#pragma unroll
+    for (int v = 0; v < NV; ++v) c[u][v] = __ldg(reinterpret_cast<const float4*>(rows[u]) + v * 32 + lane);
+#pragma unroll
+  for (int u = 0; u < RB; ++u) {
+    float s = 0.f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) s = fmaf(qv[v].x, c[u][v].x, fmaf(qv[v].y, c[u][v].y, fmaf(qv[v].z, c[u][v].z, fmaf(qv[v].w, c[u][v].w, s))));
+    acc[u] = s;
+  }
+}
+
+// partial dot products of 8 rows with the query (any D % 4 == 0); lane sums are combined by the caller.
+// 12 independent 16-byte loads per lane in flight (4 rows x 3 vectors at D = 384, 2 x 6 at D = 768): with 16 resident warps
+// per SM that is ~100 KB outstanding, enough to cover the L2 latency, and the kernel stays within 128 registers.
+template <bool WIDE = false>
+__device__ __forceinline__ void score_rows8(const float* __restrict__ qrow, const float* const (&rows)[8], int D, float (&acc)[8], int lane) {
+  // real loops (unroll 1): fully unrolled, the scheduler hoists every batch's loads to the top and the kernel needs 250 registers
+  if (D == 384) {
+    if (WIDE) {  // all 8 rows at once: 24 loads per lane in flight (the re-scoring kernel, ~170 registers)
+      score_rows_fixed<3, 8>(qrow, rows, acc, lane);
+      return;
+    }
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+      const float* r[4];
+      float t[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) r[u] = h ? rows[4 + u] : rows[u];
+      score_rows_fixed<3, 4>(qrow, r, t, lane);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        acc[u] = h ? acc[u] : t[u];
+        acc[4 + u] = h ? t[u] : 0.f;
+      }
+    }
+    return;
+  }
+  if (D == 768) {
+#pragma unroll 1
+    for (int h = 0; h < 4; ++h) {
+      const float* r[2];
+      float t[2];
+      r[0] = h == 0 ? rows[0] : (h == 1 ? rows[2] : (h == 2 ? rows[4] : rows[6]));
+      r[1] = h == 0 ? rows[1] : (h == 1 ? rows[3] : (h == 2 ? rows[5] : rows[7]));
+      score_rows_fixed<6, 2>(qrow, r, t, lane);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        acc[2 * u] = h == u ? t[0] : (h < u ? 0.f : acc[2 * u]);
+        acc[2 * u + 1] = h == u ? t[1] : (h < u ? 0.f : acc[2 * u + 1]);
+      }
+    }
+    return;
+  }
+#pragma unroll
+  for (int u = 0; u < 8; ++u) acc[u] = 0.f;
+  const int nvec = D >> 2;
+#pragma unroll 1
+  for (int v = lane; v < nvec; v += 32) {
+    const float4 qv = __ldg(reinterpret_cast<const float4*>(qrow) + v);
+    float4 c[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) c[u] = __ldg(reinterpret_cast<const float4*>(rows[u]) + v);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc[u] = fmaf(qv.x, c[u].x, fmaf(qv.y, c[u].y, fmaf(qv.z, c[u].z, fmaf(qv.w, c[u].w, acc[u]))));
+  }
+}
+
+// sel[i] <- exact key of the row held in sel[i], for i = first, first + stride, ... in batches of 8 (one warp)
+__device__ __forceinline__ void warp_rescore(uint64_t* sel, int m, int first_batch, int batch_stride, int64_t q, const HistSelectArgs& a, int lane) {
+  const float* qrow = a.rs_q + q * a.rs_ldq;
+  const float qi = a.rs_qinv[q];
+  for (int b0 = first_batch * 8; b0 < m; b0 += batch_stride * 8) {
+    const float* rows[8];
+    uint32_t rid[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      rid[u] = key_row(sel[min(b0 + u, m - 1)]);
+      rows[u] = a.rs_cat + static_cast<int64_t>(rid[u]) * a.rs_ldc;
+    }
+    float acc[8];
+    score_rows8(qrow, rows, a.rs_D, acc, lane);
+    warp_transpose_reduce<8>(acc, lane);  // lane l: full sum of row (l >> 2)
+    const int u = lane >> 2;
+    uint32_t my_row = rid[0];
+#pragma unroll
+    for (int j = 1; j < 8; ++j) my_row = (u == j) ? rid[j] : my_row;
+    __syncwarp();
+    if ((lane & 3) == 0 && b0 + u < m) sel[b0 + u] = make_key(acc[0] * qi * __ldg(a.rs_cinv + my_row), my_row);
+  }
+  __syncwarp();
+}
+
+// =====================================================================================================================
+// Warp-per-query selection, lean form. Keys live in shared memory as two 32-bit arrays - sc[] = order-preserving score
+// bits, rw[] = ~row - so every pass works on 32-bit values: a 256-bin histogram over the score range finds the bin of the
+// k-th best key, the few keys of that bin are ranked exactly as (score, ~row) pairs, and ONE in-place compaction keeps
+// every key >= the threshold key (the k-th key itself, or `band` below its score for screened keys). ~35 thread
+// instructions per key instead of ~300 for the 64-bit multi-pass version it replaces (profiles/r02_notes.md).
+// =====================================================================================================================
+#ifdef ICR_SELECT_TRACE  // development builds only (ICR_NVCC_DEFS=-DICR_SELECT_TRACE): cycles per section of the warp select, summed over warps
+__device__ unsigned long long g_sel_trace[16];
+#define ICR_ST_BEGIN() long long st_t0_ = clock64()
+#define ICR_ST_MARK(i)                                                      \
+  do {                                                                      \
+    const long long t_ = clock64();                                         \
+    if ((threadIdx.x & 31) == 0) atomicAdd(&g_sel_trace[i], static_cast<unsigned long long>(t_ - st_t0_)); \
+    st_t0_ = clock64();                                                     \
+  } while (0)
+#else
+#define ICR_ST_BEGIN() do {} while (0)
+#define ICR_ST_MARK(i) do {} while (0)
+#endif
+
+constexpr int kLsCap = 1024;   // keys buffered per query (8 KB of shared memory as two 32-bit arrays)
+constexpr int kLsList = 64;    // boundary-bin keys ranked directly, held as (sc, rw) pairs in hist[0..128)
+constexpr int kLsB = 8;        // keys per lane per batch of a pass
+
+struct LsSmem {
+  uint32_t sc[kHsWarps][kLsCap];
+  uint32_t rw[kHsWarps][kLsCap];
+  uint32_t hist[kHsWarps][kHsBins];
 };
 
-__global__ void __launch_bounds__(kHsWarps * 32) select_hist_kernel(HistSelectArgs a) {
+__device__ __forceinline__ bool pair_gt(uint32_t s1, uint32_t r1, uint32_t s2, uint32_t r2) { return s1 > s2 || (s1 == s2 && r1 > r2); }
+__device__ __forceinline__ bool pair_ge(uint32_t s1, uint32_t r1, uint32_t s2, uint32_t r2) { return s1 > s2 || (s1 == s2 && r1 >= r2); }
+
+// Every pass walks the keys in batches of 8 per lane (key c + lane + 32 u, u < 8): the eight shared-memory loads of a batch
+// are issued together and its eight iterations are independent instructions. One key per iteration made each pass a chain of
+// dependent LDS -> ballot -> add steps (~11 cycles per issued instruction at 16 warps per SM); holding ALL keys in registers
+// (32 unrolled slots) removed the chains but made the kernel 400 KB of code that thrashed the instruction cache - both
+// measured in profiles/r02_notes.md. Empty slots read as 0: no finite score has order bits 0.
+__device__ __forceinline__ void ls_batch(const uint32_t* a, int n, int c, int lane, uint32_t (&v)[kLsB]) {
+#pragma unroll
+  for (int u = 0; u < kLsB; ++u) {
+    const int i = c + lane + 32 * u;
+    v[u] = i < n ? a[i] : 0u;
+  }
+}
+
+// cumulative scan of the 256-bin histogram from the top bin down: the bin holding the `need`-th largest key, the count
+// above it (subtracted from need) and its own population
+__device__ __forceinline__ int ls_scan(const uint32_t* hist, int& need, int& cnt, int lane) {
+  unsigned int local[8], lsum = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    local[j] = hist[lane * 8 + j];
+    lsum += local[j];
+  }
+  unsigned int incl = lsum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int v = __shfl_up_sync(kFull, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const unsigned int excl = incl - lsum;
+  int t_star = -1;
+  unsigned int above = 0, c_star = 0;
+  if (excl < static_cast<unsigned int>(need) && static_cast<unsigned int>(need) <= incl) {
+    unsigned int c = excl;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (t_star < 0 && c + local[j] >= static_cast<unsigned int>(need)) {
+        t_star = lane * 8 + j;
+        above = c;
+        c_star = local[j];
+      }
+      c += local[j];
+    }
+  }
+  const unsigned owner = __ballot_sync(kFull, t_star >= 0);
+  const int src = __ffs(owner) - 1;
+  t_star = __shfl_sync(kFull, t_star, src);
+  need -= static_cast<int>(__shfl_sync(kFull, above, src));
+  cnt = static_cast<int>(__shfl_sync(kFull, c_star, src));
+  __syncwarp();
+  return 255 - t_star;
+}
+
+// One radix level over the bit patterns of val[] (the scores, or ~row among the keys whose score equals feq) inside the
+// window [lo, hi] (hi - lo < 256 << shift): returns the bin, counted from the window's lower edge, of the need-th largest.
+// Cold path (crowded boundary bins only): not inlined.
+__device__ __noinline__ int ls_level(const uint32_t* val, const uint32_t* fsc, uint32_t feq, int n, uint32_t lo, uint32_t hi, int shift, int* need_io,
+                                     int* cnt_out, uint32_t* hist) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < kHsBins / 32; ++i) hist[i * 32 + lane] = 0u;
+  __syncwarp();
+  for (int i = lane; i < n; i += 32) {
+    const uint32_t v = val[i];
+    if (v >= lo && v <= hi && (fsc == nullptr || fsc[i] == feq)) atomicAdd(&hist[255u - ((v - lo) >> shift)], 1u);
+  }
+  __syncwarp();
+  int need = *need_io, cnt = 0;
+  const int b = ls_scan(hist, need, cnt, lane);
+  *need_io = need;
+  *cnt_out = cnt;
+  return b;
+}
+
+// The k-th largest (sc, rw) pair of the n >= k >= 1 keys. hist doubles as the list of the boundary bin's keys.
+//
+// Level 1 bins the keys linearly in score VALUE (not in their bit patterns: float bits are logarithmic in the value, and a
+// dense first phase with scores on both sides of zero would put a third of all keys into the one bin that holds the k-th).
+// That leaves ~n/256 x (local density / mean density) keys in the boundary bin - a handful - which are ranked directly as
+// (score, ~row) pairs. Only if that bin is crowded (> kLsList keys: near-duplicate scores) do further levels refine it,
+// now linearly in the bit pattern over the bin's own narrow range, and finally over ~row among keys of ONE score.
+__device__ __forceinline__ void ls_kth(const uint32_t* sc, const uint32_t* rw, int n, int k, uint32_t* hist, int lane, uint32_t& ks, uint32_t& kr) {
+  const unsigned lt = (1u << lane) - 1u;
+  ICR_ST_BEGIN();
+  uint32_t mn = 0xFFFFFFFFu, mx = 0u;
+  for (int c = 0; c < n; c += 32 * kLsB) {
+    uint32_t v[kLsB];
+    ls_batch(sc, n, c, lane, v);
+#pragma unroll
+    for (int u = 0; u < kLsB; ++u) {
+      mn = min(mn, v[u] ? v[u] : 0xFFFFFFFFu);
+      mx = max(mx, v[u]);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = min(mn, __shfl_xor_sync(kFull, mn, o));
+    mx = max(mx, __shfl_xor_sync(kFull, mx, o));
+  }
+  ICR_ST_MARK(0);
+  int need = k, cnt = n;
+  uint32_t blo = mn, bhi = mx;  // the boundary bin covers score bits [blo, bhi]
+  if (mn != mx) {
+    // ---- level 1: 256 bins, linear in the score value ----
+    const float fmn = unorder_bits(mn);
+    const float scale = 256.0f / (unorder_bits(mx) - fmn);
+#pragma unroll
+    for (int i = 0; i < kHsBins / 32; ++i) hist[i * 32 + lane] = 0u;
+    __syncwarp();
+    for (int c = 0; c < n; c += 32 * kLsB) {
+      uint32_t v[kLsB];
+      ls_batch(sc, n, c, lane, v);
+#pragma unroll
+      for (int u = 0; u < kLsB; ++u) {
+        const int b = max(min(255, __float2int_rd((unorder_bits(v[u]) - fmn) * scale)), 0);
+        if (v[u] != 0u) atomicAdd(&hist[255 - b], 1u);
+      }
+    }
+    __syncwarp();
+    ICR_ST_MARK(1);
+    const int b_star = ls_scan(hist, need, cnt, lane);
+    ICR_ST_MARK(2);
+    // the bin's range in score bits (the value -> bin map is monotone, so the bin is an interval of bit patterns)
+    uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+    for (int c = 0; c < n; c += 32 * kLsB) {
+      uint32_t v[kLsB];
+      ls_batch(sc, n, c, lane, v);
+#pragma unroll
+      for (int u = 0; u < kLsB; ++u) {
+        const int b = max(min(255, __float2int_rd((unorder_bits(v[u]) - fmn) * scale)), 0);
+        const bool in = v[u] != 0u && b == b_star;
+        lo = min(lo, in ? v[u] : 0xFFFFFFFFu);
+        hi = max(hi, in ? v[u] : 0u);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = min(lo, __shfl_xor_sync(kFull, lo, o));
+      hi = max(hi, __shfl_xor_sync(kFull, hi, o));
+    }
+    blo = lo;
+    bhi = hi;
+    ICR_ST_MARK(3);
+  }
+  // ---- crowded bin: levels over its bit range ----
+  while (cnt > kLsList && blo != bhi) {
+    const int bits = 32 - __clz(static_cast<int>(bhi - blo));
+    const int shift = bits > 8 ? bits - 8 : 0;
+    const uint32_t lo = blo;
+    const int b = ls_level(sc, nullptr, 0u, n, lo, bhi, shift, &need, &cnt, hist);
+    blo = lo + (static_cast<uint32_t>(b) << shift);
+    bhi = min(bhi, blo + min((1u << shift) - 1u, 0xFFFFFFFFu - blo));
+  }
+  bool by_row = false;
+  uint32_t rlo = 0, rhi = 0xFFFFFFFFu;
+  if (cnt > kLsList) {
+    // more than kLsList keys share ONE score (duplicated catalog rows): the same levels over ~row among them
+    by_row = true;
+    uint32_t rmn = 0xFFFFFFFFu, rmx = 0u;
+    for (int i = lane; i < n; i += 32)
+      if (sc[i] == blo) {
+        rmn = min(rmn, rw[i]);
+        rmx = max(rmx, rw[i]);
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      rmn = min(rmn, __shfl_xor_sync(kFull, rmn, o));
+      rmx = max(rmx, __shfl_xor_sync(kFull, rmx, o));
+    }
+    rlo = rmn;
+    rhi = rmx;
+    while (cnt > kLsList && rlo != rhi) {
+      const int bits = 32 - __clz(static_cast<int>(rhi - rlo));
+      const int shift2 = bits > 8 ? bits - 8 : 0;
+      const uint32_t lo2 = rlo;
+      const int b = ls_level(rw, sc, blo, n, lo2, rhi, shift2, &need, &cnt, hist);
+      rlo = lo2 + (static_cast<uint32_t>(b) << shift2);
+      rhi = min(rhi, rlo + min((1u << shift2) - 1u, 0xFFFFFFFFu - rlo));
+    }
+  }
+  ICR_ST_MARK(4);
+  // ---- the boundary keys, as (sc, rw) pairs, into hist[]; then rank counting for the need-th largest of them ----
+  int nb = 0;
+  for (int c = 0; c < n; c += 32 * kLsB) {
+    uint32_t v[kLsB], r[kLsB];
+    ls_batch(sc, n, c, lane, v);
+    ls_batch(rw, n, c, lane, r);
+    unsigned m[kLsB];
+#pragma unroll
+    for (int u = 0; u < kLsB; ++u) {
+      bool in = v[u] >= blo && v[u] <= bhi && v[u] != 0u;
+      if (by_row) in = in && r[u] >= rlo && r[u] <= rhi;
+      m[u] = __ballot_sync(kFull, in);
+    }
+#pragma unroll
+    for (int u = 0; u < kLsB; ++u) {
+      const int pos = nb + __popc(m[u] & lt);
+      if (((m[u] >> lane) & 1u) && pos < kLsList) {
+        hist[2 * pos] = v[u];
+        hist[2 * pos + 1] = r[u];
+      }
+      nb += __popc(m[u]);
+    }
+  }
+  nb = min(nb, kLsList);  // identical (score, row) pairs (duplicated candidates of a shard merge) can exceed the list: any of them is right
+  need = min(need, nb);
+  __syncwarp();
+  ICR_ST_MARK(5);
+  ks = 0u;
+  kr = 0u;
+  bool found = false;
+  for (int j0 = 0; j0 < nb; j0 += 32) {
+    const int j = j0 + lane;
+    uint32_t s1 = 0, r1 = 0;
+    int rank = -1;
+    if (j < nb) {
+      s1 = hist[2 * j];
+      r1 = hist[2 * j + 1];
+      rank = 0;
+      for (int t = 0; t < nb; ++t) {
+        const uint32_t s2 = hist[2 * t], r2 = hist[2 * t + 1];  // broadcast reads
+        rank += (pair_gt(s2, r2, s1, r1) || (t < j && s2 == s1 && r2 == r1)) ? 1 : 0;  // the index breaks identical pairs
+      }
+    }
+    const unsigned hit = __ballot_sync(kFull, rank == need - 1);
+    if (hit && !found) {
+      const int srcl = __ffs(hit) - 1;
+      ks = __shfl_sync(kFull, s1, srcl);
+      kr = __shfl_sync(kFull, r1, srcl);
+      found = true;
+    }
+  }
+  __syncwarp();
+  ICR_ST_MARK(6);
+}
+
+// In place: keep the keys that can still belong to the result and return how many. band == 0: exactly the k best keys.
+// band > 0 (screened scores): every key whose score is within `band` of the k-th best score. *tau_out = the threshold
+// score (k-th best, minus band), -inf while there are fewer than k keys (all kept). Not inlined: one copy of the passes
+// serves the buffer-full squeezes, the final squeeze and the whole-catalog ranking.
+__device__ __noinline__ int ls_reduce(uint32_t* sc, uint32_t* rw, int n, int k, float band, uint32_t* hist, float* tau_out) {
+  const int lane = threadIdx.x & 31;
+  *tau_out = -INFINITY;
+  if (n < k) return n;
+  uint32_t ks, kr;
+  ls_kth(sc, rw, n, k, hist, lane, ks, kr);
+  const float tau = unorder_bits(ks) - band;
+  *tau_out = tau;
+  uint32_t ts = ks, tr = kr;
+  if (band > 0.f) {
+    ts = order_bits(tau);
+    tr = 0u;
+  }
+  const unsigned lt = (1u << lane) - 1u;
+  ICR_ST_BEGIN();
+  int m = 0;
+  for (int c = 0; c < n; c += 32 * kLsB) {
+    uint32_t v[kLsB], r[kLsB];
+    ls_batch(sc, n, c, lane, v);
+    ls_batch(rw, n, c, lane, r);
+    unsigned mk[kLsB];
+#pragma unroll
+    for (int u = 0; u < kLsB; ++u) mk[u] = __ballot_sync(kFull, v[u] != 0u && pair_ge(v[u], r[u], ts, tr));
+    // a batch's loads are issued (warp-wide, in order) before its stores, which land at positions <= the batch's own keys
+#pragma unroll
+    for (int u = 0; u < kLsB; ++u) {
+      if ((mk[u] >> lane) & 1u) {
+        const int pos = m + __popc(mk[u] & lt);
+        sc[pos] = v[u];
+        rw[pos] = r[u];
+      }
+      m += __popc(mk[u]);
+    }
+  }
+  __syncwarp();
+  ICR_ST_MARK(7);
+  return m;
+}
+
+template <bool WIDE>
+__device__ __forceinline__ void ls_rescore(uint32_t* sc, const uint32_t* rw, int m, int64_t q, const HistSelectArgs& a, int lane) {
+  const float* qrow = a.rs_q + q * a.rs_ldq;
+  const float qi = a.rs_qinv[q];
+  for (int b0 = 0; b0 < m; b0 += 8) {
+    const float* rows[8];
+    uint32_t rid[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      rid[u] = ~rw[min(b0 + u, m - 1)];
+      rows[u] = a.rs_cat + static_cast<int64_t>(rid[u]) * a.rs_ldc;
+    }
+    float acc[8];
+    score_rows8<WIDE>(qrow, rows, a.rs_D, acc, lane);
+    warp_transpose_reduce<8>(acc, lane);  // lane l: full sum of row (l >> 2)
+    const int u = lane >> 2;
+    uint32_t my_row = rid[0];
+#pragma unroll
+    for (int j = 1; j < 8; ++j) my_row = (u == j) ? rid[j] : my_row;
+    if ((lane & 3) == 0 && b0 + u < m) sc[b0 + u] = order_bits(acc[0] * qi * __ldg(a.rs_cinv + my_row));
+  }
+  __syncwarp();
+}
+
+// Exact ranking of the WHOLE catalog for one query by one warp (only for queries whose screening band overflowed: more
+// near-ties around the k-th score than the carry holds). Leaves the k best exact keys in sc/rw, returns their number.
+__device__ __forceinline__ int ls_rank_catalog(uint32_t* sc, uint32_t* rw, int buf_cap, uint32_t* hist, int64_t q, const HistSelectArgs& a, int lane) {
+  const float* qrow = a.rs_q + q * a.rs_ldq;
+  const float qi = a.rs_qinv[q];
+  const unsigned lt = (1u << lane) - 1u;
+  const int k = a.k;
+  int n = 0;
+  uint32_t fs = 0u, fr = 0u;  // keys <= (fs, fr) cannot be among the k best any more
+  for (int64_t r0 = 0; r0 < a.rs_N; r0 += 8) {
+    const float* rows[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) rows[u] = a.rs_cat + min(r0 + u, a.rs_N - 1) * a.rs_ldc;
+    float acc[8];
+    score_rows8(qrow, rows, a.rs_D, acc, lane);
+    warp_transpose_reduce<8>(acc, lane);
+    const int64_t row = r0 + (lane >> 2);
+    bool ok = (lane & 3) == 0 && row < a.rs_N && !(a.mask && a.mask[row]);
+    uint32_t s1 = 0, r1 = 0;
+    if (ok) {
+      s1 = order_bits(acc[0] * qi * __ldg(a.rs_cinv + row));
+      r1 = ~static_cast<uint32_t>(row);
+      ok = pair_gt(s1, r1, fs, fr);
+    }
+    const unsigned mk = __ballot_sync(kFull, ok);
+    if (ok) {
+      const int pos = n + __popc(mk & lt);
+      sc[pos] = s1;
+      rw[pos] = r1;
+    }
+    n += __popc(mk);
+    if (n > buf_cap - 8) {
+      __syncwarp();
+      float t;
+      n = ls_reduce(sc, rw, n, k, 0.f, hist, &t);  // exact keys: exactly k survive
+      uint32_t ms = 0xFFFFFFFFu, mr = 0xFFFFFFFFu;
+      for (int i = lane; i < n; i += 32)
+        if (pair_gt(ms, mr, sc[i], rw[i])) {
+          ms = sc[i];
+          mr = rw[i];
+        }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const uint32_t os = __shfl_xor_sync(kFull, ms, o), orr = __shfl_xor_sync(kFull, mr, o);
+        if (pair_gt(ms, mr, os, orr)) {
+          ms = os;
+          mr = orr;
+        }
+      }
+      fs = ms;
+      fr = mr;
+    }
+  }
+  __syncwarp();
+  float t;
+  return ls_reduce(sc, rw, n, k, 0.f, hist, &t);
+}
+
+// Ordered output of the k best of the `kept` (<= 512) keys. Up to 128 keys (the usual case: k <= 100 results plus a few
+// keys of the screening band) are sorted as 64-bit keys by a warp bitonic network in the idle histogram array - rank counting
+// is O(kept^2) and was half of the re-scoring kernel's time; beyond 128 each lane rank-counts four of its keys at a time.
+__device__ __forceinline__ void ls_emit_ranked(const uint32_t* sc, const uint32_t* rw, int kept, int k, float scale, int64_t q, const HistSelectArgs& a,
+                                               uint32_t* hist, int lane) {
+  if (kept <= 128) {
+    uint64_t* keys = reinterpret_cast<uint64_t*>(hist);  // kHsBins * 4 bytes = 128 keys
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = lane + 32 * u;
+      keys[i] = i < kept ? ((static_cast<uint64_t>(sc[i]) << 32) | rw[i]) : 0ull;
+    }
+    warp_bitonic_sort_desc(keys, 128, lane);
+    for (int i = lane; i < k; i += 32) {
+      const bool ok = i < kept;
+      const uint64_t key = ok ? keys[i] : 0ull;
+      a.out_scores[q * k + i] = ok ? unorder_bits(static_cast<uint32_t>(key >> 32)) * scale : -INFINITY;
+      a.out_ids[q * k + i] = ok ? static_cast<int64_t>(~static_cast<uint32_t>(key)) + a.id_offset : -1;
+    }
+    return;
+  }
+  for (int base = lane; base < kept; base += 128) {
+    uint32_t s1[4], r1[4];
+    int rank[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = base + 32 * u;
+      s1[u] = i < kept ? sc[i] : 0xFFFFFFFFu;
+      r1[u] = i < kept ? rw[i] : 0xFFFFFFFFu;
+      rank[u] = 0;
+    }
+#pragma unroll 2
+    for (int j = 0; j < kept; ++j) {
+      const uint32_t s2 = sc[j], r2 = rw[j];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) rank[u] += (pair_gt(s2, r2, s1[u], r1[u]) || (j < base + 32 * u && s2 == s1[u] && r2 == r1[u])) ? 1 : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (base + 32 * u < kept && rank[u] < k) {
+        a.out_scores[q * k + rank[u]] = unorder_bits(s1[u]) * scale;
+        a.out_ids[q * k + rank[u]] = static_cast<int64_t>(~r1[u]) + a.id_offset;
+      }
+    }
+  }
+  for (int i = min(kept, k) + lane; i < k; i += 32) {
+    a.out_scores[q * k + i] = -INFINITY;
+    a.out_ids[q * k + i] = -1;
+  }
+}
+
+__global__ void __launch_bounds__(kHsWarps * 32, 24 / kHsWarps) select_hist_kernel(HistSelectArgs a) {
   extern __shared__ __align__(16) unsigned char hs_raw[];
-  HsSmem& sm = *reinterpret_cast<HsSmem*>(hs_raw);
+  LsSmem& sm = *reinterpret_cast<LsSmem*>(hs_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t q = static_cast<int64_t>(blockIdx.x) * kHsWarps + warp;
   if (q >= a.Q) return;  // whole warps leave; nothing below synchronises across warps
-  uint64_t* buf = sm.buf[warp];
-  uint64_t* sel = sm.sel[warp];
-  unsigned int* hist = sm.hist[warp];
+  uint32_t* sc = sm.sc[warp];
+  uint32_t* rw = sm.rw[warp];
+  uint32_t* hist = sm.hist[warp];
   const int k = a.k;
+  const bool screened = a.band > 0.f;
+  const int kc = screened ? a.kc : k;  // keys carried between phases
   const int cap = min(a.seg_cap, a.seg_stride);
+  const unsigned lt = (1u << lane) - 1u;
+  float tau = -INFINITY;
+  bool lost = false;  // screened keys inside the band were dropped for lack of room: exact ranking at the end
+  int kept = 0;
+  ICR_ST_BEGIN();
 
-  int n = 0;
-  if (a.carry_in) {
-    n = min(a.carry_cnt_in[q], k);
-    for (int i = lane; i < n; i += 32) buf[i] = a.carry_in[q * k + i];
-  }
-  if (const int count = front_count(a)) {
-    const unsigned lt = (1u << lane) - 1u;
-    for (int base = 0; base < count; base += 32 * 8) {
-      if (kHsCap - n < 32 * 8) {  // buffer full: keep the k best and go on
-        warp_select_topk(buf, n, k, sel, hist, lane);
-        for (int i = lane; i < k; i += 32) buf[i] = sel[i];
-        n = k;
-        __syncwarp();
+  if (a.dense && !a.carry_in && a.nseg == 0 && a.dense_rows <= kLsCap) {
+    // ---- first phase of K2: the query's whole row of the dense score matrix is fetched with all 32 loads per lane in
+    // flight at once; without a mask key i is simply catalog row i (no compaction) ----
+    const float* row = a.dense + q * a.dense_ld;
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int t = lane + 32 * j;
+      f[j] = t < a.dense_rows ? __ldcs(row + t) : 0.f;
+    }
+    int n = 0;
+    if (a.mask == nullptr) {  // key i = catalog row i
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int t = lane + 32 * j;
+        sc[t] = order_bits(f[j]);
+        rw[t] = ~static_cast<uint32_t>(t);
       }
-      uint64_t key[8];
-      bool ok[8];
+      n = a.dense_rows;
+    } else {
 #pragma unroll
-      for (int u = 0; u < 8; ++u) ok[u] = front_fetch(a, q, base + u * 32 + lane, count, key[u]);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const unsigned m = __ballot_sync(kFull, ok[u]);
-        if (ok[u]) buf[n + __popc(m & lt)] = key[u];
+      for (int j = 0; j < 32; ++j) {
+        const int t = lane + 32 * j;
+        const bool valid = t < a.dense_rows && !a.mask[t];
+        const unsigned m = __ballot_sync(kFull, valid);
+        if (valid) {
+          const int pos = n + __popc(m & lt);
+          sc[pos] = order_bits(f[j]);
+          rw[pos] = ~static_cast<uint32_t>(t);
+        }
         n += __popc(m);
       }
     }
-  }
-  const uint64_t* qbase = a.seg_keys + q * a.nseg * static_cast<int64_t>(a.seg_stride);
-  // Segment lengths of up to kHsPref segments are fetched at once (independent loads) and prefix-summed in shared
-  // memory, then the keys are gathered by flat index (binary search for the segment): a small batch may have
-  // hundreds of short segments per query (one per chunk and CTA), and walking them 32 at a time made the gather
-  // a chain of dependent memory round trips. The prefix array lives in `sel`, which is idle until the selection.
-  int* pref = reinterpret_cast<int*>(sel);
-  for (int g0 = 0; g0 < a.nseg; g0 += kHsPref) {
-    const int ng = min(kHsPref, a.nseg - g0);
-    int top = 1;
-    while (top * 2 <= ng) top *= 2;  // first step of the binary search
-    int done = 0, total = 0;
-    bool have_pref = false;
-    do {
-      if (!have_pref) {
-        __syncwarp();
-#pragma unroll 4
-        for (int i = lane; i < ng; i += 32) pref[i] = min(__ldg(a.seg_cnt + q * a.nseg + g0 + i), cap);
-        __syncwarp();
-        int carry = 0;
-        for (int b0 = 0; b0 < ng; b0 += 32) {
-          const int v = (b0 + lane < ng) ? pref[b0 + lane] : 0;
-          int incl = v;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const int u = __shfl_up_sync(kFull, incl, o);
-            if (lane >= o) incl += u;
-          }
-          if (b0 + lane < ng) pref[b0 + lane] = carry + incl - v;
-          carry += __shfl_sync(kFull, incl, 31);
-        }
-        if (lane == 0) pref[ng] = carry;
-        total = carry;
-        have_pref = true;
-        __syncwarp();
-      }
-      if (done >= total) break;
-      if (kHsCap - n < 32) {  // buffer full: keep the k best and go on (the selection overwrites the prefix array)
-        warp_select_topk(buf, n, k, sel, hist, lane);
-        for (int i = lane; i < k; i += 32) buf[i] = sel[i];
-        n = k;
-        have_pref = false;
-        continue;
-      }
-      const int take = min(kHsCap - n, total - done);
-      // 8 independent global loads per lane in flight before the first shared-memory store: the gather is
-      // latency-bound (cold candidates), so memory-level parallelism is what sets its speed
-      for (int i0 = 0; i0 < take; i0 += 32 * 8) {
-        uint64_t v[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int i = i0 + u * 32 + lane;
-          v[u] = 0ull;
-          if (i < take) {
-            const int idx = done + i;
-            // segment holding flat index idx: largest s with pref[s] <= idx
-            int sg = 0;
-            for (int step = top; step > 0; step >>= 1)
-              if (sg + step < ng && pref[sg + step] <= idx) sg += step;
-            v[u] = __ldcs(qbase + static_cast<int64_t>(g0 + sg) * a.seg_stride + (idx - pref[sg]));
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int i = i0 + u * 32 + lane;
-          if (i < take) buf[n + i] = a.raw_keys ? canonical_from_raw(v[u]) : v[u];
-        }
-      }
-      n += take;
-      done += take;
-      __syncwarp();
-    } while (done < total);
-  }
-  __syncwarp();
-  int kept = n;
-  if (n > k) {
-    warp_select_topk(buf, n, k, sel, hist, lane);
-    kept = k;
-  } else {
-    for (int i = lane; i < n; i += 32) sel[i] = buf[i];
     __syncwarp();
+    ICR_ST_MARK(8);
+    kept = ls_reduce(sc, rw, n, k, a.band, hist, &tau);
+    ICR_ST_MARK(14);
+  } else {
+    // squeeze: reduce to the keys that can still matter (buffer nearly full, or the end); only screened keys can leave
+    // more than kc - too many near-ties - and then the query is ranked exactly at the end
+#define ICR_SQUEEZE(n_)                                        \
+  do {                                                         \
+    n_ = ls_reduce(sc, rw, n_, k, a.band, hist, &tau);         \
+    if (n_ > kc) {                                             \
+      lost = true;                                             \
+      n_ = kc;                                                 \
+    }                                                          \
+  } while (0)
+    int n = 0;
+    if (a.carry_in) {
+      n = min(a.carry_cnt_in[q], kc);
+      for (int i = lane; i < n; i += 32) {
+        const uint64_t key = a.carry_in[q * kc + i];
+        sc[i] = static_cast<uint32_t>(key >> 32);
+        rw[i] = static_cast<uint32_t>(key);
+      }
+    }
+    if (const int count = front_count(a)) {
+      for (int base = 0; base < count; base += 32 * 8) {
+        if (kLsCap - n < 32 * 8) {
+          __syncwarp();
+          ICR_SQUEEZE(n);
+        }
+        uint64_t key[8];
+        bool ok[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) ok[u] = front_fetch(a, q, base + u * 32 + lane, count, key[u]);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const unsigned m = __ballot_sync(kFull, ok[u]);
+          if (ok[u]) {
+            const int pos = n + __popc(m & lt);
+            sc[pos] = static_cast<uint32_t>(key[u] >> 32);
+            rw[pos] = static_cast<uint32_t>(key[u]);
+          }
+          n += __popc(m);
+        }
+      }
+    }
+    ICR_ST_MARK(8);
+    const uint64_t* qbase = a.seg_keys + q * a.nseg * static_cast<int64_t>(a.seg_stride);
+    // Segment lengths of up to 255 segments are fetched at once (independent loads) and prefix-summed in shared memory,
+    // then the keys are gathered by flat index: lane l takes indices l, l + 32, ... and walks its own segment cursor
+    // forward (indices only grow, so the walk is amortised ~1 step per key), 16 independent global loads in flight per
+    // lane before the first shared-memory store. The prefix array lives in hist[], idle until the selection.
+    int* pref = reinterpret_cast<int*>(hist);
+    constexpr int kPref = kHsBins - 1;
+    for (int g0 = 0; g0 < a.nseg; g0 += kPref) {
+      const int ng = min(kPref, a.nseg - g0);
+      int done = 0, total = 0;
+      bool have_pref = false;
+      do {
+        if (!have_pref) {
+          __syncwarp();
+#pragma unroll 4
+          for (int i = lane; i < ng; i += 32) pref[i] = min(__ldg(a.seg_cnt + q * a.nseg + g0 + i), cap);
+          __syncwarp();
+          int carry = 0;
+          for (int b0 = 0; b0 < ng; b0 += 32) {
+            const int v = (b0 + lane < ng) ? pref[b0 + lane] : 0;
+            int incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+              const int u = __shfl_up_sync(kFull, incl, o);
+              if (lane >= o) incl += u;
+            }
+            if (b0 + lane < ng) pref[b0 + lane] = carry + incl - v;
+            carry += __shfl_sync(kFull, incl, 31);
+          }
+          if (lane == 0) pref[ng] = carry;
+          total = carry;
+          have_pref = true;
+          __syncwarp();
+        }
+        if (done >= total) break;
+        if (kLsCap - n < 32) {  // the selection overwrites the prefix array
+          ICR_SQUEEZE(n);
+          have_pref = false;
+          if (kLsCap - n < 32) break;  // cannot happen (kc <= 512); guards the loop
+          continue;
+        }
+        const int take = min(kLsCap - n, total - done);
+        int sg = 0;  // this lane's segment cursor
+        for (int i0 = 0; i0 < take; i0 += 32 * 16) {
+          uint64_t v[16];
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            const int i = i0 + u * 32 + lane;
+            v[u] = 0ull;
+            if (i < take) {
+              const int idx = done + i;
+              while (sg + 1 < ng && pref[sg + 1] <= idx) ++sg;  // segment holding flat index idx
+              v[u] = __ldcs(qbase + static_cast<int64_t>(g0 + sg) * a.seg_stride + (idx - pref[sg]));
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            const int i = i0 + u * 32 + lane;
+            if (i < take) {
+              const uint32_t hi = static_cast<uint32_t>(v[u] >> 32);
+              sc[n + i] = a.raw_keys ? order_bits(__uint_as_float(hi)) : hi;
+              rw[n + i] = static_cast<uint32_t>(v[u]);
+            }
+          }
+        }
+        n += take;
+        done += take;
+        __syncwarp();
+      } while (done < total);
+    }
+    __syncwarp();
+    ICR_ST_MARK(9);
+    kept = n;
+    ICR_SQUEEZE(kept);
+#undef ICR_SQUEEZE
+    ICR_ST_MARK(14);
   }
+  if (kept > kc) {  // (first-phase path) only screened keys can leave more than kc
+    lost = true;
+    kept = kc;
+  }
+  if (screened && lost && lane == 0) a.overflow[q] = 1u;
 
   if (a.carry_out) {
-    for (int i = lane; i < kept; i += 32) a.carry_out[q * k + i] = sel[i];
+    for (int i = lane; i < kept; i += 32) a.carry_out[q * kc + i] = (static_cast<uint64_t>(sc[i]) << 32) | rw[i];
     if (lane == 0) a.carry_cnt_out[q] = kept;
   }
-  if (a.tau_out) {
-    uint64_t mn = ~0ull;
-    for (int i = lane; i < kept; i += 32) mn = sel[i] < mn ? sel[i] : mn;
-    mn = warp_min_u64(mn);
-    if (lane == 0) a.tau_out[q] = (kept >= k) ? key_score(mn) : -INFINITY;
-  }
-  if (a.out_scores) {
-    warp_rank_sort_desc(sel, kept, buf, kept, lane);  // buf is free again: sorted output order
+  if (a.tau_out && lane == 0) a.tau_out[q] = tau;
+  ICR_ST_MARK(10);
+  if (a.out_scores && !screened) {  // screened keys: rescore_rank_kernel finishes from the carry
     const float scale = a.out_scale * (a.out_qscale ? a.out_qscale[q] : 1.0f);
-    for (int i = lane; i < k; i += 32) {
-      const bool ok = i < kept;
-      a.out_scores[q * k + i] = ok ? key_score(buf[i]) * scale : -INFINITY;
-      a.out_ids[q * k + i] = ok ? static_cast<int64_t>(key_row(buf[i])) + a.id_offset : -1;
-    }
+    ls_emit_ranked(sc, rw, kept, k, scale, q, a, hist, lane);
+    ICR_ST_MARK(11);
   }
 }
+
+// ---- screened keys, last step: exact re-scoring of the carried candidates and the ordered top-k -----------------------
+// Its own kernel because its needs differ from the select's: no staging buffer (4 KB of keys per query, 9 KB with the
+// fallback's buffer) and ~170 registers for 24 independent 16-byte loads per lane - the candidates' rows are scattered over
+// the catalog, and the gather is bound by the bytes in flight, not by instructions.
+constexpr int kRsCap = kLsCap;  // keys per query: the carry (<= 512), or the buffer of the whole-catalog ranking
+struct RsSmem {
+  uint32_t sc[kHsWarps][kRsCap];
+  uint32_t rw[kHsWarps][kRsCap];
+  uint32_t hist[kHsWarps][kHsBins];
+};
+
+__global__ void __launch_bounds__(kHsWarps * 32, 3) rescore_rank_kernel(HistSelectArgs a) {
+  __shared__ __align__(16) RsSmem sm;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * kHsWarps + warp;
+  if (q >= a.Q) return;
+  uint32_t* sc = sm.sc[warp];
+  uint32_t* rw = sm.rw[warp];
+  int kept;
+  ICR_ST_BEGIN();
+  if (a.overflow[q]) {
+    kept = ls_rank_catalog(sc, rw, kRsCap, sm.hist[warp], q, a, lane);
+  } else {
+    kept = min(a.carry_cnt_in[q], a.kc);
+    for (int i = lane; i < kept; i += 32) rw[i] = static_cast<uint32_t>(a.carry_in[q * a.kc + i]);
+    __syncwarp();
+    ls_rescore<true>(sc, rw, kept, q, a, lane);
+  }
+  ICR_ST_MARK(12);
+  ls_emit_ranked(sc, rw, kept, a.k, 1.0f, q, a, sm.hist[warp], lane);
+  ICR_ST_MARK(13);
+}
+
+#ifdef ICR_SELECT_TRACE
+}  // namespace icr
+extern "C" int icr_debug_select_trace(unsigned long long* out16, int reset) {
+  if (out16 && cudaMemcpyFromSymbol(out16, icr::g_sel_trace, sizeof(icr::g_sel_trace)) != cudaSuccess) return -6;
+  if (reset) {
+    unsigned long long z[16] = {};
+    if (cudaMemcpyToSymbol(icr::g_sel_trace, z, sizeof(z)) != cudaSuccess) return -6;
+  }
+  return 0;
+}
+namespace icr {
+#endif
 
 // ---- block-per-query variant for small batches --------------------------------------------------------------
 // With a few dozen queries the warp-per-query kernel leaves the GPU idle while each warp walks thousands of keys on
@@ -354,27 +967,94 @@ __device__ __forceinline__ void block_select_topk(BsSmem& sm, int n, int k, int 
   }
 }
 
+// keep the kk best of sm.buf[0..n) (n > kk): they end up in sm.sel[0..kk) AND sm.buf[0..kk). Returns the smallest kept key.
+__device__ __forceinline__ uint64_t block_truncate(BsSmem& sm, int n, int kk, int tid) {
+  block_select_topk(sm, n, kk, tid);
+  uint64_t mn = ~0ull;
+  for (int i = tid; i < kk; i += kBsThreads) {
+    const uint64_t key = sm.sel[i];
+    sm.buf[i] = key;
+    mn = key < mn ? key : mn;
+  }
+  mn = warp_min_u64(mn);
+  __syncthreads();  // sm.red is free (block_select_topk ended with a barrier)
+  if ((tid & 31) == 0) sm.red[tid >> 5] = mn;
+  __syncthreads();
+  mn = sm.red[0];
+#pragma unroll
+  for (int w = 1; w < kBsThreads / 32; ++w) mn = sm.red[w] < mn ? sm.red[w] : mn;
+  __syncthreads();
+  return mn;
+}
+
+// Exact ranking of the whole catalog for one query by one CTA (screening-band overflow only; see warp_rank_catalog).
+// Leaves the result keys in sm.sel[0..return value).
+__device__ __forceinline__ int block_rank_catalog(BsSmem& sm, int64_t q, const HistSelectArgs& a, int tid) {
+  const int warp = tid >> 5, lane = tid & 31;
+  const float* qrow = a.rs_q + q * a.rs_ldq;
+  const float qi = a.rs_qinv[q];
+  const int k = a.k;
+  constexpr int kWarps = kBsThreads / 32;
+  int n = 0;
+  uint64_t floor_key = 0ull;
+  __syncthreads();
+  if (tid == 0) sm.misc[4] = 0;
+  __syncthreads();
+  for (int64_t r0 = 0; r0 < a.rs_N; r0 += 8 * kWarps) {
+    const int64_t w0 = r0 + warp * 8;
+    const float* rows[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) rows[u] = a.rs_cat + min(w0 + u, a.rs_N - 1) * a.rs_ldc;
+    float acc[8];
+    score_rows8(qrow, rows, a.rs_D, acc, lane);
+    warp_transpose_reduce<8>(acc, lane);
+    const int64_t row = w0 + (lane >> 2);
+    bool ok = (lane & 3) == 0 && row < a.rs_N && !(a.mask && a.mask[row]);
+    uint64_t key = 0ull;
+    if (ok) {
+      key = make_key(acc[0] * qi * __ldg(a.rs_cinv + row), static_cast<uint32_t>(row));
+      ok = key > floor_key;
+    }
+    if (ok) sm.buf[atomicAdd(&sm.misc[4], 1)] = key;
+    __syncthreads();
+    n = sm.misc[4];
+    if (n > kBsCap - 8 * kWarps) {
+      floor_key = block_truncate(sm, n, k, tid);
+      n = k;
+      if (tid == 0) sm.misc[4] = k;
+    }
+    __syncthreads();
+  }
+  if (n > k) {
+    block_select_topk(sm, n, k, tid);
+    return k;
+  }
+  for (int i = tid; i < n; i += kBsThreads) sm.sel[i] = sm.buf[i];
+  __syncthreads();
+  return n;
+}
+
 __global__ void __launch_bounds__(kBsThreads) select_block_kernel(HistSelectArgs a) {
   extern __shared__ __align__(16) unsigned char bs_raw[];
   BsSmem& sm = *reinterpret_cast<BsSmem*>(bs_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t q = blockIdx.x;
   const int k = a.k;
+  const int kc = a.band > 0.f ? a.kc : k;  // keys kept between phases
   const int cap = min(a.seg_cap, a.seg_stride);
   int n = 0;
+  uint64_t cut_max = 0ull;  // largest "smallest kept key" of any truncation (meaningful in thread 0's view after block_truncate)
   if (a.carry_in) {
-    n = min(a.carry_cnt_in[q], k);
-    for (int i = tid; i < n; i += kBsThreads) sm.buf[i] = a.carry_in[q * k + i];
+    n = min(a.carry_cnt_in[q], kc);
+    for (int i = tid; i < n; i += kBsThreads) sm.buf[i] = a.carry_in[q * kc + i];
   }
   if (const int count = front_count(a)) {
     const unsigned lt = (1u << lane) - 1u;
     __syncthreads();
     for (int base = 0; base < count; base += kBsThreads * 4) {
       if (kBsCap - n < kBsThreads * 4) {
-        block_select_topk(sm, n, k, tid);
-        for (int i = tid; i < k; i += kBsThreads) sm.buf[i] = sm.sel[i];
-        n = k;
-        __syncthreads();
+        cut_max = max(cut_max, block_truncate(sm, n, kc, tid));
+        n = kc;
       }
       if (tid == 0) sm.misc[4] = n;
       __syncthreads();
@@ -422,11 +1102,9 @@ __global__ void __launch_bounds__(kBsThreads) select_block_kernel(HistSelectArgs
     const int total = sm.pref[ng];
     int done = 0;
     while (done < total) {
-      if (kBsCap - n < kBsThreads) {  // buffer full: keep the k best and go on
-        block_select_topk(sm, n, k, tid);
-        for (int i = tid; i < k; i += kBsThreads) sm.buf[i] = sm.sel[i];
-        n = k;
-        __syncthreads();
+      if (kBsCap - n < kBsThreads) {  // buffer full: keep the kc best and go on
+        cut_max = max(cut_max, block_truncate(sm, n, kc, tid));
+        n = kc;
       }
       const int take = min(kBsCap - n, total - done);
       for (int i0 = 0; i0 < take; i0 += kBsThreads * 4) {
@@ -456,6 +1134,72 @@ __global__ void __launch_bounds__(kBsThreads) select_block_kernel(HistSelectArgs
   }
   __syncthreads();
   int kept = n;
+  if (a.band > 0.f) {
+    // ---- screened keys (see select_hist_kernel) ---------------------------------------------------------------------
+    if (n > kc) {
+      cut_max = max(cut_max, block_truncate(sm, n, kc, tid));  // the kc best in sm.sel and sm.buf[0..kc)
+      kept = kc;
+    } else {
+      for (int i = tid; i < n; i += kBsThreads) sm.sel[i] = sm.buf[i];
+      __syncthreads();
+    }
+    if (warp == 0) {
+      float tau = -INFINITY;
+      int m = kept;
+      if (kept >= k) {
+        uint64_t kth = ~0ull;
+        if (kept > k) {
+          warp_select_topk(sm.buf, kept, k, sm.buf + kHsSel, sm.hist, lane);
+          for (int i = lane; i < k; i += 32) kth = sm.buf[kHsSel + i] < kth ? sm.buf[kHsSel + i] : kth;
+        } else {
+          for (int i = lane; i < k; i += 32) kth = sm.sel[i] < kth ? sm.sel[i] : kth;
+        }
+        kth = warp_min_u64(kth);
+        tau = key_score(kth) - a.band;
+        const uint64_t t_key = static_cast<uint64_t>(order_bits(tau)) << 32;
+        if (cut_max >= t_key && lane == 0) a.overflow[q] = 1u;
+        const unsigned lt = (1u << lane) - 1u;
+        m = 0;
+        for (int b0 = 0; b0 < kept; b0 += 32) {
+          const int i = b0 + lane;
+          const uint64_t key = i < kept ? sm.sel[i] : 0ull;
+          const bool keep = i < kept && key >= t_key;
+          const unsigned mk = __ballot_sync(kFull, keep);
+          if (keep) sm.sel[m + __popc(mk & lt)] = key;
+          m += __popc(mk);
+        }
+      }
+      if (lane == 0) {
+        sm.misc[5] = m;
+        if (a.tau_out) a.tau_out[q] = tau;
+      }
+    }
+    __syncthreads();
+    kept = sm.misc[5];
+    if (a.carry_out) {
+      for (int i = tid; i < kept; i += kBsThreads) a.carry_out[q * kc + i] = sm.sel[i];
+      if (tid == 0) a.carry_cnt_out[q] = kept;
+    }
+    if (a.out_scores) {
+      if (a.overflow[q]) kept = block_rank_catalog(sm, q, a, tid);
+      else warp_rescore(sm.sel, kept, warp, kBsThreads / 32, q, a, lane);
+      __syncthreads();
+      for (int i = tid; i < kept; i += kBsThreads) {  // kept <= kHsSel: rank counting, as below
+        const uint64_t key = sm.sel[i];
+        int rank = 0;
+        for (int j = 0; j < kept; ++j) rank += (sm.sel[j] > key) ? 1 : 0;
+        if (rank < k) {
+          a.out_scores[q * k + rank] = key_score(key);
+          a.out_ids[q * k + rank] = static_cast<int64_t>(key_row(key)) + a.id_offset;
+        }
+      }
+      for (int i = kept + tid; i < k; i += kBsThreads) {
+        a.out_scores[q * k + i] = -INFINITY;
+        a.out_ids[q * k + i] = -1;
+      }
+    }
+    return;
+  }
   if (n > k) {
     block_select_topk(sm, n, k, tid);
     kept = k;
@@ -488,7 +1232,6 @@ __global__ void __launch_bounds__(kBsThreads) select_block_kernel(HistSelectArgs
   }
 }
 
-static int run_select(const HistSelectArgs& a, int64_t Q, cudaStream_t st);
 
 // K4: merge of G shard lists of k_in (score, id) pairs per query, [G][Q][k_in] -> sorted top k_out per query
 int launch_merge_lists(const float* cs, const int64_t* ci, int64_t Q, int G, int k_in, int k_out, float* os, int64_t* oi,
@@ -507,57 +1250,32 @@ int launch_merge_lists(const float* cs, const int64_t* ci, int64_t Q, int G, int
   return run_select(a, Q, st);
 }
 
-int launch_select_hist(const uint64_t* seg_keys, const int* seg_cnt, int64_t Q, int nseg, int seg_stride, int seg_cap,
-                       const uint64_t* carry_in, const int* carry_cnt_in, uint64_t* carry_out, int* carry_cnt_out, float* tau_out,
-                       float* out_scores, int64_t* out_ids, int64_t id_offset, int k, float out_scale, const float* out_qscale,
-                       cudaStream_t st, const float* dense, int64_t dense_ld, int dense_rows, const uint8_t* mask) {
-  if (Q == 0) return ICR_OK;
-  HistSelectArgs a{};
-  a.seg_keys = seg_keys;
-  a.seg_cnt = seg_cnt;
-  a.nseg = nseg;
-  a.seg_stride = seg_stride;
-  a.seg_cap = seg_cap;
-  a.carry_in = carry_in;
-  a.carry_cnt_in = carry_cnt_in;
-  a.carry_out = carry_out;
-  a.carry_cnt_out = carry_cnt_out;
-  a.tau_out = tau_out;
-  a.out_scores = out_scores;
-  a.out_ids = out_ids;
-  a.id_offset = id_offset;
-  a.k = k;
-  a.Q = Q;
-  a.out_scale = out_scale;
-  a.out_qscale = out_qscale;
-  a.raw_keys = 1;  // the only producer of segments is the GEMM epilogue
-  a.dense = dense;
-  a.dense_ld = dense_ld;
-  a.dense_rows = dense_rows;
-  a.mask = mask;
-  return run_select(a, Q, st);
-}
-
-static int run_select(const HistSelectArgs& a, int64_t Q, cudaStream_t st) {
-  static thread_local bool attr_set = false;
-  if (!attr_set) {
-    ICR_CUDA_CHECK(cudaFuncSetAttribute(select_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(HsSmem))));
-    attr_set = true;
-  }
+int run_select(const HistSelectArgs& a, int64_t Q, cudaStream_t st) {
+  static thread_local SmemAttrCache warp_cache, block_cache;  // per device
+  int rc = ensure_dyn_smem(warp_cache, select_hist_kernel, sizeof(LsSmem));
+  if (rc) return rc;
   static const int block_max_q = getenv("ICR_SELECT_BLOCK_MAXQ") ? atoi(getenv("ICR_SELECT_BLOCK_MAXQ")) : 512;  // tuning hook
   if (Q <= block_max_q) {
-    static thread_local bool battr_set = false;
-    if (!battr_set) {
-      ICR_CUDA_CHECK(cudaFuncSetAttribute(select_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(BsSmem))));
-      battr_set = true;
-    }
+    if ((rc = ensure_dyn_smem(block_cache, select_block_kernel, sizeof(BsSmem)))) return rc;
     select_block_kernel<<<static_cast<unsigned>(Q), kBsThreads, sizeof(BsSmem), st>>>(a);
     ICR_LAUNCH_CHECK();
     return ICR_OK;
   }
   const unsigned grid = static_cast<unsigned>((Q + kHsWarps - 1) / kHsWarps);
-  select_hist_kernel<<<grid, kHsWarps * 32, sizeof(HsSmem), st>>>(a);
+  select_hist_kernel<<<grid, kHsWarps * 32, sizeof(LsSmem), st>>>(a);
   ICR_LAUNCH_CHECK();
+  if (a.band > 0.f && a.out_scores) {
+    // screened keys: the select left the candidates within the band in carry_out; re-score them exactly and rank
+    if (!a.carry_out || !a.carry_cnt_out) {
+      set_error("select: the final phase of a screened search needs a carry buffer for its candidates");
+      return ICR_ERR_ARG;
+    }
+    HistSelectArgs r = a;
+    r.carry_in = a.carry_out;
+    r.carry_cnt_in = a.carry_cnt_out;
+    rescore_rank_kernel<<<grid, kHsWarps * 32, 0, st>>>(r);
+    ICR_LAUNCH_CHECK();
+  }
   return ICR_OK;
 }
 

@@ -24,6 +24,7 @@ from __future__ import annotations
 
 import hashlib
 import json
+import threading
 import logging
 from pathlib import Path
 
@@ -171,15 +172,19 @@ class DeviceCatalog:
                 rows = ops.convert_rows(rows, torch.empty(rows.shape, dtype=dtype, device=dev))  # fp32 -> bf16 on the device (RNE)
             else:
                 rows = rows.to(dtype)
+        self.input_dim = int(rows.shape[1]) if rows.dim() == 2 else 0  # before the 16-byte padding of _rows()
         self.rows = ops._rows(rows)
         self.row_offset = int(row_offset)
+        self.request_lock = threading.RLock()  # guards the shared static tensors of topk_small(copy=False)
         self.planes: torch.Tensor | None = None
         if build_planes is None:
             build_planes = dtype == torch.float32
-        if build_planes and dtype == torch.float32 and self.rows.shape[0] > 0:
-            self.planes = ops.split_f16_planes(self.rows)
         self.inv_norms: torch.Tensor | None = None
-        if dtype == torch.bfloat16 and self.rows.shape[0] > 0:
+        if build_planes and dtype == torch.float32 and self.rows.shape[0] > 0:
+            # fp32 catalogs: the fp32 rows serve the GEMV path and the exact re-scoring; the tensor-core sweep reads a
+            # single fp16 screening plane (half the rows' bytes) - 1.5x the catalog resident, not 2x as with hi|lo planes
+            self.planes, self.inv_norms = ops.screen_plane(self.rows)
+        elif self.rows.shape[0] > 0:
             self.inv_norms = ops.row_inv_norms(self.rows)
 
     @classmethod
@@ -226,7 +231,8 @@ class DeviceCatalog:
 
     @property
     def nbytes(self) -> int:
-        return self.rows.numel() * self.rows.element_size() + (0 if self.planes is None else self.planes.numel() * 2)
+        extra = sum(t.numel() * t.element_size() for t in (self.planes, self.inv_norms) if t is not None)
+        return self.rows.numel() * self.rows.element_size() + extra
 
     # ---- request-sized calls: one CUDA graph per (Q, k) -------------------------------------------------
     def _graph_for(self, Q: int, k: int, path: int):
@@ -265,7 +271,9 @@ class DeviceCatalog:
         """topk() for request-sized batches (Q <= 8) through a cached CUDA graph.
 
         `queries` may live on the host (numpy / CPU tensor, as SentenceTransformer.encode returns it) or on the
-        device. With copy=False the returned tensors are the graph's static outputs, overwritten by the next call.
+        device. With copy=False the returned tensors are the graph's static outputs, overwritten by the next call:
+        callers that may run concurrently hold ``self.request_lock`` around the call AND their read of the results
+        (Recommender._rank does); copy=True takes the lock itself and returns private tensors.
         """
         q = queries if isinstance(queries, torch.Tensor) else torch.as_tensor(queries)
         if q.dim() == 1:
@@ -273,11 +281,14 @@ class DeviceCatalog:
         k = min(int(k), len(self))
         if k < 1 or q.shape[0] == 0:
             return self.topk(q, max(k, 1))
-        graph, static_q, vals, ids, _ = self._graph_for(q.shape[0], k, path)
-        D = min(q.shape[1], static_q.shape[1])
-        static_q[:, :D].copy_(q[:, :D], non_blocking=True)  # H2D (or D2D) + dtype conversion in one op
-        graph.replay()
-        return (vals.clone(), ids.clone()) if copy else (vals, ids)
+        if q.shape[1] != self.input_dim:
+            raise ValueError(f"embedding dims differ: query {q.shape[1]} vs catalog {self.input_dim}")
+        with self.request_lock:
+            graph, static_q, vals, ids, _ = self._graph_for(q.shape[0], k, path)
+            D = q.shape[1]  # columns beyond the catalog's own dim are the zero padding of _rows(); they stay zero
+            static_q[:, :D].copy_(q, non_blocking=True)  # H2D (or D2D) + dtype conversion in one op
+            graph.replay()
+            return (vals.clone(), ids.clone()) if copy else (vals, ids)
 
     def topk_host(self, queries: torch.Tensor, k: int, *, out: tuple[torch.Tensor, torch.Tensor] | None = None,
                   n_chunks: int | None = None, path: int = ops.PATH_AUTO, splits: list[int] | None = None):

@@ -126,6 +126,22 @@ def split_f16_planes(x: torch.Tensor) -> torch.Tensor:
     return planes
 
 
+def screen_plane(x: torch.Tensor, *, with_inv_norms: bool = True):
+    """fp32 [rows, D] -> (fp16 screening plane [rows, round_up(D,64)] of the normalised rows x 256, f32 inverse norms [rows] or None).
+
+    The operand of the tensor-core top-k sweep over an fp32 catalog; the sweep's survivors are re-scored exactly from `x`."""
+    _require_cuda("x", x)
+    if x.dtype != torch.float32:
+        raise TypeError("screen_plane expects float32 rows")
+    x = _rows(x)
+    lib = _lib.load()
+    plane = torch.empty(x.shape[0], lib.icr_screen_plane_row_elems(x.shape[1]), dtype=torch.float16, device=x.device)
+    inv = torch.empty(x.shape[0], dtype=torch.float32, device=x.device) if with_inv_norms else None
+    with _on(x.device):
+        _lib.check(lib.icr_screen_plane(x.data_ptr(), x.shape[0], x.shape[1], _ld(x), plane.data_ptr(), _ptr(inv), _stream(x.device)))
+    return plane, inv
+
+
 def convert_rows(x: torch.Tensor, out: torch.Tensor, *, normalize: bool = False) -> torch.Tensor:
     """fp32 device rows -> `out` (float32 or bfloat16 device rows of the same shape), optionally L2-normalised first."""
     _require_cuda("x", x)
@@ -171,8 +187,8 @@ def cos_topk(
             raise ValueError("exclude_mask must be uint8/bool with one entry per catalog row")
         exclude_mask = exclude_mask.contiguous().view(torch.uint8)
     if cat_planes is not None:
-        if cat_planes.dtype != torch.float16 or cat_planes.shape != (N, lib.icr_planes_row_elems(D)) or not cat_planes.is_contiguous():
-            raise ValueError("cat_planes must be the contiguous output of split_f16_planes(catalog)")
+        if cat_planes.dtype != torch.float16 or cat_planes.shape != (N, lib.icr_screen_plane_row_elems(D)) or not cat_planes.is_contiguous():
+            raise ValueError("cat_planes must be the contiguous plane returned by screen_plane(catalog)")
     if cat_inv_norms is not None:
         if cat_inv_norms.dtype != torch.float32 or cat_inv_norms.shape != (N,) or not cat_inv_norms.is_contiguous():
             raise ValueError("cat_inv_norms must be the output of row_inv_norms(catalog)")

@@ -133,7 +133,13 @@ class Recommender:
             # exact: the best (top_k + #excluded) rows contain the best top_k non-excluded ones
             k_fetch = top_k + len(excluded_rows)
             k_fetch = min(n, next(b for b in (16, 32, 64, 128, 256) if b >= k_fetch))  # few distinct shapes -> few CUDA graphs
-            vals, ids = self.catalog.topk_small(query_emb, k_fetch, copy=False)
+            # the graph's static query / output tensors are shared by every caller of this catalog: copy-in, replay and
+            # host read happen under the catalog's lock so that concurrent requests (a sync route, run_in_executor, a batch
+            # job) cannot read each other's results - the reference's recommend() is safe to call from several threads
+            with self.catalog.request_lock:
+                vals, ids = self.catalog.topk_small(query_emb, k_fetch, copy=False)
+                vals = vals[0].tolist()  # one device->host read; synchronises the stream
+                ids = ids[0].tolist()
             mask_rows = set(excluded_rows)
         else:
             # unbounded exclusion lists: mask rows on the device instead of over-fetching
@@ -143,8 +149,8 @@ class Recommender:
             k_fetch = min(want, ops.MAX_K)
             vals, ids = self.catalog.topk(query_emb, k_fetch, exclude_mask=mask)
             mask_rows = set()
-        vals = vals[0].tolist()  # one device->host read; synchronises the stream
-        ids = ids[0].tolist()
+            vals = vals[0].tolist()
+            ids = ids[0].tolist()
         out: list[tuple[str, float]] = []
         for s, r in zip(vals, ids):
             if r < 0 or r in mask_rows:

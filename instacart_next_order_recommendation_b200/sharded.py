@@ -42,8 +42,13 @@ class PeerExchange:
 
     PyTorch's symmetric memory is the plumbing: it allocates one buffer per rank and maps every rank's buffer into
     every process; the exchange itself is one kernel of ours per call (peer stores + system-scope flags). Collective:
-    every rank of `group` constructs it and calls ``all_gather`` with the same shapes in the same order.
+    every rank of `group` constructs it and calls ``all_gather`` with the same shapes in the same order (lockstep: the
+    kernel of call e waits for every peer's call e). A rank that waits longer than ``ICR_PEER_TIMEOUT_S`` seconds (default
+    600) for a peer gives up without poisoning its CUDA context: it records the call's epoch in the buffer header and
+    ``check()`` - called at any host synchronisation point - raises. The results of such a call are invalid.
     """
+
+    STATUS_OFFSET = 768  # csrc/exchange.cu kPeerStatusOff
 
     def __init__(self, group: dist.ProcessGroup | None, device: torch.device, max_candidates: int):
         import torch.distributed._symmetric_memory as symm
@@ -68,6 +73,13 @@ class PeerExchange:
         torch.cuda.synchronize(self.device)
         dist.barrier(self.group)  # every buffer is zeroed before anyone's first push can land in it
 
+    def check(self) -> None:
+        """Raise if an exchange on this buffer timed out waiting for a peer (synchronises the device)."""
+        failed = int(self.buf[self.STATUS_OFFSET : self.STATUS_OFFSET + 4].view(torch.int32).item())
+        if failed:
+            raise RuntimeError(f"peer exchange call {failed} on rank {self.rank} timed out waiting for a peer (ICR_PEER_TIMEOUT_S): "
+                               "a rank died or the ranks are not calling in lockstep; results since that call are invalid")
+
     def all_gather(self, vals: torch.Tensor, ids: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
         """vals f32 [Q,k], ids i64 [Q,k] -> (scores [G,Q,k], ids [G,Q,k]): views of this rank's buffer, valid until the
         call after next."""
@@ -87,6 +99,9 @@ class PeerExchange:
         scores = self.buf[so.value : so.value + G * n * 4].view(torch.float32).view(G, *vals.shape)
         gids = self.buf[io.value : io.value + G * n * 8].view(torch.int64).view(G, *ids.shape)
         return scores, gids
+
+
+MAX_GLOBAL_ROWS = 2**32 - 1  # icr_topk_merge carries global ids in the 32-bit half of its candidate keys
 
 
 class ShardedCatalog:
@@ -118,6 +133,9 @@ class ShardedCatalog:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.total_rows = int(total_rows)
         self.row_offset = int(row_offset)
+        if self.total_rows >= MAX_GLOBAL_ROWS:
+            # the K4 merge keys candidates by (score, 32-bit id): larger catalogs would return truncated ids silently
+            raise ValueError(f"a sharded catalog holds at most {MAX_GLOBAL_ROWS - 1} rows in total (got {self.total_rows})")
         # test seams: the gloo/CPU tests of the host logic plug the oracle in here; product code never does
         self._local_topk = _local_topk
         self._merge = _merge

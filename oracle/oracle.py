@@ -98,6 +98,31 @@ def cos_topk(queries, catalog, k: int, sorted: bool = True, chunk: int = 1024):
     return torch.cat(vals), torch.cat(idxs)
 
 
+def cos_topk_catalog_chunked(queries, catalog, k: int, chunk_rows: int = 1 << 18):
+    """cos_topk for catalogs too large to score at once (BASELINE configs 4-5 at scale): the same expression,
+    F.normalize -> mm -> topk, evaluated over row blocks of the catalog with the per-block top-k merged by one
+    more topk. `catalog` may be bf16 (the low-precision oracle of SURVEY §8c: fp32 math on the rounded inputs);
+    each block is widened to fp32 before anything is computed. Ties inside a block keep torch.topk's order; the
+    callers compare ids tie-tolerantly.
+    """
+    q = F.normalize(_to_tensor(queries).to(torch.float32), p=2, dim=1)
+    n = catalog.shape[0]
+    k = min(k, n)
+    best_v = torch.full((q.shape[0], 0), float("-inf"))
+    best_i = torch.zeros((q.shape[0], 0), dtype=torch.int64)
+    for s in range(0, n, chunk_rows):
+        c_n = F.normalize(catalog[s : s + chunk_rows].to(torch.float32), p=2, dim=1)
+        sc = torch.mm(q, c_n.transpose(0, 1))
+        v, i = torch.topk(sc, min(k, sc.shape[1]), dim=1)
+        best_v = torch.cat([best_v, v], dim=1)
+        best_i = torch.cat([best_i, i + s], dim=1)
+        if best_v.shape[1] > k:
+            best_v, pos = torch.topk(best_v, k, dim=1)
+            best_i = torch.gather(best_i, 1, pos)
+    order = torch.argsort(best_v, dim=1, descending=True, stable=True)
+    return torch.gather(best_v, 1, order), torch.gather(best_i, 1, order)
+
+
 # --------------------------------------------------------------------------------------
 # a2: /recommend tail — serve_recommendations.py:213-225 (and :250-262)
 # --------------------------------------------------------------------------------------

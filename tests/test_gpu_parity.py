@@ -43,6 +43,10 @@ def _check_topk(v, i, rv, ri, rtol):
     assert mism == 0, f"{mism} id mismatches outside ties"
     for r in range(i.shape[0]):  # no duplicates
         assert len(set(i[r].tolist())) == i.shape[1]
+    # rank-k membership: the last returned score may not fall below the oracle's k-th score by more than the tolerance
+    # (compare_topk never treats the last rank as decisive for ids, so the boundary is asserted on the scores)
+    rk = np.asarray(rv, dtype=np.float64)[:, -1]
+    assert (v.double().numpy()[:, -1] >= rk - rtol * np.maximum(np.abs(rk), 0.05)).all(), "k-th returned score below the oracle's k-th"
 
 
 PATHS = [ops.PATH_GEMV, ops.PATH_GEMM]
@@ -739,6 +743,35 @@ def test_gemm_path_ties_duplicates_and_adversarial_order(dtype):
     v, i = ops.cos_topk(q0.to(dtype).cuda(), c_sorted.cuda(), 100, path=ops.PATH_GEMM)
     rv, ri = oracle.cos_topk(q0.to(dtype).float(), c_sorted.float(), 100)
     _check_topk(v, i, rv, ri, tol)
+
+
+@pytest.mark.parametrize("Q", [300, 700])  # block-per-query select / warp-per-query select
+def test_screened_fp32_band_overflow_is_ranked_exactly(Q):
+    """The fp32 tensor path screens with ONE fp16 MMA term and carries every row within a band of the k-th screened score
+    (k + k slots). 1,500 near-duplicates around the k-th rank overflow that band: those queries must fall back to the exact
+    ranking of the whole catalog; the others (random directions) take the normal re-scoring. Also run with an exclusion mask."""
+    if not _gemm_ok():
+        pytest.skip("GEMM path not built yet")
+    g = torch.Generator().manual_seed(5)
+    N, D, k = 20000, 384, 100
+    items = oracle.synth_isotropic(N, D, seed=11)
+    base = torch.nn.functional.normalize(torch.randn(1, D, generator=g), dim=1)
+    dup_rows = torch.randperm(N, generator=g)[:1500]
+    items[dup_rows] = torch.nn.functional.normalize(base + 2e-4 * torch.randn(1500, D, generator=g) / math.sqrt(D), dim=1)
+    near = torch.nn.functional.normalize(base + 0.3 * torch.randn(Q // 2, D, generator=g) / math.sqrt(D), dim=1)
+    queries = torch.cat([near, oracle.synth_isotropic(Q - Q // 2, D, seed=12)])[torch.randperm(Q, generator=g)]
+    full = oracle.cos_sim(queries, items)
+    cat = icr.DeviceCatalog(items)
+    for mask in (None, (torch.arange(N) % 7 == 3)):
+        v, i = cat.topk(queries.cuda(), k, exclude_mask=None if mask is None else mask.cuda(), path=ops.PATH_GEMM)
+        s = full.clone()
+        if mask is not None:
+            s[:, mask] = float("-inf")
+        rv, ri = torch.topk(s, k, dim=1)
+        _check_topk(v, i, rv, ri, F32_RTOL)
+        # every returned id carries its own exact score (a wrong row with a plausible score would pass the rank-wise check)
+        got = torch.gather(s, 1, i.cpu())
+        assert (got - v.cpu()).abs().max() < 2e-6
 
 
 def test_full_size_properties_c2_shape():
