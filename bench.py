@@ -6,9 +6,14 @@
 Workload at every N: BASELINE.json configs[1] — batched IR evaluation, 10,000 queries against the
 49,688 x 384 fp32 catalog, top-100 (one "step" = one pass over one 10,000-query batch). With N > 1 every
 rank holds a replica of the catalog and its own query batch (queries are independent units: weak scaling,
-no data-path collective), and the same run also measures the row-sharded catalog + NCCL all-gather +
-device merge path on a larger catalog (key "sharded"), which is the north_star's route for catalogs that
-do not fit one GPU.
+NO data-path collective — the headline `value` says nothing about a collective).
+
+The path that does have an exchange step is measured at EVERY N, including 1, as the `sharded` object: the
+FIXED-TOTAL catalogs of BASELINE configs 4 and 5 (10M x 768 bf16 with Q = 1 / 64 / 1024, 100M x 384 bf16 with
+Q = 4096), row-sharded over the N GPUs (strong scaling), local fused top-k -> candidate exchange (NVLink
+peer-memory kernel, NCCL all-gather timed beside it) -> device merge, with a torch fp32 witness on sampled
+queries. `c1` = the batch-1 request of config 1 (cold and graph-replay latency against the HBM roofline),
+`c3` = the MNRL step of config 3 (fwd+bwd, B = 256) next to PyTorch eager on the same GPU.
 
 Prints ONE JSON line (rank 0). `value` = device-resident throughput; `e2e` = through the public API with
 pinned-host queries in and host results out, copies inside the timed region; `roofline` = the dominant
@@ -160,7 +165,8 @@ def main():
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"], help="catalog storage dtype (headline: f32, the reference's)")
     ap.add_argument("--path", default="auto", choices=["auto", "gemv", "gemm"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-sharded", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the row-sharded strong-scaling object (configs 4 and 5)")
+    ap.add_argument("--no-side", action="store_true", help="skip the c1 / c3 / ir_eval side objects")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -270,28 +276,47 @@ def main():
         roof = {"bound": "hbm", "achieved": bytes_per_launch / (kt["ms_per_launch"] * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s"}
         roof["note"] = f"catalog bytes per GEMV launch (L2-resident after the first pass); peak = {peaks['source']} HBM copy"
     roof["frac"] = roof["achieved"] / roof["peak"]
-    roof["traffic"] = None  # bytes per launch from the committed ncu --set full capture of this workload, if there is one
+    roof["traffic"] = None  # NOT measured by this run: bytes per launch from the committed ncu --set full capture of this workload, if there is one
     try:
-        cap = json.loads((ROOT / "profiles" / "r01_kernel_traffic.json").read_text())[kt["kernel"]][args.dtype]["launch_bytes"]
-        if args.path == "auto" and world >= 1:
-            roof["traffic"] = sum(cap) / len(cap)
-            roof["traffic_note"] = "mean DRAM bytes (read+write) per launch of this kernel, ncu --set full, profiles/r01_kernel_traffic.json"
-    except (OSError, KeyError, ValueError):
+        cap = json.loads((ROOT / "profiles" / "r02_kernel_traffic.json").read_text())[kt["kernel"]][args.dtype]
+        if args.path == "auto":
+            roof["traffic"] = sum(cap["launch_bytes"]) / len(cap["launch_bytes"])
+            roof["traffic_source"] = "static: " + cap.get("source", "ncu --set full capture committed under profiles/") + " (mean dram read+write bytes per launch; not re-measured in this run)"
+    except (OSError, KeyError, ValueError, TypeError):
         pass
     roof["kernel"] = kt["kernel"]
     roof["kernel_ms_per_step"] = kt["ms_per_step"]
     roof["kernel_launches_per_step"] = kt["launches_per_step"]
 
     ir_eval = None
-    if world == 1:
+    if world == 1 and not args.no_side:
         try:
             ir_eval = bench_ir_eval(icr, ops, dev, rank, flush)
         except Exception as e:  # a side measurement must not cost the headline line
             ir_eval = {"error": f"{type(e).__name__}: {e}"[:300]}
 
+    c1 = c3 = None
+    if world == 1 and not args.no_side:
+        for name, fn in (("c1", bench_c1), ("c3", bench_c3)):
+            try:
+                res = fn(icr, ops, dev, flush)
+            except Exception as e:  # a side measurement must not cost the headline line
+                res = {"error": f"{type(e).__name__}: {e}"[:300]}
+            if name == "c1":
+                c1 = res
+            else:
+                c3 = res
+    del catalog, items, queries, queries_dev
+    torch.cuda.empty_cache()
+
     sharded = None
-    if world > 1 and not args.no_sharded:
-        sharded = bench_sharded(icr, dist, dev, rank, world, args, tdtype)
+    if not args.no_sharded:
+        try:
+            sharded = bench_sharded(icr, ops, dist, dev, rank, world, flush)
+        except Exception as e:
+            if world > 1:
+                raise  # ranks must not diverge around collectives
+            sharded = {"error": f"{type(e).__name__}: {e}"[:300]}
 
     value = world * Q * args.steps / (total_ms * 1e-3)
     e2e = world * Q * args.steps / (e2e_ms * 1e-3)
@@ -301,7 +326,8 @@ def main():
         "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": "C2: batched IR eval, 10,000 queries x 49,688x384 catalog, top-100 (BASELINE.json configs[1])",
                    "Q_per_gpu": Q, "N": N, "D": D, "k": k, "catalog_dtype": args.dtype, "path": args.path,
-                   "multi_gpu": "catalog replica + own query batch per rank (no data-path collective)" if world > 1 else "single GPU",
+                   "multi_gpu": ("catalog replica + own query batch per rank: NO data-path collective in `value` - the collective path is the `sharded` object"
+                                 if world > 1 else "single GPU"),
                    "l2": "512 MiB buffer zeroed between timed iterations (L2 flush)", "seeds": [CATALOG_SEED, QUERY_SEED]},
         "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": Q * D * 4, "d2h_bytes_per_step": Q * k * 12,
                 "note": "DeviceCatalog.topk_host: pinned-host fp32 queries in, (scores f32, ids i64) out to pinned host, 3 pieces (20/60/20 %) pipelined "
@@ -313,6 +339,10 @@ def main():
     }
     if sharded is not None:
         line["sharded"] = sharded
+    if c1 is not None:
+        line["c1"] = c1
+    if c3 is not None:
+        line["c3"] = c3
     if ir_eval is not None:
         line["ir_eval"] = ir_eval
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -376,64 +406,245 @@ def bench_ir_eval(icr, ops, dev, rank, flush):
             "recall@10": vals[0], "ndcg@10": vals[1], "mrr@10": vals[2], "map@100": vals[3]}
 
 
-def bench_sharded(icr, dist, dev, rank, world, args, tdtype):
-    """BASELINE.json config 5 per rank: a 12.5M x 384 bf16 row shard on every GPU (100M rows at 8 GPUs), 4096-query
-    batches replicated, top-100: local fused top-k -> NCCL all-gather of [Q,k] candidates -> K4 device merge.
-    Weak scaling in catalog rows: queries/s should stay flat while the catalog grows with the GPU count."""
+def bench_c1(icr, ops, dev, flush):
+    """BASELINE config 1: one query against the 49,688 x 384 fp32 catalog, top-10 (the /recommend request,
+    reference src/inference/serve_recommendations.py:213-225). PRIMARY number = HBM-cold: the request runs against a
+    rotating set of catalog copies larger than L2 (so neither L2 nor the preceding flush kernel hides anything), one
+    request per timed region, launched back to back from the host. Beside it: the same with an L2 flush in front, the
+    CUDA-graph replay of DeviceCatalog.topk_small (L2-warm: the serve path keeps hitting the same 76 MB), and the kernel
+    alone."""
     import torch
 
-    shard_rows, D, Q, k = 12_500_000, 384, 4096, 100
-    total_rows = shard_rows * world
-    lo = rank * shard_rows
-    g = torch.Generator(device=dev).manual_seed(CATALOG_SEED + 100 + rank)
-    rows = torch.empty(shard_rows, D, dtype=torch.bfloat16, device=dev)
-    for s0 in range(0, shard_rows, 1 << 20):  # generated shard by shard on the device (seed + rank), 1M rows at a time
-        s1 = min(shard_rows, s0 + (1 << 20))
-        rows[s0:s1] = torch.nn.functional.normalize(torch.randn(s1 - s0, D, device=dev, generator=g), dim=1).to(torch.bfloat16)
-    cat = icr.ShardedCatalog(rows, row_offset=lo, total_rows=total_rows, dtype=torch.bfloat16, exchange="peer")
-    cat_nccl = cat.with_exchange("nccl")  # same resident shard, NCCL all-gather instead of the peer-memory kernel
-    g2 = torch.Generator(device=dev).manual_seed(QUERY_SEED)
-    q = torch.nn.functional.normalize(torch.randn(Q, D, device=dev, generator=g2), dim=1).to(torch.bfloat16)
-    steps = 5
-
-    def run(c, qq, n):
-        for _ in range(2):
-            c.topk(qq, k)
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        dist.barrier()
+    N, D, k = C2["N"], C2["D"], 10
+    g = torch.Generator(device=dev).manual_seed(CATALOG_SEED)
+    items = torch.nn.functional.normalize(torch.randn(N, D, device=dev, generator=g), dim=1)
+    q = torch.nn.functional.normalize(torch.randn(1, D, device=dev, generator=g), dim=1)
+    peaks = _peaks()
+    out = {"workload": "C1: batch-1 query x 49,688x384 catalog, top-10 (BASELINE.json configs[0] on the GPU path)", "roofline_bytes": N * D * 4}
+    for dt, tag in ((torch.float32, "f32"), (torch.bfloat16, "bf16")):
+        copies = [icr.DeviceCatalog(items.clone(), dtype=dt) for _ in range(4 if dt == torch.float32 else 8)]  # 4 x 76 MB (+ planes) > 126 MB L2
+        qd = q.to(dt)
+        for c in copies:
+            c.topk(qd, k)
         torch.cuda.synchronize()
+
+        def timed(fn, n, pre=None):
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+            for i, (a, b) in enumerate(ev):
+                if pre is not None:
+                    pre()
+                a.record()
+                fn(i)
+                b.record()
+            torch.cuda.synchronize()
+            ts = sorted(a.elapsed_time(b) * 1e3 for a, b in ev)
+            return ts[len(ts) // 2]
+
+        cold = timed(lambda i: copies[i % len(copies)].topk(qd, k), 60)
+        flushed = timed(lambda i: copies[0].topk(qd, k), 30, pre=flush.zero_)
+        copies[0].topk_small(qd, k)
+        graph = timed(lambda i: copies[0].topk_small(qd, k, copy=False), 60)
+        kt = ops.kernel_timing(lambda: copies[1].topk(qd, k), 20, flush=flush)
+        nbytes = N * D * (4 if dt == torch.float32 else 2)
+        out[tag] = {"cold_us": cold, "l2_flushed_us": flushed, "graph_replay_us": graph, "kernel_us": kt["ms_per_launch"] * 1e3,
+                    "hbm_frac_cold": nbytes / (cold * 1e-6) / 1e9 / peaks["hbm_gbs"], "hbm_frac_kernel": nbytes / (kt["ms_per_launch"] * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                    "catalog_bytes": nbytes}
+        del copies
+        torch.cuda.empty_cache()
+    out["note"] = ("cold_us = median of 60 requests rotating over catalog copies that together exceed L2 (primary); graph_replay_us = DeviceCatalog.topk_small "
+                   "(one graph launch, L2-warm); fractions are catalog bytes / time / measured HBM copy peak")
+    return out
+
+
+def bench_c3(icr, ops, dev, flush):
+    """BASELINE config 3: MultipleNegativesRankingLoss fwd+bwd, batch 256, dim 384, scale 20, bf16 (reference
+    src/training/train_sbert.py:182-185), next to the same loss in PyTorch eager on this GPU."""
+    import torch
+
+    B, D, scale = 256, 384, 20.0
+    g = torch.Generator(device=dev).manual_seed(7)
+    a0 = torch.nn.functional.normalize(torch.randn(B, D, device=dev, generator=g), dim=1)
+    p0 = torch.nn.functional.normalize(a0 + 0.3 * torch.randn(B, D, device=dev, generator=g), dim=1)
+    res = {"workload": f"C3: MNRL fwd+bwd, B={B}, D={D}, scale={scale:g}"}
+    for dt, tag in ((torch.bfloat16, "bf16"), (torch.float32, "f32")):
+        a = a0.to(dt).requires_grad_(True)
+        p = p0.to(dt).requires_grad_(True)
+
+        def ours():
+            a.grad = p.grad = None
+            icr.mnrl_loss(a, p, scale).backward()
+
+        def eager():
+            a.grad = p.grad = None
+            an = torch.nn.functional.normalize(a.float(), dim=1)
+            pn = torch.nn.functional.normalize(p.float(), dim=1)
+            torch.nn.functional.cross_entropy(an @ pn.T * scale, torch.arange(B, device=dev)).backward()
+
+        def wall(fn, n=200):
+            for _ in range(10):
+                fn()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(n):
+                fn()
+            torch.cuda.synchronize()
+            return (time.perf_counter() - t0) / n * 1e6
+
+        res[tag] = {"fused_us": wall(ours), "eager_us": wall(eager)}
+        step = getattr(icr, "mnrl_step_graph", None)
+        if step is not None:
+            runner = step(B, D, dt, scale, device=dev)
+            res[tag]["graph_us"] = wall(lambda: runner(a.detach(), p.detach()))
+    res["note"] = "wall clock per step over 200 back-to-back steps (host launch cost included); eager = F.normalize x2 + mm + cross_entropy + autograd on the same GPU"
+    return res
+
+
+def _gen_shard(rows, d, seed, dev, torch):
+    """rows x d bf16 unit rows, generated on the device 1M rows at a time (seeded per shard)."""
+    g = torch.Generator(device=dev).manual_seed(seed)
+    out = torch.empty(rows, d, dtype=torch.bfloat16, device=dev)
+    for s0 in range(0, rows, 1 << 20):
+        s1 = min(rows, s0 + (1 << 20))
+        out[s0:s1] = torch.nn.functional.normalize(torch.randn(s1 - s0, d, device=dev, generator=g), dim=1).to(torch.bfloat16)
+    return out
+
+
+def _witness_topk(q, rows, row_offset, k, torch, chunk=1 << 18):
+    """torch fp32 eager on this rank's shard: normalize -> mm -> topk per row block -> merged top-k with global ids."""
+    qn = torch.nn.functional.normalize(q.float(), dim=1)
+    bv = torch.full((q.shape[0], 0), float("-inf"), device=q.device)
+    bi = torch.zeros((q.shape[0], 0), dtype=torch.int64, device=q.device)
+    for s in range(0, rows.shape[0], chunk):
+        cn = torch.nn.functional.normalize(rows[s : s + chunk].float(), dim=1)
+        v, i = torch.topk(qn @ cn.T, min(k, cn.shape[0]), dim=1)
+        bv, bi = torch.cat([bv, v], 1), torch.cat([bi, i + s + row_offset], 1)
+        if bv.shape[1] > k:
+            bv, pos = torch.topk(bv, k, dim=1)
+            bi = torch.gather(bi, 1, pos)
+    return bv, bi
+
+
+def bench_sharded(icr, ops, dist, dev, rank, world, flush):
+    """STRONG scaling through the collective: the fixed-total catalogs of BASELINE configs 4 and 5, row-sharded over the
+    `world` GPUs of this run (world = 1 holds the whole catalog: 15.4 GB and 76.8 GB). Per config and batch size: whole-call
+    ms per step (max over ranks, >= 20 steps), the local top-k alone, exchange + merge alone over NVLink peer memory and
+    over NCCL, the roofline fraction of the local pass, and `witness_ok`: 16 sampled queries of the merged result against
+    torch fp32 eager run on the same shards (scores within 5e-5 relative, ids tie-tolerant)."""
+    import torch
+
+    peaks = _peaks()
+    k = 100
+    configs = [
+        {"name": "C4", "total_rows": 10_000_000, "D": 768, "Qs": [1, 64, 1024], "seed": 400},
+        {"name": "C5", "total_rows": 100_000_000, "D": 384, "Qs": [4096], "seed": 500},
+    ]
+
+    def tmax(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run(fn, n, warm=3):
+        for _ in range(warm):
+            fn()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
         ev0.record()
         for _ in range(n):
-            out = c.topk(qq, k)
+            fn()
         ev1.record()
-        dist.barrier()
-        torch.cuda.synchronize()
-        t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return t.item() / n, out
+        barrier()
+        return tmax(ev0.elapsed_time(ev1)) / n
 
-    ms_nccl, (v0, i0) = run(cat_nccl, q, steps)
-    exchange, peer_error = "icr_peer_exchange: NVLink peer-memory push + flags (one kernel), then device merge", None
-    small = {}
-    try:
-        ms, (v, i) = run(cat, q, steps)
-        same = bool(torch.equal(v, v0) and torch.equal(i, i0))
-        for qs in (1, 64):  # request-sized batches: the exchange is a visible share of the call
-            a, _ = run(cat_nccl, q[:qs], 20)
-            b, _ = run(cat, q[:qs], 20)
-            small[f"Q{qs}"] = {"nccl_ms": a, "peer_ms": b}
-    except Exception as e:  # symmetric memory unavailable on this box: the NCCL route is the measured one
-        peer_error = f"{type(e).__name__}: {e}"[:300]
-        exchange = "NCCL all-gather of packed candidates, then device merge"
-        ms, v, i, same = ms_nccl, v0, i0, None
-    flops = 2.0 * Q * shard_rows * D  # per GPU
-    peaks = _peaks()
-    return {"workload": f"C5: {total_rows} x {D} bf16 catalog row-sharded over {world} GPUs ({shard_rows} rows each), {Q}-query batches, top-{k}, "
-                        "candidates exchanged over NVLink peer memory + device merge",
-            "value": Q / (ms * 1e-3), "unit": "queries/s", "scaling": "weak (catalog rows grow with GPUs)", "ms_per_step": ms, "steps": steps,
-            "exchange": exchange, "peer_exchange_error": peer_error, "exchange_bytes_per_rank": Q * k * 12,
-            "nccl_all_gather_ms_per_step": ms_nccl, "peer_equals_nccl": same, "small_batches": small, "tflops_per_gpu": flops / (ms * 1e-3) / 1e12,
-            "frac_of_bf16_peak": flops / (ms * 1e-3) / 1e12 / peaks["bf16_tflops"], "ids_in_range": bool(((i >= 0) & (i < total_rows)).all().item())}
+    out = {"scaling": "strong (total catalog fixed, rows per GPU = total / n_gpus)", "n_gpus": world, "k": k, "configs": {}}
+    peer_error = None
+    for cfg in configs:
+        total, D = cfg["total_rows"], cfg["D"]
+        per = -(-total // world)
+        lo, hi = rank * per, min(total, (rank + 1) * per)
+        rows = _gen_shard(hi - lo, D, CATALOG_SEED + cfg["seed"] + rank, dev, torch)
+        cat = icr.ShardedCatalog(rows, row_offset=lo, total_rows=total, dtype=torch.bfloat16, exchange="peer")
+        cat_nccl = cat.with_exchange("nccl")
+        g2 = torch.Generator(device=dev).manual_seed(QUERY_SEED + cfg["seed"])
+        qall = torch.nn.functional.normalize(torch.randn(max(cfg["Qs"]), D, device=dev, generator=g2), dim=1).to(torch.bfloat16)
+        centry = {"total_rows": total, "rows_per_gpu": hi - lo, "D": D, "dtype": "bf16", "shard_bytes": (hi - lo) * D * 2, "batches": {}}
+        for Q in cfg["Qs"]:
+            q = qall[:Q]
+            steps = 20
+            e = {"steps": steps}
+            use = cat
+            if world > 1 and peer_error is None:
+                try:
+                    cat.topk(q, k)
+                except Exception as ex:  # symmetric memory unavailable on this box: every rank takes the NCCL route
+                    peer_error = f"{type(ex).__name__}: {ex}"[:300]
+            if world > 1:
+                flag = torch.tensor([1.0 if peer_error else 0.0], device=dev)
+                dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+                if flag.item() > 0:
+                    peer_error = peer_error or "peer exchange failed on another rank"
+                    use = cat_nccl
+            ms = run(lambda: use.topk(q, k), steps)
+            e["ms_per_step"] = ms
+            e["queries_per_s"] = Q / (ms * 1e-3)
+            e["local_topk_ms"] = run(lambda: cat.local_topk(q, k), steps)
+            if world > 1:
+                lv, li = cat.local_topk(q, k)
+                if use is cat:
+                    e["exchange_merge_peer_us"] = run(lambda: cat.exchange_merge(lv, li, k), 50) * 1e3
+                e["exchange_merge_nccl_us"] = run(lambda: cat_nccl.exchange_merge(lv, li, k), 50) * 1e3
+                e["ms_per_step_nccl"] = run(lambda: cat_nccl.topk(q, k), steps) if use is cat else ms
+            # roofline of the local pass: HBM bytes of the shard for small batches, tensor flops for large ones
+            flops, nbytes = 2.0 * Q * (hi - lo) * D, (hi - lo) * D * 2
+            t = e["local_topk_ms"] * 1e-3
+            e["local_tflops"], e["local_gbs"] = flops / t / 1e12, nbytes / t / 1e9
+            sustained = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
+            ft, fh = e["local_tflops"] / sustained, e["local_gbs"] / peaks["hbm_gbs"]
+            e["bound"] = "tensor" if ft > fh else "hbm"
+            e["roofline_frac"] = max(ft, fh)
+            e["roofline_peak"] = "bf16 sustained" if ft > fh else "hbm copy"
+            # witness: 16 sampled queries, torch fp32 eager on the same shards, candidates merged on the host
+            sample = torch.arange(0, Q, max(1, Q // 16), device=dev)[:16]
+            v, i = use.topk(q, k)
+            wv, wi = _witness_topk(q[sample], rows, lo, k, torch)
+            if world > 1:
+                gv = [torch.empty_like(wv) for _ in range(world)]
+                gi = [torch.empty_like(wi) for _ in range(world)]
+                dist.all_gather(gv, wv)
+                dist.all_gather(gi, wi)
+                wv, wi = torch.cat(gv, 1), torch.cat(gi, 1)
+                wv, pos = torch.topk(wv, k, dim=1)
+                wi = torch.gather(wi, 1, pos)
+            order = torch.argsort(wv, dim=1, descending=True, stable=True)
+            wv, wi = torch.gather(wv, 1, order), torch.gather(wi, 1, order)
+            sv, si = v[sample], i[sample]
+            denom = wv.abs().clamp_min(0.05)
+            rel = ((sv - wv).abs() / denom).max().item()
+            gap_ok = torch.ones_like(wv, dtype=torch.bool)
+            tol = 1e-4 * denom  # ids are only held where the witness's neighbouring scores are further apart than this
+            gap_ok[:, 1:] &= (wv[:, :-1] - wv[:, 1:]) > tol[:, 1:]
+            gap_ok[:, :-1] &= (wv[:, :-1] - wv[:, 1:]) > tol[:, :-1]
+            gap_ok[:, -1] = False
+            mism = int(((si != wi) & gap_ok).sum().item())
+            e["witness_max_rel_err"] = rel
+            e["witness_id_mismatch"] = mism
+            e["witness_ok"] = bool(rel <= 5e-5 and mism == 0 and bool(((i >= 0) & (i < total)).all().item()))
+            centry["batches"][f"Q{Q}"] = e
+        out["configs"][cfg["name"]] = centry
+        del cat, cat_nccl, rows, qall
+        torch.cuda.empty_cache()
+    out["exchange"] = ("NCCL all-gather of packed candidates + device merge (peer exchange unavailable)" if peer_error else
+                       "icr_peer_exchange: NVLink peer-memory push + flags (one kernel) + device merge; NCCL route timed beside it") if world > 1 else "none (one GPU holds the whole catalog)"
+    out["peer_exchange_error"] = peer_error
+    out["witness"] = "torch fp32 eager (normalize -> mm -> topk) on the same bf16 shards, 16 sampled queries per batch size, per-rank top-k gathered and merged"
+    out["oracle_ok"] = all(b["witness_ok"] for c in out["configs"].values() for b in c["batches"].values())
+    return out
 
 
 if __name__ == "__main__":

@@ -43,7 +43,11 @@ typedef enum {
   ICR_ERR_DEVICE = -7     /* current device is not sm_100                */
 } icr_status;
 
-typedef enum { ICR_F32 = 0, ICR_BF16 = 1 } icr_dtype;
+typedef enum {
+  ICR_F32 = 0,
+  ICR_BF16 = 1,
+  ICR_F16 = 2 /* MNRL entry points only: embeddings as the reference's fp16-autocast training produces them (train_sbert.py:210,232) */
+} icr_dtype;
 
 /* which kernel family serves a cos_topk call */
 typedef enum {
@@ -182,7 +186,7 @@ int icr_peer_exchange(const float* scores, const int64_t* ids, int64_t n, int ra
  * src/training/train_sbert.py:182-185):
  *   loss = mean_i CE( scale * cos_sim(A, P)[i, :], i )
  * fwd saves per-row lse / inverse norms for bwd. Internal math is fp32.
- *   a, p        [B, D] dtype;  loss: 1 float;  lse, inv_a, inv_p: B floats each
+ *   a, p        [B, D] dtype (ICR_F32, ICR_BF16 or ICR_F16);  loss: 1 float;  lse, inv_a, inv_p: B floats each
  *   grad_out    1 float (dL/dloss);  grad_a, grad_p [B, D] dtype (row strides ldga, ldgp)
  * ------------------------------------------------------------------------------------- */
 size_t icr_mnrl_workspace_bytes(int64_t B, int64_t D);

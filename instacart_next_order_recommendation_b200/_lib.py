@@ -13,7 +13,7 @@ from pathlib import Path
 
 LIB_PATH = Path(__file__).resolve().parent / "lib" / "libicr_b200.so"
 
-ICR_F32, ICR_BF16 = 0, 1
+ICR_F32, ICR_BF16, ICR_F16 = 0, 1, 2
 PATH_AUTO, PATH_GEMV, PATH_GEMM = 0, 1, 2
 PATH_WS_RESIDENT = 0x100  # OR-ed into a path: resident workspace, see include/icr_b200.h
 MAX_K = 256

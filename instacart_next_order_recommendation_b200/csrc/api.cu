@@ -98,9 +98,9 @@ int launch_ir_metrics(const int64_t* ids, int64_t Q, int K, int64_t ld, const in
 static int elem_size(int dtype) { return dtype == ICR_F32 ? 4 : 2; }
 static int vec_elems(int dtype) { return dtype == ICR_F32 ? 4 : 8; }
 
-static int check_matrix(const char* name, const void* p, int64_t rows, int64_t dim, int64_t ld, int dtype) {
-  if (dtype != ICR_F32 && dtype != ICR_BF16) {
-    set_error("%s: unsupported dtype %d (0 = f32, 1 = bf16)", name, dtype);
+static int check_matrix(const char* name, const void* p, int64_t rows, int64_t dim, int64_t ld, int dtype, bool allow_f16 = false) {
+  if (dtype != ICR_F32 && dtype != ICR_BF16 && !(allow_f16 && dtype == ICR_F16)) {
+    set_error("%s: unsupported dtype %d (0 = f32, 1 = bf16%s)", name, dtype, allow_f16 ? ", 2 = f16" : "; f16 is accepted by the MNRL entry points only");
     return ICR_ERR_DTYPE;
   }
   if (rows < 0 || dim <= 0 || ld < dim) {
@@ -411,8 +411,8 @@ size_t icr_mnrl_workspace_bytes(int64_t B, int64_t D) {
 static int mnrl_common(const void* a, int64_t lda, const void* p, int64_t ldp, int64_t B, int64_t D, int dtype, void* workspace,
                        size_t workspace_bytes) {
   int rc;
-  if ((rc = check_matrix("mnrl.anchors", a, B, D, lda, dtype))) return rc;
-  if ((rc = check_matrix("mnrl.positives", p, B, D, ldp, dtype))) return rc;
+  if ((rc = check_matrix("mnrl.anchors", a, B, D, lda, dtype, true))) return rc;
+  if ((rc = check_matrix("mnrl.positives", p, B, D, ldp, dtype, true))) return rc;
   if (B < 1 || B > (1 << 24)) {
     set_error("mnrl: batch %lld outside [1, 2^24]", (long long)B);
     return ICR_ERR_ARG;
@@ -599,7 +599,7 @@ int icr_mnrl_fwd_bwd(const void* a, int64_t lda, const void* p, int64_t ldp, int
 int icr_mnrl_scale_grads(const void* grad_a, const void* grad_p, int64_t n, int dtype, const float* grad_out, void* out_a, void* out_p,
                          void* stream) {
   g_launches = 0;
-  if (n < 0 || (dtype != ICR_F32 && dtype != ICR_BF16) || (n > 0 && (!grad_a || !grad_p || !grad_out || !out_a || !out_p))) {
+  if (n < 0 || (dtype != ICR_F32 && dtype != ICR_BF16 && dtype != ICR_F16) || (n > 0 && (!grad_a || !grad_p || !grad_out || !out_a || !out_p))) {
     set_error("mnrl_scale_grads: bad arguments (n=%lld dtype=%d)", (long long)n, dtype);
     return ICR_ERR_ARG;
   }
@@ -617,8 +617,8 @@ size_t icr_mnrl_rect_workspace_bytes(int64_t B, int64_t Bc, int64_t D) {
 static int mnrl_rect_common(const void* a, int64_t lda, const void* c, int64_t ldc, int64_t B, int64_t Bc, int64_t label_offset, int64_t D,
                             int dtype, void* workspace, size_t workspace_bytes) {
   int rc;
-  if ((rc = check_matrix("mnrl.anchors", a, B, D, lda, dtype))) return rc;
-  if ((rc = check_matrix("mnrl.candidates", c, Bc, D, ldc, dtype))) return rc;
+  if ((rc = check_matrix("mnrl.anchors", a, B, D, lda, dtype, true))) return rc;
+  if ((rc = check_matrix("mnrl.candidates", c, Bc, D, ldc, dtype, true))) return rc;
   if (B < 1 || Bc < 2 || label_offset < 0 || label_offset + B > Bc || D % 8 != 0 || D > 4096 || B > 65536 || Bc > (1 << 20)) {
     set_error("mnrl (rectangular): need 1 <= B <= 65536, label_offset + B <= Bc <= 2^20, D %% 8 == 0, D <= 4096; got B=%lld Bc=%lld offset=%lld D=%lld",
               (long long)B, (long long)Bc, (long long)label_offset, (long long)D);

@@ -143,6 +143,22 @@ struct Elem<__nv_bfloat16> {
   __device__ static __forceinline__ __nv_bfloat16 from_f32(float x) { return __float2bfloat16_rn(x); }
 };
 
+template <>
+struct Elem<__half> {
+  static constexpr int VEC = 8;
+  __device__ static __forceinline__ void unpack(const uint4& v, float* f) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 p = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      f[2 * i] = p.x;
+      f[2 * i + 1] = p.y;
+    }
+  }
+  __device__ static __forceinline__ float to_f32(__half x) { return __half2float(x); }
+  __device__ static __forceinline__ __half from_f32(float x) { return __float2half_rn(x); }
+};
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);

@@ -315,6 +315,9 @@ int launch_scale2(const void* x0, const void* x1, int64_t n, int dtype, const fl
   if (dtype == ICR_F32)
     scale2_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(x0), static_cast<const float*>(x1), n, s, static_cast<float*>(o0),
                                                  static_cast<float*>(o1));
+  else if (dtype == ICR_F16)
+    scale2_kernel<__half><<<blocks, 256, 0, st>>>(static_cast<const __half*>(x0), static_cast<const __half*>(x1), n, s, static_cast<__half*>(o0),
+                                                  static_cast<__half*>(o1));
   else
     scale2_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x0), static_cast<const __nv_bfloat16*>(x1), n, s,
                                                          static_cast<__nv_bfloat16*>(o0), static_cast<__nv_bfloat16*>(o1));
@@ -333,6 +336,11 @@ int launch_mnrl_dispatch(const MnrlArgs& g, int dtype, bool bwd, cudaStream_t st
     ICR_MNRL_CASE(float, 2);
     ICR_MNRL_CASE(float, 3);
     ICR_MNRL_CASE(float, 6);
+  } else if (dtype == ICR_F16) {
+    ICR_MNRL_CASE(__half, 1);
+    ICR_MNRL_CASE(__half, 2);
+    ICR_MNRL_CASE(__half, 3);
+    ICR_MNRL_CASE(__half, 6);
   } else {
     ICR_MNRL_CASE(__nv_bfloat16, 1);
     ICR_MNRL_CASE(__nv_bfloat16, 2);
@@ -340,7 +348,7 @@ int launch_mnrl_dispatch(const MnrlArgs& g, int dtype, bool bwd, cudaStream_t st
     ICR_MNRL_CASE(__nv_bfloat16, 6);
   }
 #undef ICR_MNRL_CASE
-  set_error("mnrl: embedding dim %d too large (max 768 for f32, 1536 for bf16)", g.D);
+  set_error("mnrl: embedding dim %d too large (max 768 for f32, 1536 for bf16 / f16)", g.D);
   return ICR_ERR_ARG;
 }
 

@@ -623,6 +623,7 @@ int launch_mnrl_tc(const MnrlArgs& m, int dtype, int mode, void* ws, size_t ws_b
   // split planes lie INSIDE the tensor maps' bounds (no out-of-bounds zero fill between a hi and a lo plane): padding must be zero
   if (bwd && w.split) ICR_CUDA_CHECK(cudaMemsetAsync(base + w.at, 0, w.raw_a - w.at, st));
   if (dtype == ICR_F32) rc = launch_prep<float>(m, w, base, bwd, fwd, st);
+  else if (dtype == ICR_F16) rc = launch_prep<__half>(m, w, base, bwd, fwd, st);
   else rc = launch_prep<__nv_bfloat16>(m, w, base, bwd, fwd, st);
   if (rc) return rc;
 
@@ -697,6 +698,10 @@ int launch_mnrl_tc(const MnrlArgs& m, int dtype, int mode, void* ws, size_t ws_b
     mnrl_tc_jacobian_kernel<float><<<jb, 256, 0, st>>>(static_cast<const float*>(m.a), m.lda, static_cast<const float*>(m.p), m.ldp, m.B, m.Bc,
                                                        m.D, m.inv_a, m.inv_p, g.raw[0], g.raw[1], m.grad_out, m.scale,
                                                        static_cast<float*>(m.grad_a), m.ldga, static_cast<float*>(m.grad_p), m.ldgp);
+  else if (dtype == ICR_F16)
+    mnrl_tc_jacobian_kernel<__half><<<jb, 256, 0, st>>>(static_cast<const __half*>(m.a), m.lda, static_cast<const __half*>(m.p), m.ldp, m.B, m.Bc,
+                                                        m.D, m.inv_a, m.inv_p, g.raw[0], g.raw[1], m.grad_out, m.scale,
+                                                        static_cast<__half*>(m.grad_a), m.ldga, static_cast<__half*>(m.grad_p), m.ldgp);
   else
     mnrl_tc_jacobian_kernel<__nv_bfloat16><<<jb, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(m.a), m.lda, static_cast<const __nv_bfloat16*>(m.p),
                                                                m.ldp, m.B, m.Bc, m.D, m.inv_a, m.inv_p, g.raw[0], g.raw[1], m.grad_out, m.scale,

@@ -260,6 +260,35 @@ __device__ __noinline__ int ls_level(const uint32_t* val, const uint32_t* fsc, u
   return b;
 }
 
+// the need-th largest (1-based) of the nb (sc, rw) pairs held in list[0 .. 2 nb) by rank counting (broadcast reads)
+__device__ __forceinline__ void ls_rank_list(const uint32_t* list, int nb, int need, int lane, uint32_t& ks, uint32_t& kr) {
+  ks = 0u;
+  kr = 0u;
+  bool found = false;
+  for (int j0 = 0; j0 < nb; j0 += 32) {
+    const int j = j0 + lane;
+    uint32_t s1 = 0, r1 = 0;
+    int rank = -1;
+    if (j < nb) {
+      s1 = list[2 * j];
+      r1 = list[2 * j + 1];
+      rank = 0;
+      for (int t = 0; t < nb; ++t) {
+        const uint32_t s2 = list[2 * t], r2 = list[2 * t + 1];
+        rank += (pair_gt(s2, r2, s1, r1) || (t < j && s2 == s1 && r2 == r1)) ? 1 : 0;  // the index breaks identical pairs
+      }
+    }
+    const unsigned hit = __ballot_sync(kFull, rank == need - 1);
+    if (hit && !found) {
+      const int srcl = __ffs(hit) - 1;
+      ks = __shfl_sync(kFull, s1, srcl);
+      kr = __shfl_sync(kFull, r1, srcl);
+      found = true;
+    }
+  }
+  __syncwarp();
+}
+
 // The k-th largest (sc, rw) pair of the n >= k >= 1 keys. hist doubles as the list of the boundary bin's keys.
 //
 // Level 1 bins the keys linearly in score VALUE (not in their bit patterns: float bits are logarithmic in the value, and a
@@ -308,7 +337,37 @@ __device__ __forceinline__ void ls_kth(const uint32_t* sc, const uint32_t* rw, i
     ICR_ST_MARK(1);
     const int b_star = ls_scan(hist, need, cnt, lane);
     ICR_ST_MARK(2);
-    // the bin's range in score bits (the value -> bin map is monotone, so the bin is an interval of bit patterns)
+    if (cnt <= kLsList) {
+      // the usual case: the bin's few keys are collected by bin number, no bit range needed
+      const unsigned lt0 = (1u << lane) - 1u;
+      int nb0 = 0;
+      for (int c = 0; c < n; c += 32 * kLsB) {
+        uint32_t v[kLsB], r[kLsB];
+        ls_batch(sc, n, c, lane, v);
+        ls_batch(rw, n, c, lane, r);
+        unsigned m[kLsB];
+#pragma unroll
+        for (int u = 0; u < kLsB; ++u) {
+          const int b = max(min(255, __float2int_rd((unorder_bits(v[u]) - fmn) * scale)), 0);
+          m[u] = __ballot_sync(kFull, v[u] != 0u && b == b_star);
+        }
+#pragma unroll
+        for (int u = 0; u < kLsB; ++u) {
+          if ((m[u] >> lane) & 1u) {
+            const int pos = nb0 + __popc(m[u] & lt0);
+            hist[2 * pos] = v[u];
+            hist[2 * pos + 1] = r[u];
+          }
+          nb0 += __popc(m[u]);
+        }
+      }
+      __syncwarp();
+      ICR_ST_MARK(5);
+      ls_rank_list(hist, nb0, need, lane, ks, kr);
+      ICR_ST_MARK(6);
+      return;
+    }
+    // crowded bin: its range in score bits (the value -> bin map is monotone, so the bin is an interval of bit patterns)
     uint32_t lo = 0xFFFFFFFFu, hi = 0u;
     for (int c = 0; c < n; c += 32 * kLsB) {
       uint32_t v[kLsB];
@@ -394,31 +453,7 @@ __device__ __forceinline__ void ls_kth(const uint32_t* sc, const uint32_t* rw, i
   need = min(need, nb);
   __syncwarp();
   ICR_ST_MARK(5);
-  ks = 0u;
-  kr = 0u;
-  bool found = false;
-  for (int j0 = 0; j0 < nb; j0 += 32) {
-    const int j = j0 + lane;
-    uint32_t s1 = 0, r1 = 0;
-    int rank = -1;
-    if (j < nb) {
-      s1 = hist[2 * j];
-      r1 = hist[2 * j + 1];
-      rank = 0;
-      for (int t = 0; t < nb; ++t) {
-        const uint32_t s2 = hist[2 * t], r2 = hist[2 * t + 1];  // broadcast reads
-        rank += (pair_gt(s2, r2, s1, r1) || (t < j && s2 == s1 && r2 == r1)) ? 1 : 0;  // the index breaks identical pairs
-      }
-    }
-    const unsigned hit = __ballot_sync(kFull, rank == need - 1);
-    if (hit && !found) {
-      const int srcl = __ffs(hit) - 1;
-      ks = __shfl_sync(kFull, s1, srcl);
-      kr = __shfl_sync(kFull, r1, srcl);
-      found = true;
-    }
-  }
-  __syncwarp();
+  ls_rank_list(hist, nb, need, lane, ks, kr);
   ICR_ST_MARK(6);
 }
 

@@ -17,6 +17,9 @@ from torch import nn
 from . import ops
 
 
+_KERNEL_DTYPES = (torch.float32, torch.bfloat16, torch.float16)  # read natively by icr_mnrl_* (no eager up-cast)
+
+
 class _FusedMNRL(torch.autograd.Function):
     """loss = mean_i CE(scale * cos_sim(A, P)[i], i) with one kernel forward, one backward."""
 
@@ -90,16 +93,18 @@ def mnrl_loss_gathered(anchors: torch.Tensor, positives: torch.Tensor, scale: fl
         raise RuntimeError("cross-device negatives need an initialised torch.distributed process group")
     if anchors.dtype != positives.dtype:
         positives = positives.to(anchors.dtype)
-    if anchors.dtype not in (torch.float32, torch.bfloat16):
+    if anchors.dtype not in _KERNEL_DTYPES:
         anchors, positives = anchors.float(), positives.float()
     return _FusedMNRLGathered.apply(anchors, positives, scale, group if group is not None else dist.group.WORLD, _kernels)
 
 
 def mnrl_loss(anchors: torch.Tensor, positives: torch.Tensor, scale: float = 20.0) -> torch.Tensor:
-    """Functional form on embeddings [B, D] (float32 or bfloat16 CUDA tensors)."""
+    """Functional form on embeddings [B, D]: float32, bfloat16 or float16 CUDA tensors. float16 is what the reference's
+    training produces under ``fp16=True`` autocast (src/training/train_sbert.py:210,232); the kernels read it natively and
+    return float16 gradients (internal math is fp32 for every input type)."""
     if anchors.dtype != positives.dtype:
         positives = positives.to(anchors.dtype)
-    if anchors.dtype not in (torch.float32, torch.bfloat16):
+    if anchors.dtype not in _KERNEL_DTYPES:
         anchors, positives = anchors.float(), positives.float()
     return _FusedMNRL.apply(anchors, positives, scale)
 

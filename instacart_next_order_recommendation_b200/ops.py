@@ -11,16 +11,16 @@ import contextlib
 import torch
 
 from . import _lib
-from ._lib import ICR_BF16, ICR_F32, MAX_K, PATH_AUTO, PATH_GEMM, PATH_GEMV, PATH_WS_RESIDENT  # noqa: F401
+from ._lib import ICR_BF16, ICR_F16, ICR_F32, MAX_K, PATH_AUTO, PATH_GEMM, PATH_GEMV, PATH_WS_RESIDENT  # noqa: F401
 
-_DTYPES = {torch.float32: ICR_F32, torch.bfloat16: ICR_BF16}
+_DTYPES = {torch.float32: ICR_F32, torch.bfloat16: ICR_BF16, torch.float16: ICR_F16}  # float16: MNRL entry points only
 
 
 def _dtype_code(t: torch.Tensor) -> int:
     try:
         return _DTYPES[t.dtype]
     except KeyError:
-        raise TypeError(f"libicr_b200 supports float32 and bfloat16 embeddings, got {t.dtype}") from None
+        raise TypeError(f"libicr_b200 supports float32 and bfloat16 embeddings (float16 for the MNRL loss only), got {t.dtype}") from None
 
 
 def _require_cuda(name: str, t: torch.Tensor) -> None:

@@ -200,6 +200,10 @@ class ShardedCatalog:
         """Global (values [Q,k'], ids [Q,k']) on every rank, k' = min(k, total rows)."""
         k = min(int(k), self.total_rows)
         vals, ids = self.local_topk(queries, k)
+        return self.exchange_merge(vals, ids, k)
+
+    def exchange_merge(self, vals: torch.Tensor, ids: torch.Tensor, k: int):
+        """The collective half of ``topk``: every rank's [Q,k] candidates -> the global top-k on every rank."""
         if self.world_size == 1:
             return vals, ids
         if self.exchange == "peer":

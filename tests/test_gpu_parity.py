@@ -550,6 +550,52 @@ def test_mnrl_forward_backward_vs_autograd(dtype, B, D, scale):
     assert (pd.grad.float().cpu() - 1.7 * rgp).abs().max() <= rel * 1.7 * rgp.abs().max()
 
 
+@pytest.mark.parametrize("B,D,scale", [(256, 384, 20.0), (64, 384, 30.0), (37, 768, 20.0), (512, 384, 30.0), (300, 768, 20.0), (2048, 384, 20.0)])
+def test_mnrl_fp16_inputs_are_read_natively(B, D, scale, monkeypatch):
+    """The reference trains with fp16=use_fp16 on CUDA (src/training/train_sbert.py:210,232): under autocast the embeddings
+    reach the loss as float16. Both kernel families take them as they are (no eager .float() round trip) and return float16
+    gradients; the oracle is fp32 math on the fp16-rounded inputs."""
+    g = torch.Generator().manual_seed(77)
+    items, _ = oracle.synth_clustered(B, D, seed=77, n_centres=12)
+    a = torch.nn.functional.normalize(items + 0.3 * torch.randn(B, D, generator=g), dim=1).half()
+    p = (items * (1.0 + 0.5 * torch.rand(B, 1, generator=g))).half()
+    ad = a.cuda().requires_grad_(True)
+    pd = p.cuda().requires_grad_(True)
+    called = []
+    real = torch.Tensor.float
+    monkeypatch.setattr(torch.Tensor, "float", lambda self, *a_, **k_: (called.append(self.dtype), real(self, *a_, **k_))[1])
+    loss = icr.mnrl_loss(ad, pd, scale)
+    loss.backward()
+    monkeypatch.undo()
+    assert torch.float16 not in called, "fp16 embeddings were up-cast eagerly"
+    assert ad.grad.dtype == torch.float16 and pd.grad.dtype == torch.float16 and loss.dtype == torch.float32
+    rl, rga, rgp = oracle.mnrl_loss_and_grads(a.float(), p.float(), scale)
+    assert abs(loss.item() - rl.item()) <= MNRL_ATOL
+    tol = MNRL_ATOL + 2 ** -10 * rga.abs().max().item()  # fp16 rounding of the stored gradients
+    assert (ad.grad.float().cpu() - rga).abs().max() <= tol
+    assert (pd.grad.float().cpu() - rgp).abs().max() <= MNRL_ATOL + 2 ** -10 * rgp.abs().max().item()
+    # the module form under autocast, as the trainer calls it
+    class Enc(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Linear(D, D, bias=False)
+
+        def forward(self, f):
+            return {"sentence_embedding": self.w(f["x"])}
+
+    enc = Enc().cuda()
+    mod = icr.MultipleNegativesRankingLoss(enc, scale=scale)
+    with torch.autocast("cuda", dtype=torch.float16):
+        la = mod([{"x": a.cuda().float()}, {"x": p.cuda().float()}])
+    la.backward()
+    assert torch.isfinite(la) and enc.w.weight.grad is not None and torch.isfinite(enc.w.weight.grad).all()
+    with torch.autocast("cuda", dtype=torch.float16):
+        ea, ep = enc.w(a.cuda().float()), enc.w(p.cuda().float())
+    assert ea.dtype == torch.float16
+    rl2, _, _ = oracle.mnrl_loss_and_grads(ea.detach().float().cpu(), ep.detach().float().cpu(), scale)
+    assert abs(la.item() - rl2.item()) <= MNRL_ATOL
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("B,Bc,off,D,scale", [(64, 512, 128, 384, 20.0), (256, 2048, 1792, 384, 20.0), (48, 96, 48, 128, 30.0),
                                               (100, 800, 300, 768, 20.0), (8, 16, 0, 64, 20.0), (300, 300, 0, 384, 20.0)])
