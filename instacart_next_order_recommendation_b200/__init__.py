@@ -9,14 +9,14 @@ point does, and raises otherwise (there is no CPU fallback).
 
 from .evaluation import InformationRetrievalEvaluator, compute_ir_metrics, rank_all
 from .index import DeviceCatalog, EmbeddingIndex
-from .losses import MultipleNegativesRankingLoss, mnrl_loss, mnrl_loss_gathered
+from .losses import MnrlStepGraph, MultipleNegativesRankingLoss, mnrl_loss, mnrl_loss_gathered, mnrl_step_graph
 from .recommender import MonitoredRecommender, RecommendationMetrics, Recommender
 from .sharded import ShardedCatalog, shard_bounds
 from .similarity import cos_sim, cos_topk
 
 __all__ = [
     "cos_sim", "cos_topk", "DeviceCatalog", "EmbeddingIndex", "Recommender", "MonitoredRecommender",
-    "RecommendationMetrics", "MultipleNegativesRankingLoss", "mnrl_loss", "InformationRetrievalEvaluator",
+    "RecommendationMetrics", "MultipleNegativesRankingLoss", "MnrlStepGraph", "mnrl_step_graph", "mnrl_loss", "InformationRetrievalEvaluator",
     "rank_all", "compute_ir_metrics", "ShardedCatalog", "shard_bounds",
 ]
 __version__ = "0.1.0"

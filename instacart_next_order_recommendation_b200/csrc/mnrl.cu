@@ -12,6 +12,8 @@
 //
 // Replaces sentence_transformers.losses.MultipleNegativesRankingLoss.forward + autograd
 // (constructed at reference src/training/train_sbert.py:182-185).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace icr {
@@ -45,10 +47,12 @@ __device__ __forceinline__ void load_slice(const T* row, int nvec, int lane, flo
 
 // MODE 0: forward (tile = anchors, stream = positives)
 // MODE 1: backward; blockIdx.x < tiles -> tile = anchors (writes grad_a), else tile = positives (grad_p)
-template <typename T, int NCV, int MODE>
+// TMV: tile rows per CTA (0 = the default of MnrlCfg). Small batches take TMV = 2: at B = 256 the default tiles (4-8 rows)
+// make only 32-64 CTAs and each walks all B stream rows serially - a latency-bound 40 us per kernel for 50 MFLOP.
+template <typename T, int NCV, int MODE, int TMV = 0>
 __global__ void __launch_bounds__(kMnrlThreads) mnrl_kernel(MnrlArgs g) {
   using C = MnrlCfg<T, NCV>;
-  constexpr int VEC = C::VEC, EPL = C::EPL, TM = C::TM;
+  constexpr int VEC = C::VEC, EPL = C::EPL, TM = TMV ? TMV : C::TM;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int D = g.D, B = g.B;
   const int nvec = D / VEC;
@@ -279,21 +283,31 @@ __global__ void __launch_bounds__(kMnrlThreads) mnrl_kernel(MnrlArgs g) {
   }
 }
 
-template <typename T, int NCV>
-static int launch_mnrl(const MnrlArgs& g, bool bwd, cudaStream_t st) {
+template <typename T, int NCV, int TMV>
+static int launch_mnrl_tm(const MnrlArgs& g, bool bwd, cudaStream_t st) {
   using C = MnrlCfg<T, NCV>;
+  constexpr int TM = TMV ? TMV : C::TM;
   const int dpad = NCV * 32 * C::VEC;
-  const size_t smem = (2 * C::TM * dpad + C::TM + 8 + 3 * kMnrlWarps * C::TM) * sizeof(float);
-  const int tiles = (g.B + C::TM - 1) / C::TM;
+  const size_t smem = (2 * TM * dpad + TM + 8 + 3 * kMnrlWarps * TM) * sizeof(float);
+  const int tiles = (g.B + TM - 1) / TM;
   if (!bwd) {
-    if (smem > 48 * 1024) ICR_CUDA_CHECK(cudaFuncSetAttribute(mnrl_kernel<T, NCV, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    mnrl_kernel<T, NCV, 0><<<tiles, kMnrlThreads, smem, st>>>(g);
+    if (smem > 48 * 1024) ICR_CUDA_CHECK(cudaFuncSetAttribute(mnrl_kernel<T, NCV, 0, TMV>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    mnrl_kernel<T, NCV, 0, TMV><<<tiles, kMnrlThreads, smem, st>>>(g);
   } else {
-    if (smem > 48 * 1024) ICR_CUDA_CHECK(cudaFuncSetAttribute(mnrl_kernel<T, NCV, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    mnrl_kernel<T, NCV, 1><<<2 * tiles, kMnrlThreads, smem, st>>>(g);
+    if (smem > 48 * 1024) ICR_CUDA_CHECK(cudaFuncSetAttribute(mnrl_kernel<T, NCV, 1, TMV>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    mnrl_kernel<T, NCV, 1, TMV><<<2 * tiles, kMnrlThreads, smem, st>>>(g);
   }
   ICR_LAUNCH_CHECK();
   return ICR_OK;
+}
+
+template <typename T, int NCV>
+static int launch_mnrl(const MnrlArgs& g, bool bwd, cudaStream_t st) {
+  using C = MnrlCfg<T, NCV>;
+  // fewer CTAs than SMs with the default tile: spread the batch over 2-row tiles (ICR_MNRL_TM=0 keeps the default, for A/B runs)
+  static const int tm_env = getenv("ICR_MNRL_TM") ? atoi(getenv("ICR_MNRL_TM")) : 2;
+  if (C::TM > 2 && tm_env == 2 && (g.B + C::TM - 1) / C::TM < 148) return launch_mnrl_tm<T, NCV, 2>(g, bwd, st);
+  return launch_mnrl_tm<T, NCV, 0>(g, bwd, st);
 }
 
 // out[i] = x[i] * s[0] for two equally sized buffers at once (the two gradients of a step scaled by the incoming dL/dloss)

@@ -12,6 +12,7 @@
 // refinement always terminates. The final phase sorts the k selected keys; earlier phases only need the set
 // and its minimum (the new threshold tau).
 #include "common.cuh"
+#include "ptx.cuh"
 #include "select_args.cuh"
 #include "select_warp.cuh"
 
@@ -840,7 +841,17 @@ struct RsSmem {
   uint32_t hist[kHsWarps][kHsBins];
 };
 
-__global__ void __launch_bounds__(kHsWarps * 32, 3) rescore_rank_kernel(HistSelectArgs a) {
+// Tried and dropped: staging the rows with 1-D bulk async copies (cp.async.bulk, two 18 KB halves per warp, 5 warps per SM =
+// 180 KB in flight). 426 us instead of 184: only 740 queries are in flight chip-wide instead of 1,776, and every catalog row
+// is wanted by ~23 queries - with fewer of them running at the same time the 76 MB of fp32 rows (more than one die's share of
+// the L2) are fetched from DRAM once per wave of queries (13 waves instead of 6).
+#ifndef ICR_RS_MINB
+#define ICR_RS_MINB 3  // CTAs per SM the kernel is compiled for: 3 -> up to 170 registers
+#endif
+#ifndef ICR_RS_WIDE
+#define ICR_RS_WIDE 1  // 1: 8 rows x 3 vectors = 24 loads per lane in flight (D = 384); 0: 4 x 3
+#endif
+__global__ void __launch_bounds__(kHsWarps * 32, ICR_RS_MINB) rescore_rank_kernel(HistSelectArgs a) {
   __shared__ __align__(16) RsSmem sm;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t q = static_cast<int64_t>(blockIdx.x) * kHsWarps + warp;
@@ -855,7 +866,7 @@ __global__ void __launch_bounds__(kHsWarps * 32, 3) rescore_rank_kernel(HistSele
     kept = min(a.carry_cnt_in[q], a.kc);
     for (int i = lane; i < kept; i += 32) rw[i] = static_cast<uint32_t>(a.carry_in[q * a.kc + i]);
     __syncwarp();
-    ls_rescore<true>(sc, rw, kept, q, a, lane);
+    ls_rescore<(ICR_RS_WIDE != 0)>(sc, rw, kept, q, a, lane);
   }
   ICR_ST_MARK(12);
   ls_emit_ranked(sc, rw, kept, a.k, 1.0f, q, a, sm.hist[warp], lane);

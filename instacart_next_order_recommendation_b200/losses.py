@@ -98,6 +98,55 @@ def mnrl_loss_gathered(anchors: torch.Tensor, positives: torch.Tensor, scale: fl
     return _FusedMNRLGathered.apply(anchors, positives, scale, group if group is not None else dist.group.WORLD, _kernels)
 
 
+class MnrlStepGraph:
+    """Loss + both gradients of MNRL for a FIXED batch shape as ONE CUDA-graph replay.
+
+    A training step at the reference's batch size (256 x 384, src/training/train_sbert.py:182-185, configs/train.yaml:15)
+    is 151 MFLOP: the kernels take ~20 us, the Python / ctypes / autograd glue around them several times that. The graph
+    holds static input buffers; ``__call__`` copies the step's embeddings in, replays, and returns the static outputs
+    (loss f32 scalar, d loss / d anchors, d loss / d positives - for dL/dloss = 1), which the next call overwrites.
+    Use ``backward_into(anchors, positives)`` inside a training loop to feed the gradients to autograd.
+    """
+
+    def __init__(self, B: int, D: int, dtype: torch.dtype = torch.bfloat16, scale: float = 20.0, device: torch.device | None = None):
+        if dtype not in _KERNEL_DTYPES:
+            raise TypeError(f"MNRL kernels read float32, bfloat16 or float16 embeddings, got {dtype}")
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.scale = float(scale)
+        self.a = torch.zeros(B, D, dtype=dtype, device=dev)
+        self.p = torch.zeros(B, D, dtype=dtype, device=dev)
+        self.a[:, 0] = 1.0  # any non-degenerate rows for the warm-up
+        self.p[:, 0] = 1.0
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):  # warm-up outside capture: lazy module load, one-time attribute setting
+            ops.mnrl_forward_backward(self.a, self.p, self.scale)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss, self.grads = ops.mnrl_forward_backward(self.a, self.p, self.scale)
+
+    def __call__(self, anchors: torch.Tensor, positives: torch.Tensor):
+        if anchors.shape != self.a.shape or positives.shape != self.p.shape:
+            raise ValueError(f"this graph was captured for batches of shape {tuple(self.a.shape)}")
+        self.a.copy_(anchors, non_blocking=True)
+        self.p.copy_(positives, non_blocking=True)
+        self.graph.replay()
+        D = self.a.shape[1]
+        return self.loss, self.grads[0][:, :D], self.grads[1][:, :D]
+
+    def backward_into(self, anchors: torch.Tensor, positives: torch.Tensor) -> torch.Tensor:
+        """One training step: returns the loss and pushes its gradients into the graph that produced the embeddings."""
+        loss, ga, gp = self(anchors.detach(), positives.detach())
+        torch.autograd.backward([anchors, positives], [ga.to(anchors.dtype), gp.to(positives.dtype)])
+        return loss
+
+
+def mnrl_step_graph(B: int, D: int, dtype: torch.dtype = torch.bfloat16, scale: float = 20.0, device=None) -> MnrlStepGraph:
+    return MnrlStepGraph(B, D, dtype, scale, device)
+
+
 def mnrl_loss(anchors: torch.Tensor, positives: torch.Tensor, scale: float = 20.0) -> torch.Tensor:
     """Functional form on embeddings [B, D]: float32, bfloat16 or float16 CUDA tensors. float16 is what the reference's
     training produces under ``fp16=True`` autocast (src/training/train_sbert.py:210,232); the kernels read it natively and
