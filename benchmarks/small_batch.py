@@ -35,5 +35,7 @@ for dt in (torch.float32, torch.bfloat16):
         for Q in (1, 2, 4, 7, 8, 16, 32, 64, 128, 256, 512, 1024):
             q = torch.nn.functional.normalize(torch.randn(Q, D, device=dev, generator=g), dim=1).to(dt)
             t = timed(lambda: cat.topk(q, k))
-            row.append(f"Q={Q}: {t:.0f} us ({ops.last_launch_count()} launches)")
+            n_launch = ops.last_launch_count()
+            tg = timed(lambda: cat.topk_small(q, k, copy=False)) if Q <= 256 else float("nan")
+            row.append(f"Q={Q}: {t:.0f} us, graph {tg:.0f} us ({n_launch} launches)")
         print(f"{str(dt):15s} k={k}: " + " | ".join(row))

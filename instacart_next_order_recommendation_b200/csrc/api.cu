@@ -49,9 +49,11 @@ void profile_end(cudaStream_t st) {
 }
 
 // kernels' host launchers (defined in the other translation units)
-int launch_row_inv_norms(const void* x, int64_t rows, int64_t dim, int64_t ld, int dtype, float* inv, cudaStream_t st);
+int launch_row_inv_norms(const void* x, int64_t rows, int64_t dim, int64_t ld, int dtype, float* inv, cudaStream_t st, float* tau_init = nullptr,
+                         unsigned int* ovf_init = nullptr);
 int launch_split_planes(const float* x, int64_t rows, int64_t dim, int64_t ld, uint16_t* planes, cudaStream_t st);
-int launch_screen_plane(const float* x, int64_t rows, int64_t dim, int64_t ld, uint16_t* plane, float* inv, cudaStream_t st);
+int launch_screen_plane(const float* x, int64_t rows, int64_t dim, int64_t ld, uint16_t* plane, float* inv, cudaStream_t st, float* tau_init = nullptr,
+                        unsigned int* ovf_init = nullptr);
 int launch_convert_rows(const float* x, int64_t rows, int64_t dim, int64_t ldx, void* out, int64_t ldo, int out_dtype, int normalize,
                         cudaStream_t st);
 void peer_layout(int64_t n_max, int world, uint32_t epoch, size_t* scores_off, size_t* ids_off, size_t* total);
@@ -395,10 +397,11 @@ int icr_topk_merge(const float* cand_scores, const int64_t* cand_ids, int64_t Q,
   return launch_merge_lists(cand_scores, cand_ids, Q, G, k_in, k_out, out_scores, out_ids, static_cast<cudaStream_t>(stream));
 }
 
-// the CUDA-core kernels hold a row slice per lane: D <= 768 (f32) / 1536 (bf16); wider rows take the tensor path at any batch size
+// the CUDA-core kernels hold a row slice per lane: D <= 768; wider rows take the tensor path at any batch size
 static bool mnrl_use_tc(int64_t B, int64_t D, int dtype) {
+  (void)dtype;
   if (mnrl_tc_applies(B, B, D)) return true;
-  const int64_t simt_max = dtype == ICR_F32 ? 768 : 1536;
+  const int64_t simt_max = 768;
   return D > simt_max && D % 8 == 0 && D <= 4096 && B >= 2;
 }
 

@@ -239,6 +239,9 @@ __device__ __forceinline__ void filter32(const uint32_t (&r)[32], SegState& s, c
       }
       s.cnt = off[32];
     }
+    // Tried in round 2 and dropped: appending quad by quad (one more vote per quad, four chained predicated appends in the
+    // quads that have a survivor) instead of 32-wide prefix sums. At C2's survivor density nearly every quad is taken and the
+    // chained appends are latency-bound: the 163-tile launch went from 272 to 286 us.
   } else {
     // last (partial) tile of the catalog, or an exclusion mask: rows are checked one by one
 #pragma unroll
@@ -814,9 +817,11 @@ gemm_swap_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
 }
 
 // ---- host side ---------------------------------------------------------------------------------------
-int launch_row_inv_norms(const void* x, int64_t rows, int64_t dim, int64_t ld, int dtype, float* inv, cudaStream_t st);
+int launch_row_inv_norms(const void* x, int64_t rows, int64_t dim, int64_t ld, int dtype, float* inv, cudaStream_t st, float* tau_init = nullptr,
+                         unsigned int* ovf_init = nullptr);
 int launch_split_planes(const float* x, int64_t rows, int64_t dim, int64_t ld, uint16_t* planes, cudaStream_t st);
-int launch_screen_plane(const float* x, int64_t rows, int64_t dim, int64_t ld, uint16_t* plane, float* inv, cudaStream_t st);
+int launch_screen_plane(const float* x, int64_t rows, int64_t dim, int64_t ld, uint16_t* plane, float* inv, cudaStream_t st, float* tau_init = nullptr,
+                        unsigned int* ovf_init = nullptr);
 
 constexpr size_t kGemmSmemBytes = static_cast<size_t>(kRingBytes) + kEpiWarps * kEpiCols * sizeof(float) +
                                   (2 * kMaxStages + 6) * sizeof(uint64_t) + 16 + 1024;
@@ -1072,6 +1077,7 @@ int launch_gemm_topk(const void* queries, int64_t Q, int64_t ldq, const void* ca
   sa.id_offset = row_offset;
   sa.raw_keys = 1;  // the only producer of segments is the GEMM epilogue
   CUtensorMap map_a, map_b;
+  bool state_ready = false;
   const void* q_operand = queries;  // what the TMA map of the swapped kernel is built over
   int64_t q_cols = D, q_ld = ldq;
   if (mode == 3) {
@@ -1089,7 +1095,8 @@ int launch_gemm_topk(const void* queries, int64_t Q, int64_t ldq, const void* ca
   } else if (mode == 2) {
     uint16_t* qp = reinterpret_cast<uint16_t*>(base + L.q_planes);
     float* qinv = reinterpret_cast<float*>(base + L.qinv);
-    if ((rc = launch_screen_plane(static_cast<const float*>(queries), Q, D, ldq, qp, qinv, st))) return rc;
+    if ((rc = launch_screen_plane(static_cast<const float*>(queries), Q, D, ldq, qp, qinv, st, const_cast<float*>(g.tau), g.overflow))) return rc;
+    state_ready = true;
     const uint16_t* cp = cat_planes;
     const float* cinv = cat_inv_norms;
     if (!cp) {
@@ -1124,7 +1131,8 @@ int launch_gemm_topk(const void* queries, int64_t Q, int64_t ldq, const void* ca
     sa.mask = mask;  // the exact ranking of an overflowed query walks the catalog itself
   } else {
     float* qinv = reinterpret_cast<float*>(base + L.qinv);
-    if ((rc = launch_row_inv_norms(queries, Q, D, ldq, dtype, qinv, st))) return rc;
+    if ((rc = launch_row_inv_norms(queries, Q, D, ldq, dtype, qinv, st, const_cast<float*>(g.tau), g.overflow))) return rc;
+    state_ready = true;
     const float* cinv = cat_inv_norms;
     if (!cinv) {
       float* built = reinterpret_cast<float*>(base + L.cinv);
@@ -1151,8 +1159,10 @@ int launch_gemm_topk(const void* queries, int64_t Q, int64_t ldq, const void* ca
     g.qpad = static_cast<int>((Q + 31) / 32 * 32);
     if ((rc = make_map(&map_a, q_operand, Q, q_cols, q_ld, mode == 1, g.qpad / 2))) return rc;
   }
-  init_phase_state_kernel<<<static_cast<unsigned>((Q + 255) / 256), 256, 0, st>>>(const_cast<float*>(g.tau), g.overflow, Q);
-  ICR_LAUNCH_CHECK();
+  if (!state_ready) {  // the query-side preparation kernels of the one-term paths initialise tau / overflow themselves
+    init_phase_state_kernel<<<static_cast<unsigned>((Q + 255) / 256), 256, 0, st>>>(const_cast<float*>(g.tau), g.overflow, Q);
+    ICR_LAUNCH_CHECK();
+  }
 
   // ---- first phase, dense: rows of the first kDense0Tiles tiles have no threshold to beat yet, so every score would
   // be appended through uncoalesced 8-byte stores (measured: 27 us per tile). They are written as a dense [Q, 1024]

@@ -21,9 +21,28 @@ namespace icr {
 constexpr int kMnrlThreads = 256;
 constexpr int kMnrlWarps = kMnrlThreads / 32;
 
+// Four elements per lane and load for EVERY storage type (16-byte loads of fp32, 8-byte loads of bf16 / fp16): with eight
+// 16-bit elements per load a 384-wide row is 48 vectors, i.e. a second chunk with half the lanes idle and 16 instead of 12
+// accumulators per row pair - the 16-bit kernels ran 1.6x slower than the fp32 ones on the same batch (profiles/r02_notes.md).
+template <typename T>
+struct MVec {
+  static constexpr int VEC = 4;
+  __device__ static __forceinline__ void load(const T* p, float* f) {
+    if constexpr (sizeof(T) == 4) {
+      Elem<float>::unpack(ldg_stream(p), f);
+    } else {
+      uint2 w;
+      asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(w.x), "=r"(w.y) : "l"(p));
+      const T* h = reinterpret_cast<const T*>(&w);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) f[i] = Elem<T>::to_f32(h[i]);
+    }
+  }
+};
+
 template <typename T, int NCV>
 struct MnrlCfg {
-  static constexpr int VEC = Elem<T>::VEC;
+  static constexpr int VEC = MVec<T>::VEC;
   static constexpr int EPL = NCV * VEC;                              // elements per lane of one row
   static constexpr int TM = EPL <= 12 ? 8 : (EPL <= 24 ? 4 : 2);     // tile rows per CTA
 };
@@ -31,13 +50,13 @@ struct MnrlCfg {
 
 // load this lane's slice of a row as fp32: vector c of the slice is vector (c*32 + lane) of the row
 template <typename T, int NCV>
-__device__ __forceinline__ void load_slice(const T* row, int nvec, int lane, float (&y)[NCV * Elem<T>::VEC]) {
-  constexpr int VEC = Elem<T>::VEC;
+__device__ __forceinline__ void load_slice(const T* row, int nvec, int lane, float (&y)[NCV * MVec<T>::VEC]) {
+  constexpr int VEC = MVec<T>::VEC;
 #pragma unroll
   for (int c = 0; c < NCV; ++c) {
     const int v = c * 32 + lane;
     if (v < nvec) {
-      Elem<T>::unpack(ldg_stream(row + static_cast<int64_t>(v) * VEC), &y[c * VEC]);
+      MVec<T>::load(row + static_cast<int64_t>(v) * VEC, &y[c * VEC]);
     } else {
 #pragma unroll
       for (int i = 0; i < VEC; ++i) y[c * VEC + i] = 0.f;
@@ -340,7 +359,7 @@ int launch_scale2(const void* x0, const void* x1, int64_t n, int dtype, const fl
 }
 
 int launch_mnrl_dispatch(const MnrlArgs& g, int dtype, bool bwd, cudaStream_t st) {
-  const int vec = dtype == ICR_F32 ? 4 : 8;
+  const int vec = 4;
   const int nvec = g.D / vec;
   const int ncv = (nvec + 31) / 32;
 #define ICR_MNRL_CASE(T, N) \
@@ -362,7 +381,7 @@ int launch_mnrl_dispatch(const MnrlArgs& g, int dtype, bool bwd, cudaStream_t st
     ICR_MNRL_CASE(__nv_bfloat16, 6);
   }
 #undef ICR_MNRL_CASE
-  set_error("mnrl: embedding dim %d too large (max 768 for f32, 1536 for bf16 / f16)", g.D);
+  set_error("mnrl: embedding dim %d too large (max 768 on the CUDA-core path)", g.D);
   return ICR_ERR_ARG;
 }
 

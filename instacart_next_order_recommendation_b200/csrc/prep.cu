@@ -9,9 +9,12 @@ __device__ __forceinline__ float4 ldg_stream_f4(const float* p) {
 }
 
 // one warp per row; 128-bit loads; inv = 1 / max(||x||, eps)   (torch F.normalize semantics)
+// tau_init / ovf_init (optional, query side of a top-k call): the per-query threshold starts at -inf and the overflow flag at 0;
+// written here so that the call needs no separate initialisation launch
 template <typename T>
 __global__ void __launch_bounds__(256) row_inv_norms_kernel(const T* __restrict__ x, int64_t rows, int64_t dim, int64_t ld,
-                                                            float* __restrict__ inv) {
+                                                            float* __restrict__ inv, float* __restrict__ tau_init,
+                                                            unsigned int* __restrict__ ovf_init) {
   constexpr int VEC = Elem<T>::VEC;
   const int lane = threadIdx.x & 31;
   const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -31,7 +34,11 @@ __global__ void __launch_bounds__(256) row_inv_norms_kernel(const T* __restrict_
       ss = fmaf(f, f, ss);
     }
     ss = warp_sum(ss);
-    if (lane == 0) inv[r] = 1.0f / fmaxf(sqrtf(ss), kNormEps);
+    if (lane == 0) {
+      inv[r] = 1.0f / fmaxf(sqrtf(ss), kNormEps);
+      if (tau_init) tau_init[r] = -INFINITY;
+      if (ovf_init) ovf_init[r] = 0u;
+    }
   }
 }
 
@@ -69,7 +76,8 @@ __global__ void __launch_bounds__(256) split_f16_planes_kernel(const float* __re
 // A single fp16 plane carries 11 significant bits per element: the screened score differs from the exact cosine by
 // at most 2^-10 (Cauchy-Schwarz over the two rounding-error vectors), which the caller turns into a safety band.
 __global__ void __launch_bounds__(256) screen_plane_kernel(const float* __restrict__ x, int64_t rows, int64_t dim, int64_t ld,
-                                                           __half* __restrict__ plane, int64_t dim_pad, float* __restrict__ inv_out) {
+                                                           __half* __restrict__ plane, int64_t dim_pad, float* __restrict__ inv_out,
+                                                           float* __restrict__ tau_init, unsigned int* __restrict__ ovf_init) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
@@ -83,7 +91,11 @@ __global__ void __launch_bounds__(256) screen_plane_kernel(const float* __restri
     }
     ss = warp_sum(ss);
     const float inv = 1.0f / fmaxf(sqrtf(ss), kNormEps);
-    if (lane == 0 && inv_out) inv_out[r] = inv;
+    if (lane == 0) {
+      if (inv_out) inv_out[r] = inv;
+      if (tau_init) tau_init[r] = -INFINITY;
+      if (ovf_init) ovf_init[r] = 0u;
+    }
     const float sc = 256.0f * inv;
     __half* dst = plane + r * dim_pad;
     for (int v = lane; v < nvec_pad; v += 32) {
@@ -98,25 +110,27 @@ __global__ void __launch_bounds__(256) screen_plane_kernel(const float* __restri
   }
 }
 
-int launch_screen_plane(const float* x, int64_t rows, int64_t dim, int64_t ld, uint16_t* plane, float* inv, cudaStream_t st) {
+int launch_screen_plane(const float* x, int64_t rows, int64_t dim, int64_t ld, uint16_t* plane, float* inv, cudaStream_t st, float* tau_init,
+                        unsigned int* ovf_init) {
   if (rows == 0) return ICR_OK;
   const int64_t dim_pad = (dim + 63) / 64 * 64;
   const int64_t want = (rows + 7) / 8;
   const int blocks = static_cast<int>(want < 148 * 16 ? want : 148 * 16);
-  screen_plane_kernel<<<blocks, 256, 0, st>>>(x, rows, dim, ld, reinterpret_cast<__half*>(plane), dim_pad, inv);
+  screen_plane_kernel<<<blocks, 256, 0, st>>>(x, rows, dim, ld, reinterpret_cast<__half*>(plane), dim_pad, inv, tau_init, ovf_init);
   ICR_LAUNCH_CHECK();
   return ICR_OK;
 }
 
-int launch_row_inv_norms(const void* x, int64_t rows, int64_t dim, int64_t ld, int dtype, float* inv, cudaStream_t st) {
+int launch_row_inv_norms(const void* x, int64_t rows, int64_t dim, int64_t ld, int dtype, float* inv, cudaStream_t st, float* tau_init,
+                         unsigned int* ovf_init) {
   if (rows == 0) return ICR_OK;
   const int threads = 256;
   const int64_t want = (rows + 7) / 8;
   const int blocks = static_cast<int>(want < 148 * 16 ? want : 148 * 16);
   if (dtype == ICR_F32)
-    row_inv_norms_kernel<float><<<blocks, threads, 0, st>>>(static_cast<const float*>(x), rows, dim, ld, inv);
+    row_inv_norms_kernel<float><<<blocks, threads, 0, st>>>(static_cast<const float*>(x), rows, dim, ld, inv, tau_init, ovf_init);
   else
-    row_inv_norms_kernel<__nv_bfloat16><<<blocks, threads, 0, st>>>(static_cast<const __nv_bfloat16*>(x), rows, dim, ld, inv);
+    row_inv_norms_kernel<__nv_bfloat16><<<blocks, threads, 0, st>>>(static_cast<const __nv_bfloat16*>(x), rows, dim, ld, inv, tau_init, ovf_init);
   ICR_LAUNCH_CHECK();
   return ICR_OK;
 }

@@ -63,7 +63,10 @@ __device__ __forceinline__ void score_rows_fixed(const float* __restrict__ qrow,
 #pragma unroll
   for (int u = 0; u < RB; ++u)
 #pragma unroll
-    for (int v = 0; v < NV; ++v) c[u][v] = __ldg(reinterpret_cast<const float4*>(rows[u]) + v * 32 + lane);
+    for (int v = 0; v < NV; ++v) {  // a candidate's row is read once per query: do not allocate it in L1
+      const uint4 w = ldg_stream(reinterpret_cast<const float4*>(rows[u]) + v * 32 + lane);
+      c[u][v] = make_float4(__uint_as_float(w.x), __uint_as_float(w.y), __uint_as_float(w.z), __uint_as_float(w.w));
+    }
 #pragma unroll
   for (int u = 0; u < RB; ++u) {
     float s = 0.f;
