@@ -191,6 +191,26 @@ __device__ __forceinline__ void warp_transpose_reduce(float (&acc)[V], int lane)
   for (; off > 0; off >>= 1) acc[0] += __shfl_xor_sync(kFull, acc[0], off);
 }
 
+// The same exchange pattern with max instead of +: on return lane l holds in acc[0] the maximum over the 32 lanes of value
+// index (l >> (5 - log2 V)).
+template <int V>
+__device__ __forceinline__ void warp_transpose_max(float (&acc)[V], int lane) {
+  static_assert(V == 1 || V == 2 || V == 4 || V == 8 || V == 16 || V == 32, "V must be a power of two <= 32");
+  int off = 16;
+#pragma unroll
+  for (int n = V; n > 1; n >>= 1, off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float send = upper ? acc[i] : acc[i + n / 2];
+      const float keep = upper ? acc[i + n / 2] : acc[i];
+      acc[i] = fmaxf(keep, __shfl_xor_sync(kFull, send, off));
+    }
+  }
+#pragma unroll
+  for (; off > 0; off >>= 1) acc[0] = fmaxf(acc[0], __shfl_xor_sync(kFull, acc[0], off));
+}
+
 // ---- shared-memory bitonic sort of 64-bit keys, DESCENDING, n = power of two ------------------
 // All threads of the CTA must call it; ends with __syncthreads().
 __device__ __forceinline__ void block_bitonic_sort_desc(uint64_t* keys, int n) {

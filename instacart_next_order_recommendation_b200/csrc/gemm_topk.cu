@@ -30,6 +30,7 @@
 // InformationRetrievalEvaluator (built at reference src/training/train_sbert.py:197-202) and the
 // cos_sim -> np.argsort loops of src/baselines/content_based.py:54-63.
 #include "select_args.cuh"
+#include "select_lean.cuh"
 #include "tc.cuh"  // BM, BN, BK, tile geometry, PTX wrappers, tensor maps
 
 namespace icr {
@@ -83,6 +84,10 @@ struct GemmArgs {
   uint64_t* compact_scratch; // [gridDim.x][kEpiWarps][kSegCapMax] global scratch of the (rare) in-kernel compaction
   int qpad;                  // swapped kernel: queries rounded up to a multiple of 32 (the MMA's N)
   int dense_raw;             // dense mode stores raw-unit scores (no per-query factor): first phase of the top-k path
+  // swapped kernel, single-launch mode: the thresholds are bootstrapped inside the kernel (see gemm_swap_kernel)
+  int boot;                  // 1 = on
+  float* gmax;               // [qpad][4 * gridDim.x] group maxima of the bootstrap tiles
+  unsigned int* gsync;       // [2] grid-barrier counters, zero before the launch
   float band;                // screened scores (MODE 2): tau already sits `band` below the k-th best; 0 = exact scores
   unsigned int* overflow;    // [Q] screened scores: set when a segment cannot be cut back without losing keys of the band
 };
@@ -560,11 +565,36 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 // Epilogue thread = catalog row (TMEM lane); per-query thresholds live in shared memory; survivors go to the
 // (query, chunk, CTA) segment through a shared-memory counter. Same phases, segments and select as K2.
 // =====================================================================================================
+constexpr int kBootCap = 640;  // group maxima per query the in-kernel bootstrap can rank (4 per CTA: up to 160 CTAs)
+constexpr size_t kSwapBootBytes = 4 * (2 * kBootCap + kHsBins) * sizeof(uint32_t);  // per epilogue warp: values, indices, histogram
 constexpr int kSwapMaxStages = 12;
 constexpr int kSwapThreads = 256;  // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 epilogue
 constexpr int kSwapResidentMax = 64 * 1024;  // leaves >= 8 catalog stages: measured, a 5-stage ring loses to K2
 
 __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// Barrier over the epilogue warps of EVERY CTA of the grid (all co-resident: one CTA per SM, grid <= 148). The counter is
+// zero before the launch and counts CTAs. A barrier that cannot complete (a CTA that never became resident) traps after
+// ~2 s instead of hanging the GPU.
+__device__ __forceinline__ void swap_grid_barrier(unsigned int* counter, unsigned int ctas, int et) {
+  epi_sync();  // this CTA's global writes are done
+  if (et == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+      unsigned int v;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+      if (v >= ctas) break;
+      __nanosleep(100);
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 2000000000ull) __trap();
+    }
+    __threadfence();
+  }
+  epi_sync();
+}
 
 template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSwapThreads, 1)
@@ -593,6 +623,7 @@ gemm_swap_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
   uint64_t* tempty_bar = bars + 2 * kSwapMaxStages + 2;
   uint64_t* qfull_bar = bars + 2 * kSwapMaxStages + 4;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kSwapMaxStages + 5);
+  uint32_t* boot_s = reinterpret_cast<uint32_t*>(bars + 2 * kSwapMaxStages + 6);  // [4 warps][2 * kBootCap + kHsBins], boot mode only
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -631,7 +662,8 @@ gemm_swap_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
     uint32_t phase = 0;
     for (int w = pair; w < items; w += npairs) {
       const int t0 = chunk_first_tile(g, w), t1 = chunk_first_tile(g, w + 1);
-      for (int tile = t0; tile < t1; ++tile) {
+      for (int tt = g.boot ? t0 - 1 : t0; tt < t1; ++tt) {  // boot mode: the chunk's first tile is streamed twice (see the epilogue)
+        const int tile = tt < t0 ? t0 : tt;
         const int crow = tile * BN + static_cast<int>(rank) * BNH;
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
@@ -663,7 +695,7 @@ gemm_swap_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
     uint32_t acc_phase = 0;
     for (int w = pair; w < items; w += npairs) {
       const int t0 = chunk_first_tile(g, w), t1 = chunk_first_tile(g, w + 1);
-      for (int tile = t0; tile < t1; ++tile) {
+      for (int tt = g.boot ? t0 - 1 : t0; tt < t1; ++tt) {
         mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * 256);
@@ -708,8 +740,59 @@ gemm_swap_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
     for (int w = pair; w < items; w += npairs) {
       const int t0 = chunk_first_tile(g, w), t1 = chunk_first_tile(g, w + 1);
       const int64_t seg0 = static_cast<int64_t>(w) * 2 + rank;  // + q * chunks * 2
+      if (g.boot) {
+        // ---- single-launch mode: bootstrap the thresholds from the chunk's first tile --------------------------------
+        // Every epilogue warp takes the maximum of its 32 rows for each query: 4 * gridDim.x group maxima per query, each
+        // the score of a distinct catalog row, so the k-th largest of them is a lower bound of the final k-th best score
+        // (k <= 4 * gridDim.x is the host's condition for this mode). After a grid barrier the warps of all CTAs rank the
+        // maxima of their share of the queries and publish tau; after a second barrier the chunk - including its first
+        // tile, streamed again - is filtered as in the phased path. Two launches (first-phase GEMM + select) and, for small
+        // catalogs, most of the call's latency disappear (profiles/r02_notes.md).
+        const int row = t0 * BN + static_cast<int>(rank) * BNH + ew * 32 + lane;
+        const bool valid = row < g.N && !(g.mask && g.mask[row]);
+        const float cinv_r = BF16 ? (row < g.N ? __ldg(g.cinv + row) : 0.f) : 1.0f;
+        const int gstride = 4 * static_cast<int>(gridDim.x);
+        mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * 256);
+        for (int jb = 0; jb < g.qpad; jb += 32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + jb, r);
+          tmem_ld_wait(r);
+          float sc[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sc[j] = valid ? __uint_as_float(r[j]) * cinv_r : -INFINITY;
+          warp_transpose_max<32>(sc, lane);  // lane l: the maximum over this warp's rows for query jb + l
+          if (jb + lane < g.Q) g.gmax[static_cast<int64_t>(jb + lane) * gstride + blockIdx.x * 4 + ew] = sc[0];
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(smem_u32(&tempty_bar[acc]), 0);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+        swap_grid_barrier(g.gsync, gridDim.x, et);
+        uint32_t* bsc = boot_s + ew * (2 * kBootCap + kHsBins);
+        uint32_t* brw = bsc + kBootCap;
+        uint32_t* bhist = brw + kBootCap;
+        for (int j = blockIdx.x * 4 + ew; j < g.Q; j += gstride) {
+          for (int i = lane; i < gstride; i += 32) {
+            bsc[i] = order_bits(__ldcg(g.gmax + static_cast<int64_t>(j) * gstride + i));
+            brw[i] = ~static_cast<uint32_t>(i);
+          }
+          __syncwarp();
+          uint32_t ks, kr;
+          ls_kth(bsc, brw, gstride, g.k, bhist, lane, ks, kr);
+          // the filter is a strict ">", and the bootstrap rows are filtered again: the threshold sits one ulp BELOW the k-th
+          // group maximum so that the row it came from (and its exact ties) survive
+          if (lane == 0) const_cast<float*>(g.tau)[j] = unorder_bits(ks > 1u ? ks - 1u : ks) - g.band;
+          __syncwarp();
+        }
+        swap_grid_barrier(g.gsync + 1, gridDim.x, et);
+      }
       for (int j = et; j < 256; j += 128) {
-        tau_s[j] = j < g.Q ? g.tau[j] : INFINITY;
+        tau_s[j] = j < g.Q ? __ldcg(g.tau + j) : INFINITY;
         cnt_s[j] = 0;
       }
       if (et == 0) flag_s[0] = 0;
@@ -829,7 +912,7 @@ constexpr size_t kGemmSmemBytes = static_cast<size_t>(kRingBytes) + kEpiWarps * 
 // in-kernel cut-back, whose margin is 32 keys
 static int seg_cap_for(int k) { return k <= 128 ? 288 : kSegCapMax; }
 static_assert(kGemmSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
-constexpr size_t kSwapSmemBytes = static_cast<size_t>(kRingBytes) + 2 * 256 * 4 + 16 + (2 * kSwapMaxStages + 6) * sizeof(uint64_t) + 16 + 1024;
+constexpr size_t kSwapSmemBytes = static_cast<size_t>(kRingBytes) + 2 * 256 * 4 + 16 + (2 * kSwapMaxStages + 6) * sizeof(uint64_t) + 16 + kSwapBootBytes + 1024;
 static_assert(kSwapSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
 
 // the swapped kernel applies when one block of queries is small enough to stay resident next to a useful ring
@@ -976,9 +1059,22 @@ static bool dense0_applies(int64_t Q, int64_t D, int dtype) {
 }
 
 struct GemmWs {
-  size_t q_planes, c_planes, qinv, cinv, tau, overflow, carry[2], carry_cnt[2], cand, cand_cnt, scratch, dense0, total;
+  size_t q_planes, c_planes, qinv, cinv, tau, overflow, carry[2], carry_cnt[2], cand, cand_cnt, scratch, dense0, gmax, total;
   int max_chunks, seg_cap, kc;
+  int boot_pairs;  // > 0: single-launch swapped path with in-kernel threshold bootstrap on this many CTA pairs
 };
+
+// Single-launch mode of the swapped kernel: one chunk per CTA pair, thresholds bootstrapped in the kernel from 4 group maxima
+// per CTA. Needs at least k groups (and leaves headroom: 2k), at most kBootCap, and one chunk per pair.
+static int boot_pairs_for(int64_t Q, int64_t N, int64_t D, int dtype, int k) {
+  static const bool disabled = getenv("ICR_NO_BOOT") != nullptr;  // A/B switch for benchmarks
+  if (disabled || !swap_applies(Q, D, dtype)) return 0;
+  const int64_t T = (N + BN - 1) / BN;
+  const int pairs = static_cast<int>(T < kNumSMs / 2 ? T : kNumSMs / 2);
+  const int groups = 8 * pairs;  // 2 CTAs x 4 epilogue warps
+  if (groups < 2 * k || groups > kBootCap) return 0;
+  return pairs;
+}
 
 static GemmWs gemm_ws_layout(int64_t Q, int64_t N, int64_t D, int dtype, int k, int have_planes, int have_cinv) {
   GemmWs w{};
@@ -989,6 +1085,8 @@ static GemmWs gemm_ws_layout(int64_t Q, int64_t N, int64_t D, int dtype, int k, 
   const int np = plan_phases(N, qblocks, k, ph, kMaxPhases, swap_applies(Q, D, dtype), dense0 ? kDense0Tiles : 0);
   int maxc = 1;
   for (int i = 0; i < np; ++i) maxc = ph[i].chunks > maxc ? ph[i].chunks : maxc;
+  w.boot_pairs = boot_pairs_for(Q, N, D, dtype, k);
+  if (w.boot_pairs > maxc) maxc = w.boot_pairs;
   w.max_chunks = maxc;
   const int64_t dp = (D + 63) / 64 * 64;
   const int64_t plane_elems = mode == 3 ? 2 * dp : dp;  // hi|lo planes, or the screen plane
@@ -1003,7 +1101,7 @@ static GemmWs gemm_ws_layout(int64_t Q, int64_t N, int64_t D, int dtype, int k, 
   w.qinv = take(mode != 3 ? static_cast<size_t>(Q) * 4 : 0);
   w.cinv = take((mode != 3 && !have_cinv) ? static_cast<size_t>(N) * 4 : 0);
   w.tau = take(static_cast<size_t>(Q) * 4);
-  w.overflow = take(static_cast<size_t>(Q) * 4);
+  w.overflow = take(static_cast<size_t>(Q) * 4 + 32);  // + the grid-barrier counters of the boot mode (zeroed with the flags)
   w.kc = carry_cap(k, mode);
   for (int i = 0; i < 2; ++i) {
     w.carry[i] = take(static_cast<size_t>(Q) * w.kc * 8);
@@ -1015,6 +1113,7 @@ static GemmWs gemm_ws_layout(int64_t Q, int64_t N, int64_t D, int dtype, int k, 
   w.cand_cnt = take(static_cast<size_t>(Q) * maxc * halves * 4);
   w.scratch = take(static_cast<size_t>(kNumSMs) * kEpiWarps * kSegCapMax * 8);  // in-kernel compaction scratch
   w.dense0 = take(dense0 ? static_cast<size_t>(Q) * kDense0Tiles * BN * 4 : 0);
+  w.gmax = take(w.boot_pairs ? static_cast<size_t>((Q + 31) / 32 * 32) * 8 * w.boot_pairs * 4 : 0);
   w.total = off + 1024;
   return w;
 }
@@ -1039,6 +1138,7 @@ __global__ void init_phase_state_kernel(float* tau, unsigned int* overflow, int6
     tau[i] = -INFINITY;
     overflow[i] = 0u;
   }
+  if (i < 8) overflow[n + i] = 0u;  // the grid-barrier counters kept behind the flags
 }
 
 int launch_gemm_topk(const void* queries, int64_t Q, int64_t ldq, const void* catalog, int64_t N, int64_t ldc, int64_t D,
@@ -1162,6 +1262,24 @@ int launch_gemm_topk(const void* queries, int64_t Q, int64_t ldq, const void* ca
   if (!state_ready) {  // the query-side preparation kernels of the one-term paths initialise tau / overflow themselves
     init_phase_state_kernel<<<static_cast<unsigned>((Q + 255) / 256), 256, 0, st>>>(const_cast<float*>(g.tau), g.overflow, Q);
     ICR_LAUNCH_CHECK();
+  }
+
+  if (L.boot_pairs > 0) {
+    // ---- single launch over the whole catalog: thresholds bootstrapped in the kernel, then one select ----
+    g.boot = 1;
+    g.gmax = reinterpret_cast<float*>(base + L.gmax);
+    g.gsync = g.overflow + Q;  // zeroed by the query preparation kernel together with the flags
+    g.tile_begin = 0;
+    g.tile_end = static_cast<int>((N + BN - 1) / BN);
+    g.chunks = L.boot_pairs;
+    if ((rc = launch_swap_variant(which, 2 * L.boot_pairs, map_a, map_b, g, st))) return rc;
+    HistSelectArgs sp = sa;
+    sp.nseg = g.chunks * 2;
+    sp.carry_out = mode == 2 ? reinterpret_cast<uint64_t*>(base + L.carry[0]) : nullptr;
+    sp.carry_cnt_out = mode == 2 ? reinterpret_cast<int*>(base + L.carry_cnt[0]) : nullptr;
+    sp.out_scores = out_scores;
+    sp.out_ids = out_ids;
+    return run_select(sp, Q, st);
   }
 
   // ---- first phase, dense: rows of the first kDense0Tiles tiles have no threshold to beat yet, so every score would

@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(256) row_inv_norms_kernel(const T* __restrict_
       if (tau_init) tau_init[r] = -INFINITY;
       if (ovf_init) ovf_init[r] = 0u;
     }
+    if (ovf_init && r == 0 && lane < 8) ovf_init[rows + lane] = 0u;  // the grid-barrier counters kept behind the flags
   }
 }
 
@@ -96,6 +97,7 @@ __global__ void __launch_bounds__(256) screen_plane_kernel(const float* __restri
       if (tau_init) tau_init[r] = -INFINITY;
       if (ovf_init) ovf_init[r] = 0u;
     }
+    if (ovf_init && r == 0 && lane < 8) ovf_init[rows + lane] = 0u;  // the grid-barrier counters kept behind the flags
     const float sc = 256.0f * inv;
     __half* dst = plane + r * dim_pad;
     for (int v = lane; v < nvec_pad; v += 32) {

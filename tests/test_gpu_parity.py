@@ -820,6 +820,33 @@ def test_screened_fp32_band_overflow_is_ranked_exactly(Q):
         assert (got - v.cpu()).abs().max() < 2e-6
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("Q,N,D,k", [(8, 49688, 384, 10), (16, 49688, 384, 100), (64, 30000, 384, 10), (128, 49688, 384, 100), (9, 20000, 768, 256),
+                                      (33, 19200, 128, 1), (5, 100000, 384, 37), (2, 262144, 64, 5)])
+def test_single_launch_swapped_path_vs_oracle(dtype, Q, N, D, k):
+    """Request-sized batches on the tensor path: ONE GEMM launch whose thresholds are bootstrapped in the kernel (k-th largest
+    of the per-warp group maxima of every CTA's first tile, grid barrier, then the filtered sweep) + one select. Covers ties
+    at the bootstrap threshold (exact duplicates of the best rows), exclusion masks and k = 1 / 256."""
+    if not _gemm_ok():
+        pytest.skip("GEMM path not built yet")
+    items, _ = oracle.synth_clustered(N, D, seed=99)
+    queries, src = oracle.synth_queries_from_items(items, Q, seed=98)
+    items[::997] = items[src[0]]  # exact duplicates of one query's best row: equal scores at the threshold
+    it, qt = items.to(dtype), queries.to(dtype)
+    cat = icr.DeviceCatalog(it.cuda(), dtype=dtype)
+    rtol = F32_RTOL if dtype == torch.float32 else 5e-5
+    full = oracle.cos_sim(qt.float(), it.float())
+    for mask in (None, (torch.arange(N) % 5 == 1)):
+        v, i = cat.topk(qt.cuda(), k, exclude_mask=None if mask is None else mask.cuda(), path=ops.PATH_GEMM)
+        if Q <= 128 and dtype == torch.bfloat16 or Q <= 128 and D <= 384:
+            assert ops.last_launch_count() <= 3, "expected the single-launch path (prep + GEMM + select)"
+        sc = full.clone()
+        if mask is not None:
+            sc[:, mask] = float("-inf")
+        rv, ri = torch.topk(sc, k, dim=1)
+        _check_topk(v, i, rv, ri, rtol)
+
+
 def test_full_size_properties_c2_shape():
     """BASELINE config 2 at full size through size-independent properties (the oracle is too slow for all of it):
     a row-permuted catalog returns the permuted ids with identical scores, every returned score is reproduced by
