@@ -85,7 +85,7 @@ struct GemmArgs {
   int qpad;                  // swapped kernel: queries rounded up to a multiple of 32 (the MMA's N)
   int dense_raw;             // dense mode stores raw-unit scores (no per-query factor): first phase of the top-k path
   // swapped kernel, single-launch mode: the thresholds are bootstrapped inside the kernel (see gemm_swap_kernel)
-  int boot;                  // 1 = on
+  int boot;                  // 0 = off, else the number of bootstrap tiles per chunk (its first tiles, streamed twice)
   float* gmax;               // [qpad][4 * gridDim.x] group maxima of the bootstrap tiles
   unsigned int* gsync;       // [2] grid-barrier counters, zero before the launch
   float band;                // screened scores (MODE 2): tau already sits `band` below the k-th best; 0 = exact scores
@@ -569,7 +569,12 @@ constexpr int kBootCap = 640;  // group maxima per query the in-kernel bootstrap
 constexpr size_t kSwapBootBytes = 4 * (2 * kBootCap + kHsBins) * sizeof(uint32_t);  // per epilogue warp: values, indices, histogram
 constexpr int kSwapMaxStages = 12;
 constexpr int kSwapThreads = 256;  // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 epilogue
-constexpr int kSwapResidentMax = 64 * 1024;  // leaves >= 8 catalog stages: measured, a 5-stage ring loses to K2
+// Resident queries may take 64 KB of the ring's shared memory: that leaves >= 8 catalog stages, and a 5-stage ring loses to K2 on
+// catalogs that stream from HBM (C4 shard, Q = 128: 0.49 against 0.46 ms, profiles/r02_notes.md). A catalog small enough to
+// sit in L2 does not need the deep ring: up to 100 KB there, which takes the single-launch path to Q = 256 at D = 384.
+constexpr int kSwapResidentMax = 64 * 1024;
+constexpr int kSwapResidentMaxSmallCatalog = 100 * 1024;
+constexpr int64_t kSmallCatalogBytes = 96ll << 20;
 
 __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
@@ -662,8 +667,8 @@ gemm_swap_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
     uint32_t phase = 0;
     for (int w = pair; w < items; w += npairs) {
       const int t0 = chunk_first_tile(g, w), t1 = chunk_first_tile(g, w + 1);
-      for (int tt = g.boot ? t0 - 1 : t0; tt < t1; ++tt) {  // boot mode: the chunk's first tile is streamed twice (see the epilogue)
-        const int tile = tt < t0 ? t0 : tt;
+      for (int tt = t0 - g.boot; tt < t1; ++tt) {  // boot mode: the chunk's first g.boot tiles are streamed twice (see the epilogue)
+        const int tile = tt < t0 ? tt + g.boot : tt;
         const int crow = tile * BN + static_cast<int>(rank) * BNH;
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
@@ -695,7 +700,7 @@ gemm_swap_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
     uint32_t acc_phase = 0;
     for (int w = pair; w < items; w += npairs) {
       const int t0 = chunk_first_tile(g, w), t1 = chunk_first_tile(g, w + 1);
-      for (int tt = g.boot ? t0 - 1 : t0; tt < t1; ++tt) {
+      for (int tt = t0 - g.boot; tt < t1; ++tt) {
         mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * 256);
@@ -741,37 +746,48 @@ gemm_swap_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
       const int t0 = chunk_first_tile(g, w), t1 = chunk_first_tile(g, w + 1);
       const int64_t seg0 = static_cast<int64_t>(w) * 2 + rank;  // + q * chunks * 2
       if (g.boot) {
-        // ---- single-launch mode: bootstrap the thresholds from the chunk's first tile --------------------------------
-        // Every epilogue warp takes the maximum of its 32 rows for each query: 4 * gridDim.x group maxima per query, each
+        // ---- single-launch mode: bootstrap the thresholds from the chunk's first g.boot tiles ------------------------
+        // Every epilogue warp takes the maximum of its rows (32 per tile) for each query: 4 * gridDim.x group maxima per query, each
         // the score of a distinct catalog row, so the k-th largest of them is a lower bound of the final k-th best score
         // (k <= 4 * gridDim.x is the host's condition for this mode). After a grid barrier the warps of all CTAs rank the
         // maxima of their share of the queries and publish tau; after a second barrier the chunk - including its first
         // tile, streamed again - is filtered as in the phased path. Two launches (first-phase GEMM + select) and, for small
         // catalogs, most of the call's latency disappear (profiles/r02_notes.md).
-        const int row = t0 * BN + static_cast<int>(rank) * BNH + ew * 32 + lane;
-        const bool valid = row < g.N && !(g.mask && g.mask[row]);
-        const float cinv_r = BF16 ? (row < g.N ? __ldg(g.cinv + row) : 0.f) : 1.0f;
         const int gstride = 4 * static_cast<int>(gridDim.x);
-        mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * 256);
-        for (int jb = 0; jb < g.qpad; jb += 32) {
-          uint32_t r[32];
-          tmem_ld32(taddr + jb, r);
-          tmem_ld_wait(r);
-          float sc[32];
+        float best[8];  // lane l: running maximum of this warp's rows for query 32 * b + l (qpad <= 256)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) sc[j] = valid ? __uint_as_float(r[j]) * cinv_r : -INFINITY;
-          warp_transpose_max<32>(sc, lane);  // lane l: the maximum over this warp's rows for query jb + l
-          if (jb + lane < g.Q) g.gmax[static_cast<int64_t>(jb + lane) * gstride + blockIdx.x * 4 + ew] = sc[0];
+        for (int b = 0; b < 8; ++b) best[b] = -INFINITY;
+        for (int bt = 0; bt < g.boot; ++bt) {
+          const int row = (t0 + bt) * BN + static_cast<int>(rank) * BNH + ew * 32 + lane;
+          const bool valid = row < g.N && !(g.mask && g.mask[row]);
+          const float cinv_r = BF16 ? (row < g.N ? __ldg(g.cinv + row) : 0.f) : 1.0f;
+          mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * 256);
+#pragma unroll
+          for (int b = 0; b < 8; ++b) {
+            if (b * 32 < g.qpad) {
+              uint32_t r[32];
+              tmem_ld32(taddr + b * 32, r);
+              tmem_ld_wait(r);
+              float sc[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) sc[j] = valid ? __uint_as_float(r[j]) * cinv_r : -INFINITY;
+              warp_transpose_max<32>(sc, lane);  // lane l: the maximum over this warp's rows for query 32 * b + l
+              best[b] = fmaxf(best[b], sc[0]);
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(smem_u32(&tempty_bar[acc]), 0);
+          if (++acc == 2) {
+            acc = 0;
+            acc_phase ^= 1;
+          }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(smem_u32(&tempty_bar[acc]), 0);
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1;
-        }
+#pragma unroll
+        for (int b = 0; b < 8; ++b)
+          if (b * 32 + lane < g.Q) g.gmax[static_cast<int64_t>(b * 32 + lane) * gstride + blockIdx.x * 4 + ew] = best[b];
         swap_grid_barrier(g.gsync, gridDim.x, et);
         uint32_t* bsc = boot_s + ew * (2 * kBootCap + kHsBins);
         uint32_t* brw = bsc + kBootCap;
@@ -930,13 +946,14 @@ static int carry_cap(int k, int mode) {
   return kc < 512 ? kc : 512;
 }
 
-static bool swap_applies(int64_t Q, int64_t D, int dtype) {
+static bool swap_applies(int64_t Q, int64_t N, int64_t D, int dtype) {
   static const bool disabled = getenv("ICR_NO_SWAP") != nullptr;  // A/B switch for benchmarks
   if (disabled || Q > 256) return false;
   const int64_t qpad = (Q + 31) / 32 * 32;
   const int64_t kb = (D + BK - 1) / BK;
   const int64_t res = (mode_for(dtype) == 3 ? 2 : 1) * kb * (qpad / 2) * 128;
-  return res <= kSwapResidentMax;
+  const int64_t sweep_bytes = N * ((D + BK - 1) / BK * BK) * 2 * (mode_for(dtype) == 3 ? 2 : 1);
+  return res <= (sweep_bytes <= kSmallCatalogBytes ? kSwapResidentMaxSmallCatalog : kSwapResidentMax);
 }
 
 struct Phase {
@@ -1053,26 +1070,36 @@ static int launch_swap_variant(int which, int grid, const CUtensorMap& map_q, co
   return ICR_OK;
 }
 
-static bool dense0_applies(int64_t Q, int64_t D, int dtype) {
+static bool dense0_applies(int64_t Q, int64_t N, int64_t D, int dtype) {
   static const bool disabled = getenv("ICR_NO_DENSE0") != nullptr;  // A/B switch for benchmarks
-  return !disabled && !swap_applies(Q, D, dtype);
+  return !disabled && !swap_applies(Q, N, D, dtype);
 }
 
 struct GemmWs {
   size_t q_planes, c_planes, qinv, cinv, tau, overflow, carry[2], carry_cnt[2], cand, cand_cnt, scratch, dense0, gmax, total;
   int max_chunks, seg_cap, kc;
   int boot_pairs;  // > 0: single-launch swapped path with in-kernel threshold bootstrap on this many CTA pairs
+  int boot_tiles;  // bootstrap tiles per chunk
 };
 
 // Single-launch mode of the swapped kernel: one chunk per CTA pair, thresholds bootstrapped in the kernel from 4 group maxima
 // per CTA. Needs at least k groups (and leaves headroom: 2k), at most kBootCap, and one chunk per pair.
-static int boot_pairs_for(int64_t Q, int64_t N, int64_t D, int dtype, int k) {
+// The bootstrap threshold lets ~N * k / (rows scored in the bootstrap) keys per query through: the number of bootstrap tiles per
+// chunk is chosen so that this stays near 4,000 (cheap for the select, far from the segments' capacity), and the mode is
+// refused when that would re-stream more than a quarter of a chunk.
+static int boot_pairs_for(int64_t Q, int64_t N, int64_t D, int dtype, int k, int* boot_tiles) {
   static const bool disabled = getenv("ICR_NO_BOOT") != nullptr;  // A/B switch for benchmarks
-  if (disabled || !swap_applies(Q, D, dtype)) return 0;
+  if (disabled || !swap_applies(Q, N, D, dtype)) return 0;
   const int64_t T = (N + BN - 1) / BN;
   const int pairs = static_cast<int>(T < kNumSMs / 2 ? T : kNumSMs / 2);
   const int groups = 8 * pairs;  // 2 CTAs x 4 epilogue warps
   if (groups < 2 * k || groups > kBootCap) return 0;
+  const int64_t want_rows = N / 4000 * k;
+  int tiles = static_cast<int>((want_rows + static_cast<int64_t>(BN) * pairs - 1) / (static_cast<int64_t>(BN) * pairs));
+  if (tiles < 1) tiles = 1;
+  const int64_t per_chunk = T / pairs;  // the shortest chunk
+  if (tiles > 1 && tiles * 4 > per_chunk) return 0;
+  if (boot_tiles) *boot_tiles = tiles;
   return pairs;
 }
 
@@ -1081,11 +1108,12 @@ static GemmWs gemm_ws_layout(int64_t Q, int64_t N, int64_t D, int dtype, int k, 
   const int mode = mode_for(dtype);
   const int qblocks = static_cast<int>((Q + 2 * BM - 1) / (2 * BM));
   Phase ph[kMaxPhases];
-  const bool dense0 = dense0_applies(Q, D, dtype);
-  const int np = plan_phases(N, qblocks, k, ph, kMaxPhases, swap_applies(Q, D, dtype), dense0 ? kDense0Tiles : 0);
+  const bool dense0 = dense0_applies(Q, N, D, dtype);
+  const int np = plan_phases(N, qblocks, k, ph, kMaxPhases, swap_applies(Q, N, D, dtype), dense0 ? kDense0Tiles : 0);
   int maxc = 1;
   for (int i = 0; i < np; ++i) maxc = ph[i].chunks > maxc ? ph[i].chunks : maxc;
-  w.boot_pairs = boot_pairs_for(Q, N, D, dtype, k);
+  w.boot_tiles = 0;
+  w.boot_pairs = boot_pairs_for(Q, N, D, dtype, k, &w.boot_tiles);
   if (w.boot_pairs > maxc) maxc = w.boot_pairs;
   w.max_chunks = maxc;
   const int64_t dp = (D + 63) / 64 * 64;
@@ -1108,7 +1136,7 @@ static GemmWs gemm_ws_layout(int64_t Q, int64_t N, int64_t D, int dtype, int k, 
     w.carry_cnt[i] = take(static_cast<size_t>(Q) * 4);
   }
   w.seg_cap = seg_cap_for(k);
-  const int halves = swap_applies(Q, D, dtype) ? 2 : epi_warps(mode == 3 ? 3 : 1) / 4;
+  const int halves = swap_applies(Q, N, D, dtype) ? 2 : epi_warps(mode == 3 ? 3 : 1) / 4;
   w.cand = take(static_cast<size_t>(Q) * maxc * halves * w.seg_cap * 8);
   w.cand_cnt = take(static_cast<size_t>(Q) * maxc * halves * 4);
   w.scratch = take(static_cast<size_t>(kNumSMs) * kEpiWarps * kSegCapMax * 8);  // in-kernel compaction scratch
@@ -1250,7 +1278,7 @@ int launch_gemm_topk(const void* queries, int64_t Q, int64_t ldq, const void* ca
   sa.out_scale = g.acc_scale;
   sa.out_qscale = g.qinv;
   const int terms = mode == 3 ? 3 : 1;
-  const bool swap = swap_applies(Q, D, dtype);
+  const bool swap = swap_applies(Q, N, D, dtype);
   const bool astat = terms == 1 && g.kb_per_term <= kAStatMaxKB;
   int which;
   if (swap) which = mode == 3 ? 3 : (mode == 1 ? 4 : 7);
@@ -1266,7 +1294,7 @@ int launch_gemm_topk(const void* queries, int64_t Q, int64_t ldq, const void* ca
 
   if (L.boot_pairs > 0) {
     // ---- single launch over the whole catalog: thresholds bootstrapped in the kernel, then one select ----
-    g.boot = 1;
+    g.boot = L.boot_tiles;
     g.gmax = reinterpret_cast<float*>(base + L.gmax);
     g.gsync = g.overflow + Q;  // zeroed by the query preparation kernel together with the flags
     g.tile_begin = 0;
@@ -1287,7 +1315,7 @@ int launch_gemm_topk(const void* queries, int64_t Q, int64_t ldq, const void* ca
   // score matrix instead (full 128-byte lines) and the select builds its keys from that.
   Phase ph[kMaxPhases];
   const int T = static_cast<int>((N + BN - 1) / BN);
-  const bool dense0 = dense0_applies(Q, D, dtype);
+  const bool dense0 = dense0_applies(Q, N, D, dtype);
   int done_phases = 0;
   if (dense0) {
     const int T0 = T < kDense0Tiles ? T : kDense0Tiles;
