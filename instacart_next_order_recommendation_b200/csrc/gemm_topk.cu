@@ -277,6 +277,30 @@ __device__ __forceinline__ void dense_store32(const uint32_t (&r)[32], float* ou
   }
 }
 
+constexpr int kK2BootCap = 512;  // block maxima per query the in-kernel bootstrap of K2 can rank
+
+// Barrier over the epilogue warps of every CTA of the grid (all CTAs co-resident: one per SM, grid <= 148): named barrier 2
+// joins this CTA's epilogue warps, one thread counts the CTA in and waits. Traps after ~2 s instead of hanging the GPU.
+__device__ __forceinline__ void k2_grid_barrier(unsigned int* counter, unsigned int ctas, int ewarp, int ewarps) {
+  asm volatile("bar.sync 2, %0;" ::"r"(ewarps * 32) : "memory");
+  if (ewarp == 0 && (threadIdx.x & 31) == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+      unsigned int v;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+      if (v >= ctas) break;
+      __nanosleep(100);
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 2000000000ull) __trap();
+    }
+    __threadfence();
+  }
+  asm volatile("bar.sync 2, %0;" ::"r"(ewarps * 32) : "memory");
+}
+
 // MODE = 3: fp16 hi/lo planes, three MMA terms (fp32 parity of every score: the dense K2' path);
 // MODE = 1: raw bf16 rows, one term, inverse norms applied in the epilogue;
 // MODE = 2: one fp16 plane of the normalised fp32 rows, one term: SCREENING scores (select_args.cuh), the survivors
@@ -312,6 +336,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   uint64_t* afull_bar = bars + 2 * kMaxStages + 4;   // ASTAT: resident queries loaded
   uint64_t* aempty_bar = bars + 2 * kMaxStages + 5;  // ASTAT: every MMA of the work item has read them
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 6);
+  uint32_t* boot_s = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 7);  // [EW][kK2BootCap + kHsBins], boot mode only
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();  // 0 = leader of the pair
@@ -345,9 +370,12 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     // ================= TMA producer (both CTAs; each loads its own queries and its half of B) =================
     int stage = 0;
     uint32_t phase = 0, a_phase = 0;
+    // boot mode (g.boot > 0): pass 0 streams only the first g.boot tiles of every work item (the epilogue takes group maxima
+    // from them and the thresholds are computed in the kernel), pass 1 the whole items
+    for (int pass = g.boot > 0 ? 0 : 1; pass < 2; ++pass)
     for (int w = pair; w < items; w += npairs) {
       const int chunk = w / g.qblocks, qb = w - chunk * g.qblocks;
-      const int t0 = chunk_first_tile(g, chunk), t1 = chunk_first_tile(g, chunk + 1);
+      const int t0 = chunk_first_tile(g, chunk), t1 = pass == 0 ? t0 + g.boot : chunk_first_tile(g, chunk + 1);
       const int qrow = qb * (2 * BM) + static_cast<int>(rank) * BM;
       if (ASTAT) {
         // the previous work item's MMAs must have finished reading the resident queries
@@ -399,9 +427,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0, a_phase = 0;
+    for (int pass = g.boot > 0 ? 0 : 1; pass < 2; ++pass)
     for (int w = pair; w < items; w += npairs) {
       const int chunk = w / g.qblocks;
-      const int t0 = chunk_first_tile(g, chunk), t1 = chunk_first_tile(g, chunk + 1);
+      const int t0 = chunk_first_tile(g, chunk), t1 = pass == 0 ? t0 + g.boot : chunk_first_tile(g, chunk + 1);
       if (ASTAT) {
         mbar_wait(smem_u32(afull_bar), a_phase);
         tc_fence_after();
@@ -469,6 +498,78 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     const int cap = g.seg_cap;
     int acc = 0;
     uint32_t acc_phase = 0;
+    if (!DENSE && g.boot > 0) {
+      // ---- single-launch mode, pass 0: group maxima of the first g.boot tiles of every work item ----------------------
+      // A thread owns one query and sees 32 catalog scores per TMEM load: the maximum of each such block is the score of
+      // a distinct row, so the k-th largest of a query's block maxima (chunks * g.boot * 8 of them) is a lower bound of its
+      // final k-th best score. The whole grid meets at a barrier, every epilogue warp ranks the maxima of its share of the
+      // queries and publishes tau, a second barrier, and pass 1 filters the whole catalog against those thresholds: the
+      // dense first phase, one sparse phase and the two selects between them (a third of the C2 step) are gone.
+      const int gstride = g.chunks * g.boot * (BN / 32);
+      for (int w = pair; w < items; w += npairs) {
+        const int chunk = w / g.qblocks, qb = w - chunk * g.qblocks;
+        const int t0 = chunk_first_tile(g, chunk);
+        const int q = qb * (2 * BM) + static_cast<int>(rank) * BM + ew * 32 + lane;
+        const bool live = q < g.Q;
+        float* gq = g.gmax + static_cast<int64_t>(live ? q : 0) * gstride + (chunk * g.boot * EH + half) * (ECOLS / 32);
+        for (int bt = 0; bt < g.boot; ++bt) {
+          const int row0 = (t0 + bt) * BN + half * ECOLS;
+          if (BF16) {
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < ECOLS / 32; ++u) {
+              const int i = u * 32 + lane;
+              cinv_s[i] = (row0 + i < g.N) ? __ldg(g.cinv + row0 + i) : 0.f;
+            }
+            __syncwarp();
+          }
+          mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * BN + half * ECOLS);
+          const bool plain = (row0 + ECOLS <= g.N) && (g.mask == nullptr);
+#pragma unroll 1
+          for (int cb = 0; cb < ECOLS / 32; ++cb) {
+            uint32_t r[32];
+            tmem_ld32(taddr + cb * 32, r);
+            tmem_ld_wait(r);
+            float m = -INFINITY;
+            if (plain) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) m = fmaxf(m, BF16 ? __uint_as_float(r[j]) * cinv_s[cb * 32 + j] : __uint_as_float(r[j]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int row = row0 + cb * 32 + j;
+                if (row < g.N && !(g.mask && g.mask[row]))
+                  m = fmaxf(m, BF16 ? __uint_as_float(r[j]) * cinv_s[cb * 32 + j] : __uint_as_float(r[j]));
+              }
+            }
+            if (live) gq[bt * (EH * (ECOLS / 32)) + cb] = m;
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(smem_u32(&tempty_bar[acc]), 0);
+          if (++acc == 2) {
+            acc = 0;
+            acc_phase ^= 1;
+          }
+        }
+      }
+      k2_grid_barrier(g.gsync, gridDim.x, warp - 4, EW);
+      uint32_t* bsc = boot_s + (warp - 4) * (kK2BootCap + kHsBins);
+      uint32_t* bhist = bsc + kK2BootCap;
+      const int nwarps = static_cast<int>(gridDim.x) * EW;
+      for (int j = blockIdx.x * EW + (warp - 4); j < g.Q; j += nwarps) {
+        for (int i = lane; i < gstride; i += 32) bsc[i] = order_bits(__ldcg(g.gmax + static_cast<int64_t>(j) * gstride + i));
+        __syncwarp();
+        uint32_t ks, kr;
+        ls_kth(bsc, bsc, gstride, g.k, bhist, lane, ks, kr);  // only the k-th VALUE matters: the tie-break word is the value itself
+        // the filter is a strict ">" and the bootstrap rows are filtered again in pass 1: one ulp below the k-th maximum
+        if (lane == 0) const_cast<float*>(g.tau)[j] = unorder_bits(ks > 1u ? ks - 1u : ks) - g.band;
+        __syncwarp();
+      }
+      k2_grid_barrier(g.gsync + 1, gridDim.x, warp - 4, EW);
+    }
     for (int w = pair; w < items; w += npairs) {
       const int chunk = w / g.qblocks, qb = w - chunk * g.qblocks;
       const int t0 = chunk_first_tile(g, chunk), t1 = chunk_first_tile(g, chunk + 1);
@@ -479,7 +580,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       s.seg = g.cand + seg_index * cap;
       s.cnt = 0;
       constexpr bool dense = DENSE;  // compile-time: the top-k instantiation keeps its register budget
-      s.tau_ob = (live && !dense) ? order_bits(g.tau[q]) : 0xFFFFFFFFu;
+      s.tau_ob = (live && !dense) ? order_bits(__ldcg(g.tau + q)) : 0xFFFFFFFFu;
       float* out_q = dense ? g.dense_out + static_cast<int64_t>(live ? q : 0) * g.dense_ld : nullptr;
       const float qscale = dense ? (g.dense_raw ? 1.0f : g.acc_scale * ((BF16 && live) ? g.qinv[q] : 1.0f)) : 0.f;
       const bool vec_ok = dense && (g.dense_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.dense_out) & 15) == 0);
@@ -923,7 +1024,7 @@ int launch_screen_plane(const float* x, int64_t rows, int64_t dim, int64_t ld, u
                         unsigned int* ovf_init = nullptr);
 
 constexpr size_t kGemmSmemBytes = static_cast<size_t>(kRingBytes) + kEpiWarps * kEpiCols * sizeof(float) +
-                                  (2 * kMaxStages + 6) * sizeof(uint64_t) + 16 + 1024;
+                                  (2 * kMaxStages + 6) * sizeof(uint64_t) + 16 + kEpiWarps * (kK2BootCap + kHsBins) * sizeof(uint32_t) + 1024;
 // 256 + 32: a whole 256-row tile of a first phase (threshold -inf, every row survives) fits without tripping the
 // in-kernel cut-back, whose margin is 32 keys
 static int seg_cap_for(int k) { return k <= 128 ? 288 : kSegCapMax; }
@@ -1080,7 +1181,44 @@ struct GemmWs {
   int max_chunks, seg_cap, kc;
   int boot_pairs;  // > 0: single-launch swapped path with in-kernel threshold bootstrap on this many CTA pairs
   int boot_tiles;  // bootstrap tiles per chunk
+  int k2_boot_chunks, k2_boot_tiles;  // > 0: single-launch K2 (queries on M) with in-kernel bootstrap
 };
+
+// Single-launch mode of K2: one phase over the whole catalog, `chunks` tile ranges per query block, the first `tiles` tiles of
+// every work item scored twice (once for the block maxima the thresholds come from). The bootstrap rows are chosen so that
+// ~ICR_K2_BOOT_TARGET keys per query pass the threshold (N * k / rows); the mode needs 2k..kK2BootCap block maxima per query and
+// re-streams at most a quarter of a chunk - i.e. it serves catalogs of up to a few hundred thousand rows, where the phased
+// path spends a third of its time on the two bootstrap phases and their selects; larger catalogs keep the phased path.
+static int k2_boot_plan(int64_t Q, int64_t N, int64_t D, int dtype, int k, int* chunks_out) {
+  static const bool disabled = getenv("ICR_NO_BOOT_K2") != nullptr;  // A/B switch for benchmarks
+  static const int target = getenv("ICR_K2_BOOT_TARGET") ? atoi(getenv("ICR_K2_BOOT_TARGET")) : 550;
+  if (disabled || mode_for(dtype) == 3 || swap_applies(Q, N, D, dtype)) return 0;
+  const int T = static_cast<int>((N + BN - 1) / BN);
+  const int qblocks = static_cast<int>((Q + 2 * BM - 1) / (2 * BM));
+  const int npairs = kNumSMs / 2;
+  int c0 = (2 * npairs + qblocks - 1) / qblocks;
+  const int by_load = (target + 71) / 72;  // survivors spread over 2 * chunks segments, kept under a quarter of their capacity
+  if (c0 < by_load) c0 = by_load;
+  if (c0 > T) c0 = T;
+  int best = c0;
+  int64_t best_load = -1;
+  for (int c = c0; c <= T && c < c0 + 24; ++c) {
+    const int64_t rounds = (static_cast<int64_t>(qblocks) * c + npairs - 1) / npairs;
+    const int64_t load = rounds * ((T + c - 1) / c);
+    if (best_load < 0 || load < best_load) {
+      best_load = load;
+      best = c;
+    }
+  }
+  const int64_t want_rows = N * k / (target > 0 ? target : 1);
+  int tiles = static_cast<int>((want_rows + static_cast<int64_t>(BN) * best - 1) / (static_cast<int64_t>(BN) * best));
+  if (tiles < 1) tiles = 1;
+  while (best * tiles * (BN / 32) < 2 * k) ++tiles;
+  if (best * tiles * (BN / 32) > kK2BootCap) return 0;
+  if (tiles * 4 > T / best) return 0;
+  *chunks_out = best;
+  return tiles;
+}
 
 // Single-launch mode of the swapped kernel: one chunk per CTA pair, thresholds bootstrapped in the kernel from 4 group maxima
 // per CTA. Needs at least k groups (and leaves headroom: 2k), at most kBootCap, and one chunk per pair.
@@ -1115,6 +1253,9 @@ static GemmWs gemm_ws_layout(int64_t Q, int64_t N, int64_t D, int dtype, int k, 
   w.boot_tiles = 0;
   w.boot_pairs = boot_pairs_for(Q, N, D, dtype, k, &w.boot_tiles);
   if (w.boot_pairs > maxc) maxc = w.boot_pairs;
+  w.k2_boot_chunks = 0;
+  w.k2_boot_tiles = k2_boot_plan(Q, N, D, dtype, k, &w.k2_boot_chunks);
+  if (w.k2_boot_chunks > maxc) maxc = w.k2_boot_chunks;
   w.max_chunks = maxc;
   const int64_t dp = (D + 63) / 64 * 64;
   const int64_t plane_elems = mode == 3 ? 2 * dp : dp;  // hi|lo planes, or the screen plane
@@ -1141,7 +1282,9 @@ static GemmWs gemm_ws_layout(int64_t Q, int64_t N, int64_t D, int dtype, int k, 
   w.cand_cnt = take(static_cast<size_t>(Q) * maxc * halves * 4);
   w.scratch = take(static_cast<size_t>(kNumSMs) * kEpiWarps * kSegCapMax * 8);  // in-kernel compaction scratch
   w.dense0 = take(dense0 ? static_cast<size_t>(Q) * kDense0Tiles * BN * 4 : 0);
-  w.gmax = take(w.boot_pairs ? static_cast<size_t>((Q + 31) / 32 * 32) * 8 * w.boot_pairs * 4 : 0);
+  size_t gmax_bytes = w.boot_pairs ? static_cast<size_t>((Q + 31) / 32 * 32) * 8 * w.boot_pairs * 4 : 0;
+  if (w.k2_boot_tiles) gmax_bytes = static_cast<size_t>(Q) * w.k2_boot_chunks * w.k2_boot_tiles * (BN / 32) * 4;
+  w.gmax = take(gmax_bytes);
   w.total = off + 1024;
   return w;
 }
@@ -1303,6 +1446,26 @@ int launch_gemm_topk(const void* queries, int64_t Q, int64_t ldq, const void* ca
     if ((rc = launch_swap_variant(which, 2 * L.boot_pairs, map_a, map_b, g, st))) return rc;
     HistSelectArgs sp = sa;
     sp.nseg = g.chunks * 2;
+    sp.carry_out = mode == 2 ? reinterpret_cast<uint64_t*>(base + L.carry[0]) : nullptr;
+    sp.carry_cnt_out = mode == 2 ? reinterpret_cast<int*>(base + L.carry_cnt[0]) : nullptr;
+    sp.out_scores = out_scores;
+    sp.out_ids = out_ids;
+    return run_select(sp, Q, st);
+  }
+
+  if (L.k2_boot_tiles > 0) {
+    // ---- K2, single launch over the whole catalog (thresholds bootstrapped in the kernel), then one select ----
+    g.boot = L.k2_boot_tiles;
+    g.gmax = reinterpret_cast<float*>(base + L.gmax);
+    g.gsync = g.overflow + Q;
+    g.tile_begin = 0;
+    g.tile_end = static_cast<int>((N + BN - 1) / BN);
+    g.chunks = L.k2_boot_chunks;
+    const int items = qblocks * g.chunks;
+    const int pairs = items < kNumSMs / 2 ? items : kNumSMs / 2;
+    if ((rc = launch_gemm_variant<false>(which, 2 * pairs, map_a, map_b, g, st))) return rc;
+    HistSelectArgs sp = sa;
+    sp.nseg = g.chunks * (epi_warps(terms) / 4);
     sp.carry_out = mode == 2 ? reinterpret_cast<uint64_t*>(base + L.carry[0]) : nullptr;
     sp.carry_cnt_out = mode == 2 ? reinterpret_cast<int*>(base + L.carry_cnt[0]) : nullptr;
     sp.out_scores = out_scores;
