@@ -246,7 +246,10 @@ __device__ __forceinline__ void filter32(const uint32_t (&r)[32], SegState& s, c
     }
     // Tried in round 2 and dropped: appending quad by quad (one more vote per quad, four chained predicated appends in the
     // quads that have a survivor) instead of 32-wide prefix sums. At C2's survivor density nearly every quad is taken and the
-    // chained appends are latency-bound: the 163-tile launch went from 272 to 286 us.
+    // chained appends are latency-bound: the 163-tile launch went from 272 to 286 us. Likewise parking the block in shared memory
+    // and letting every lane walk only the quads whose maximum beats its threshold (~140 instructions instead of ~275, but a
+    // per-lane loop of dependent ffs -> LDS -> compare -> store steps): 421 -> 519 us for the single-launch C2 sweep. The
+    // prefix-sum form below has more instructions and all of them independent, which is what this epilogue needs.
   } else {
     // last (partial) tile of the catalog, or an exclusion mask: rows are checked one by one
 #pragma unroll
