@@ -916,7 +916,7 @@ __global__ void __launch_bounds__(kBsThreads) select_block_kernel(HistSelectArgs
       for (int i = tid; i < kept; i += kBsThreads) {  // kept <= kHsSel: rank counting, as below
         const uint64_t key = sm.sel[i];
         int rank = 0;
-        for (int j = 0; j < kept; ++j) rank += (sm.sel[j] > key) ? 1 : 0;
+        for (int j = 0; j < kept; ++j) rank += (sm.sel[j] > key || (sm.sel[j] == key && j < i)) ? 1 : 0;  // the index orders exact duplicates
         if (rank < k) {
           a.out_scores[q * k + rank] = key_score(key);
           a.out_ids[q * k + rank] = static_cast<int64_t>(key_row(key)) + a.id_offset;
@@ -945,7 +945,7 @@ __global__ void __launch_bounds__(kBsThreads) select_block_kernel(HistSelectArgs
   const uint64_t key = mine ? sm.sel[tid] : 0ull;
   int rank = 0;
   if (mine)
-    for (int j = 0; j < kept; ++j) rank += (sm.sel[j] > key) ? 1 : 0;
+    for (int j = 0; j < kept; ++j) rank += (sm.sel[j] > key || (sm.sel[j] == key && j < tid)) ? 1 : 0;  // the index orders exact duplicates
   if (a.tau_out && mine && rank == kept - 1) a.tau_out[q] = (kept >= k) ? key_score(key) : -INFINITY;
   if (a.tau_out && kept == 0 && tid == 0) a.tau_out[q] = -INFINITY;
   if (a.out_scores) {

@@ -550,6 +550,53 @@ def test_mnrl_forward_backward_vs_autograd(dtype, B, D, scale):
     assert (pd.grad.float().cpu() - 1.7 * rgp).abs().max() <= rel * 1.7 * rgp.abs().max()
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("B,D", [(256, 384), (64, 768), (512, 384)])
+def test_mnrl_step_graph_equals_the_autograd_path(dtype, B, D):
+    """MnrlStepGraph replays loss + both gradients of a fixed-shape step as one CUDA graph: same numbers as mnrl_loss().backward(),
+    on fresh inputs at every replay, and usable inside an autograd graph through backward_into()."""
+    g = torch.Generator().manual_seed(5)
+    step = icr.mnrl_step_graph(B, D, dtype, 20.0)
+    for it in range(3):
+        a = torch.nn.functional.normalize(torch.randn(B, D, generator=g), dim=1).to(dtype).cuda()
+        p = (a.float().cpu() + 0.4 * torch.randn(B, D, generator=g)).to(dtype).cuda()
+        loss, ga, gp = step(a, p)
+        ar, pr = a.clone().requires_grad_(True), p.clone().requires_grad_(True)
+        ref = icr.mnrl_loss(ar, pr, 20.0)
+        ref.backward()
+        assert abs(loss.item() - ref.item()) <= 1e-6
+        assert torch.equal(ga, ar.grad) and torch.equal(gp, pr.grad)
+    w = torch.nn.Parameter(torch.eye(D, device="cuda"))
+    a32, p32 = a.float(), p.float()
+    loss = step.backward_into((a32 @ w).to(dtype), (p32 @ w).to(dtype))
+    assert torch.isfinite(loss) and w.grad is not None and torch.isfinite(w.grad).all() and w.grad.abs().max() > 0
+    with pytest.raises(ValueError):
+        step(a[:-1], p[:-1])
+
+
+def test_shard_merge_tolerates_duplicated_candidates():
+    """Replicated shards hand the merge identical (score, id) pairs: the selection must terminate and return k entries in
+    (score desc, id asc) order (round-1 advice: >128 identical keys in the boundary bin never terminated)."""
+    g = torch.Generator().manual_seed(9)
+    Q, k = 37, 100
+    base_v = torch.sort(torch.rand(Q, k, generator=g), dim=1, descending=True).values
+    base_i = torch.stack([torch.randperm(5000, generator=g)[:k] for _ in range(Q)])
+    G = 4
+    vals = base_v[None].repeat(G, 1, 1).cuda()
+    ids = base_i[None].repeat(G, 1, 1).cuda()
+    v, i = ops.topk_merge(vals, ids, k)
+    torch.cuda.synchronize()
+    assert (v[:, :-1] >= v[:, 1:]).all()
+    # the k best of G copies of a k-list: its best ceil(k / G) entries, each G times
+    top = base_v[:, : (k + G - 1) // G]
+    assert torch.allclose(v.cpu()[:, ::G][:, : top.shape[1]], top)
+    same = torch.full((1, 1, 300), 0.5).repeat(1, 3, 1).cuda()
+    same_ids = torch.full((1, 3, 300), 7, dtype=torch.int64).cuda()
+    v2, i2 = ops.topk_merge(same, same_ids, 100)
+    torch.cuda.synchronize()
+    assert (v2 == 0.5).all() and (i2 == 7).all()
+
+
 @pytest.mark.parametrize("B,D,scale", [(256, 384, 20.0), (64, 384, 30.0), (37, 768, 20.0), (512, 384, 30.0), (300, 768, 20.0), (2048, 384, 20.0)])
 def test_mnrl_fp16_inputs_are_read_natively(B, D, scale, monkeypatch):
     """The reference trains with fp16=use_fp16 on CUDA (src/training/train_sbert.py:210,232): under autocast the embeddings
