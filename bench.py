@@ -330,8 +330,8 @@ def main():
                                  if world > 1 else "single GPU"),
                    "l2": "512 MiB buffer zeroed between timed iterations (L2 flush)", "seeds": [CATALOG_SEED, QUERY_SEED]},
         "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": Q * D * 4, "d2h_bytes_per_step": Q * k * 12,
-                "note": "DeviceCatalog.topk_host: pinned-host fp32 queries in, (scores f32, ids i64) out to pinned host, 3 pieces (20/60/20 %) pipelined "
-                        "over 2 streams; catalog resident in HBM as the reference keeps its index in memory"},
+                "note": "DeviceCatalog.topk_host: pinned-host fp32 queries in, (scores f32, ids i64) out to pinned host, 3 pieces (15/70/15 %) flowing "
+                        "through upload / rank / download streams; catalog resident in HBM as the reference keeps its index in memory"},
         "gpu_launches": launches_per_step * args.steps,
         "roofline": roof,
         "clocks": clocks.summary(),

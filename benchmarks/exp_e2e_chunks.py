@@ -9,7 +9,9 @@ cat = icr.DeviceCatalog(items)
 qh = torch.nn.functional.normalize(torch.randn(Q, D, generator=torch.Generator().manual_seed(1)), dim=1).pin_memory()
 ov = torch.empty(Q, k).pin_memory(); oi = torch.empty(Q, k, dtype=torch.int64).pin_memory()
 flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
-cases = [dict(n_chunks=n) for n in (1, 2, 3, 4)] + [dict(splits=s) for s in ([3000, 7000], [7000, 3000], [2000, 5000, 3000], [2000, 6000, 2000], [1500, 3500, 3500, 1500], [1024, 4096, 3856, 1024], [4000, 4000, 2000], [1000, 8000, 1000], [1536, 6928, 1536], [1024, 7952, 1024], [512, 8976, 512], [1024, 4476, 3476, 1024], [2560, 5120, 2320], [768, 4608, 4624])]
+cases = [dict(n_chunks=n) for n in (1, 2, 3)] + [dict(splits=s) for s in (
+    [2500, 7500], [3000, 7000], [3500, 6500], [4000, 6000], [7000, 3000], [1500, 7000, 1500], [2000, 6000, 2000], [2000, 5000, 3000],
+    [2500, 5000, 2500], [1500, 6000, 2500], [3000, 5000, 2000], [1000, 3000, 6000], [2000, 3000, 3000, 2000], [1500, 3500, 3500, 1500])]
 for kw in cases:
     nch = kw
     for _ in range(3): cat.topk_host(qh, k, out=(ov, oi), **kw)

@@ -1,4 +1,5 @@
 """Request-sized batches on the config-1 catalog (49,688 x 384): whole-call time per batch, L2 flushed before each call."""
+import os
 import sys
 
 import torch
@@ -12,6 +13,7 @@ dev = torch.device("cuda")
 g = torch.Generator(device=dev).manual_seed(1234)
 items = torch.nn.functional.normalize(torch.randn(N, D, device=dev, generator=g), dim=1)
 flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+QS = [int(x) for x in os.environ.get("ICR_SMALL_QS", "1,2,4,7,8,16,32,64,128,256,512,1024").split(",")]
 
 
 def timed(fn, n=30):
@@ -32,7 +34,7 @@ for dt in (torch.float32, torch.bfloat16):
     cat = icr.DeviceCatalog(items, dtype=dt)
     for k in (10, 100):
         row = []
-        for Q in (1, 2, 4, 7, 8, 16, 32, 64, 128, 256, 512, 1024):
+        for Q in QS:
             q = torch.nn.functional.normalize(torch.randn(Q, D, device=dev, generator=g), dim=1).to(dt)
             t = timed(lambda: cat.topk(q, k))
             n_launch = ops.last_launch_count()

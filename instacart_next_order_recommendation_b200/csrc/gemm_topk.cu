@@ -29,6 +29,8 @@
 // Replaces cos_sim [Q,N] -> torch.topk(100) -> Python heap of sentence-transformers'
 // InformationRetrievalEvaluator (built at reference src/training/train_sbert.py:197-202) and the
 // cos_sim -> np.argsort loops of src/baselines/content_based.py:54-63.
+#include <cstdio>
+
 #include "select_args.cuh"
 #include "select_lean.cuh"
 #include "tc.cuh"  // BM, BN, BK, tile geometry, PTX wrappers, tensor maps
@@ -280,7 +282,7 @@ __device__ __forceinline__ void dense_store32(const uint32_t (&r)[32], float* ou
   }
 }
 
-constexpr int kK2BootCap = 512;  // block maxima per query the in-kernel bootstrap of K2 can rank
+constexpr int kK2BootCap = 640;  // block maxima per query the in-kernel bootstrap of K2 can rank
 
 // Barrier over the epilogue warps of every CTA of the grid (all CTAs co-resident: one per SM, grid <= 148): named barrier 2
 // joins this CTA's epilogue warps, one thread counts the CTA in and waits. Traps after ~2 s instead of hanging the GPU.
@@ -1026,7 +1028,8 @@ int launch_split_planes(const float* x, int64_t rows, int64_t dim, int64_t ld, u
 int launch_screen_plane(const float* x, int64_t rows, int64_t dim, int64_t ld, uint16_t* plane, float* inv, cudaStream_t st, float* tau_init = nullptr,
                         unsigned int* ovf_init = nullptr);
 
-constexpr size_t kGemmSmemBytes = static_cast<size_t>(kRingBytes) + kEpiWarps * kEpiCols * sizeof(float) +
+constexpr size_t kGemmSmemBytes = static_cast<size_t>(kRingBytes) + 4 * BN * sizeof(float) +  // EW * ECOLS = 4 * BN inverse norms
+                                 
                                   (2 * kMaxStages + 6) * sizeof(uint64_t) + 16 + kEpiWarps * (kK2BootCap + kHsBins) * sizeof(uint32_t) + 1024;
 // 256 + 32: a whole 256-row tile of a first phase (threshold -inf, every row survives) fits without tripping the
 // in-kernel cut-back, whose margin is 32 keys
@@ -1137,6 +1140,37 @@ static int variant_terms(int which) { return (which == 0 || which == 3) ? 3 : 1;
   X(5, (gemm_topk_kernel<2, false, DENSE>))    \
   X(6, (gemm_topk_kernel<2, true, DENSE>))
 
+// Launch helper of the GEMM kernels. The single-launch modes (g.boot > 0) synchronise the whole grid through a counter in
+// global memory, which needs every CTA resident at once: those launches carry the cooperative attribute, so the driver
+// rejects a grid that cannot be co-resident and never starts one piecemeal beside kernels of other streams. A driver that
+// refuses the attribute on a cluster kernel gets the plain launch (the grid is sized to one CTA per SM either way).
+template <typename... KArgs, typename... Args>
+static void launch_gemm_grid(void (*kernel)(KArgs...), int grid, int threads, size_t smem, cudaStream_t st, bool coop, Args&&... args) {
+  static const bool no_coop = getenv("ICR_NO_COOP") != nullptr;  // A/B switch for benchmarks
+  static thread_local bool refused = false;
+  if (coop && !no_coop && !refused) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(static_cast<unsigned>(threads));
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+    if (e == cudaSuccess) return;
+    if (e != cudaErrorNotSupported && e != cudaErrorInvalidValue && e != cudaErrorInvalidConfiguration &&
+        e != cudaErrorCooperativeLaunchTooLarge)
+      return;  // left for ICR_LAUNCH_CHECK
+    (void)cudaGetLastError();
+    if (e != cudaErrorCooperativeLaunchTooLarge) refused = true;
+    if (getenv("ICR_DEBUG_COOP")) fprintf(stderr, "icr: cooperative launch refused (%s), plain launch used\n", cudaGetErrorName(e));
+  }
+  kernel<<<grid, threads, smem, st>>>(KArgs(args)...);
+}
+
 // launches instantiation `which` of the queries-on-M kernel, DENSE (K2' / first phase) or filtering
 template <bool DENSE>
 static int launch_gemm_variant(int which, int grid, const CUtensorMap& map_a, const CUtensorMap& map_b, const GemmArgs& g, cudaStream_t st) {
@@ -1150,7 +1184,7 @@ static int launch_gemm_variant(int which, int grid, const CUtensorMap& map_a, co
   profile_begin(kKernelGemm, variant_terms(which), st);
   const int threads = 128 + epi_warps(variant_terms(which)) * 32;
 #define ICR_RUN(ID, K) \
-  if (which == ID) K<<<grid, threads, kGemmSmemBytes, st>>>(map_a, map_b, g);
+  if (which == ID) launch_gemm_grid(K, grid, threads, kGemmSmemBytes, st, g.boot > 0, map_a, map_b, g);
   ICR_GEMM_VARIANTS(ICR_RUN, DENSE)
 #undef ICR_RUN
   profile_end(st);
@@ -1166,9 +1200,9 @@ static int launch_swap_variant(int which, int grid, const CUtensorMap& map_q, co
   if (which == 7) rc = ensure_dyn_smem(cache[2], gemm_swap_kernel<2>, kSwapSmemBytes);
   if (rc) return rc;
   profile_begin(kKernelGemm, variant_terms(which), st);
-  if (which == 3) gemm_swap_kernel<3><<<grid, kSwapThreads, kSwapSmemBytes, st>>>(map_q, map_c, g);
-  if (which == 4) gemm_swap_kernel<1><<<grid, kSwapThreads, kSwapSmemBytes, st>>>(map_q, map_c, g);
-  if (which == 7) gemm_swap_kernel<2><<<grid, kSwapThreads, kSwapSmemBytes, st>>>(map_q, map_c, g);
+  if (which == 3) launch_gemm_grid(gemm_swap_kernel<3>, grid, kSwapThreads, kSwapSmemBytes, st, g.boot > 0, map_q, map_c, g);
+  if (which == 4) launch_gemm_grid(gemm_swap_kernel<1>, grid, kSwapThreads, kSwapSmemBytes, st, g.boot > 0, map_q, map_c, g);
+  if (which == 7) launch_gemm_grid(gemm_swap_kernel<2>, grid, kSwapThreads, kSwapSmemBytes, st, g.boot > 0, map_q, map_c, g);
   profile_end(st);
   ICR_LAUNCH_CHECK();
   return ICR_OK;
@@ -1218,7 +1252,11 @@ static int k2_boot_plan(int64_t Q, int64_t N, int64_t D, int dtype, int k, int* 
   if (tiles < 1) tiles = 1;
   while (best * tiles * (BN / 32) < 2 * k) ++tiles;
   if (best * tiles * (BN / 32) > kK2BootCap) return 0;
-  if (tiles * 4 > T / best) return 0;
+  // at most a quarter of a chunk is scored twice; half for a catalog the L2 holds, where the second read is cheap and the
+  // phased path's extra launches are the larger cost (Q = 512 on the 49,688-row catalog: 74 chunks of 2-3 tiles)
+  const int64_t dp = (D + 63) / 64 * 64;
+  const bool l2_sized = N * dp * 2 <= (96ll << 20);
+  if (tiles * (l2_sized ? 2 : 4) > T / best) return 0;
   *chunks_out = best;
   return tiles;
 }

@@ -294,13 +294,16 @@ class DeviceCatalog:
                   n_chunks: int | None = None, path: int = ops.PATH_AUTO, splits: list[int] | None = None):
         """Host-to-host top-k: CPU query matrix in, CPU (values [Q,k] f32, ids [Q,k] i64) out.
 
-        The batch is cut into pieces that go round-robin over two side streams, each doing H2D copy -> fused top-k
-        -> D2H copy, so the copies of one piece overlap the kernels of another (the B200 has separate copy engines
-        for each direction). Default cut for large batches: 20 % / 60 % / 20 % — the kernels themselves do not overlap,
-        so what is exposed is the first piece's upload and the last piece's download, and short end pieces shrink
-        both (measured on C2: 1.21 ms against 1.29 ms for two halves and 1.50 ms unpipelined). Pass pinned tensors (and pinned `out`)
-        for truly asynchronous copies. Returns after enqueueing; the current stream waits on the side
-        streams, so `torch.cuda.current_stream().synchronize()` makes the outputs valid.
+        The batch is cut into pieces that flow through three side streams - upload, rank, download - so the copies of
+        one piece overlap the kernels of another (the B200 has a copy engine per direction). All uploads are enqueued
+        first: they then run back to back from the first microsecond instead of waiting for the host to enqueue the
+        kernels of the piece before. The kernels of the pieces run in order on ONE stream: side by side they only slow
+        each other down (measured, benchmarks/e2e_timeline.py). What stays exposed is the first piece's upload and the
+        last piece's download, while every piece costs ~0.1 ms of fixed kernel time on the 49,688-row catalog; the
+        default cut for large batches is 15 % / 70 % / 15 % (C2: 1.00 ms against 1.04 ms for 30 % / 70 % and 1.21 ms
+        unpipelined; the round-1 layout, one stream per piece, measured 1.16 ms). Pass pinned tensors
+        (and pinned `out`) for truly asynchronous copies. Returns after enqueueing; the current stream waits on the
+        side streams, so `torch.cuda.current_stream().synchronize()` makes the outputs valid.
         """
         if queries.is_cuda:
             raise ValueError("topk_host takes host tensors; use topk() for device-resident queries")
@@ -314,13 +317,15 @@ class DeviceCatalog:
         if Q == 0 or k < 1:
             return vals_h, ids_h
         if not hasattr(self, "_side_streams"):
-            self._side_streams = [torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)]
+            self._side_streams = [torch.cuda.Stream(self.device) for _ in range(3)]
+        up, rank, down = self._side_streams
         cur = torch.cuda.current_stream(self.device)
         if splits is None and n_chunks is None:
             if Q >= 2048:
-                splits = [Q // 5, Q - 2 * (Q // 5), Q // 5]
+                edge = 3 * Q // 20
+                splits = [edge, Q - 2 * edge, edge]
             else:
-                n_chunks = 2
+                n_chunks = 1
         if splits is None:
             n_chunks = max(1, min(n_chunks, (Q + 255) // 256))
             per = -(-Q // n_chunks)
@@ -331,23 +336,35 @@ class DeviceCatalog:
                 edges.append(min(Q, edges[-1] + int(n)))
             edges[-1] = Q
             bounds = list(zip(edges[:-1], edges[1:]))
+        bounds = [(lo, hi) for lo, hi in bounds if lo < hi]
         start = torch.cuda.Event()
         start.record(cur)
-        for c, (lo, hi) in enumerate(bounds):
-            if lo >= hi:
-                continue
-            st = self._side_streams[c % 2]
+        for st in (up, rank, down):
             st.wait_event(start)
-            with torch.cuda.stream(st):
+        staged = []
+        with torch.cuda.stream(up):
+            for lo, hi in bounds:
                 qd = queries[lo:hi].to(self.device, non_blocking=True)
+                qd.record_stream(rank)  # allocated on `up`, read on `rank`
+                ev = torch.cuda.Event()
+                ev.record(up)
+                staged.append((qd, ev))
+        for (lo, hi), (qd, ev) in zip(bounds, staged):
+            rank.wait_event(ev)
+            with torch.cuda.stream(rank):
                 if qd.dtype != self.dtype:
                     qd = qd.to(self.dtype)
                 v, i = ops.cos_topk(qd, self.rows, k, cat_planes=self.planes, cat_inv_norms=self.inv_norms,
                                     row_offset=self.row_offset, path=path)
+                v.record_stream(down)
+                i.record_stream(down)
+                done = torch.cuda.Event()
+                done.record(rank)
+            down.wait_event(done)
+            with torch.cuda.stream(down):
                 vals_h[lo:hi].copy_(v, non_blocking=True)
                 ids_h[lo:hi].copy_(i, non_blocking=True)
-        for st in self._side_streams:
-            cur.wait_stream(st)
+        cur.wait_stream(down)  # `down` waited on every piece of `rank`, which waited on every upload
         return vals_h, ids_h
 
     def topk(self, queries, k: int, *, exclude_mask: torch.Tensor | None = None, path: int = ops.PATH_AUTO):
