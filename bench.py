@@ -598,6 +598,13 @@ def bench_sharded(icr, ops, dist, dev, rank, world, flush):
                 lv, li = cat.local_topk(q, k)
                 if use is cat:
                     e["exchange_merge_peer_us"] = run(lambda: cat.exchange_merge(lv, li, k), 50) * 1e3
+
+                    def two_kernels():
+                        s_, g_ = cat._peer.all_gather(lv, li)
+                        return icr.ops.topk_merge(s_, g_, k)
+
+                    e["exchange_merge_peer_2launch_us"] = run(two_kernels, 50) * 1e3
+                    e["fused_launches"] = _launches_of(lambda: cat.topk(q, k), icr)
                 e["exchange_merge_nccl_us"] = run(lambda: cat_nccl.exchange_merge(lv, li, k), 50) * 1e3
                 e["ms_per_step_nccl"] = run(lambda: cat_nccl.topk(q, k), steps) if use is cat else ms
             # roofline of the local pass: HBM bytes of the shard for small batches, tensor flops for large ones
@@ -640,11 +647,18 @@ def bench_sharded(icr, ops, dist, dev, rank, world, flush):
         del cat, cat_nccl, rows, qall
         torch.cuda.empty_cache()
     out["exchange"] = ("NCCL all-gather of packed candidates + device merge (peer exchange unavailable)" if peer_error else
-                       "icr_peer_exchange: NVLink peer-memory push + flags (one kernel) + device merge; NCCL route timed beside it") if world > 1 else "none (one GPU holds the whole catalog)"
+                       "icr_cos_topk_sharded: shard search + NVLink peer-memory push + flags + merge in one library call (one launch for Q <= 7: the "
+                       "exchange and merge run in the tail of the GEMV kernel; otherwise the search, then ONE exchange+merge kernel); "
+                       "the round-1 two-launch exchange and the NCCL route timed beside it") if world > 1 else "none (one GPU holds the whole catalog)"
     out["peer_exchange_error"] = peer_error
     out["witness"] = "torch fp32 eager (normalize -> mm -> topk) on the same bf16 shards, 16 sampled queries per batch size, per-rank top-k gathered and merged"
     out["oracle_ok"] = all(b["witness_ok"] for c in out["configs"].values() for b in c["batches"].values())
     return out
+
+
+def _launches_of(fn, icr):
+    fn()
+    return int(icr.ops.last_launch_count())
 
 
 if __name__ == "__main__":

@@ -41,7 +41,8 @@ for Q in (1, 8, 64, 1024, 4096):
         e0.record()
         for _ in range(50):
             if ex == "peer":
-                s_, g_ = cat._peer.all_gather(lv, li)
+                cat._peer.exchange_merge(lv, li)  # one kernel: push, flags, wait, merge
+                continue
             else:
                 mine = icr.sharded.pack_candidates(lv, li)
                 out = torch.empty((world * 2, *mine.shape[1:]), dtype=mine.dtype, device=dev)

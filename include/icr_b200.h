@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define ICR_ABI_VERSION 2
+#define ICR_ABI_VERSION 3
 #define ICR_MAX_K 256 /* largest k of one fused top-k call (reference: top_k <= 100, schemas.py:34) */
 
 typedef enum {
@@ -180,6 +180,35 @@ size_t icr_peer_buffer_bytes(int64_t n_max, int world);
 int icr_peer_exchange(const float* scores, const int64_t* ids, int64_t n, int rank, int world,
                       const uint64_t* peer_buffers, uint32_t epoch, int64_t n_max,
                       size_t* scores_off, size_t* ids_off, void* stream);
+
+/* Exchange AND merge in one kernel (K4f): this rank's [Q, k] lists (descending or not) are pushed to every peer as in
+ * icr_peer_exchange, and the same launch waits for the peers' lists and writes the global top-k of every query to
+ * out_scores / out_ids [Q, k] - the result of icr_peer_exchange followed by icr_topk_merge(G = world, k_in = k_out = k).
+ * Same buffers, epochs and lock-step rule as icr_peer_exchange (the two may be mixed call by call, and a rank may use one
+ * while its peers use the other). Global ids must lie below 2^32 - 1, as for icr_topk_merge. */
+int icr_peer_exchange_merge(const float* scores, const int64_t* ids, int64_t Q, int k, int rank, int world,
+                            const uint64_t* peer_buffers, uint32_t epoch, int64_t n_max,
+                            float* out_scores, int64_t* out_ids, void* stream);
+
+/* One rank's call of a search over a ROW-SHARDED catalog: icr_cos_topk over this rank's shard (arguments as there;
+ * row_offset = global id of the shard's first row), the exchange of every rank's [Q, k] candidates over NVLink peer memory
+ * and the merge - out_scores / out_ids [Q, k] receive the GLOBAL top-k, identical on every rank. Every rank of the group
+ * makes the same call (same Q, k, epoch; the shards may differ in size). Request-sized batches (Q <= 7 on the GEMV path,
+ * world * k keys within the kernel's merge buffer) are ONE launch: the CTA that merges the shard's partial lists pushes the
+ * result to the peers, waits for theirs and merges them, all in the kernel's tail. Larger batches: the local search, then
+ * the K4f kernel. No reference counterpart (the reference is single-GPU); the single-GPU call it extends stands in for
+ * serve_recommendations.py:213-225. */
+size_t icr_cos_topk_sharded_workspace_bytes(int64_t Q, int64_t N, int64_t D, int dtype, int k, int path,
+                                            int have_planes);
+int icr_cos_topk_sharded(const void* queries, int64_t Q, int64_t ldq,
+                         const void* catalog, int64_t N, int64_t ldc,
+                         int64_t D, int dtype,
+                         const uint16_t* cat_planes, const float* cat_inv_norms,
+                         const uint8_t* exclude_mask,
+                         int k, int64_t row_offset, int path,
+                         int rank, int world, const uint64_t* peer_buffers, uint32_t epoch, int64_t n_max,
+                         float* out_scores, int64_t* out_ids,
+                         void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * MultipleNegativesRankingLoss (sentence-transformers; constructed at

@@ -17,7 +17,7 @@ ICR_F32, ICR_BF16, ICR_F16 = 0, 1, 2
 PATH_AUTO, PATH_GEMV, PATH_GEMM = 0, 1, 2
 PATH_WS_RESIDENT = 0x100  # OR-ed into a path: resident workspace, see include/icr_b200.h
 MAX_K = 256
-ABI_VERSION = 2  # include/icr_b200.h ICR_ABI_VERSION
+ABI_VERSION = 3  # include/icr_b200.h ICR_ABI_VERSION
 
 _STATUS = {
     -1: ("ICR_ERR_ARG", ValueError),
@@ -58,6 +58,13 @@ SIGNATURES = {
     "icr_topk_merge": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "icr_peer_buffer_bytes": (c_size_t, [c_int64, c_int]),
     "icr_peer_exchange": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_uint32, c_int64, c_void_p, c_void_p, c_void_p]),
+    "icr_peer_exchange_merge": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_uint32, c_int64, c_void_p, c_void_p, c_void_p]),
+    "icr_cos_topk_sharded_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int]),
+    "icr_cos_topk_sharded": (
+        c_int,
+        [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int64,
+         c_int, c_int, c_int, c_void_p, c_uint32, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p],
+    ),
     "icr_mnrl_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "icr_mnrl_fwd": (
         c_int,

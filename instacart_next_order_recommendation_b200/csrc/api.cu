@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "peer.cuh"
 
 namespace icr {
 
@@ -56,13 +57,16 @@ int launch_screen_plane(const float* x, int64_t rows, int64_t dim, int64_t ld, u
                         unsigned int* ovf_init = nullptr);
 int launch_convert_rows(const float* x, int64_t rows, int64_t dim, int64_t ldx, void* out, int64_t ldo, int out_dtype, int normalize,
                         cudaStream_t st);
-void peer_layout(int64_t n_max, int world, uint32_t epoch, size_t* scores_off, size_t* ids_off, size_t* total);
+int launch_peer_exchange_merge(const float* scores, const int64_t* ids, int64_t Q, int k, const PeerTail& peer, float* os, int64_t* oi,
+                               cudaStream_t st);
+bool gemv_peer_tail_fits(int Q, int k, int world);
 int launch_peer_exchange(const float* scores, const int64_t* ids, int64_t n, int rank, int world, const uint64_t* peer_buffers, uint32_t epoch,
                          int64_t n_max, cudaStream_t st);
 int gemv_grid(int64_t N);
 int launch_gemv_topk(const void* cat, int64_t N, int64_t ldc, int D, int dtype, const void* q, int64_t ldq, int Q,
                      const uint8_t* mask, int k, uint64_t* part_keys, int* part_cnt, int grid, float* out_scores, int64_t* out_ids,
-                     int64_t id_offset, unsigned int* done_counter, cudaStream_t st, const float* cat_inv);
+                     int64_t id_offset, unsigned int* done_counter, cudaStream_t st, const float* cat_inv, const PeerTail* peer = nullptr,
+                     float* fin_scores = nullptr, int64_t* fin_ids = nullptr);
 size_t select_scratch_bytes(int64_t Q, int nseg, int seg_cap, int k);
 int launch_select(const uint64_t* seg_keys, const int* seg_cnt, int64_t Q, int nseg, int seg_stride, int seg_cap,
                   const uint64_t* carry_in, const int* carry_cnt_in, uint64_t* carry_out, int* carry_cnt_out,
@@ -264,11 +268,12 @@ size_t icr_cos_topk_workspace_bytes(int64_t Q, int64_t N, int64_t D, int dtype, 
   return gemv_ws_bytes(Q, N, k);
 }
 
-int icr_cos_topk(const void* queries, int64_t Q, int64_t ldq, const void* catalog, int64_t N, int64_t ldc, int64_t D,
-                 int dtype, const uint16_t* cat_planes, const float* cat_inv_norms, const uint8_t* exclude_mask, int k,
-                 int64_t row_offset, int path, float* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes,
-                 void* stream) {
-  g_launches = 0;
+// `peer` != null (request-sized sharded call on the GEMV path, gemv_peer_tail_fits): the exchange and the global merge happen
+// in the tail of the scoring kernel; out_* then receive the GLOBAL top-k and stage_* hold the shard's own lists.
+static int cos_topk_impl(const void* queries, int64_t Q, int64_t ldq, const void* catalog, int64_t N, int64_t ldc, int64_t D,
+                         int dtype, const uint16_t* cat_planes, const float* cat_inv_norms, const uint8_t* exclude_mask, int k,
+                         int64_t row_offset, int path, float* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes,
+                         void* stream, const PeerTail* peer, float* stage_scores, int64_t* stage_ids) {
   int rc;
   if ((rc = check_matrix("cos_topk.queries", queries, Q, D, ldq, dtype))) return rc;
   if ((rc = check_matrix("cos_topk.catalog", catalog, N, D, ldc, dtype))) return rc;
@@ -328,6 +333,9 @@ int icr_cos_topk(const void* queries, int64_t Q, int64_t ldq, const void* catalo
   const size_t esz = elem_size(dtype);
   // the last CTA of every GEMV launch merges the per-CTA lists itself (no select launch on the latency path)
   if (!ws_resident) ICR_CUDA_CHECK(cudaMemsetAsync(done_counter, 0, sizeof(unsigned int), st));
+  if (peer)  // the merging CTA of the one GEMV launch also exchanges and merges (gemv_topk.cu peer_tail_merge)
+    return launch_gemv_topk(catalog, N, ldc, static_cast<int>(D), dtype, queries, ldq, static_cast<int>(Q), exclude_mask, k, part_keys, part_cnt,
+                            grid, stage_scores, stage_ids, row_offset, done_counter, st, cat_inv_norms, peer, out_scores, out_ids);
   for (int64_t q0 = 0; q0 < Q; q0 += qc) {
     const int nq = static_cast<int>(Q - q0 < qc ? Q - q0 : qc);
     const char* qptr = static_cast<const char*>(queries) + q0 * ldq * esz;
@@ -336,6 +344,88 @@ int icr_cos_topk(const void* queries, int64_t Q, int64_t ldq, const void* catalo
     if (rc) return rc;
   }
   return ICR_OK;
+}
+
+int icr_cos_topk(const void* queries, int64_t Q, int64_t ldq, const void* catalog, int64_t N, int64_t ldc, int64_t D,
+                 int dtype, const uint16_t* cat_planes, const float* cat_inv_norms, const uint8_t* exclude_mask, int k,
+                 int64_t row_offset, int path, float* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes,
+                 void* stream) {
+  g_launches = 0;
+  return cos_topk_impl(queries, Q, ldq, catalog, N, ldc, D, dtype, cat_planes, cat_inv_norms, exclude_mask, k, row_offset, path, out_scores,
+                       out_ids, workspace, workspace_bytes, stream, nullptr, nullptr, nullptr);
+}
+
+static int check_peer_args(const char* who, int64_t n, int rank, int world, const uint64_t* peer_buffers, uint32_t epoch, int64_t n_max) {
+  if (world < 1 || world > ICR_MAX_PEERS || rank < 0 || rank >= world || n < 0 || n > n_max || !peer_buffers || epoch == 0) {
+    set_error("%s: bad arguments n=%lld n_max=%lld rank=%d world=%d (<= %d) epoch=%u", who, (long long)n, (long long)n_max, rank, world,
+              ICR_MAX_PEERS, epoch);
+    return ICR_ERR_ARG;
+  }
+  for (int p = 0; p < world; ++p) {
+    if (peer_buffers[p] == 0 || (peer_buffers[p] & 255)) {
+      set_error("%s: buffer of rank %d is null or not 256-byte aligned", who, p);
+      return ICR_ERR_ALIGN;
+    }
+  }
+  return ICR_OK;
+}
+
+int icr_peer_exchange_merge(const float* scores, const int64_t* ids, int64_t Q, int k, int rank, int world, const uint64_t* peer_buffers,
+                            uint32_t epoch, int64_t n_max, float* out_scores, int64_t* out_ids, void* stream) {
+  g_launches = 0;
+  int rc;
+  if (Q < 0 || k < 1 || k > ICR_MAX_K) {
+    set_error("peer_exchange_merge: bad arguments Q=%lld k=%d", (long long)Q, k);
+    return ICR_ERR_ARG;
+  }
+  if ((rc = check_peer_args("peer_exchange_merge", Q * k, rank, world, peer_buffers, epoch, n_max))) return rc;
+  if (Q > 0 && (!scores || !ids || !out_scores || !out_ids || (reinterpret_cast<uintptr_t>(scores) & 3) || (reinterpret_cast<uintptr_t>(ids) & 7))) {
+    set_error("peer_exchange_merge: null or misaligned candidates / outputs");
+    return ICR_ERR_ARG;
+  }
+  if ((rc = check_device())) return rc;
+  const PeerTail tail = make_peer_tail(rank, world, peer_buffers, epoch, n_max);
+  return launch_peer_exchange_merge(scores, ids, Q, k, tail, out_scores, out_ids, static_cast<cudaStream_t>(stream));
+}
+
+static size_t sharded_stage_bytes(int64_t Q, int k) {
+  const size_t n = static_cast<size_t>(Q > 0 ? Q : 0) * static_cast<size_t>(k > 0 ? k : 0);
+  return align_up(n * sizeof(float), 256) + align_up(n * sizeof(int64_t), 256);
+}
+
+size_t icr_cos_topk_sharded_workspace_bytes(int64_t Q, int64_t N, int64_t D, int dtype, int k, int path, int have_planes) {
+  return align_up(icr_cos_topk_workspace_bytes(Q, N, D, dtype, k, path, have_planes), 256) + sharded_stage_bytes(Q, k);
+}
+
+int icr_cos_topk_sharded(const void* queries, int64_t Q, int64_t ldq, const void* catalog, int64_t N, int64_t ldc, int64_t D, int dtype,
+                         const uint16_t* cat_planes, const float* cat_inv_norms, const uint8_t* exclude_mask, int k, int64_t row_offset,
+                         int path, int rank, int world, const uint64_t* peer_buffers, uint32_t epoch, int64_t n_max, float* out_scores,
+                         int64_t* out_ids, void* workspace, size_t workspace_bytes, void* stream) {
+  g_launches = 0;
+  int rc;
+  if (k < 1 || k > ICR_MAX_K) {
+    set_error("cos_topk_sharded: k=%d outside [1, %d]", k, ICR_MAX_K);
+    return ICR_ERR_K;
+  }
+  if ((rc = check_peer_args("cos_topk_sharded", Q * k, rank, world, peer_buffers, epoch, n_max))) return rc;
+  const size_t local_ws = align_up(icr_cos_topk_workspace_bytes(Q, N, D, dtype, k, path & ~ICR_PATH_WS_RESIDENT, cat_planes != nullptr), 256);
+  if (!workspace || workspace_bytes < local_ws + sharded_stage_bytes(Q, k)) {
+    set_error("cos_topk_sharded: workspace %zu bytes < required %zu", workspace_bytes, local_ws + sharded_stage_bytes(Q, k));
+    return ICR_ERR_WORKSPACE;
+  }
+  if (Q == 0) return ICR_OK;  // nothing to exchange either: every rank passes the same Q
+  float* stage_scores = reinterpret_cast<float*>(static_cast<char*>(workspace) + local_ws);
+  int64_t* stage_ids = reinterpret_cast<int64_t*>(static_cast<char*>(workspace) + local_ws + align_up(static_cast<size_t>(Q) * k * sizeof(float), 256));
+  const PeerTail tail = make_peer_tail(rank, world, peer_buffers, epoch, n_max);
+  const int p = resolve_path(path & ~ICR_PATH_WS_RESIDENT, Q, N, D, dtype, k, exclude_mask);
+  if (p == ICR_PATH_GEMV && gemv_peer_tail_fits(static_cast<int>(Q < 8 ? Q : 8), k, world))  // one launch for the whole sharded request
+    return cos_topk_impl(queries, Q, ldq, catalog, N, ldc, D, dtype, cat_planes, cat_inv_norms, exclude_mask, k, row_offset, path, out_scores, out_ids,
+                         workspace, local_ws, stream, &tail, stage_scores, stage_ids);
+  // otherwise the shard's lists go to the staging area and the exchange + merge kernel writes the outputs
+  rc = cos_topk_impl(queries, Q, ldq, catalog, N, ldc, D, dtype, cat_planes, cat_inv_norms, exclude_mask, k, row_offset, path, stage_scores, stage_ids,
+                     workspace, local_ws, stream, nullptr, nullptr, nullptr);
+  if (rc) return rc;
+  return launch_peer_exchange_merge(stage_scores, stage_ids, Q, k, tail, out_scores, out_ids, static_cast<cudaStream_t>(stream));
 }
 
 size_t icr_cos_sim_dense_workspace_bytes(int64_t Qa, int64_t Nb, int64_t D, int dtype) {

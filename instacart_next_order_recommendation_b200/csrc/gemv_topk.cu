@@ -17,6 +17,7 @@
 // Replaces, for one request: torch.tensor(catalog) + F.normalize x2 + torch.mm + argsort
 // (reference src/inference/serve_recommendations.py:213-215 via sentence_transformers.util.cos_sim).
 #include "common.cuh"
+#include "peer.cuh"
 #include "ptx.cuh"
 #include "select_warp.cuh"
 
@@ -74,6 +75,12 @@ struct GemvArgs {
   int64_t* out_ids;            // [Q][k]
   int64_t id_offset;
   unsigned int* done_counter;  // zero before the first launch; the merging CTA resets it
+  // sharded request (peer_on): out_scores / out_ids are a staging area for this shard's lists; the merging CTA pushes them to
+  // every peer, waits for theirs and writes the global top-k to fin_scores / fin_ids (one pass only: Q <= 7, q0 = 0)
+  int peer_on;
+  float* fin_scores;
+  int64_t* fin_ids;
+  PeerTail peer;
 };
 
 // barrier over the 256 compute threads: the whole CTA in the direct kernel, a named barrier in the ring kernel
@@ -375,6 +382,75 @@ __device__ __forceinline__ void merge_query(const GemvArgs& a, GemvSmem<QT>& sm,
   }
 }
 
+// ---- sharded request: exchange + global merge in the tail of the merging CTA ------------------------------------------------
+// The shard's nq sorted lists (just written to out_scores / out_ids, global ids) go to slot `rank` of every peer's buffer
+// (exchange.cu: layout and protocol), the epoch is published, and once every rank's lists are in the local buffer the `world`
+// lists of each query are merged: they are sorted, so the rank of a key is its own position plus, per other list, the number
+// of keys ahead of it - a binary search (7 steps for k = 100) instead of a selection. Equal keys (shards that overlap) are
+// ordered by rank, so the ranks stay a permutation. No second launch, no host round trip: the request ends in this kernel.
+template <int QT, bool NAMED>
+__device__ __forceinline__ void peer_tail_merge(const GemvArgs& a, GemvSmem<QT>& sm, int nq, int tid) {
+  const PeerTail& p = a.peer;
+  const int k = a.k, W = p.world, tot = W * k;
+  peer_push(p, a.out_scores, a.out_ids, static_cast<int64_t>(nq) * k, tid, kGemvThreads);
+  __threadfence_system();
+  compute_sync<NAMED>();
+  peer_publish(p, tid);
+  peer_wait(p, tid);
+  compute_sync<NAMED>();
+  const float* ls = reinterpret_cast<const float*>(p.peer_base[p.rank] + p.scores_off);
+  const int64_t* li = reinterpret_cast<const int64_t*>(p.peer_base[p.rank] + p.ids_off);
+  uint64_t* buf = sm.cand;  // QT * CAND keys, one query at a time (the launcher checked world * k against it)
+  for (int t = 0; t < nq; ++t) {
+    for (int i = tid; i < tot; i += kGemvThreads) {
+      const int g = i / k, j = i - g * k;
+      const int64_t off = (static_cast<int64_t>(g) * nq + t) * k + j;
+      const int64_t id = __ldcg(li + off);
+      const float sc = __ldcg(ls + off);
+      buf[i] = id < 0 ? 0ull : make_key(sc, static_cast<uint32_t>(id));
+    }
+    compute_sync<NAMED>();
+    int valid = 0;  // eligible candidates of all shards together (every thread counts: W short searches)
+    for (int r = 0; r < W; ++r) {
+      const uint64_t* list = buf + r * k;
+      int lo = 0, hi = k;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (list[mid] != 0ull) lo = mid + 1;
+        else hi = mid;
+      }
+      valid += lo;
+    }
+    for (int i = tid; i < tot; i += kGemvThreads) {
+      const uint64_t key = buf[i];
+      if (key == 0ull) continue;
+      const int g = i / k;
+      int rank = i - g * k;
+      for (int r = 0; r < W; ++r) {
+        if (r == g) continue;
+        const uint64_t* list = buf + r * k;
+        int lo = 0, hi = k;  // first position whose key does not come before `key`
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          const uint64_t o = list[mid];
+          if (o > key || (o == key && r < g)) lo = mid + 1;
+          else hi = mid;
+        }
+        rank += lo;
+      }
+      if (rank < k) {
+        a.fin_scores[t * k + rank] = key_score(key);
+        a.fin_ids[t * k + rank] = static_cast<int64_t>(key_row(key));
+      }
+    }
+    for (int i = valid + tid; i < k; i += kGemvThreads) {  // fewer than k eligible rows in the whole catalog
+      a.fin_scores[t * k + i] = -INFINITY;
+      a.fin_ids[t * k + i] = -1;
+    }
+    compute_sync<NAMED>();
+  }
+}
+
 // ---- emit this CTA's lists; the last CTA to finish merges all of them -----------------------------------
 template <int QT, bool NAMED>
 __device__ __forceinline__ void emit_and_merge(const GemvArgs& a, GemvSmem<QT>& sm, int nq, bool has_rows, int tid) {
@@ -416,6 +492,7 @@ __device__ __forceinline__ void emit_and_merge(const GemvArgs& a, GemvSmem<QT>& 
   }
   compute_sync<NAMED>();
   ICR_MSTAMP(4);
+  if (a.peer_on) peer_tail_merge<QT, NAMED>(a, sm, nq, tid);
   if (tid == 0) *a.done_counter = 0u;  // ready for the next launch that shares this workspace
 }
 
@@ -703,6 +780,15 @@ static bool ring_ok(int64_t ldc, int D, int dtype, int qt) {
   return qt == 7 ? slots >= 2 * kGemvWarps : slots >= kGemvWarps;
 }
 
+// the tail of a sharded request merges `world` lists of k keys per query in the candidate area of the merging CTA: one pass
+// (Q <= 7) and world * k keys must fit
+bool gemv_peer_tail_fits(int Q, int k, int world) {
+  if (Q < 1 || Q > 7) return false;
+  const int qt = Q == 1 ? 1 : (Q <= 3 ? 3 : 7);
+  const int cap = qt == 1 ? GemvSmem<1>::CAND : (qt == 3 ? 3 * GemvSmem<3>::CAND : 7 * GemvSmem<7>::CAND);
+  return world * k <= cap;
+}
+
 int gemv_grid(int64_t N) {
   // one CTA per SM for the ring kernel, two for the direct kernel; at least 64 rows per CTA. The workspace is
   // sized for the larger of the two.
@@ -715,8 +801,15 @@ int gemv_grid(int64_t N) {
 // Runs ceil(Q/7) passes (one for Q <= 7). part_keys/part_cnt sized [Q][grid][k] / [Q][grid].
 int launch_gemv_topk(const void* cat, int64_t N, int64_t ldc, int D, int dtype, const void* q, int64_t ldq, int Q,
                      const uint8_t* mask, int k, uint64_t* part_keys, int* part_cnt, int grid, float* out_scores, int64_t* out_ids,
-                     int64_t id_offset, unsigned int* done_counter, cudaStream_t st, const float* cat_inv) {
+                     int64_t id_offset, unsigned int* done_counter, cudaStream_t st, const float* cat_inv, const PeerTail* peer, float* fin_scores,
+                     int64_t* fin_ids) {
   GemvArgs a{};
+  if (peer) {
+    a.peer_on = 1;
+    a.peer = *peer;
+    a.fin_scores = fin_scores;
+    a.fin_ids = fin_ids;
+  }
   a.cat_inv = cat_inv;
   a.cat = cat;
   a.N = N;

@@ -11,11 +11,14 @@
 // Keys are distinct 64-bit values (score bits, ~row), so ties in score are resolved exactly by row and the
 // refinement always terminates. The final phase sorts the k selected keys; earlier phases only need the set
 // and its minimum (the new threshold tau).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 #include "select_args.cuh"
 #include "select_warp.cuh"
 #define ICR_ST_OWNER 1  // this translation unit owns the trace counters of select_lean.cuh
+#include "peer.cuh"
 #include "select_lean.cuh"
 
 namespace icr {
@@ -961,6 +964,122 @@ __global__ void __launch_bounds__(kBsThreads) select_block_kernel(HistSelectArgs
   }
 }
 
+
+// ---- K4f: shard-candidate exchange and merge in ONE kernel ----------------------------------------------------------------
+// Every rank calls it with its own [Q][k] (score, global id) lists. The CTAs push them into slot `rank` of every peer's
+// buffer over NVLink (protocol and layout: exchange.cu), the last CTA to finish its part publishes the epoch to the peers, and
+// then EVERY CTA waits until the local buffer holds all ranks' lists of this epoch and merges its share of the queries from
+// it, one warp per query (the list path of the select above). One launch instead of push + merge, and no host round trip
+// between the two; every CTA waits, so the grid must be co-resident (sized from the occupancy, launched cooperatively).
+struct PeerMergeArgs {
+  const float* scores;  // this rank's candidates, [Q][k]
+  const int64_t* ids;
+  PeerTail peer;
+  HistSelectArgs sel;  // list_scores / list_ids = the local buffer's slot of this epoch, list_g = world
+};
+
+__global__ void __launch_bounds__(kHsWarps * 32, 24 / kHsWarps) peer_exchange_merge_kernel(const PeerMergeArgs m) {
+  extern __shared__ __align__(16) unsigned char hs_raw[];
+  LsSmem& sm = *reinterpret_cast<LsSmem*>(hs_raw);
+  __shared__ bool is_last;
+  const PeerTail& p = m.peer;
+  const HistSelectArgs& a = m.sel;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  peer_push(p, m.scores, m.ids, a.Q * a.list_k, static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x, static_cast<size_t>(gridDim.x) * blockDim.x);
+  __threadfence_system();
+  __syncthreads();
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(p.peer_base[p.rank] + kPeerTicketOff);
+  if (threadIdx.x == 0) is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (is_last) {
+    __threadfence_system();
+    peer_publish(p, threadIdx.x);
+    if (threadIdx.x == 0) *ticket = 0u;  // every CTA of this launch has taken its ticket
+  }
+  peer_wait(p, threadIdx.x);
+  __syncthreads();
+
+  uint32_t* sc = sm.sc[warp];
+  uint32_t* rw = sm.rw[warp];
+  uint32_t* hist = sm.hist[warp];
+  const int k = a.k, count = a.list_g * a.list_k;
+  const unsigned lt = (1u << lane) - 1u;
+  for (int64_t q = static_cast<int64_t>(blockIdx.x) * kHsWarps + warp; q < a.Q; q += static_cast<int64_t>(gridDim.x) * kHsWarps) {
+    int n = 0;
+    float tau;
+    for (int base = 0; base < count; base += 32 * 8) {
+      if (kLsCap - n < 32 * 8) {
+        __syncwarp();
+        n = min(ls_reduce(sc, rw, n, k, 0.f, hist, &tau), k);
+      }
+      uint64_t key[8];
+      bool ok[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) ok[u] = front_fetch(a, q, base + u * 32 + lane, count, key[u]);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const unsigned mk = __ballot_sync(kFull, ok[u]);
+        if (ok[u]) {
+          const int pos = n + __popc(mk & lt);
+          sc[pos] = static_cast<uint32_t>(key[u] >> 32);
+          rw[pos] = static_cast<uint32_t>(key[u]);
+        }
+        n += __popc(mk);
+      }
+    }
+    __syncwarp();
+    const int kept = min(ls_reduce(sc, rw, n, k, 0.f, hist, &tau), k);  // identical (score, id) pairs can leave more than k: any k of them
+    ls_emit_ranked(sc, rw, kept, k, 1.0f, q, a, hist, lane);
+    __syncwarp();
+  }
+}
+
+int launch_peer_exchange_merge(const float* scores, const int64_t* ids, int64_t Q, int k, const PeerTail& peer, float* os, int64_t* oi,
+                               cudaStream_t st) {
+  if (Q == 0) return ICR_OK;
+  static thread_local SmemAttrCache cache;  // per device
+  int rc = ensure_dyn_smem(cache, peer_exchange_merge_kernel, sizeof(LsSmem));
+  if (rc) return rc;
+  static thread_local int resident[64] = {};  // co-resident CTAs per device
+  int dev = 0;
+  ICR_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (resident[dev] == 0) {
+    int per_sm = 0, sms = 0;
+    ICR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, peer_exchange_merge_kernel, kHsWarps * 32, sizeof(LsSmem)));
+    ICR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    resident[dev] = per_sm * sms > 0 ? per_sm * sms : 1;
+  }
+  PeerMergeArgs m{};
+  m.scores = scores;
+  m.ids = ids;
+  m.peer = peer;
+  m.sel.k = k;
+  m.sel.Q = Q;
+  m.sel.out_scores = os;
+  m.sel.out_ids = oi;
+  m.sel.out_scale = 1.0f;
+  m.sel.list_scores = reinterpret_cast<const float*>(peer.peer_base[peer.rank] + peer.scores_off);
+  m.sel.list_ids = reinterpret_cast<const int64_t*>(peer.peer_base[peer.rank] + peer.ids_off);
+  m.sel.list_g = peer.world;
+  m.sel.list_k = k;
+  int64_t grid = (Q + kHsWarps - 1) / kHsWarps;
+  if (grid > resident[dev]) grid = resident[dev];
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  cfg.blockDim = dim3(kHsWarps * 32);
+  cfg.dynamicSmemBytes = sizeof(LsSmem);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  static const bool no_coop = getenv("ICR_NO_COOP") != nullptr;  // A/B switch (the grid is sized to be co-resident either way)
+  cfg.attrs = attr;
+  cfg.numAttrs = no_coop ? 0 : 1;
+  ICR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, peer_exchange_merge_kernel, m));
+  count_launch();
+  return ICR_OK;
+}
 
 // K4: merge of G shard lists of k_in (score, id) pairs per query, [G][Q][k_in] -> sorted top k_out per query
 int launch_merge_lists(const float* cs, const int64_t* ci, int64_t Q, int G, int k_in, int k_out, float* os, int64_t* oi,

@@ -367,26 +367,31 @@ class DeviceCatalog:
         cur.wait_stream(down)  # `down` waited on every piece of `rank`, which waited on every upload
         return vals_h, ids_h
 
-    def topk(self, queries, k: int, *, exclude_mask: torch.Tensor | None = None, path: int = ops.PATH_AUTO):
-        """(values [Q,k], global ids [Q,k]) of the k most cosine-similar rows per query."""
+    def topk(self, queries, k: int, *, exclude_mask: torch.Tensor | None = None, path: int = ops.PATH_AUTO, peer=None):
+        """(values [Q,k], global ids [Q,k]) of the k most cosine-similar rows per query. With ``peer``
+        (``PeerExchange.next_call()``; needs k <= len(self)) the rows are one rank's shard and the result is the global
+        top-k over all ranks' shards (``ops.cos_topk``)."""
         q = to_device_matrix(queries, device=self.device, dtype=self.dtype)
+        if peer is not None and int(k) > len(self):
+            raise ValueError("a sharded call needs k <= the shard's rows (pad the shard's own lists and use peer_exchange_merge instead)")
         k = min(int(k), len(self))
         if k < 1:
             return (torch.empty(q.shape[0], 0, device=self.device), torch.empty(q.shape[0], 0, dtype=torch.int64, device=self.device))
-        ws = self._resident_workspace(q.shape[0], k, path) if q.shape[0] <= 8 else None
+        ws = self._resident_workspace(q.shape[0], k, path, peer is not None) if q.shape[0] <= 8 else None
         return ops.cos_topk(q, self.rows, k, cat_planes=self.planes, cat_inv_norms=self.inv_norms, exclude_mask=exclude_mask,
-                            row_offset=self.row_offset, path=path, workspace=ws)
+                            row_offset=self.row_offset, path=path, workspace=ws, peer=peer)
 
-    def _resident_workspace(self, Q: int, k: int, path: int) -> torch.Tensor:
+    def _resident_workspace(self, Q: int, k: int, path: int, sharded: bool = False) -> torch.Tensor:
         """Request-sized calls keep one zero-initialised workspace per (shape, stream): the library then skips the memset of
         its merge counter (ICR_PATH_WS_RESIDENT), 2-3 µs of a ~30 µs request. Keyed by stream: calls on one stream are ordered."""
         if not hasattr(self, "_resident"):
             self._resident = {}
-        key = (Q, k, path, torch.cuda.current_stream(self.device).cuda_stream)
+        key = (Q, k, path, sharded, torch.cuda.current_stream(self.device).cuda_stream)
         ws = self._resident.get(key)
         if ws is None:
-            need = ops._lib.load().icr_cos_topk_workspace_bytes(Q, self.rows.shape[0], self.rows.shape[1], ops._dtype_code(self.rows), k, path,
-                                                                int(self.planes is not None))
+            lib = ops._lib.load()
+            ws_bytes = lib.icr_cos_topk_sharded_workspace_bytes if sharded else lib.icr_cos_topk_workspace_bytes
+            need = ws_bytes(Q, self.rows.shape[0], self.rows.shape[1], ops._dtype_code(self.rows), k, path, int(self.planes is not None))
             ws = torch.zeros(max(int(need), 256), dtype=torch.uint8, device=self.device)
             if len(self._resident) >= 64:  # many distinct request shapes: start over rather than grow without bound
                 self._resident.clear()

@@ -167,8 +167,13 @@ def cos_topk(
     path: int = PATH_AUTO,
     out: tuple[torch.Tensor, torch.Tensor] | None = None,
     workspace: torch.Tensor | None = None,
+    peer: tuple[int, int, int, int, int] | None = None,
 ):
-    """(values f32 [Q,k] descending, ids int64 [Q,k]) == torch.topk(cos_sim(q, c), k, dim=1)."""
+    """(values f32 [Q,k] descending, ids int64 [Q,k]) == torch.topk(cos_sim(q, c), k, dim=1).
+
+    ``peer`` = (rank, world, address of the uint64 buffer-pointer array, epoch, n_max) from ``PeerExchange.next_call()``:
+    `catalog` is this rank's row shard and the call also exchanges and merges the candidates of all ranks
+    (``icr_cos_topk_sharded``): the outputs are the GLOBAL top-k, identical on every rank. Collective: every rank calls."""
     _require_cuda("queries", queries)
     _require_cuda("catalog", catalog)
     if queries.dtype != catalog.dtype:
@@ -198,7 +203,8 @@ def cos_topk(
     else:
         vals, ids = out
     with _on(dev):
-        need = lib.icr_cos_topk_workspace_bytes(Q, N, D, dt, k, path, int(cat_planes is not None))
+        ws_bytes = lib.icr_cos_topk_workspace_bytes if peer is None else lib.icr_cos_topk_sharded_workspace_bytes
+        need = ws_bytes(Q, N, D, dt, k, path, int(cat_planes is not None))
         if workspace is not None:
             # resident workspace (zero-filled once by its owner, reused call after call on one stream): no merge-counter memset
             if workspace.numel() < need or workspace.dtype != torch.uint8 or workspace.device != dev:
@@ -206,6 +212,16 @@ def cos_topk(
             ws, path = workspace, path | PATH_WS_RESIDENT
         else:
             ws = _workspace(need, dev)
+        if peer is not None:
+            rank, world, ptrs, epoch, n_max = peer
+            _lib.check(
+                lib.icr_cos_topk_sharded(
+                    queries.data_ptr(), Q, _ld(queries), catalog.data_ptr(), N, _ld(catalog), D, dt, _ptr(cat_planes), _ptr(cat_inv_norms),
+                    _ptr(exclude_mask), k, row_offset, path, rank, world, ptrs, epoch, n_max, vals.data_ptr(), ids.data_ptr(),
+                    ws.data_ptr(), ws.numel(), _stream(dev),
+                )
+            )
+            return vals, ids
         _lib.check(
             lib.icr_cos_topk(
                 queries.data_ptr(), Q, _ld(queries), catalog.data_ptr(), N, _ld(catalog), D, dt, _ptr(cat_planes), _ptr(cat_inv_norms),
@@ -213,6 +229,26 @@ def cos_topk(
             )
         )
     return vals, ids
+
+
+def peer_exchange_merge(vals: torch.Tensor, ids: torch.Tensor, peer: tuple[int, int, int, int, int]):
+    """This rank's [Q,k] candidates (f32 scores, i64 global ids) -> the global top-k of every query on every rank, in ONE kernel
+    (``icr_peer_exchange_merge``: NVLink push, flags, wait, merge). ``peer`` as for ``cos_topk``. Collective."""
+    _require_cuda("vals", vals)
+    if vals.dtype != torch.float32 or ids.dtype != torch.int64 or vals.shape != ids.shape or vals.dim() != 2:
+        raise ValueError("candidates must be f32 scores and i64 ids of one [Q, k] shape")
+    vals, ids = vals.contiguous(), ids.contiguous()
+    Q, k = vals.shape
+    out_v, out_i = torch.empty_like(vals), torch.empty_like(ids)
+    rank, world, ptrs, epoch, n_max = peer
+    with _on(vals.device):
+        _lib.check(lib_call("icr_peer_exchange_merge")(vals.data_ptr(), ids.data_ptr(), Q, k, rank, world, ptrs, epoch, n_max,
+                                                       out_v.data_ptr(), out_i.data_ptr(), _stream(vals.device)))
+    return out_v, out_i
+
+
+def lib_call(name: str):
+    return getattr(_lib.load(), name)
 
 
 def cos_sim_dense(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:

@@ -16,7 +16,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib, ops
-from .index import DeviceCatalog
+from .index import DeviceCatalog, to_device_matrix
 
 
 def shard_bounds(n_rows: int, world_size: int, rank: int) -> tuple[int, int]:
@@ -79,6 +79,20 @@ class PeerExchange:
         if failed:
             raise RuntimeError(f"peer exchange call {failed} on rank {self.rank} timed out waiting for a peer (ICR_PEER_TIMEOUT_S): "
                                "a rank died or the ranks are not calling in lockstep; results since that call are invalid")
+
+    def next_call(self) -> tuple[int, int, int, int, int]:
+        """Counts one exchange call and returns its (rank, world, pointer-array address, epoch, n_max) for ``ops.cos_topk(peer=)`` /
+        ``ops.peer_exchange_merge``. Every rank must then make that call."""
+        import ctypes
+
+        self.epoch += 1
+        return (self.rank, self.world_size, ctypes.addressof(self._ptrs), self.epoch, self.n_max)
+
+    def exchange_merge(self, vals: torch.Tensor, ids: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+        """vals f32 [Q,k], ids i64 [Q,k] of this rank -> the global top-k per query on every rank, one kernel."""
+        if vals.numel() > self.n_max:
+            raise ValueError(f"peer exchange sized for {self.n_max} candidates per rank, got {vals.numel()}")
+        return ops.peer_exchange_merge(vals, ids, self.next_call())
 
     def all_gather(self, vals: torch.Tensor, ids: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
         """vals f32 [Q,k], ids i64 [Q,k] -> (scores [G,Q,k], ids [G,Q,k]): views of this rank's buffer, valid until the
@@ -199,18 +213,25 @@ class ShardedCatalog:
     def topk(self, queries, k: int):
         """Global (values [Q,k'], ids [Q,k']) on every rank, k' = min(k, total rows)."""
         k = min(int(k), self.total_rows)
+        if self.exchange == "peer" and self.world_size > 1 and self._local_topk is None and 1 <= k <= self.n_local:
+            # one library call: the shard's search with the exchange and the merge behind it - a single launch for request-sized
+            # batches (icr_cos_topk_sharded). Ranks whose shard is shorter than k take the route below; the protocols mix.
+            q = to_device_matrix(queries, device=self.device, dtype=self.local.dtype)
+            return self.local.topk(q, k, peer=self._peer_for(q.shape[0] * k).next_call())
         vals, ids = self.local_topk(queries, k)
         return self.exchange_merge(vals, ids, k)
+
+    def _peer_for(self, n: int) -> "PeerExchange":
+        if self._peer is None or self._peer.n_max < n:
+            self._peer = PeerExchange(self.group, self.device, max(n, 1 << 16))
+        return self._peer
 
     def exchange_merge(self, vals: torch.Tensor, ids: torch.Tensor, k: int):
         """The collective half of ``topk``: every rank's [Q,k] candidates -> the global top-k on every rank."""
         if self.world_size == 1:
             return vals, ids
         if self.exchange == "peer":
-            if self._peer is None or self._peer.n_max < vals.numel():
-                self._peer = PeerExchange(self.group, self.device, max(vals.numel(), 1 << 16))
-            scores, gids = self._peer.all_gather(vals, ids)
-            return ops.topk_merge(scores, gids, k)
+            return self._peer_for(vals.numel()).exchange_merge(vals, ids)
         mine = pack_candidates(vals, ids)
         # output concatenated along dim 0 (the layout every backend's all_gather_into_tensor accepts)
         gathered = torch.empty((self.world_size * mine.shape[0], *mine.shape[1:]), dtype=mine.dtype, device=mine.device)

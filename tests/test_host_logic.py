@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol(lib):
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.icr_abi_version() == _lib.ABI_VERSION == 2
+    assert lib.icr_abi_version() == _lib.ABI_VERSION == 3
     assert lib.icr_planes_row_elems(384) == 768 and lib.icr_planes_row_elems(100) == 256
     assert lib.icr_screen_plane_row_elems(384) == 384 and lib.icr_screen_plane_row_elems(100) == 128
 
