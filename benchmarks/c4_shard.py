@@ -17,7 +17,9 @@ for s in range(0, N, 1 << 18):
 cat = icr.DeviceCatalog(rows, dtype=torch.bfloat16)
 nbytes = N * D * 2
 peak = 6550.7
-for Q in (1, 2, 4, 16, 64, 128, 256, 512, 1024):
+import os  # noqa: E402
+
+for Q in [int(x) for x in os.environ.get("ICR_C4_QS", "1,2,4,16,64,128,256,512,1024").split(",")]:
     q = torch.nn.functional.normalize(torch.randn(Q, D, device=dev, generator=g), dim=1).to(torch.bfloat16)
     for _ in range(3):
         cat.topk(q, k)

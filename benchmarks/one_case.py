@@ -19,6 +19,10 @@ CASES = {
     "c1q4": (49_688, 384, 4, 10, torch.float32),
     "c4q16": (1_250_000, 768, 16, 100, torch.bfloat16),
     "c1q32": (49_688, 384, 32, 10, torch.float32),
+    "c1q32bf16": (49_688, 384, 32, 10, torch.bfloat16),
+    "c1q256": (49_688, 384, 256, 10, torch.float32),
+    "c4q128": (1_250_000, 768, 128, 100, torch.bfloat16),
+    "c4q256": (1_250_000, 768, 256, 100, torch.bfloat16),
 }
 
 if __name__ == "__main__":

@@ -11,7 +11,11 @@ import ctypes
 from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_uint32, c_void_p
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "lib" / "libicr_b200.so"
+import os
+
+# ICR_B200_LIB: a development build of the same sources (e.g. lib/libicr_b200_trace.so, built with -DICR_TRACE by
+# `python -m ...build --trace`); the default is the library build() produces
+LIB_PATH = Path(os.environ.get("ICR_B200_LIB") or Path(__file__).resolve().parent / "lib" / "libicr_b200.so")
 
 ICR_F32, ICR_BF16, ICR_F16 = 0, 1, 2
 PATH_AUTO, PATH_GEMV, PATH_GEMM = 0, 1, 2

@@ -35,6 +35,25 @@ def source_digest() -> str:
     return h.hexdigest()
 
 
+def build_trace() -> Path:
+    """Development build with the per-CTA %globaltimer stamps of the K1 ring kernel (benchmarks/k1_trace.py):
+    lib/libicr_b200_trace.so, selected at run time with ICR_B200_LIB. Never the product library."""
+    LIB_DIR.mkdir(exist_ok=True)
+    out = LIB_DIR / "libicr_b200_trace.so"
+    tdir = LIB_DIR / "trace_obj"
+    tdir.mkdir(exist_ok=True)
+    procs = []
+    for src in SOURCES:
+        cmd = [_nvcc(), *NVCC_FLAGS, "-DICR_TRACE", "-c", str(CSRC / src), "-o", str(tdir / (src + ".o"))]
+        procs.append(subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        o, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError("nvcc failed building the trace library:\n" + o)
+    subprocess.run([_nvcc(), "-shared", "-cudart", "static", "-o", str(out), *[str(tdir / (s + ".o")) for s in SOURCES]], check=True)
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
     """Compile every .cu of the package into lib/libicr_b200.so (skipped when up to date)."""
     LIB_DIR.mkdir(exist_ok=True)
@@ -66,4 +85,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
 
 if __name__ == "__main__":
+    if "--trace" in sys.argv:
+        print(build_trace())
+        sys.exit(0)
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -332,7 +332,7 @@ static int cos_topk_impl(const void* queries, int64_t Q, int64_t ldq, const void
   unsigned int* done_counter = reinterpret_cast<unsigned int*>(w);
   const size_t esz = elem_size(dtype);
   // the last CTA of every GEMV launch merges the per-CTA lists itself (no select launch on the latency path)
-  if (!ws_resident) ICR_CUDA_CHECK(cudaMemsetAsync(done_counter, 0, sizeof(unsigned int), st));
+  if (!ws_resident) ICR_CUDA_CHECK(cudaMemsetAsync(done_counter, 0, 2 * sizeof(unsigned int), st));  // ticket + slab-chunk counter
   if (peer)  // the merging CTA of the one GEMV launch also exchanges and merges (gemv_topk.cu peer_tail_merge)
     return launch_gemv_topk(catalog, N, ldc, static_cast<int>(D), dtype, queries, ldq, static_cast<int>(Q), exclude_mask, k, part_keys, part_cnt,
                             grid, stage_scores, stage_ids, row_offset, done_counter, st, cat_inv_norms, peer, out_scores, out_ids);

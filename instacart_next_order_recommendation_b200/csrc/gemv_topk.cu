@@ -16,6 +16,8 @@
 //
 // Replaces, for one request: torch.tensor(catalog) + F.normalize x2 + torch.mm + argsort
 // (reference src/inference/serve_recommendations.py:213-215 via sentence_transformers.util.cos_sim).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "peer.cuh"
 #include "ptx.cuh"
@@ -75,6 +77,14 @@ struct GemvArgs {
   int64_t* out_ids;            // [Q][k]
   int64_t id_offset;
   unsigned int* done_counter;  // zero before the first launch; the merging CTA resets it
+  // ring kernel: rows are handed out as slabs. Every CTA owns `static_slabs` slabs up front (its ring is in flight before
+  // the first atomic returns); the rest of the catalog is pulled in chunks of kProducers slabs from a device-wide counter
+  // (done_counter[1], same reset rule), so that no SM is still streaming while the others sit in the tail of the request
+  unsigned int* chunk_counter;
+  int static_slabs;
+#ifdef ICR_TRACE
+  int dbg;  // development builds: ICR_K1_DBG bit 0 = consumers skip the arithmetic, bit 1 = static row blocks only, bit 2 = 8-slot ring
+#endif
   // sharded request (peer_on): out_scores / out_ids are a staging area for this shard's lists; the merging CTA pushes them to
   // every peer, waits for theirs and writes the global top-k to fin_scores / fin_ids (one pass only: Q <= 7, q0 = 0)
   int peer_on;
@@ -256,6 +266,38 @@ __device__ __forceinline__ void refresh_thresholds(const GemvArgs& a, GemvSmem<Q
   compute_sync<NAMED>();
 }
 
+// Rank (0 = largest) of `mine` among the distinct keys[0..n) in shared memory, by counting. One function, not inlined, shared by
+// the threshold refresh, the list emit and the final merge of the single-query kernel: the tail of a request runs once per
+// launch, the merge on ONE CTA, and after another model's kernels have run in between its instructions come from DRAM
+// (~0.1 us per 128-byte line: 350 straight-line instructions of merge measured 5.5 us cold against 2 us warm). Code every CTA
+// has just executed is resident in the SM when the merge needs it.
+__device__ __noinline__ int cta_key_rank(const uint64_t* keys, int n, uint64_t mine) {
+  int rank = 0;
+#pragma unroll 4
+  for (int j = 0; j < n; ++j) rank += (keys[j] > mine) ? 1 : 0;
+  return rank;
+}
+
+// Single-query kernels: the whole CTA orders a list of <= 256 candidates (thread i ranks key i), instead of one warp doing
+// it while seven wait at the barrier (the first refresh, 64 keys after 64 rows, held the CTA for ~1 us).
+template <bool NAMED>
+__device__ __forceinline__ void refresh_single(const GemvArgs& a, GemvSmem<1>& sm, int block_rows, int tid, bool early) {
+  constexpr int CAND = GemvSmem<1>::CAND;
+  const int n = min(sm.ncand[0], CAND);
+  if (!(n > CAND - block_rows || (early && n >= 2 * a.k + 32))) return;  // uniform: ncand was read after a barrier
+  if (n > kGemvThreads) {
+    refresh_thresholds<1, NAMED>(a, sm, 1, false, block_rows, tid, early);
+    return;
+  }
+  const uint64_t mine = tid < n ? sm.cand[tid] : 0ull;
+  const int rank = tid < n ? cta_key_rank(sm.cand, n, mine) : n;
+  compute_sync<NAMED>();  // every thread has read the list
+  if (rank < a.k) sm.cand[rank] = mine;
+  if (rank == a.k - 1) sm.tau[0] = key_score(mine);
+  if (tid == 0) sm.ncand[0] = min(n, a.k);
+  compute_sync<NAMED>();
+}
+
 // Merge of the G per-CTA lists of query t by a group of GT threads (gtid = index in the group); LISTS * GT >= G.
 template <int QT, int GT, int LISTS, typename Sync>
 __device__ __forceinline__ void merge_query(const GemvArgs& a, GemvSmem<QT>& sm, int t, int gtid, Sync sync) {
@@ -382,6 +424,80 @@ __device__ __forceinline__ void merge_query(const GemvArgs& a, GemvSmem<QT>& sm,
   }
 }
 
+// "flat" tail of a single-query request with short lists (k <= 16, at most 256 CTAs and 8 keys per merging thread): every CTA
+// leaves its k best keys sorted and zero-padded to k, so the merging CTA fetches the whole [G][k] block and the G list heads
+// in ONE memory round trip of independent loads (the walk over list tails in dependent chunks was 2.7 us of a 24 us
+// request). A key can only be among the k best if it reaches `floor`, the largest over the 8 warps of the k-th largest of a
+// warp's 32 heads (ranked by counting over shuffles - a short loop, not a sorting network: this code starts from a cold
+// instruction cache): k distinct keys >= floor exist. What survives (typically 50-100 keys) is ranked by counting, which
+// yields the sorted output positions directly.
+constexpr int kFlatPer = 8;
+constexpr int kFlatSurv = 256;
+__device__ __forceinline__ bool flat_tail(const GemvArgs& a, int nq) {
+  return nq == 1 && a.k <= 16 && gridDim.x <= kGemvThreads && static_cast<int>(gridDim.x) * a.k <= kFlatPer * kGemvThreads &&
+         a.out_scores != nullptr;
+}
+
+// returns false when more keys than the buffer holds reach the floor (the caller then takes the general merge)
+template <int QT, typename Sync>
+__device__ __forceinline__ bool merge_query_flat(const GemvArgs& a, GemvSmem<QT>& sm, int tid, Sync sync) {
+  const int k = a.k, G = gridDim.x, tot = G * k, lane = tid & 31, warp = tid >> 5;
+  uint64_t* surv = sm.cand;  // [kFlatSurv]
+  uint64_t* warp_floor = reinterpret_cast<uint64_t*>(sm.list_cnt);  // [8]
+  int* counter = sm.list_cnt + 64;
+  const int64_t slot0 = static_cast<int64_t>(a.q0) * G;
+  const uint64_t* keys_g = a.part_keys + slot0 * k;
+  uint64_t key[kFlatPer];
+#pragma unroll
+  for (int j = 0; j < kFlatPer; ++j) {
+    const int e = tid + j * kGemvThreads;
+    key[j] = e < tot ? __ldcg(keys_g + e) : 0ull;
+  }
+  uint64_t head = tid < G ? __ldcg(keys_g + static_cast<int64_t>(tid) * k) : 0ull;
+  int head_rank = 0;  // among the warp's 32 heads; empty lists (0) tie and are ordered by lane, so the ranks are a permutation
+#pragma unroll 4
+  for (int i = 0; i < 32; ++i) {
+    const uint64_t o = __shfl_sync(kFull, head, i);
+    head_rank += (o > head || (o == head && i < lane)) ? 1 : 0;
+  }
+  if (head_rank == k - 1) warp_floor[warp] = head;  // 0 when the warp holds fewer than k non-empty lists
+  if (tid == 0) *counter = 0;
+  sync();
+  ICR_MSTAMP(1);
+  uint64_t floor_key = 0ull;
+#pragma unroll
+  for (int w = 0; w < kGemvWarps; ++w) floor_key = warp_floor[w] > floor_key ? warp_floor[w] : floor_key;
+#pragma unroll
+  for (int j = 0; j < kFlatPer; ++j) {
+    if (key[j] != 0ull && key[j] >= floor_key) {
+      const int pos = atomicAdd(counter, 1);
+      if (pos < kFlatSurv) surv[pos] = key[j];
+    }
+  }
+  sync();
+  ICR_MSTAMP(2);
+  const int n = *counter;
+  if (n > kFlatSurv) {
+    sync();  // everyone has read the counter before the general merge re-uses it
+    return false;
+  }
+  const int64_t qo = static_cast<int64_t>(a.q0) * k;
+  if (tid < n) {
+    const uint64_t mine = surv[tid];
+    const int rank = cta_key_rank(surv, n, mine);
+    if (rank < k) {
+      a.out_scores[qo + rank] = key_score(mine);
+      a.out_ids[qo + rank] = static_cast<int64_t>(key_row(mine)) + a.id_offset;
+    }
+  }
+  for (int i = n + tid; i < k; i += kGemvThreads) {  // fewer than k eligible rows in the whole catalog
+    a.out_scores[qo + i] = -INFINITY;
+    a.out_ids[qo + i] = -1;
+  }
+  ICR_MSTAMP(3);
+  return true;
+}
+
 // ---- sharded request: exchange + global merge in the tail of the merging CTA ------------------------------------------------
 // The shard's nq sorted lists (just written to out_scores / out_ids, global ids) go to slot `rank` of every peer's buffer
 // (exchange.cu: layout and protocol), the epoch is published, and once every rank's lists are in the local buffer the `world`
@@ -452,29 +568,56 @@ __device__ __forceinline__ void peer_tail_merge(const GemvArgs& a, GemvSmem<QT>&
 }
 
 // ---- emit this CTA's lists; the last CTA to finish merges all of them -----------------------------------
+// `pending`: the caller has not run the final threshold refresh (ring kernel): it happens here, and on a flat tail the whole
+// CTA ranks the (<= 256) candidates by counting and stores the k best straight into the global list - one warp ordering
+// ~50 keys alone took 1.4-1.9 us per CTA, on the critical path of the slowest one.
 template <int QT, bool NAMED>
-__device__ __forceinline__ void emit_and_merge(const GemvArgs& a, GemvSmem<QT>& sm, int nq, bool has_rows, int tid) {
+__device__ __forceinline__ void emit_and_merge(const GemvArgs& a, GemvSmem<QT>& sm, int nq, bool has_rows, int tid, bool pending = false) {
   const int lane = tid & 31, warp = tid >> 5;
   const int k = a.k, G = gridDim.x;
-  for (int t = 0; t < nq; ++t) {
-    const int n = has_rows ? sm.ncand[t] : 0;
-    const int64_t slot = static_cast<int64_t>(a.q0 + t) * G + blockIdx.x;
-    for (int i = tid; i < n; i += kGemvThreads) a.part_keys[slot * k + i] = sm.cand[t * GemvSmem<QT>::CAND + i];
-    if (tid == 0) a.part_cnt[slot] = n;
+  const bool flat = QT == 1 && flat_tail(a, nq);
+  bool emitted = false;
+  if (pending) {
+    const int n0 = min(sm.ncand[0], GemvSmem<QT>::CAND);
+    if (flat && n0 <= kGemvThreads) {
+      const uint64_t mine = tid < n0 ? sm.cand[tid] : 0ull;
+      const int rank = tid < n0 ? cta_key_rank(sm.cand, n0, mine) : n0;
+      const int64_t slot = static_cast<int64_t>(a.q0) * G + blockIdx.x;
+      const int kept = min(n0, k);
+      if (tid < n0 && rank < k) a.part_keys[slot * k + rank] = mine;
+      if (tid >= kept && tid < k) a.part_keys[slot * k + tid] = 0ull;
+      if (tid == 0) a.part_cnt[slot] = kept;
+      emitted = true;
+    } else {
+      refresh_thresholds<QT, NAMED>(a, sm, nq, true, 0, tid);
+    }
+  }
+  if (!emitted) {
+    for (int t = 0; t < nq; ++t) {
+      const int n = has_rows ? sm.ncand[t] : 0;
+      const int64_t slot = static_cast<int64_t>(a.q0 + t) * G + blockIdx.x;
+      for (int i = tid; i < n; i += kGemvThreads) a.part_keys[slot * k + i] = sm.cand[t * GemvSmem<QT>::CAND + i];
+      if (flat)  // the flat merge reads whole lists without their counts
+        for (int i = n + tid; i < k; i += kGemvThreads) a.part_keys[slot * k + i] = 0ull;
+      if (tid == 0) a.part_cnt[slot] = n;
+    }
   }
   if (a.out_scores == nullptr) return;  // the caller merges the per-CTA lists with a separate select launch
 
-  // the barrier orders the CTA's list writes before thread 0's fence, which publishes them device-wide (cumulativity)
+  // The barrier orders the CTA's list writes before thread 0's ticket, whose release (cumulative, device scope) publishes them;
+  // its acquire side orders the merging CTA's reads (after the second barrier) behind every earlier ticket. One acq_rel
+  // atomic instead of fence + atomic + fence: the two stand-alone fences were ~0.4 us each on the request's critical path.
+  ICR_STAMP(5);
   compute_sync<NAMED>();
   int* is_last = sm.list_cnt + 128;
   if (tid == 0) {
-    __threadfence();
-    *is_last = (atomicAdd(a.done_counter, 1u) == static_cast<unsigned int>(G) - 1u) ? 1 : 0;
+    unsigned int prev;
+    asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(prev) : "l"(a.done_counter) : "memory");
+    *is_last = (prev == static_cast<unsigned int>(G) - 1u) ? 1 : 0;
   }
   compute_sync<NAMED>();
   ICR_STAMP(6);
   if (!*is_last) return;
-  __threadfence();
   ICR_MSTAMP(0);
 
   // Every per-CTA list is sorted, so the k best list HEADS are k distinct keys >= head_floor (the k-th largest
@@ -483,7 +626,8 @@ __device__ __forceinline__ void emit_and_merge(const GemvArgs& a, GemvSmem<QT>& 
   // which also yields the sorted output positions directly. One query: the whole CTA works on it. Several
   // queries: one warp each, side by side.
   if (nq == 1) {
-    merge_query<QT, kGemvThreads, 2>(a, sm, 0, tid, [] { compute_sync<NAMED>(); });
+    if (!flat || !merge_query_flat<QT>(a, sm, tid, [] { compute_sync<NAMED>(); }))
+      merge_query<QT, kGemvThreads, 2>(a, sm, 0, tid, [] { compute_sync<NAMED>(); });
   } else if (nq <= 4) {  // two warps per query, each pair on its own named barrier
     const int t = warp >> 1;
     if (t < nq) merge_query<QT, 64, 5>(a, sm, t, tid & 63, [t] { ptx::named_sync(2 + t, 64); });
@@ -493,7 +637,10 @@ __device__ __forceinline__ void emit_and_merge(const GemvArgs& a, GemvSmem<QT>& 
   compute_sync<NAMED>();
   ICR_MSTAMP(4);
   if (a.peer_on) peer_tail_merge<QT, NAMED>(a, sm, nq, tid);
-  if (tid == 0) *a.done_counter = 0u;  // ready for the next launch that shares this workspace
+  if (tid == 0) {  // ready for the next launch that shares this workspace
+    *a.done_counter = 0u;
+    *a.chunk_counter = 0u;
+  }
 }
 
 // =====================================================================================================
@@ -572,19 +719,20 @@ __global__ void __launch_bounds__(kRingThreads, 1) gemv_ring_kernel(GemvArgs a) 
   unsigned char* ring = ring_smem_raw;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + static_cast<size_t>(NS) * slot_bytes);
   uint64_t* empty_bar = full_bar + kMaxSlots;
-  GemvSmem<QT> sm(reinterpret_cast<unsigned char*>(empty_bar + kMaxSlots), dpad);
+  int64_t* slot_row = reinterpret_cast<int64_t*>(empty_bar + kMaxSlots);  // first catalog row of the slab in a slot (producer -> consumer)
+  // precomputed inverse norms of the slab's rows, copied next to it (NORMS): a global load per slab from the consumer waited
+  // behind the whole ring's worth of queued catalog reads - 3.7 us of an 18 us stream on a cold 76 MB catalog
+  float* slot_inv = reinterpret_cast<float*>(slot_row + kMaxSlots);  // [kMaxSlots][8]
+  GemvSmem<QT> sm(reinterpret_cast<unsigned char*>(slot_inv + kMaxSlots * 8), dpad);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nq = min(QT, a.Q - a.q0);
-  const int64_t row_begin = static_cast<int64_t>(blockIdx.x) * a.rows_per_cta;
-  const int64_t row_end = min(a.N, row_begin + a.rows_per_cta);
-  const int nb = row_begin < row_end ? static_cast<int>((row_end - row_begin + kSlabRows - 1) / kSlabRows) : 0;
+  constexpr int kProducers = 4;
+  const int64_t total_slabs = (a.N + kSlabRows - 1) / kSlabRows;
 
   ICR_STAMP(0);
-  if (tid == 0) {
-    for (int s = 0; s < NS; ++s) {
-      ptx::mbar_init(ptx::smem_u32(&full_bar[s]), 1);
-      ptx::mbar_init(ptx::smem_u32(&empty_bar[s]), 1);
-    }
+  if (tid < NS) {
+    ptx::mbar_init(ptx::smem_u32(&full_bar[tid]), 1);
+    ptx::mbar_init(ptx::smem_u32(&empty_bar[tid]), 1);
     ptx::mbar_fence_init();
   }
   __syncthreads();  // the only CTA-wide barrier: the producer warp never joins another one
@@ -592,23 +740,59 @@ __global__ void __launch_bounds__(kRingThreads, 1) gemv_ring_kernel(GemvArgs a) 
 
   if (warp == kGemvWarps) {
     // ================= producer: the whole ring is in flight before the first FMA =================
-    // kProducers lanes issue the copies, lane j those of slabs j, j + kProducers, ...: with 768-byte rows a slab is
+    // kProducers lanes issue the copies, lane j those of local slabs j, j + kProducers, ...: with 768-byte rows a slab is
     // 6 KB and one lane's wait / expect / copy loop (~450 cycles per slab) was what held the stream at 58 % of the
-    // HBM rate. NS is a multiple of 8, so the lanes own disjoint slot sets (slot = slab % NS) and every slot still
+    // HBM rate. NS is a multiple of 8, so the lanes own disjoint slot sets (slot = local slab % NS) and every slot still
     // has exactly one producer and one consumer; slot and parity advance incrementally (no division per slab).
-    constexpr int kProducers = 4;
+    //
+    // Which catalog slab a local slab is: the first static_slabs are the CTA's own block, after that each step of the four
+    // lanes takes one chunk of kProducers consecutive slabs from the device-wide counter (the first dynamic chunk is the
+    // CTA's index, so nothing waits for an atomic before the ring is full; lane 0 fetches the NEXT chunk before it blocks
+    // on the ring). The row of a slot travels in slot_row[]; -1 = nothing in this slot, -2 = end of the stream. The end
+    // markers fill one whole iteration of the eight consumer warps, so all of them leave the loop in the same iteration.
     if (lane < kProducers) {
-      const char* src = static_cast<const char*>(a.cat) + row_begin * row_bytes + static_cast<int64_t>(lane) * slot_bytes;
-      const uint32_t last_bytes = static_cast<uint32_t>(row_end - row_begin - static_cast<int64_t>(nb - 1) * kSlabRows) * row_bytes;
+      const unsigned int G = gridDim.x;
+      const int static_steps = a.static_slabs / kProducers;
+      const int64_t dyn_base = static_cast<int64_t>(G) * a.static_slabs;
+      const char* cat = static_cast<const char*>(a.cat);
       int slot = lane;  // lane < kProducers <= NS
       uint32_t parity = 0;
-      for (int b = lane; b < nb; b += kProducers) {
+      unsigned int nx = blockIdx.x;
+      int tail = -1;  // >= 0: padding / end steps still to emit
+      for (int step = 0;; ++step) {
+        int64_t slab = -1;
+        if (tail < 0) {
+          int64_t first;
+          if (step < static_steps) {
+            first = static_cast<int64_t>(blockIdx.x) * a.static_slabs + static_cast<int64_t>(step) * kProducers;
+          } else {
+            const unsigned int cur = __shfl_sync(0xFu, nx, 0);
+            first = dyn_base + static_cast<int64_t>(cur) * kProducers;
+            if (lane == 0 && first < total_slabs) nx = G + atomicAdd(a.chunk_counter, 1u);
+          }
+          if (first >= total_slabs) tail = (step & 1) ? 3 : 2;  // odd: a step of empty slots completes the iteration first
+          else if (first + lane < total_slabs) slab = first + lane;
+        }
+        if (tail >= 0) {
+          if (tail == 0) break;
+          slab = (tail == 3) ? -1 : -2;
+          --tail;
+        }
         ptx::mbar_wait(ptx::smem_u32(&empty_bar[slot]), parity ^ 1u);
-        const uint32_t bytes = (b == nb - 1) ? last_bytes : static_cast<uint32_t>(slot_bytes);
         const uint32_t fb = ptx::smem_u32(&full_bar[slot]);
-        ptx::mbar_expect_tx(fb, bytes);
-        ptx::bulk_g2s(ptx::smem_u32(ring + static_cast<size_t>(slot) * slot_bytes), src, bytes, fb);
-        src += static_cast<int64_t>(kProducers) * slot_bytes;
+        if (slab >= 0) {
+          const int64_t row0 = slab * kSlabRows;
+          const int64_t rows = a.N - row0 < kSlabRows ? a.N - row0 : kSlabRows;
+          const uint32_t bytes = static_cast<uint32_t>(rows) * static_cast<uint32_t>(row_bytes);
+          *reinterpret_cast<volatile int64_t*>(&slot_row[slot]) = row0;
+          const bool inv_too = NORMS && rows == kSlabRows;  // whole slabs only (16-byte granules); the last one loads them itself
+          ptx::mbar_expect_tx(fb, bytes + (inv_too ? kSlabRows * 4u : 0u));
+          ptx::bulk_g2s(ptx::smem_u32(ring + static_cast<size_t>(slot) * slot_bytes), cat + row0 * row_bytes, bytes, fb);
+          if (inv_too) ptx::bulk_g2s(ptx::smem_u32(slot_inv + slot * 8), a.cat_inv + row0, kSlabRows * 4u, fb);
+        } else {
+          *reinterpret_cast<volatile int64_t*>(&slot_row[slot]) = slab;
+          ptx::mbar_arrive(fb);  // release: the marker is visible to the consumer that acquires this phase
+        }
         slot += kProducers;
         if (slot >= NS) {
           slot -= NS;
@@ -628,89 +812,87 @@ __global__ void __launch_bounds__(kRingThreads, 1) gemv_ring_kernel(GemvArgs a) 
   compute_sync<true>();
   ICR_STAMP(2);
 
-  const int iters = (nb + kGemvWarps - 1) / kGemvWarps;
   constexpr int kItersPerRefresh = 4;
   constexpr int kBlockRows = kItersPerRefresh * kGemvWarps * kSlabRows;
-  int slot = warp;  // slab b = it * 8 + warp lives in slot b % NS; NS is a multiple of 8: advance by 8, wrap, flip the parity
+  int slot = warp;  // local slab b = it * 8 + warp lives in slot b % NS; NS is a multiple of 8: advance by 8, wrap, flip the parity
   uint32_t parity = 0;
-  for (int it = 0; it < iters; ++it) {
-    const int b = it * kGemvWarps + warp;
-    if (b < nb) {
-      ptx::mbar_wait(ptx::smem_u32(&full_bar[slot]), parity);
-      if (it == 0) ICR_STAMP(3);
+  for (int it = 0;; ++it) {
+    ptx::mbar_wait(ptx::smem_u32(&full_bar[slot]), parity);
+    if (it == 0) ICR_STAMP(3);
+    const int64_t r0 = *reinterpret_cast<volatile int64_t*>(&slot_row[slot]);
+#ifdef ICR_TRACE
+    if (r0 >= 0 && !(a.dbg & 1)) {
+#else
+    if (r0 >= 0) {
+#endif
       const unsigned char* slab = ring + static_cast<size_t>(slot) * slot_bytes;
-      const int64_t r0 = row_begin + static_cast<int64_t>(b) * kSlabRows;
-      {
-        constexpr int g = 0;
-        float acc[V];
+      constexpr int g = 0;
+      float acc[V];
 #pragma unroll
-        for (int i = 0; i < V; ++i) acc[i] = 0.f;
-        float inv_lane = 0.f;  // issued before the FMAs: one 32-byte load per slab, its latency hides behind them
-        if (NORMS && lane < RB && r0 + lane < row_end) inv_lane = __ldg(a.cat_inv + r0 + lane);
-        const int nfull = nvec & ~31;  // vectors covered by iterations in which every lane has one
-        for (int v = lane; v < nfull; v += 32) {
-          uint4 c[RB];
+      for (int i = 0; i < V; ++i) acc[i] = 0.f;
+      float inv_lane = 0.f;
+      if (NORMS && lane < RB && r0 + lane < a.N) inv_lane = (r0 + RB <= a.N) ? slot_inv[slot * 8 + lane] : __ldg(a.cat_inv + r0 + lane);
+      const int nfull = nvec & ~31;  // vectors covered by iterations in which every lane has one
+      for (int v = lane; v < nfull; v += 32) {
+        uint4 c[RB];
 #pragma unroll
-          for (int r = 0; r < RB; ++r) {
-            // rows past the end of the catalog were not copied: stale ring bytes, masked by row_limit below
-            c[r] = *reinterpret_cast<const uint4*>(slab + static_cast<size_t>(g * RB + r) * row_bytes + static_cast<size_t>(v) * 16);
+        for (int r = 0; r < RB; ++r) {
+          // rows past the end of the catalog were not copied: stale ring bytes, masked by row_limit below
+          c[r] = *reinterpret_cast<const uint4*>(slab + static_cast<size_t>(g * RB + r) * row_bytes + static_cast<size_t>(v) * 16);
+        }
+        fma_vector<T, RB, QT, NORMS>(c, sm.qs, dpad, v, acc);
+      }
+      if (nvec - nfull == 16) {
+        // Half-filled last iteration (768-byte and 256-byte bf16 rows, ...): instead of idling 16 lanes, the two
+        // half-warps split the ROWS of the tail — lanes 0-15 take rows 0,2,4,.., lanes 16-31 rows 1,3,5,.. — and
+        // the partial sums are folded into the full-width accumulators with predicated adds (static indices).
+        constexpr int HB = RB / 2;
+        constexpr int VT = QT + (NORMS ? 0 : 1);
+        const int h = lane >> 4, v = nfull + (lane & 15);
+        uint4 c[HB];
+#pragma unroll
+        for (int i = 0; i < HB; ++i)
+          c[i] = *reinterpret_cast<const uint4*>(slab + static_cast<size_t>(g * RB + 2 * i + h) * row_bytes + static_cast<size_t>(v) * 16);
+        float tacc[HB * VT];
+#pragma unroll
+        for (int i = 0; i < HB * VT; ++i) tacc[i] = 0.f;
+        fma_vector<T, HB, QT, NORMS>(c, sm.qs, dpad, v, tacc);
+#pragma unroll
+        for (int t = 0; t < VT; ++t)
+#pragma unroll
+          for (int i = 0; i < HB; ++i) {
+            acc[t * RB + 2 * i] += h == 0 ? tacc[t * HB + i] : 0.f;
+            acc[t * RB + 2 * i + 1] += h == 1 ? tacc[t * HB + i] : 0.f;
           }
-          fma_vector<T, RB, QT, NORMS>(c, sm.qs, dpad, v, acc);
-        }
-        if (nvec - nfull == 16) {
-          // Half-filled last iteration (768-byte and 256-byte bf16 rows, ...): instead of idling 16 lanes, the two
-          // half-warps split the ROWS of the tail — lanes 0-15 take rows 0,2,4,.., lanes 16-31 rows 1,3,5,.. — and
-          // the partial sums are folded into the full-width accumulators with predicated adds (static indices).
-          constexpr int HB = RB / 2;
-          constexpr int VT = QT + (NORMS ? 0 : 1);
-          const int h = lane >> 4, v = nfull + (lane & 15);
-          uint4 c[HB];
+      } else if (lane < nvec - nfull) {
+        const int v = nfull + lane;
+        uint4 c[RB];
 #pragma unroll
-          for (int i = 0; i < HB; ++i)
-            c[i] = *reinterpret_cast<const uint4*>(slab + static_cast<size_t>(g * RB + 2 * i + h) * row_bytes + static_cast<size_t>(v) * 16);
-          float tacc[HB * VT];
-#pragma unroll
-          for (int i = 0; i < HB * VT; ++i) tacc[i] = 0.f;
-          fma_vector<T, HB, QT, NORMS>(c, sm.qs, dpad, v, tacc);
-#pragma unroll
-          for (int t = 0; t < VT; ++t)
-#pragma unroll
-            for (int i = 0; i < HB; ++i) {
-              acc[t * RB + 2 * i] += h == 0 ? tacc[t * HB + i] : 0.f;
-              acc[t * RB + 2 * i + 1] += h == 1 ? tacc[t * HB + i] : 0.f;
-            }
-        } else if (lane < nvec - nfull) {
-          const int v = nfull + lane;
-          uint4 c[RB];
-#pragma unroll
-          for (int r = 0; r < RB; ++r)
-            c[r] = *reinterpret_cast<const uint4*>(slab + static_cast<size_t>(g * RB + r) * row_bytes + static_cast<size_t>(v) * 16);
-          fma_vector<T, RB, QT, NORMS>(c, sm.qs, dpad, v, acc);
-        }
-        reduce_and_append<RB, QT, NORMS>(acc, a, sm, nq, r0 + g * RB, row_end, lane, inv_lane);
+        for (int r = 0; r < RB; ++r)
+          c[r] = *reinterpret_cast<const uint4*>(slab + static_cast<size_t>(g * RB + r) * row_bytes + static_cast<size_t>(v) * 16);
+        fma_vector<T, RB, QT, NORMS>(c, sm.qs, dpad, v, acc);
       }
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&empty_bar[slot]));
-      slot += kGemvWarps;
-      if (slot >= NS) {
-        slot -= NS;
-        parity ^= 1u;
-      }
+      reduce_and_append<RB, QT, NORMS>(acc, a, sm, nq, r0 + g * RB, a.N, lane, inv_lane);
     }
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&empty_bar[slot]));
+    slot += kGemvWarps;
+    if (slot >= NS) {
+      slot -= NS;
+      parity ^= 1u;
+    }
+    if (r0 == -2) break;  // the end markers fill one whole iteration: every warp leaves here together
     // early thresholds (as soon as a list holds 2k + 32 keys) keep the final list short: the selection at the end
     // of the stream is on the critical path of a request, the ones in the middle hide behind the ring
-    if ((it + 1) % kItersPerRefresh == 0 || it + 1 == iters || it == 0) {
+    if ((it + 1) % kItersPerRefresh == 0 || it == 0) {
       compute_sync<true>();
-      if (it + 1 == iters) ICR_STAMP(4);
-      refresh_thresholds<QT, true>(a, sm, nq, it + 1 == iters, kBlockRows, tid, true);
+      if constexpr (QT == 1) refresh_single<true>(a, sm, kBlockRows, tid, true);
+      else refresh_thresholds<QT, true>(a, sm, nq, false, kBlockRows, tid, true);
     }
   }
-  if (iters == 0) {
-    compute_sync<true>();
-    refresh_thresholds<QT, true>(a, sm, nq, true, kBlockRows, tid);
-  }
-  ICR_STAMP(5);
-  emit_and_merge<QT, true>(a, sm, nq, row_begin < row_end, tid);
+  compute_sync<true>();
+  ICR_STAMP(4);
+  emit_and_merge<QT, true>(a, sm, nq, true, tid, true);
   ICR_STAMP(7);
 }
 
@@ -734,7 +916,7 @@ static int launch_direct(const GemvArgs& a, int grid, cudaStream_t st) {
 
 template <typename T, int QT>
 static int ring_slots_for(int D) {
-  const size_t fixed = GemvSmem<QT>::bytes(D) + 2 * kMaxSlots * sizeof(uint64_t) + 128;
+  const size_t fixed = GemvSmem<QT>::bytes(D) + 3 * kMaxSlots * sizeof(uint64_t) + kMaxSlots * 8 * sizeof(float) + 128;
   const size_t slot = static_cast<size_t>(QT == 7 ? 4 : 8) * D * sizeof(T);
   if (fixed + kGemvWarps * slot > kSmemBudget) return 0;
   const size_t n = (kSmemBudget - fixed) / slot;
@@ -752,7 +934,18 @@ static int ring_slots_for(int D) {
 template <typename T, int QT, bool NORMS = false>
 static int launch_ring(GemvArgs a, int grid, cudaStream_t st) {
   a.ring_slots = ring_slots_for<T, QT>(a.D);
-  const size_t smem = static_cast<size_t>(a.ring_slots) * (QT == 7 ? 4 : 8) * a.D * sizeof(T) + 2 * kMaxSlots * sizeof(uint64_t) + GemvSmem<QT>::bytes(a.D) + 128;
+  {
+    // up-front share of every CTA: one ring filling, or less when the catalog is too small for that (whole chunks only)
+    const int64_t total_slabs = (a.N + (QT == 7 ? 4 : 8) - 1) / (QT == 7 ? 4 : 8);
+    const int64_t share = total_slabs / grid / 4 * 4;
+    a.static_slabs = static_cast<int>(share < a.ring_slots ? share : a.ring_slots);
+#ifdef ICR_TRACE
+    a.dbg = getenv("ICR_K1_DBG") ? atoi(getenv("ICR_K1_DBG")) : 0;
+    if (a.dbg & 4) a.ring_slots = 8;
+    if (a.dbg & 2) a.static_slabs = static_cast<int>((total_slabs + grid - 1) / grid + 3) / 4 * 4;
+#endif
+  }
+  const size_t smem = static_cast<size_t>(a.ring_slots) * (QT == 7 ? 4 : 8) * a.D * sizeof(T) + 3 * kMaxSlots * sizeof(uint64_t) + kMaxSlots * 8 * sizeof(float) + GemvSmem<QT>::bytes(a.D) + 128;
   static thread_local SmemSizeCache configured;  // per device
   {
     const int rc = ensure_dyn_smem_size(configured, gemv_ring_kernel<T, QT, NORMS>, smem);
@@ -810,7 +1003,9 @@ int launch_gemv_topk(const void* cat, int64_t N, int64_t ldc, int D, int dtype, 
     a.fin_scores = fin_scores;
     a.fin_ids = fin_ids;
   }
-  a.cat_inv = cat_inv;
+  // the ring kernel copies the inverse norms with 16-byte bulk copies; an unaligned array falls back to norms from the rows
+  a.cat_inv = (reinterpret_cast<uintptr_t>(cat_inv) & 15) == 0 ? cat_inv : nullptr;
+  cat_inv = a.cat_inv;
   a.cat = cat;
   a.N = N;
   a.ldc = ldc;
@@ -826,6 +1021,7 @@ int launch_gemv_topk(const void* cat, int64_t N, int64_t ldc, int D, int dtype, 
   a.out_ids = out_ids;
   a.id_offset = id_offset;
   a.done_counter = done_counter;
+  a.chunk_counter = done_counter + 1;
   for (int q0 = 0; q0 < Q;) {
     a.q0 = q0;
     const int rem = Q - q0;

@@ -283,12 +283,56 @@ class DeviceCatalog:
             return self.topk(q, max(k, 1))
         if q.shape[1] != self.input_dim:
             raise ValueError(f"embedding dims differ: query {q.shape[1]} vs catalog {self.input_dim}")
+        if q.is_cuda and q.dtype == self.dtype and q.device == self.device and q.shape[1] == self.rows.shape[1] and q.is_contiguous() \
+                and q.data_ptr() % 16 == 0 and q.shape[0] <= 7:
+            # a device-resident query in the catalog's own layout (what encode(convert_to_tensor=True) hands over): the kernel
+            # reads it where it lies - no copy into a graph's input buffer, one kernel launch through a prepared argument list
+            with self.request_lock:
+                vals, ids = self._prepared_call(q, k, path)
+                return (vals.clone(), ids.clone()) if copy else (vals, ids)
         with self.request_lock:
             graph, static_q, vals, ids, _ = self._graph_for(q.shape[0], k, path)
             D = q.shape[1]  # columns beyond the catalog's own dim are the zero padding of _rows(); they stay zero
             static_q[:, :D].copy_(q, non_blocking=True)  # H2D (or D2D) + dtype conversion in one op
             graph.replay()
             return (vals.clone(), ids.clone()) if copy else (vals, ids)
+
+    def _prepared_call(self, q: torch.Tensor, k: int, path: int):
+        """icr_cos_topk for a request-sized device query with everything but the query pointer bound once per
+        (Q, k, path, stream): static outputs, a resident zero-filled workspace, ready-made ctypes arguments. The Python
+        side of a request is then ~5 us (ops.cos_topk: ~40 us of checks, allocations and argument conversion) and the
+        device side is the one GEMV kernel."""
+        Q = q.shape[0]
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        key = (Q, k, path, stream)
+        plans = self.__dict__.setdefault("_plans", {})
+        plan = plans.get(key)
+        if plan is None:
+            import ctypes
+
+            lib = ops._lib.load()
+            N, D = self.rows.shape
+            dt = ops._dtype_code(self.rows)
+            need = lib.icr_cos_topk_workspace_bytes(Q, N, D, dt, k, path, int(self.planes is not None))
+            ws = torch.zeros(max(int(need), 256), dtype=torch.uint8, device=self.device)
+            vals = torch.empty(Q, k, dtype=torch.float32, device=self.device)
+            ids = torch.empty(Q, k, dtype=torch.int64, device=self.device)
+            c64, cvp = ctypes.c_int64, ctypes.c_void_p
+            args = [None, c64(Q), c64(D), cvp(self.rows.data_ptr()), c64(N), c64(ops._ld(self.rows)), c64(D), ctypes.c_int(dt),
+                    cvp(ops._ptr(self.planes)), cvp(ops._ptr(self.inv_norms)), cvp(None), ctypes.c_int(k), c64(self.row_offset),
+                    ctypes.c_int(path | ops.PATH_WS_RESIDENT), cvp(vals.data_ptr()), cvp(ids.data_ptr()), cvp(ws.data_ptr()),
+                    ctypes.c_size_t(ws.numel()), cvp(stream)]
+            if len(plans) >= 64:
+                plans.clear()
+            plan = plans[key] = (lib.icr_cos_topk, args, vals, ids, ws)
+        fn, args, vals, ids, _ = plan
+        args[0] = q.data_ptr()
+        if self.device.index is not None and self.device.index != torch.cuda.current_device():
+            with torch.cuda.device(self.device):
+                ops._lib.check(fn(*args))
+        else:
+            ops._lib.check(fn(*args))
+        return vals, ids
 
     def topk_host(self, queries: torch.Tensor, k: int, *, out: tuple[torch.Tensor, torch.Tensor] | None = None,
                   n_chunks: int | None = None, path: int = ops.PATH_AUTO, splits: list[int] | None = None):

@@ -792,6 +792,30 @@ def test_topk_small_cuda_graph_equals_plain_call():
         assert len(cat._graphs) == 2
 
 
+def test_topk_small_device_query_takes_the_prepared_call_and_matches_the_oracle():
+    """A device-resident query in the catalog's layout is scored where it lies (no graph, no copy): one launch through the
+    prepared argument list; repeated requests re-use the resident workspace (ticket and slab counters left at zero)."""
+    items, _ = oracle.synth_clustered(49_688, 384, seed=41)
+    queries, _ = oracle.synth_queries_from_items(items, 12, seed=42)
+    for dtype, tol in ((torch.float32, F32_RTOL), (torch.bfloat16, BF16_RTOL)):
+        cat = icr.DeviceCatalog(items, dtype=dtype)
+        ref_items = cat.rows.float().cpu()
+        for qn, k in ((1, 10), (1, 16), (1, 100), (2, 10), (7, 16)):
+            for rep in range(3):
+                q = queries[rep : rep + qn].to(dtype).cuda()
+                v, i = cat.topk_small(q, k)
+                if dtype == torch.float32 or qn <= 3:  # GEMV path: the whole request is one kernel
+                    assert ops.last_launch_count() == 1
+                rv, ri = oracle.cos_topk(q.float().cpu(), ref_items, k)
+                _check_topk(v, i, rv, ri, tol)
+        assert len(cat._plans) == 5 and not getattr(cat, "_graphs", {})
+        # a query in another dtype or on the host still goes through the graph path
+        v, i = cat.topk_small(queries[:1].numpy(), 10)
+        rv, ri = oracle.cos_topk(queries[:1].to(dtype).float(), ref_items, 10)
+        _check_topk(v, i, rv, ri, tol)
+        assert len(cat._graphs) == 1
+
+
 def test_topk_host_pipeline_equals_device_path():
     items, _ = oracle.synth_clustered(30000, 384, seed=21)
     queries, _ = oracle.synth_queries_from_items(items, 3001, seed=22)
