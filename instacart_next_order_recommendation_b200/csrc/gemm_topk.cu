@@ -33,6 +33,7 @@
 
 #include "select_args.cuh"
 #include "select_lean.cuh"
+#include "select_finish.cuh"
 #include "tc.cuh"  // BM, BN, BK, tile geometry, PTX wrappers, tensor maps
 
 namespace icr {
@@ -89,7 +90,8 @@ struct GemmArgs {
   // swapped kernel, single-launch mode: the thresholds are bootstrapped inside the kernel (see gemm_swap_kernel)
   int boot;                  // 0 = off, else the number of bootstrap tiles per chunk (its first tiles, streamed twice)
   float* gmax;               // [qpad][4 * gridDim.x] group maxima of the bootstrap tiles
-  unsigned int* gsync;       // [2] grid-barrier counters, zero before the launch
+  unsigned int* gsync;       // [3] grid-barrier counters, zero before the launch
+  int fuse_select;           // swapped kernel, single-launch mode: the select runs in the kernel's tail (swap_select_tail)
   float band;                // screened scores (MODE 2): tau already sits `band` below the k-th best; 0 = exact scores
   unsigned int* overflow;    // [Q] screened scores: set when a segment cannot be cut back without losing keys of the band
 };
@@ -707,9 +709,183 @@ __device__ __forceinline__ void swap_grid_barrier(unsigned int* counter, unsigne
   epi_sync();
 }
 
+// ---- single-launch mode, last step: the select runs in the tail of the GEMM kernel ----------------------------------------
+// After a third grid barrier every query's survivors are complete, and CTA b finishes queries b, b + gridDim.x, ... with its
+// four epilogue warps: the lengths of the query's 2 * chunks segments (one per CTA: many segments, a handful of keys) are
+// prefix-summed, the keys gathered by flat index (every thread finds its keys' segments by binary search: all loads of a
+// round independent), ranked by counting - which orders them - and cut at the k-th key (minus the screening band); screened
+// keys are re-scored exactly (8 rows per warp and batch, every load of a batch in flight at once), ranked again and written
+// out. What select_block_kernel and its launch did in 13-23 us beside a 29 us GEMM on the 49,688-row catalog.
+//
+// The code is deliberately SMALL: it runs once per launch on a few CTAs, so its instructions come from L2 or DRAM, ~0.1 us
+// per 128-byte line - a first version that called the histogram selection (ls_reduce, ~4,000 instructions) per query was
+// slower than the separate select launch. The host only asks for the tail when the expected number of survivors per query is
+// far below its buffer; a query that exceeds it anyway (or whose screening band overflows) takes the general routines on
+// warp 0 - slow, exact.
+constexpr int kTailSegs = 160;   // 2 * chunks <= 160 segments per query (5 per lane of warp 0)
+constexpr int kTailCap = 1024;   // keys of one query ranked in shared memory (two 8 KB arrays in the idle operand ring)
+
+// rank (0 = largest) of `mine` among the distinct keys[0..n): one small loop shared by both rankings of the tail
+__device__ __noinline__ int tail_rank(const uint64_t* keys, int n, uint64_t mine) {
+  int rank = 0;
+#pragma unroll 4
+  for (int j = 0; j < n; ++j) rank += (keys[j] > mine) ? 1 : 0;
+  return rank;
+}
+
+// dst[rank of src[i]] = src[i] for all i < n, by the 128 epilogue threads (n <= kTailCap)
+__device__ __forceinline__ void tail_order(const uint64_t* src, uint64_t* dst, int n, int et) {
+  for (int i = et; i < n; i += 128) {
+    const uint64_t key = src[i];
+    dst[tail_rank(src, n, key)] = key;
+  }
+  epi_sync();
+}
+
+__device__ __noinline__ void swap_select_tail(unsigned int* gsync, const HistSelectArgs& a, unsigned char* ring, int ew, int lane, int et) {
+  swap_grid_barrier(gsync, gridDim.x, et);
+  uint64_t* kin = reinterpret_cast<uint64_t*>(ring);               // [kTailCap] gathered keys
+  uint64_t* kso = kin + kTailCap;                                   // [kTailCap] the same in descending order
+  int* start = reinterpret_cast<int*>(kso + kTailCap);              // [kTailSegs + 1] first flat index of each segment
+  uint32_t* sc = reinterpret_cast<uint32_t*>(start + kTailSegs + 8);  // general routines (warp 0 only): [kLsCap] x 2 + histogram
+  uint32_t* rw = sc + kLsCap;
+  uint32_t* hist = rw + kLsCap;
+  const int k = a.k, nseg = a.nseg;
+  const bool screened = a.band > 0.f;
+  const int kc = screened ? a.kc : k;
+  const int cap = min(a.seg_cap, a.seg_stride);
+  for (int64_t q = blockIdx.x; q < a.Q; q += gridDim.x) {
+    const uint64_t* qbase = a.seg_keys + q * nseg * static_cast<int64_t>(a.seg_stride);
+    if (ew == 0) {
+      int c[5];
+      int mine = 0;
+#pragma unroll
+      for (int u = 0; u < 5; ++u) {
+        const int sg = lane * 5 + u;
+        c[u] = sg < nseg ? min(__ldcg(a.seg_cnt + q * nseg + sg), cap) : 0;
+        mine += c[u];
+      }
+      int incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += v;
+      }
+      int run = incl - mine;
+#pragma unroll
+      for (int u = 0; u < 5; ++u) {
+        start[lane * 5 + u] = run;
+        run += c[u];
+      }
+      if (lane == 31) start[kTailSegs] = run;
+    }
+    epi_sync();
+    const int total = start[kTailSegs];
+    if (total <= kTailCap) {
+      for (int base = 0; base < total; base += 4 * 128) {
+        uint64_t raw[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int i = base + j * 128 + et;
+          raw[j] = 0ull;
+          if (i < total) {
+            int sg = 0;
+#pragma unroll
+            for (int step = 128; step > 0; step >>= 1)
+              if (sg + step < kTailSegs && start[sg + step] <= i) sg += step;
+            raw[j] = __ldcg(qbase + static_cast<int64_t>(sg) * a.seg_stride + (i - start[sg]));
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int i = base + j * 128 + et;
+          if (i < total) kin[i] = (static_cast<uint64_t>(order_bits(__uint_as_float(static_cast<uint32_t>(raw[j] >> 32)))) << 32) | (raw[j] & 0xFFFFFFFFull);
+        }
+      }
+      epi_sync();
+      tail_order(kin, kso, total, et);
+      int kept = min(total, k);
+      bool lost = false;
+      if (screened) {
+        if (total >= k) {  // every key within the band below the k-th best screened score goes on to the exact re-scoring
+          const uint64_t t_key = static_cast<uint64_t>(order_bits(key_score(kso[k - 1]) - a.band)) << 32;
+          int lo = k, hi = total;  // first position whose key falls below the threshold
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (kso[mid] >= t_key) lo = mid + 1;
+            else hi = mid;
+          }
+          kept = lo;
+        }
+        lost = kept > kc || __ldcg(a.overflow + q) != 0u;
+      }
+      if (!screened) {
+        const float scale = a.out_scale * (a.out_qscale ? a.out_qscale[q] : 1.0f);
+        for (int i = et; i < k; i += 128) {
+          const bool ok = i < kept;
+          a.out_scores[q * k + i] = ok ? key_score(kso[i]) * scale : -INFINITY;
+          a.out_ids[q * k + i] = ok ? static_cast<int64_t>(key_row(kso[i])) + a.id_offset : -1;
+        }
+      } else if (lost) {  // too many near-ties inside the band: rank the whole catalog for this query
+        if (ew == 0) {
+          const int kr = ls_rank_catalog(sc, rw, kLsCap, hist, q, a, lane);
+          ls_emit_ranked(sc, rw, kr, k, 1.0f, q, a, hist, lane);
+        }
+      } else {
+        warp_rescore<true>(kso, kept, ew, 4, q, a, lane);  // kso[i] <- exact (score, row) of its row
+        epi_sync();
+        tail_order(kso, kin, kept, et);
+        for (int i = et; i < k; i += 128) {
+          const bool ok = i < kept;
+          a.out_scores[q * k + i] = ok ? key_score(kin[i]) : -INFINITY;
+          a.out_ids[q * k + i] = ok ? static_cast<int64_t>(key_row(kin[i])) + a.id_offset : -1;
+        }
+      }
+    } else if (ew == 0) {
+      // more survivors than the buffer holds: the general routines, segment by segment with squeezes in between
+      float tau = -INFINITY;
+      bool lost = false;
+      int n = 0;
+      for (int sg = 0; sg < nseg; ++sg) {
+        const int cs = start[sg + 1] - start[sg];
+        if (n + cs > kLsCap) {
+          __syncwarp();
+          n = ls_reduce(sc, rw, n, k, a.band, hist, &tau);
+          if (n > kc) {
+            lost = true;
+            n = kc;
+          }
+        }
+        const uint64_t* seg = qbase + static_cast<int64_t>(sg) * a.seg_stride;
+        for (int i = lane; i < cs; i += 32) {
+          const uint64_t raw = __ldcg(seg + i);
+          sc[n + i] = order_bits(__uint_as_float(static_cast<uint32_t>(raw >> 32)));
+          rw[n + i] = static_cast<uint32_t>(raw);
+        }
+        n += cs;
+      }
+      __syncwarp();
+      int kept = ls_reduce(sc, rw, n, k, a.band, hist, &tau);
+      if (kept > kc) {
+        lost = true;
+        kept = kc;
+      }
+      if (screened) {
+        if (lost || __ldcg(a.overflow + q) != 0u) kept = ls_rank_catalog(sc, rw, kLsCap, hist, q, a, lane);
+        else ls_rescore<false>(sc, rw, kept, q, a, lane);
+        ls_emit_ranked(sc, rw, kept, k, 1.0f, q, a, hist, lane);
+      } else {
+        ls_emit_ranked(sc, rw, kept, k, a.out_scale * (a.out_qscale ? a.out_qscale[q] : 1.0f), q, a, hist, lane);
+      }
+    }
+    epi_sync();  // the buffers are free for the CTA's next query
+  }
+}
+
 template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSwapThreads, 1)
-gemm_swap_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_c, const GemmArgs g) {
+gemm_swap_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_c, const GemmArgs g,
+                 const __grid_constant__ HistSelectArgs sel) {
   constexpr int TERMS = (MODE == 3) ? 3 : 1;
   constexpr bool BF16 = (MODE == 1);
   constexpr int CT = (TERMS == 3) ? 2 : 1;  // catalog tiles per stage: hi | lo plane
@@ -1010,6 +1186,7 @@ gemm_swap_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
       for (int j = et; j < g.Q; j += 128) g.cand_cnt[static_cast<int64_t>(j) * g.chunks * 2 + seg0] = min(cnt_s[j], cap);
       epi_sync();
     }
+    if (g.fuse_select) swap_select_tail(g.gsync + 2, sel, smem, ew, lane, et);
   }
 
   tc_fence_before();
@@ -1074,7 +1251,10 @@ struct Phase {
 static int plan_phases(int64_t N, int qblocks, int k, Phase* out, int max_phases, bool swap, int begin0 = 0) {
   const int T = static_cast<int>((N + BN - 1) / BN);
   static const int swap_growth = getenv("ICR_SWAP_GROWTH") ? atoi(getenv("ICR_SWAP_GROWTH")) : 32;  // tuning hook
-  static const int k2_growth = getenv("ICR_K2_GROWTH") ? atoi(getenv("ICR_K2_GROWTH")) : 8;  // tuning hook
+  // tuning hook; default 8, or 32 for ONE query block on a catalog that streams from HBM: there every phase costs ~35-45 us of
+  // small GEMM + select beside a stream of a few hundred us, and 3 sparse phases beat 4 (profiles/r02_c4_phase_sweep.txt)
+  static const int k2_growth_env = getenv("ICR_K2_GROWTH") ? atoi(getenv("ICR_K2_GROWTH")) : 0;
+  const int k2_growth = k2_growth_env > 0 ? k2_growth_env : ((qblocks == 1 && T >= 2048) ? 32 : 8);
   const int growth = swap ? swap_growth : k2_growth;
   const int npairs = kNumSMs / 2;
   static const int k2_first = getenv("ICR_K2_FIRST") ? atoi(getenv("ICR_K2_FIRST")) : 4;  // tuning hook
@@ -1126,7 +1306,12 @@ static int plan_phases(int64_t N, int qblocks, int k, Phase* out, int max_phases
 constexpr int kMaxPhases = 16;
 // rows 0..1023 (4 tiles) are scored densely in the first phase of the (non-swapped) top-k path; ICR_K2_DENSE0 / ICR_K2_GROWTH:
 // tuning hooks (profiles/r01_notes.md)
-static const int kDense0Tiles = getenv("ICR_K2_DENSE0") ? atoi(getenv("ICR_K2_DENSE0")) : 4;
+static const int kDense0Env = getenv("ICR_K2_DENSE0") ? atoi(getenv("ICR_K2_DENSE0")) : 0;
+// 4 tiles, or 16 for one query block on a catalog that streams from HBM (one sparse phase less, see plan_phases)
+static int dense0_tiles(int64_t Q, int64_t N) {
+  if (kDense0Env > 0) return kDense0Env;
+  return (Q <= 2 * BM && (N + BN - 1) / BN >= 2048) ? 16 : 4;
+}
 
 // kernel variants: 0 = fp16 hi|lo planes (3 terms), 1 = bf16 streaming both operands, 2 = bf16 with resident queries,
 // 3 / 4 = swapped kernel (small batches) on planes / bf16, 5 / 6 = fp16 screen plane streaming / resident queries,
@@ -1192,7 +1377,8 @@ static int launch_gemm_variant(int which, int grid, const CUtensorMap& map_a, co
   return ICR_OK;
 }
 
-static int launch_swap_variant(int which, int grid, const CUtensorMap& map_q, const CUtensorMap& map_c, const GemmArgs& g, cudaStream_t st) {
+static int launch_swap_variant(int which, int grid, const CUtensorMap& map_q, const CUtensorMap& map_c, const GemmArgs& g, cudaStream_t st,
+                               const HistSelectArgs& sel = HistSelectArgs{}) {
   static thread_local SmemAttrCache cache[3];
   int rc = ICR_OK;
   if (which == 3) rc = ensure_dyn_smem(cache[0], gemm_swap_kernel<3>, kSwapSmemBytes);
@@ -1200,9 +1386,9 @@ static int launch_swap_variant(int which, int grid, const CUtensorMap& map_q, co
   if (which == 7) rc = ensure_dyn_smem(cache[2], gemm_swap_kernel<2>, kSwapSmemBytes);
   if (rc) return rc;
   profile_begin(kKernelGemm, variant_terms(which), st);
-  if (which == 3) launch_gemm_grid(gemm_swap_kernel<3>, grid, kSwapThreads, kSwapSmemBytes, st, g.boot > 0, map_q, map_c, g);
-  if (which == 4) launch_gemm_grid(gemm_swap_kernel<1>, grid, kSwapThreads, kSwapSmemBytes, st, g.boot > 0, map_q, map_c, g);
-  if (which == 7) launch_gemm_grid(gemm_swap_kernel<2>, grid, kSwapThreads, kSwapSmemBytes, st, g.boot > 0, map_q, map_c, g);
+  if (which == 3) launch_gemm_grid(gemm_swap_kernel<3>, grid, kSwapThreads, kSwapSmemBytes, st, g.boot > 0, map_q, map_c, g, sel);
+  if (which == 4) launch_gemm_grid(gemm_swap_kernel<1>, grid, kSwapThreads, kSwapSmemBytes, st, g.boot > 0, map_q, map_c, g, sel);
+  if (which == 7) launch_gemm_grid(gemm_swap_kernel<2>, grid, kSwapThreads, kSwapSmemBytes, st, g.boot > 0, map_q, map_c, g, sel);
   profile_end(st);
   ICR_LAUNCH_CHECK();
   return ICR_OK;
@@ -1288,7 +1474,7 @@ static GemmWs gemm_ws_layout(int64_t Q, int64_t N, int64_t D, int dtype, int k, 
   const int qblocks = static_cast<int>((Q + 2 * BM - 1) / (2 * BM));
   Phase ph[kMaxPhases];
   const bool dense0 = dense0_applies(Q, N, D, dtype);
-  const int np = plan_phases(N, qblocks, k, ph, kMaxPhases, swap_applies(Q, N, D, dtype), dense0 ? kDense0Tiles : 0);
+  const int np = plan_phases(N, qblocks, k, ph, kMaxPhases, swap_applies(Q, N, D, dtype), dense0 ? dense0_tiles(Q, N) : 0);
   int maxc = 1;
   for (int i = 0; i < np; ++i) maxc = ph[i].chunks > maxc ? ph[i].chunks : maxc;
   w.boot_tiles = 0;
@@ -1322,7 +1508,7 @@ static GemmWs gemm_ws_layout(int64_t Q, int64_t N, int64_t D, int dtype, int k, 
   w.cand = take(static_cast<size_t>(Q) * maxc * halves * w.seg_cap * 8);
   w.cand_cnt = take(static_cast<size_t>(Q) * maxc * halves * 4);
   w.scratch = take(static_cast<size_t>(kNumSMs) * kEpiWarps * kSegCapMax * 8);  // in-kernel compaction scratch
-  w.dense0 = take(dense0 ? static_cast<size_t>(Q) * kDense0Tiles * BN * 4 : 0);
+  w.dense0 = take(dense0 ? static_cast<size_t>(Q) * dense0_tiles(Q, N) * BN * 4 : 0);
   size_t gmax_bytes = w.boot_pairs ? static_cast<size_t>((Q + 31) / 32 * 32) * 8 * w.boot_pairs * 4 : 0;
   if (w.k2_boot_tiles) gmax_bytes = static_cast<size_t>(Q) * w.k2_boot_chunks * w.k2_boot_tiles * (BN / 32) * 4;
   w.gmax = take(gmax_bytes);
@@ -1484,13 +1670,25 @@ int launch_gemm_topk(const void* queries, int64_t Q, int64_t ldq, const void* ca
     g.tile_begin = 0;
     g.tile_end = static_cast<int>((N + BN - 1) / BN);
     g.chunks = L.boot_pairs;
-    if ((rc = launch_swap_variant(which, 2 * L.boot_pairs, map_a, map_b, g, st))) return rc;
     HistSelectArgs sp = sa;
     sp.nseg = g.chunks * 2;
     sp.carry_out = mode == 2 ? reinterpret_cast<uint64_t*>(base + L.carry[0]) : nullptr;
     sp.carry_cnt_out = mode == 2 ? reinterpret_cast<int*>(base + L.carry_cnt[0]) : nullptr;
     sp.out_scores = out_scores;
     sp.out_ids = out_ids;
+    // The select moves into the kernel's tail when a query's survivors are expected to be few: the bootstrap threshold is the
+    // k-th largest of `groups` maxima of 32 rows each, so ~N * k / (32 * groups * boot_tiles) rows pass it (plus the screening
+    // band's share): that has to stay under a third of the tail's buffer (a query that overflows it anyway is still exact). Larger cases (catalogs that
+    // stream from HBM, where the select is a few percent of the call) keep the separate select launch.
+    static const bool no_fuse = getenv("ICR_NO_FUSED_SELECT") != nullptr;  // A/B switch for benchmarks and tests
+    const double expect = static_cast<double>(N) * k / (256.0 * L.boot_pairs * L.boot_tiles);
+    // One CTA finishes one query at a time: more queries than CTAs means rounds, which only short lists (k <= 32) afford
+    // (Q = 256 on the 49,688-row catalog: k = 10 75 us against 89 us with the select launch, k = 100 134 against 118).
+    const bool one_round = Q <= 2 * L.boot_pairs || k <= 32;
+    g.fuse_select = (!no_fuse && mode != 3 && one_round && sp.nseg <= kTailSegs && expect <= kTailCap / 3 &&
+                     (mode != 2 || D % 4 == 0)) ? 1 : 0;
+    if ((rc = launch_swap_variant(which, 2 * L.boot_pairs, map_a, map_b, g, st, sp))) return rc;
+    if (g.fuse_select) return ICR_OK;
     return run_select(sp, Q, st);
   }
 
@@ -1514,7 +1712,7 @@ int launch_gemm_topk(const void* queries, int64_t Q, int64_t ldq, const void* ca
     return run_select(sp, Q, st);
   }
 
-  // ---- first phase, dense: rows of the first kDense0Tiles tiles have no threshold to beat yet, so every score would
+  // ---- first phase, dense: rows of the first dense0_tiles() tiles have no threshold to beat yet, so every score would
   // be appended through uncoalesced 8-byte stores (measured: 27 us per tile). They are written as a dense [Q, 1024]
   // score matrix instead (full 128-byte lines) and the select builds its keys from that.
   Phase ph[kMaxPhases];
@@ -1522,6 +1720,7 @@ int launch_gemm_topk(const void* queries, int64_t Q, int64_t ldq, const void* ca
   const bool dense0 = dense0_applies(Q, N, D, dtype);
   int done_phases = 0;
   if (dense0) {
+    const int kDense0Tiles = dense0_tiles(Q, N);
     const int T0 = T < kDense0Tiles ? T : kDense0Tiles;
     float* d0 = reinterpret_cast<float*>(base + L.dense0);
     GemmArgs gd = g;
@@ -1551,7 +1750,7 @@ int launch_gemm_topk(const void* queries, int64_t Q, int64_t ldq, const void* ca
     if (last) return ICR_OK;
     done_phases = 1;
   }
-  const int np = plan_phases(N, qblocks, k, ph, kMaxPhases, swap, dense0 ? kDense0Tiles : 0);
+  const int np = plan_phases(N, qblocks, k, ph, kMaxPhases, swap, dense0 ? dense0_tiles(Q, N) : 0);
   for (int pp = 0; pp < np; ++pp) {
     const int p = pp + done_phases;  // index for the carry ping-pong
     g.tile_begin = ph[pp].tile_begin;

@@ -918,6 +918,36 @@ def test_single_launch_swapped_path_vs_oracle(dtype, Q, N, D, k):
         _check_topk(v, i, rv, ri, rtol)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("Q,k", [(16, 100), (8, 10), (64, 37)])
+def test_select_in_the_gemm_tail_on_a_catalog_sorted_by_similarity(dtype, Q, k):
+    """Single-launch swapped path with the select in the kernel's tail (prep + ONE GEMM launch, no select launch). A catalog
+    sorted by similarity to the queries is the worst case for its bootstrap threshold: the best rows all sit in the first
+    chunks, the k-th largest group maximum comes from far down the order, thousands of rows pass the filter, the GEMM cuts
+    its segments back and the tail's buffer overflows into the segment-by-segment loop. Results stay exact."""
+    if not _gemm_ok():
+        pytest.skip("GEMM path not built yet")
+    N, D = 49_688, 384
+    g = torch.Generator().manual_seed(77)
+    direction = torch.nn.functional.normalize(torch.randn(D, generator=g), dim=0)
+    items = torch.nn.functional.normalize(torch.randn(N, D, generator=g), dim=1)
+    order = torch.argsort(items @ direction, descending=True)
+    items = items[order].contiguous()
+    queries = torch.nn.functional.normalize(direction[None, :] + 0.05 * torch.randn(Q, D, generator=g), dim=1)
+    it, qt = items.to(dtype), queries.to(dtype)
+    cat = icr.DeviceCatalog(it.cuda(), dtype=dtype)
+    v, i = cat.topk(qt.cuda(), k, path=ops.PATH_GEMM)
+    assert ops.last_launch_count() == 2, "expected prep + one GEMM launch with the select in its tail"
+    rv, ri = oracle.cos_topk(qt.float(), it.float(), k)
+    _check_topk(v, i, rv, ri, F32_RTOL if dtype == torch.float32 else 5e-5)
+    # the ordinary case on the same catalog object: random queries, few survivors, the sparse gather
+    q2 = torch.nn.functional.normalize(torch.randn(Q, D, generator=g), dim=1).to(dtype)
+    v, i = cat.topk(q2.cuda(), k, path=ops.PATH_GEMM)
+    assert ops.last_launch_count() == 2
+    rv, ri = oracle.cos_topk(q2.float(), it.float(), k)
+    _check_topk(v, i, rv, ri, F32_RTOL if dtype == torch.float32 else 5e-5)
+
+
 def test_full_size_properties_c2_shape():
     """BASELINE config 2 at full size through size-independent properties (the oracle is too slow for all of it):
     a row-permuted catalog returns the permuted ids with identical scores, every returned score is reproduced by
