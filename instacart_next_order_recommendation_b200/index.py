@@ -34,6 +34,9 @@ import torch
 from . import ops
 from .similarity import default_device, to_device_matrix
 
+# the current stream's handle without building a torch.cuda.Stream object (the request path asks for it on every call)
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None) or (lambda idx: torch.cuda.current_stream(idx).cuda_stream)
+
 logger = logging.getLogger(__name__)
 
 INDEX_SUBDIR = ".embedding_index"
@@ -176,6 +179,7 @@ class DeviceCatalog:
         self.rows = ops._rows(rows)
         self.row_offset = int(row_offset)
         self.request_lock = threading.RLock()  # guards the shared static tensors of topk_small(copy=False)
+        self._plans: dict = {}  # prepared request calls, see _prepared_call
         self.planes: torch.Tensor | None = None
         if build_planes is None:
             build_planes = dtype == torch.float32
@@ -278,13 +282,15 @@ class DeviceCatalog:
         q = queries if isinstance(queries, torch.Tensor) else torch.as_tensor(queries)
         if q.dim() == 1:
             q = q.unsqueeze(0)
-        k = min(int(k), len(self))
-        if k < 1 or q.shape[0] == 0:
+        rows = self.rows
+        k = min(int(k), rows.shape[0])
+        Q, D = q.shape
+        if k < 1 or Q == 0:
             return self.topk(q, max(k, 1))
-        if q.shape[1] != self.input_dim:
-            raise ValueError(f"embedding dims differ: query {q.shape[1]} vs catalog {self.input_dim}")
-        if q.is_cuda and q.dtype == self.dtype and q.device == self.device and q.shape[1] == self.rows.shape[1] and q.is_contiguous() \
-                and q.data_ptr() % 16 == 0 and q.shape[0] <= 7:
+        if D != self.input_dim:
+            raise ValueError(f"embedding dims differ: query {D} vs catalog {self.input_dim}")
+        if Q <= 7 and q.is_cuda and q.dtype == rows.dtype and q.device == rows.device and D == rows.shape[1] and q.is_contiguous() \
+                and q.data_ptr() % 16 == 0:
             # a device-resident query in the catalog's own layout (what encode(convert_to_tensor=True) hands over): the kernel
             # reads it where it lies - no copy into a graph's input buffer, one kernel launch through a prepared argument list
             with self.request_lock:
@@ -303,9 +309,10 @@ class DeviceCatalog:
         side of a request is then ~5 us (ops.cos_topk: ~40 us of checks, allocations and argument conversion) and the
         device side is the one GEMV kernel."""
         Q = q.shape[0]
-        stream = torch.cuda.current_stream(self.device).cuda_stream
+        dev_index = self.rows.device.index
+        stream = _raw_stream(dev_index)
         key = (Q, k, path, stream)
-        plans = self.__dict__.setdefault("_plans", {})
+        plans = self._plans
         plan = plans.get(key)
         if plan is None:
             import ctypes
@@ -327,15 +334,17 @@ class DeviceCatalog:
             plan = plans[key] = (lib.icr_cos_topk, args, vals, ids, ws)
         fn, args, vals, ids, _ = plan
         args[0] = q.data_ptr()
-        if self.device.index is not None and self.device.index != torch.cuda.current_device():
+        if dev_index != torch.cuda.current_device():
             with torch.cuda.device(self.device):
-                ops._lib.check(fn(*args))
+                rc = fn(*args)
         else:
-            ops._lib.check(fn(*args))
+            rc = fn(*args)
+        if rc:
+            ops._lib.check(rc)
         return vals, ids
 
     def topk_host(self, queries: torch.Tensor, k: int, *, out: tuple[torch.Tensor, torch.Tensor] | None = None,
-                  n_chunks: int | None = None, path: int = ops.PATH_AUTO, splits: list[int] | None = None):
+                  n_chunks: int | None = None, path: int = ops.PATH_AUTO, splits: list[int] | None = None, join: bool = True):
         """Host-to-host top-k: CPU query matrix in, CPU (values [Q,k] f32, ids [Q,k] i64) out.
 
         The batch is cut into pieces that flow through three side streams - upload, rank, download - so the copies of
@@ -348,6 +357,12 @@ class DeviceCatalog:
         unpipelined; the round-1 layout, one stream per piece, measured 1.16 ms). Pass pinned tensors
         (and pinned `out`) for truly asynchronous copies. Returns after enqueueing; the current stream waits on the
         side streams, so `torch.cuda.current_stream().synchronize()` makes the outputs valid.
+
+        ``join=False`` (batches in flight): the current stream does NOT wait; the call returns ``(values, ids, done)`` with
+        ``done`` a CUDA event recorded behind the last download. Successive calls then pipeline through the three side
+        streams - the upload of batch s+1 runs under the kernels of batch s and the download of batch s-1 - which is how a
+        bulk job keeps both copy engines and the SMs busy at once. Each batch in flight needs its own `out` buffers; wait on
+        ``done`` (``done.synchronize()``) before reading or re-using them.
         """
         if queries.is_cuda:
             raise ValueError("topk_host takes host tensors; use topk() for device-resident queries")
@@ -408,6 +423,10 @@ class DeviceCatalog:
             with torch.cuda.stream(down):
                 vals_h[lo:hi].copy_(v, non_blocking=True)
                 ids_h[lo:hi].copy_(i, non_blocking=True)
+        if not join:
+            done_all = torch.cuda.Event()
+            done_all.record(down)
+            return vals_h, ids_h, done_all
         cur.wait_stream(down)  # `down` waited on every piece of `rank`, which waited on every upload
         return vals_h, ids_h
 

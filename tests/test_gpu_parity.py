@@ -826,6 +826,20 @@ def test_topk_host_pipeline_equals_device_path():
     assert torch.equal(vh, v.cpu()) and torch.equal(ih, i.cpu())
     rv, ri = oracle.cos_topk(queries[:200], items, 100)
     _check_topk(vh[:200], ih[:200], rv, ri, F32_RTOL)
+    # batches in flight: join=False returns at once with an event; four different batches through two rotating output buffers
+    qp = queries.pin_memory()
+    outs = [(torch.empty(1000, 100).pin_memory(), torch.empty(1000, 100, dtype=torch.int64).pin_memory()) for _ in range(2)]
+    done, got = [], []
+    for b in range(4):
+        if b >= 2:
+            done[b - 2].synchronize()
+            got.append((outs[b % 2][0].clone(), outs[b % 2][1].clone()))
+        done.append(cat.topk_host(qp[b * 700 : b * 700 + 1000], 100, out=outs[b % 2], join=False, n_chunks=1)[2])
+    for b in (2, 3):
+        done[b].synchronize()
+        got.append((outs[b % 2][0].clone(), outs[b % 2][1].clone()))
+    for b, (gv, gi) in enumerate(got):
+        assert torch.equal(gv, v[b * 700 : b * 700 + 1000].cpu()) and torch.equal(gi, i[b * 700 : b * 700 + 1000].cpu())
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
