@@ -834,12 +834,12 @@ def test_topk_host_pipeline_equals_device_path():
         if b >= 2:
             done[b - 2].synchronize()
             got.append((outs[b % 2][0].clone(), outs[b % 2][1].clone()))
-        done.append(cat.topk_host(qp[b * 700 : b * 700 + 1000], 100, out=outs[b % 2], join=False, n_chunks=1)[2])
+        done.append(cat.topk_host(qp[b * 600 : b * 600 + 1000], 100, out=outs[b % 2], join=False, n_chunks=1)[2])
     for b in (2, 3):
         done[b].synchronize()
         got.append((outs[b % 2][0].clone(), outs[b % 2][1].clone()))
     for b, (gv, gi) in enumerate(got):
-        assert torch.equal(gv, v[b * 700 : b * 700 + 1000].cpu()) and torch.equal(gi, i[b * 700 : b * 700 + 1000].cpu())
+        assert torch.equal(gv, v[b * 600 : b * 600 + 1000].cpu()) and torch.equal(gi, i[b * 600 : b * 600 + 1000].cpu())
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
