@@ -92,6 +92,7 @@ struct GemmArgs {
   float* gmax;               // [qpad][4 * gridDim.x] group maxima of the bootstrap tiles
   unsigned int* gsync;       // [3] grid-barrier counters, zero before the launch
   int fuse_select;           // swapped kernel, single-launch mode: the select runs in the kernel's tail (swap_select_tail)
+  int boot_coarse;           // K2 single-launch mode: ONE maximum per (bootstrap tile, column group) instead of one per 32 scores
   float band;                // screened scores (MODE 2): tau already sits `band` below the k-th best; 0 = exact scores
   unsigned int* overflow;    // [Q] screened scores: set when a segment cannot be cut back without losing keys of the band
 };
@@ -512,14 +513,18 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       // final k-th best score. The whole grid meets at a barrier, every epilogue warp ranks the maxima of its share of the
       // queries and publishes tau, a second barrier, and pass 1 filters the whole catalog against those thresholds: the
       // dense first phase, one sparse phase and the two selects between them (a third of the C2 step) are gone.
-      const int gstride = g.chunks * g.boot * (BN / 32);
+      // boot_coarse: one maximum per tile and column group (ECOLS rows) - a large catalog streamed by ONE query block would
+      // otherwise bring more maxima per query than the in-kernel ranking holds (C4 shard, Q = 128: 148 chunks x 8 per tile)
+      const int per_tile = g.boot_coarse ? 1 : (ECOLS / 32);
+      const int gstride = g.chunks * g.boot * EH * per_tile;
       for (int w = pair; w < items; w += npairs) {
         const int chunk = w / g.qblocks, qb = w - chunk * g.qblocks;
         const int t0 = chunk_first_tile(g, chunk);
         const int q = qb * (2 * BM) + static_cast<int>(rank) * BM + ew * 32 + lane;
         const bool live = q < g.Q;
-        float* gq = g.gmax + static_cast<int64_t>(live ? q : 0) * gstride + (chunk * g.boot * EH + half) * (ECOLS / 32);
+        float* gq = g.gmax + static_cast<int64_t>(live ? q : 0) * gstride + (chunk * g.boot * EH + half) * per_tile;
         for (int bt = 0; bt < g.boot; ++bt) {
+          float m_tile = -INFINITY;
           const int row0 = (t0 + bt) * BN + half * ECOLS;
           if (BF16) {
             __syncwarp();
@@ -551,8 +556,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                   m = fmaxf(m, BF16 ? __uint_as_float(r[j]) * cinv_s[cb * 32 + j] : __uint_as_float(r[j]));
               }
             }
-            if (live) gq[bt * (EH * (ECOLS / 32)) + cb] = m;
+            m_tile = fmaxf(m_tile, m);
+            if (live && !g.boot_coarse) gq[bt * (EH * (ECOLS / 32)) + cb] = m;
           }
+          if (live && g.boot_coarse) gq[bt * EH] = m_tile;
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(smem_u32(&tempty_bar[acc]), 0);
@@ -1405,6 +1412,7 @@ struct GemmWs {
   int boot_pairs;  // > 0: single-launch swapped path with in-kernel threshold bootstrap on this many CTA pairs
   int boot_tiles;  // bootstrap tiles per chunk
   int k2_boot_chunks, k2_boot_tiles;  // > 0: single-launch K2 (queries on M) with in-kernel bootstrap
+  int k2_boot_coarse;                 // its maxima are per tile and column group (k2_boot_plan)
 };
 
 // Single-launch mode of K2: one phase over the whole catalog, `chunks` tile ranges per query block, the first `tiles` tiles of
@@ -1412,7 +1420,8 @@ struct GemmWs {
 // ~ICR_K2_BOOT_TARGET keys per query pass the threshold (N * k / rows); the mode needs 2k..kK2BootCap block maxima per query and
 // re-streams at most a quarter of a chunk - i.e. it serves catalogs of up to a few hundred thousand rows, where the phased
 // path spends a third of its time on the two bootstrap phases and their selects; larger catalogs keep the phased path.
-static int k2_boot_plan(int64_t Q, int64_t N, int64_t D, int dtype, int k, int* chunks_out) {
+static int k2_boot_plan(int64_t Q, int64_t N, int64_t D, int dtype, int k, int* chunks_out, int* coarse_out = nullptr) {
+  if (coarse_out) *coarse_out = 0;
   static const bool disabled = getenv("ICR_NO_BOOT_K2") != nullptr;  // A/B switch for benchmarks
   static const int target = getenv("ICR_K2_BOOT_TARGET") ? atoi(getenv("ICR_K2_BOOT_TARGET")) : 550;
   if (disabled || mode_for(dtype) == 3 || swap_applies(Q, N, D, dtype)) return 0;
@@ -1437,7 +1446,23 @@ static int k2_boot_plan(int64_t Q, int64_t N, int64_t D, int dtype, int k, int* 
   int tiles = static_cast<int>((want_rows + static_cast<int64_t>(BN) * best - 1) / (static_cast<int64_t>(BN) * best));
   if (tiles < 1) tiles = 1;
   while (best * tiles * (BN / 32) < 2 * k) ++tiles;
-  if (best * tiles * (BN / 32) > kK2BootCap) return 0;
+  if (best * tiles * (BN / 32) > kK2BootCap) {
+    // Too many 32-score block maxima for the in-kernel ranking. ONE query block on a catalog that streams from HBM (C4 shard,
+    // Q = 65...256) is worth a coarser bootstrap: one maximum per tile and column group, as many bootstrap tiles as the
+    // ranking holds. Fewer sampled rows let more keys pass (C4 shard, k = 100: ~1,650 per query instead of ~550), but the
+    // four sparse phases with their selects that this replaces cost ~100 us beside a 0.33 ms stream.
+    const int eh = epi_warps(1) / 4;
+    const int qblocks1 = static_cast<int>((Q + 2 * BM - 1) / (2 * BM));
+    int ct = kK2BootCap / (best * eh);
+    if (ct > tiles) ct = tiles;
+    static const bool no_coarse = getenv("ICR_NO_BOOT_COARSE") != nullptr;  // A/B switch for benchmarks
+    if (no_coarse || qblocks1 != 1 || T < 2048 || mode_for(dtype) == 3 || ct < 1 || best * ct * eh < 2 * k) return 0;
+    if (static_cast<double>(N) * k / (static_cast<double>(BN) * best * ct) > 2500.0) return 0;  // survivors per query the segments and the select take in their stride
+    if (ct * 4 > T / best) return 0;
+    if (coarse_out) *coarse_out = 1;
+    *chunks_out = best;
+    return ct;
+  }
   // at most a quarter of a chunk is scored twice; half for a catalog the L2 holds, where the second read is cheap and the
   // phased path's extra launches are the larger cost (Q = 512 on the 49,688-row catalog: 74 chunks of 2-3 tiles)
   const int64_t dp = (D + 63) / 64 * 64;
@@ -1481,7 +1506,8 @@ static GemmWs gemm_ws_layout(int64_t Q, int64_t N, int64_t D, int dtype, int k, 
   w.boot_pairs = boot_pairs_for(Q, N, D, dtype, k, &w.boot_tiles);
   if (w.boot_pairs > maxc) maxc = w.boot_pairs;
   w.k2_boot_chunks = 0;
-  w.k2_boot_tiles = k2_boot_plan(Q, N, D, dtype, k, &w.k2_boot_chunks);
+  w.k2_boot_coarse = 0;
+  w.k2_boot_tiles = k2_boot_plan(Q, N, D, dtype, k, &w.k2_boot_chunks, &w.k2_boot_coarse);
   if (w.k2_boot_chunks > maxc) maxc = w.k2_boot_chunks;
   w.max_chunks = maxc;
   const int64_t dp = (D + 63) / 64 * 64;
@@ -1510,7 +1536,7 @@ static GemmWs gemm_ws_layout(int64_t Q, int64_t N, int64_t D, int dtype, int k, 
   w.scratch = take(static_cast<size_t>(kNumSMs) * kEpiWarps * kSegCapMax * 8);  // in-kernel compaction scratch
   w.dense0 = take(dense0 ? static_cast<size_t>(Q) * dense0_tiles(Q, N) * BN * 4 : 0);
   size_t gmax_bytes = w.boot_pairs ? static_cast<size_t>((Q + 31) / 32 * 32) * 8 * w.boot_pairs * 4 : 0;
-  if (w.k2_boot_tiles) gmax_bytes = static_cast<size_t>(Q) * w.k2_boot_chunks * w.k2_boot_tiles * (BN / 32) * 4;
+  if (w.k2_boot_tiles) gmax_bytes = static_cast<size_t>(Q) * w.k2_boot_chunks * w.k2_boot_tiles * (BN / 32) * 4;  // upper bound for the coarse form
   w.gmax = take(gmax_bytes);
   w.total = off + 1024;
   return w;
@@ -1695,6 +1721,7 @@ int launch_gemm_topk(const void* queries, int64_t Q, int64_t ldq, const void* ca
   if (L.k2_boot_tiles > 0) {
     // ---- K2, single launch over the whole catalog (thresholds bootstrapped in the kernel), then one select ----
     g.boot = L.k2_boot_tiles;
+    g.boot_coarse = L.k2_boot_coarse;
     g.gmax = reinterpret_cast<float*>(base + L.gmax);
     g.gsync = g.overflow + Q;
     g.tile_begin = 0;

@@ -962,6 +962,30 @@ def test_select_in_the_gemm_tail_on_a_catalog_sorted_by_similarity(dtype, Q, k):
     _check_topk(v, i, rv, ri, F32_RTOL if dtype == torch.float32 else 5e-5)
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_single_launch_k2_with_coarse_bootstrap_maxima(dtype):
+    """One query block (Q = 200) on a catalog that streams from HBM (600,000 x 384): the queries-on-M kernel runs as ONE launch
+    whose thresholds come from one maximum per bootstrap tile and column group (the 32-score block maxima would be more than the
+    in-kernel ranking holds) - prep + GEMM + select, instead of four phases with a select each."""
+    if not _gemm_ok():
+        pytest.skip("GEMM path not built yet")
+    N, D, Q, k = 600_000, 384, 200, 100
+    g = torch.Generator(device="cuda").manual_seed(5)
+    items = torch.nn.functional.normalize(torch.randn(N, D, device="cuda", generator=g), dim=1)
+    items[::1009] = items[7]  # exact duplicates: equal scores at and around the thresholds
+    queries = torch.nn.functional.normalize(items[torch.arange(Q, device="cuda") * 2999] + 0.3 * torch.randn(Q, D, device="cuda", generator=g), dim=1)
+    cat = icr.DeviceCatalog(items, dtype=dtype)
+    qd = queries.to(dtype)
+    v, i = cat.topk(qd, k)
+    assert ops.last_launch_count() == 3, "expected prep + one GEMM launch + one select"
+    ref = torch.nn.functional.normalize(qd.float(), dim=1) @ torch.nn.functional.normalize(cat.rows.float(), dim=1).T  # fp32 witness on the stored rows
+    rv, ri = torch.topk(ref, k, dim=1)
+    _check_topk(v, i, rv.cpu(), ri.cpu(), 2e-5 if dtype == torch.float32 else 5e-5)
+    sample = torch.arange(0, Q, 25)
+    ov, oi = oracle.cos_topk(qd[sample.cuda()].float().cpu(), cat.rows.float().cpu(), k)
+    _check_topk(v[sample.cuda()], i[sample.cuda()], ov, oi, F32_RTOL if dtype == torch.float32 else 5e-5)
+
+
 def test_full_size_properties_c2_shape():
     """BASELINE config 2 at full size through size-independent properties (the oracle is too slow for all of it):
     a row-permuted catalog returns the permuted ids with identical scores, every returned score is reproduced by
