@@ -490,11 +490,28 @@ def bench_c1(icr, ops, dev, flush):
         cold_replay = timed(lambda i: graphs[i % len(graphs)].replay(), 60)
         warm_replay = timed(lambda i: graphs[0].replay(), 60)
         kt = ops.kernel_timing(lambda: copies[1].topk(qd, k), 20, flush=flush)
+
+        def wall(fn, n=200):  # host wall clock per request, query on the device -> Python lists on the host
+            for i in range(10):
+                fn(i)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for i in range(n):
+                fn(i)
+            return (time.perf_counter() - t0) / n * 1e6
+
+        def two_reads(i):
+            v, ix = copies[i % len(copies)].topk_small(qd, k, copy=False)
+            return v.tolist(), ix.tolist()
+
+        req_host = wall(lambda i: copies[i % len(copies)].topk_request(qd, k))
+        req_two_reads = wall(two_reads)
         nbytes = N * D * (4 if dt == torch.float32 else 2)
         frac = lambda us: nbytes / (us * 1e-6) / 1e9 / peaks["hbm_gbs"]  # noqa: E731
         out[tag] = {"cold_us": cold, "cold_device_us": cold_dev, "cold_graph_replay_us": cold_replay, "cold_eager_call_us": cold_eager,
                     "l2_flushed_us": flushed, "l2_warm_us": warm, "l2_warm_device_us": warm_dev, "graph_replay_us": warm_replay,
-                    "kernel_us": kt["ms_per_launch"] * 1e3, "hbm_frac_cold": frac(cold), "hbm_frac_cold_device": frac(cold_dev),
+                    "kernel_us": kt["ms_per_launch"] * 1e3, "request_to_host_wall_us": req_host, "request_two_device_reads_wall_us": req_two_reads,
+                    "hbm_frac_cold": frac(cold), "hbm_frac_cold_device": frac(cold_dev),
                     "hbm_frac_kernel": frac(kt["ms_per_launch"] * 1e3), "catalog_bytes": nbytes}
         del copies
         torch.cuda.empty_cache()
@@ -503,8 +520,10 @@ def bench_c1(icr, ops, dev, flush):
                    "host launch cost included; cold_device_us = the same with the host running ahead (spin kernel in front of the start event): device-side "
                    "time; cold_graph_replay_us = the request as a CUDA graph, graph.replay() alone; cold_eager_call_us = the rotation through "
                    "DeviceCatalog.topk (generic Python entry: host-bound); l2_flushed_us = one catalog, 512 MB fill before each request (L2 left full of "
-                   "dirty lines); l2_warm_* / graph_replay_us = one catalog, L2-warm; kernel_us = the kernel alone, L2 flushed; fractions = catalog bytes "
-                   "/ time / measured HBM copy peak")
+                   "dirty lines); l2_warm_* / graph_replay_us = one catalog, L2-warm; kernel_us = the kernel alone, L2 flushed; request_to_host_wall_us = host "
+                   "wall clock of DeviceCatalog.topk_request (query on the device -> Python lists on the host: one launch whose last CTA writes "
+                   "pinned host memory, one stream sync; cold rotation) and request_two_device_reads_wall_us = the same through topk_small + two "
+                   ".tolist() reads; fractions = catalog bytes / time / measured HBM copy peak")
     return out
 
 

@@ -303,7 +303,29 @@ class DeviceCatalog:
             graph.replay()
             return (vals.clone(), ids.clone()) if copy else (vals, ids)
 
-    def _prepared_call(self, q: torch.Tensor, k: int, path: int):
+    def topk_request(self, q: torch.Tensor, k: int, *, path: int = ops.PATH_AUTO):
+        """One request, query on the device, result on the HOST: ``(scores, ids)`` as Python lists of Q lists of k.
+
+        The kernel's last CTA stores the k results straight into pinned, device-mapped host memory (16 x 12 bytes over PCIe
+        behind the merge), so the request is one kernel launch and one stream synchronisation - no device-to-host copies
+        (two ``.tolist()`` reads of device tensors cost two synchronising copies, ~10 us each). Takes the same queries as the
+        prepared-call path of ``topk_small`` (device tensor in the catalog's dtype and layout, Q <= 7); anything else falls
+        back to ``topk_small`` + ``.tolist()``. Holds ``request_lock`` until the results are Python objects."""
+        if q.dim() == 1:
+            q = q.unsqueeze(0)
+        rows = self.rows
+        k = min(int(k), rows.shape[0])
+        Q, D = q.shape
+        with self.request_lock:
+            if not (1 <= Q <= 7 and k >= 1 and q.is_cuda and q.dtype == rows.dtype and q.device == rows.device and D == rows.shape[1]
+                    and D == self.input_dim and q.is_contiguous() and q.data_ptr() % 16 == 0):
+                vals, ids = self.topk_small(q, k, path=path, copy=False)
+                return vals.tolist(), ids.tolist()
+            vals, ids = self._prepared_call(q, k, path, host_out=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            return vals.tolist(), ids.tolist()
+
+    def _prepared_call(self, q: torch.Tensor, k: int, path: int, host_out: bool = False):
         """icr_cos_topk for a request-sized device query with everything but the query pointer bound once per
         (Q, k, path, stream): static outputs, a resident zero-filled workspace, ready-made ctypes arguments. The Python
         side of a request is then ~5 us (ops.cos_topk: ~40 us of checks, allocations and argument conversion) and the
@@ -311,7 +333,7 @@ class DeviceCatalog:
         Q = q.shape[0]
         dev_index = self.rows.device.index
         stream = _raw_stream(dev_index)
-        key = (Q, k, path, stream)
+        key = (Q, k, path, stream, host_out)
         plans = self._plans
         plan = plans.get(key)
         if plan is None:
@@ -322,8 +344,12 @@ class DeviceCatalog:
             dt = ops._dtype_code(self.rows)
             need = lib.icr_cos_topk_workspace_bytes(Q, N, D, dt, k, path, int(self.planes is not None))
             ws = torch.zeros(max(int(need), 256), dtype=torch.uint8, device=self.device)
-            vals = torch.empty(Q, k, dtype=torch.float32, device=self.device)
-            ids = torch.empty(Q, k, dtype=torch.int64, device=self.device)
+            if host_out:  # pinned host memory is mapped into the device's address space (UVA): the kernel writes it directly
+                vals = torch.empty(Q, k, dtype=torch.float32).pin_memory()
+                ids = torch.empty(Q, k, dtype=torch.int64).pin_memory()
+            else:
+                vals = torch.empty(Q, k, dtype=torch.float32, device=self.device)
+                ids = torch.empty(Q, k, dtype=torch.int64, device=self.device)
             c64, cvp = ctypes.c_int64, ctypes.c_void_p
             args = [None, c64(Q), c64(D), cvp(self.rows.data_ptr()), c64(N), c64(ops._ld(self.rows)), c64(D), ctypes.c_int(dt),
                     cvp(ops._ptr(self.planes)), cvp(ops._ptr(self.inv_norms)), cvp(None), ctypes.c_int(k), c64(self.row_offset),

@@ -136,10 +136,15 @@ class Recommender:
             # the graph's static query / output tensors are shared by every caller of this catalog: copy-in, replay and
             # host read happen under the catalog's lock so that concurrent requests (a sync route, run_in_executor, a batch
             # job) cannot read each other's results - the reference's recommend() is safe to call from several threads
-            with self.catalog.request_lock:
-                vals, ids = self.catalog.topk_small(query_emb, k_fetch, copy=False)
-                vals = vals[0].tolist()  # one device->host read; synchronises the stream
-                ids = ids[0].tolist()
+            if isinstance(query_emb, torch.Tensor) and query_emb.is_cuda:
+                # one kernel launch; its last CTA writes the k results into pinned host memory, one stream synchronisation
+                vals, ids = self.catalog.topk_request(query_emb, k_fetch)
+                vals, ids = vals[0], ids[0]
+            else:
+                with self.catalog.request_lock:
+                    vals, ids = self.catalog.topk_small(query_emb, k_fetch, copy=False)
+                    vals = vals[0].tolist()  # device->host reads; they synchronise the stream
+                    ids = ids[0].tolist()
             mask_rows = set(excluded_rows)
         else:
             # unbounded exclusion lists: mask rows on the device instead of over-fetching

@@ -816,6 +816,27 @@ def test_topk_small_device_query_takes_the_prepared_call_and_matches_the_oracle(
         assert len(cat._graphs) == 1
 
 
+def test_topk_request_writes_pinned_host_results():
+    """Query on the device, result on the host: the kernel's last CTA stores into pinned host memory (no device-to-host copy)."""
+    items, _ = oracle.synth_clustered(49_688, 384, seed=51)
+    queries, _ = oracle.synth_queries_from_items(items, 8, seed=52)
+    for dtype, tol in ((torch.float32, F32_RTOL), (torch.bfloat16, BF16_RTOL)):
+        cat = icr.DeviceCatalog(items, dtype=dtype)
+        for qn, k in ((1, 16), (1, 10), (1, 128), (3, 32), (7, 16)):
+            for rep in range(2):
+                q = queries[rep : rep + qn].to(dtype).cuda()
+                vals, ids = cat.topk_request(q, k)
+                assert isinstance(vals, list) and len(vals) == qn and len(vals[0]) == k
+                dv, di = cat.topk(q, k)
+                assert torch.equal(torch.tensor(vals), dv.cpu()) and torch.equal(torch.tensor(ids), di.cpu())
+        rv, ri = oracle.cos_topk(q.float().cpu(), cat.rows.float().cpu(), k)
+        _check_topk(torch.tensor(vals), torch.tensor(ids), rv, ri, tol)
+        # host queries and 1-D queries fall back to the graph path, same results
+        vals, ids = cat.topk_request(queries[0].to(dtype).cuda(), 10)
+        dv, di = cat.topk(queries[:1].to(dtype).cuda(), 10)
+        assert torch.equal(torch.tensor(vals), dv.cpu()) and torch.equal(torch.tensor(ids), di.cpu())
+
+
 def test_topk_host_pipeline_equals_device_path():
     items, _ = oracle.synth_clustered(30000, 384, seed=21)
     queries, _ = oracle.synth_queries_from_items(items, 3001, seed=22)
