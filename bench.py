@@ -262,6 +262,7 @@ def main():
         outs = [(torch.empty(Q, k, dtype=torch.float32).pin_memory(), torch.empty(Q, k, dtype=torch.int64).pin_memory()) for _ in range(depth)]
         catalog.topk_host(queries_host, k, out=outs[0], path=path)  # creates the side streams
         rank_stream = catalog._side_streams[1]
+        flush_e2e = flush[: 256 << 20]  # 2x the 126 MB L2; this flush is INSIDE the timed region (0.07 ms per batch)
         cur = torch.cuda.current_stream(dev)
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         done = []
@@ -272,7 +273,7 @@ def main():
             if s >= depth:
                 done[s - depth].synchronize()  # the consumer has this batch's results; its buffers are free again
             with torch.cuda.stream(rank_stream):
-                flush.zero_()
+                flush_e2e.zero_()
             done.append(catalog.topk_host(queries_host, k, out=outs[s % depth], path=path, join=False, n_chunks=1)[2])
         cur.wait_event(done[-1])
         t1.record()
@@ -363,8 +364,8 @@ def main():
                 "note": "DeviceCatalog.topk_host: pinned-host fp32 queries in, (scores f32, ids i64) out to pinned host through upload / rank / download "
                         "streams; catalog resident in HBM as the reference keeps its index in "
                         "memory. value: up to 3 whole batches in flight (join=False, one piece per batch: the upload of batch s+1 and the download of "
-                        "batch s-1 run under the kernels of batch s), ONE timed region around all steps, each batch's copies and a 512 MiB L2 flush in "
-                        "front of its kernels inside it; one_batch_at_a_time: every batch waits for the one before and is cut into 3 pieces (15/70/15 %) "
+                        "batch s-1 run under the kernels of batch s), ONE timed region around all steps, each batch's copies and a 256 MiB L2 flush (2x L2) "
+                        "in front of its kernels inside it; one_batch_at_a_time: every batch waits for the one before and is cut into 3 pieces (15/70/15 %) "
                         "that pipeline inside it (per-batch events, flush outside them) - the round-1/2 number"},
         "gpu_launches": launches_per_step * args.steps,
         "roofline": roof,

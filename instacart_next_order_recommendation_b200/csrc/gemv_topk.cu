@@ -1,7 +1,8 @@
 // K1: streaming cosine GEMV with fused top-k for small query batches (Q <= 7 per pass).
 //
 // HBM-bound by design: every catalog row is read exactly once; the row's squared norm is accumulated from
-// the same data, so no separate normalisation pass or inverse-norm array is read. Scores never reach HBM:
+// the same data (or, for a single query against a catalog that carries precomputed inverse norms, the 32 bytes of
+// norms ride into the ring with their slab). Scores never reach HBM:
 // each CTA keeps, per query, a shared-memory candidate list guarded by a running threshold (the CTA's k-th
 // best so far) and emits its k best keys; the last CTA to finish merges the per-CTA lists in the same launch
 // (no second kernel on the batch-1 latency path).
@@ -10,7 +11,9 @@
 //   gemv_ring_kernel  (default, contiguous catalogs): a producer warp streams 8-row slabs with 1-D bulk async
 //       copies (cp.async.bulk, the TMA engine) into a shared-memory ring guarded by mbarriers; eight consumer
 //       warps read slabs with conflict-free 128-bit shared loads. The whole ring (up to 192 KB per SM) is in
-//       flight from the first microsecond, independent of consumer register pressure.
+//       flight from the first microsecond, independent of consumer register pressure. Every CTA owns one ring
+//       filling of slabs; the rest of the catalog is handed out in chunks from a device-wide counter, so the
+//       slowest SM does not hold up the request's tail.
 //   gemv_topk_kernel  (row-strided catalogs): 128-bit ld.global.nc.L1::no_allocate, RB rows x 3 vectors per
 //       lane in flight.
 //

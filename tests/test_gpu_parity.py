@@ -928,6 +928,7 @@ def test_screened_fp32_band_overflow_is_ranked_exactly(Q):
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("Q,N,D,k", [(8, 49688, 384, 10), (16, 49688, 384, 100), (64, 30000, 384, 10), (128, 49688, 384, 100), (9, 20000, 768, 256),
+                                      (200, 49688, 384, 10), (256, 49688, 384, 32), (160, 40000, 384, 100),  # more queries than CTAs: rounds in the select tail / the select launch
                                       (33, 19200, 128, 1), (5, 100000, 384, 37), (2, 262144, 64, 5)])
 def test_single_launch_swapped_path_vs_oracle(dtype, Q, N, D, k):
     """Request-sized batches on the tensor path: ONE GEMM launch whose thresholds are bootstrapped in the kernel (k-th largest
