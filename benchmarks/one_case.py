@@ -16,6 +16,8 @@ CASES = {
     "c5": (4_000_000, 384, 4096, 100, torch.bfloat16),
     "c2bf16": (49_688, 384, 10_000, 100, torch.bfloat16),
     "c2": (49_688, 384, 10_000, 100, torch.float32),
+    "c2half": (24_844, 384, 10_000, 100, torch.float32),  # 38 MB of fp32 rows: the re-scoring's gathers stay in one die's share of L2
+    "c2quarter": (12_422, 384, 10_000, 100, torch.float32),
     "c1q4": (49_688, 384, 4, 10, torch.float32),
     "c4q16": (1_250_000, 768, 16, 100, torch.bfloat16),
     "c1q32": (49_688, 384, 32, 10, torch.float32),
