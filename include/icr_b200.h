@@ -56,8 +56,9 @@ typedef enum {
   ICR_PATH_GEMM = 2  /* K2: tcgen05/TMEM GEMM + threshold-filter epilogue                */
 } icr_path;
 /* OR-ed into `path`: the workspace is RESIDENT — the caller zero-filled it once and since then only icr_cos_topk calls of
- * the same shape, on one stream, have used it. The GEMV path then skips re-zeroing its merge counter (the merging CTA
- * leaves it at zero): one memset less on the latency path of a request. */
+ * the same shape, on one stream, have used it. The GEMV path then skips re-zeroing its two counters - the merge ticket and
+ * the slab-chunk counter of the ring kernel, both left at zero by the merging CTA: one memset less on the latency path of
+ * a request. */
 #define ICR_PATH_WS_RESIDENT 0x100
 
 int icr_abi_version(void);
@@ -117,7 +118,10 @@ int icr_convert_rows(const float* x, int64_t rows, int64_t dim, int64_t ldx,
  *                (exclude_product_ids semantics, serve_recommendations.py:216-221)
  *   row_offset   added to every returned id (global numbering of a row shard)
  *   out_scores   [Q, k] f32 descending; out_ids [Q, k] i64. If fewer than k rows are
- *                eligible the tail is (-inf, -1).
+ *                eligible the tail is (-inf, -1). Both are only ever written; they may be pinned,
+ *                device-mapped HOST memory (cudaHostAlloc): the last kernel of the call then
+ *                delivers the result over PCIe itself and a request needs no device-to-host copy
+ *                (DeviceCatalog.topk_request; every other pointer must be device memory).
  * ------------------------------------------------------------------------------------- */
 size_t icr_cos_topk_workspace_bytes(int64_t Q, int64_t N, int64_t D, int dtype, int k, int path,
                                     int have_planes);
