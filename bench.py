@@ -306,6 +306,10 @@ def main():
         roof = {"bound": "hbm", "achieved": bytes_per_launch / (kt["ms_per_launch"] * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s"}
         roof["note"] = f"catalog bytes per GEMV launch (L2-resident after the first pass); peak = {peaks['source']} HBM copy"
     roof["frac"] = roof["achieved"] / roof["peak"]
+    if roof["bound"] == "tensor" and peaks.get("bf16_tflops_sustained"):  # report against the burst figure and state the sustained one
+        roof["peak_sustained"] = peaks["bf16_tflops_sustained"]
+        roof["frac_of_sustained"] = roof["achieved"] / peaks["bf16_tflops_sustained"]
+    roof["whole_step_frac"] = (flops / (total_ms / args.steps * 1e-3) / 1e12 / peaks["bf16_tflops"]) if roof["bound"] == "tensor" else None
     roof["traffic"] = None  # NOT measured by this run: bytes per launch from the committed ncu --set full capture of this workload, if there is one
     try:
         cap = json.loads((ROOT / "profiles" / "r02_kernel_traffic.json").read_text())[kt["kernel"]][args.dtype]
