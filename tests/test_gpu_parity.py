@@ -790,6 +790,18 @@ def test_topk_small_cuda_graph_equals_plain_call():
                 vs, is_ = cat.topk_small(q.numpy(), 16)  # host numpy in, like SentenceTransformer.encode
                 assert torch.equal(vs, v) and torch.equal(is_, i)
         assert len(cat._graphs) == 2
+    # a captured call that contains a select launch: 8 queries against 300,000 rows leave too many survivors for the in-kernel
+    # select, so prep + GEMM + select are all in the graph
+    big, _ = oracle.synth_clustered(300_000, 128, seed=33)
+    q8, _ = oracle.synth_queries_from_items(big, 8, seed=34)
+    cat = icr.DeviceCatalog(big, dtype=torch.bfloat16)
+    for rep in range(3):
+        q = torch.roll(q8, rep, 0)
+        v, i = cat.topk(q.cuda(), 100)
+        vs, is_ = cat.topk_small(q.numpy(), 100)
+        assert torch.equal(vs, v) and torch.equal(is_, i)
+    rv, ri = oracle.cos_topk(q.to(torch.bfloat16).float(), cat.rows.float().cpu(), 100)
+    _check_topk(vs, is_, rv, ri, 5e-5)
 
 
 def test_topk_small_device_query_takes_the_prepared_call_and_matches_the_oracle():
