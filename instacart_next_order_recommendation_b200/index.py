@@ -325,7 +325,7 @@ class DeviceCatalog:
             torch.cuda.current_stream(self.device).synchronize()
             return vals.tolist(), ids.tolist()
 
-    def _prepared_call(self, q: torch.Tensor, k: int, path: int, host_out: bool = False):
+    def _prepared_call(self, q: torch.Tensor, k: int, path: int, host_out: bool = False, fresh_out: bool = False):
         """icr_cos_topk for a request-sized device query with everything but the query pointer bound once per
         (Q, k, path, stream): static outputs, a resident zero-filled workspace, ready-made ctypes arguments. The Python
         side of a request is then ~5 us (ops.cos_topk: ~40 us of checks, allocations and argument conversion) and the
@@ -357,9 +357,16 @@ class DeviceCatalog:
                     ctypes.c_size_t(ws.numel()), cvp(stream)]
             if len(plans) >= 64:
                 plans.clear()
-            plan = plans[key] = (lib.icr_cos_topk, args, vals, ids, ws)
-        fn, args, vals, ids, _ = plan
+            plan = plans[key] = (lib.icr_cos_topk, args, vals, ids, ws, vals.data_ptr(), ids.data_ptr())
+        fn, args, vals, ids = plan[:4]
         args[0] = q.data_ptr()
+        if fresh_out:  # the caller keeps the result: new tensors instead of the plan's static ones
+            out_v = torch.empty(Q, k, dtype=torch.float32, device=self.device)
+            out_i = torch.empty(Q, k, dtype=torch.int64, device=self.device)
+            args[14], args[15] = out_v.data_ptr(), out_i.data_ptr()
+        else:
+            out_v, out_i = vals, ids
+            args[14], args[15] = plan[5], plan[6]
         if dev_index != torch.cuda.current_device():
             with torch.cuda.device(self.device):
                 rc = fn(*args)
@@ -367,7 +374,7 @@ class DeviceCatalog:
             rc = fn(*args)
         if rc:
             ops._lib.check(rc)
-        return vals, ids
+        return out_v, out_i
 
     def topk_host(self, queries: torch.Tensor, k: int, *, out: tuple[torch.Tensor, torch.Tensor] | None = None,
                   n_chunks: int | None = None, path: int = ops.PATH_AUTO, splits: list[int] | None = None, join: bool = True):
@@ -460,6 +467,14 @@ class DeviceCatalog:
         """(values [Q,k], global ids [Q,k]) of the k most cosine-similar rows per query. With ``peer``
         (``PeerExchange.next_call()``; needs k <= len(self)) the rows are one rank's shard and the result is the global
         top-k over all ranks' shards (``ops.cos_topk``)."""
+        q = queries
+        rows = self.rows
+        if (exclude_mask is None and peer is None and isinstance(q, torch.Tensor) and q.dim() == 2 and 1 <= q.shape[0] <= 7 and q.is_cuda
+                and q.dtype == rows.dtype and q.device == rows.device and q.shape[1] == rows.shape[1] == self.input_dim and q.is_contiguous()
+                and q.data_ptr() % 16 == 0 and 1 <= int(k) <= rows.shape[0]):
+            # request-sized device query in the catalog's layout: the prepared argument list of the request path, fresh outputs
+            with self.request_lock:
+                return self._prepared_call(q, int(k), path, fresh_out=True)
         q = to_device_matrix(queries, device=self.device, dtype=self.dtype)
         if peer is not None and int(k) > len(self):
             raise ValueError("a sharded call needs k <= the shard's rows (pad the shard's own lists and use peer_exchange_merge instead)")
