@@ -60,7 +60,11 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     stamp = LIB_DIR / "libicr_b200.digest"
     digest = source_digest()
     if not force and LIB_PATH.exists() and stamp.exists() and stamp.read_text() == digest:
-        return LIB_PATH
+        # the stamp is tracked by git: a checkout can restore it next to a library built from other sources, so the library
+        # must also be newer than every source it was built from
+        newest = max(p.stat().st_mtime for p in list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "icr_b200.h"])
+        if LIB_PATH.stat().st_mtime >= newest:
+            return LIB_PATH
     objs = []
     procs = []
     for src in SOURCES:

@@ -812,7 +812,7 @@ def test_topk_small_device_query_takes_the_prepared_call_and_matches_the_oracle(
     for dtype, tol in ((torch.float32, F32_RTOL), (torch.bfloat16, BF16_RTOL)):
         cat = icr.DeviceCatalog(items, dtype=dtype)
         ref_items = cat.rows.float().cpu()
-        for qn, k in ((1, 10), (1, 16), (1, 100), (2, 10), (7, 16)):
+        for qn, k in ((1, 10), (1, 16), (1, 100), (2, 10), (7, 16), (1, 32), (1, 24), (1, 14), (1, 33)):  # k <= 16: the one-trip merge; above: heads + walk
             for rep in range(3):
                 q = queries[rep : rep + qn].to(dtype).cuda()
                 v, i = cat.topk_small(q, k)
@@ -820,7 +820,7 @@ def test_topk_small_device_query_takes_the_prepared_call_and_matches_the_oracle(
                     assert ops.last_launch_count() == 1
                 rv, ri = oracle.cos_topk(q.float().cpu(), ref_items, k)
                 _check_topk(v, i, rv, ri, tol)
-        assert len(cat._plans) == 5 and not getattr(cat, "_graphs", {})
+        assert len(cat._plans) == 9 and not getattr(cat, "_graphs", {})
         # a query in another dtype or on the host still goes through the graph path
         v, i = cat.topk_small(queries[:1].numpy(), 10)
         rv, ri = oracle.cos_topk(queries[:1].to(dtype).float(), ref_items, 10)
