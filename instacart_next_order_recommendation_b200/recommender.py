@@ -132,7 +132,9 @@ class Recommender:
         if top_k + len(excluded_rows) <= ops.MAX_K:
             # exact: the best (top_k + #excluded) rows contain the best top_k non-excluded ones
             k_fetch = top_k + len(excluded_rows)
-            k_fetch = min(n, next(b for b in (16, 32, 64, 128, 256) if b >= k_fetch))  # few distinct shapes -> few CUDA graphs
+            # few distinct shapes -> few prepared calls / CUDA graphs; exact up to 16 (the one-trip merge: top-10 with no
+            # exclusions is 2 us faster at k = 10 than at k = 16), then steps (profiles/r02_k1_request_by_k.txt)
+            k_fetch = min(n, k_fetch if k_fetch <= 16 else next(b for b in (24, 32, 48, 64, 100, 128, 192, 256) if b >= k_fetch))
             # the graph's static query / output tensors are shared by every caller of this catalog: copy-in, replay and
             # host read happen under the catalog's lock so that concurrent requests (a sync route, run_in_executor, a batch
             # job) cannot read each other's results - the reference's recommend() is safe to call from several threads
