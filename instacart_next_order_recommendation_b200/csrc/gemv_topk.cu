@@ -427,14 +427,14 @@ __device__ __forceinline__ void merge_query(const GemvArgs& a, GemvSmem<QT>& sm,
   }
 }
 
-// "flat" tail of a single-query request with short lists (k <= 16, at most 256 CTAs and 8 keys per merging thread): every CTA
+// "flat" tail of a single-query request with short lists (k <= 16, at most 256 CTAs and 10 keys per merging thread): every CTA
 // leaves its k best keys sorted and zero-padded to k, so the merging CTA fetches the whole [G][k] block and the G list heads
 // in ONE memory round trip of independent loads (the walk over list tails in dependent chunks was 2.7 us of a 24 us
 // request). A key can only be among the k best if it reaches `floor`, the largest over the 8 warps of the k-th largest of a
 // warp's 32 heads (ranked by counting over shuffles - a short loop, not a sorting network: this code starts from a cold
 // instruction cache): k distinct keys >= floor exist. What survives (typically 50-100 keys) is ranked by counting, which
 // yields the sorted output positions directly.
-constexpr int kFlatPer = 8;
+constexpr int kFlatPer = 10;  // keys per merging thread: k <= 16 at 148 CTAs
 constexpr int kFlatSurv = 256;
 __device__ __forceinline__ bool flat_tail(const GemvArgs& a, int nq) {
   return nq == 1 && a.k <= 16 && gridDim.x <= kGemvThreads && static_cast<int>(gridDim.x) * a.k <= kFlatPer * kGemvThreads &&
